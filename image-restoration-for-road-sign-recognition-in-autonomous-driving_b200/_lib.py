@@ -1,0 +1,102 @@
+"""ctypes binding of libb2r.so (the C-ABI declared in include/b2r.h).
+
+There is no CPU fallback: if the shared object is missing the import of any op raises, and every op raises on a
+non-zero return code with the library's own message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import build as _build
+
+B2R_ACT_NONE, B2R_ACT_RELU, B2R_ACT_PRELU = 0, 1, 2
+B2R_ORDER_BLUR_FOG_NOISE, B2R_ORDER_FOG_NOISE_BLUR = 0, 1
+B2R_DEG_CLIP_AFTER_NOISE = 1
+B2R_IN_F32_NCHW, B2R_IN_U8_NHWC = 0, 1
+B2R_OUT_NHWC, B2R_OUT_CONVT2X2 = 0, 1
+B2R_MAX_SRC, B2R_MAX_KBLOCKS, B2R_MAX_BLUR = 3, 96, 15
+
+# every symbol include/b2r.h declares (tests/test_abi.py checks the list against the header and the .so)
+SYMBOLS = (
+    "b2r_version", "b2r_last_error", "b2r_degrade", "b2r_conv3x3_c3", "b2r_conv_gemm", "b2r_final_conv1x1",
+    "b2r_maxpool2x2", "b2r_adaptive_avgpool7", "b2r_linear_f32out", "b2r_argmax_count",
+)
+
+
+class ConvGemmDesc(C.Structure):
+    """struct b2r_conv_gemm_desc (include/b2r.h)."""
+    _fields_ = [
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("num_src", C.c_int32),
+        ("src", C.c_void_p * B2R_MAX_SRC),
+        ("src_C", C.c_int32 * B2R_MAX_SRC),
+        ("weights", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("cout_total", C.c_int32),
+        ("num_kblocks", C.c_int32),
+        ("kblocks_host", C.POINTER(C.c_uint32)),
+        ("act", C.c_int32),
+        ("slope", C.c_float),
+        ("out_mode", C.c_int32),
+        ("out", C.c_void_p),
+        ("out_pool", C.c_void_p),
+        ("out_C", C.c_int32),
+        ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("tile_n", C.c_int32),
+        ("block_n", C.c_int32),
+        ("max_ctas", C.c_int32),
+    ]
+
+
+class B2RError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """dlopen libb2r.so (building it first when nvcc is available and the sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not path.exists():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this box
+            raise B2RError(f"libb2r.so is missing at {path} and could not be built: {e}") from e
+    lib = C.CDLL(str(path))
+    vp, i32, f32, u64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64
+    lib.b2r_version.restype = C.c_int
+    lib.b2r_version.argtypes = []
+    lib.b2r_last_error.restype = C.c_char_p
+    lib.b2r_last_error.argtypes = []
+    lib.b2r_degrade.restype = C.c_int
+    lib.b2r_degrade.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, u64, u64, i32, i32, vp]
+    lib.b2r_conv3x3_c3.restype = C.c_int
+    lib.b2r_conv3x3_c3.argtypes = [vp, i32, C.POINTER(f32), C.POINTER(f32), vp, vp, i32, f32, vp, i32, i32, i32, vp]
+    lib.b2r_conv_gemm.restype = C.c_int
+    lib.b2r_conv_gemm.argtypes = [C.POINTER(ConvGemmDesc), vp]
+    lib.b2r_final_conv1x1.restype = C.c_int
+    lib.b2r_final_conv1x1.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.b2r_maxpool2x2.restype = C.c_int
+    lib.b2r_maxpool2x2.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.b2r_adaptive_avgpool7.restype = C.c_int
+    lib.b2r_adaptive_avgpool7.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.b2r_linear_f32out.restype = C.c_int
+    lib.b2r_linear_f32out.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.b2r_argmax_count.restype = C.c_int
+    lib.b2r_argmax_count.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().b2r_last_error()
+        raise B2RError(f"libb2r error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,521 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   M = output pixels (128 per tile: a TW x TH x TN box of the NHWC pixel grid)
+//   N = output channels (BLOCK_N = 64 / 128 / 256 per tile)
+//   K = list of "k-blocks": 64 input channels of one source tensor at one spatial offset (dh, dw)
+//
+// A k-block's A operand is ONE 4-D TMA box load (64 ch x TW x TH x TN) at coordinates shifted by (dw, dh):
+// out-of-bounds rows/columns are zero-filled by the TMA unit, which is exactly conv padding=1, and the box lands
+// in shared memory as 128 rows x 128 B with the 128-byte swizzle — the canonical K-major UMMA operand layout.
+// The B operand is a 2-D TMA box (64 x BLOCK_N) of the packed weight matrix.  Accumulators live in TMEM
+// (2 stages x BLOCK_N fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> bf16 -> swizzled smem -> TMA store, plus the
+// fused 2x2 max-pool computed from the staged tile).  Persistent: one CTA per SM walks tiles round-robin.
+//
+// Reference semantics replaced: nn.Conv2d(3x3, pad 1) / ConvTranspose2d(2,2) / BatchNorm2d(eval) / ReLU / PReLU /
+// MaxPool2d(2,2) / torch.cat / the ResidualBlock add, as used by SimpleUNet.forward (07_train_restoration.py:99-120),
+// ResUNet.forward (14_train_unified_advanced.py:151-186) and torchvision VGG16 (18_test_unified_benchmark.py:46).
+#include <cstring>
+
+#include "b2r_internal.h"
+#include "ptx_sm100.cuh"
+
+namespace b2r {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kStagingFull = 16384;                  // 128 px x 64 ch bf16
+constexpr int kStagingPool = 4096;                   // 32 px x 64 ch bf16
+constexpr int kNumThreads = 192;
+constexpr int kEpiThreads = 128;
+
+struct alignas(64) ConvGemmParams {
+    CUtensorMap a_map[B2R_MAX_SRC];
+    CUtensorMap b_map;
+    CUtensorMap out_map[4];
+    CUtensorMap pool_map;
+    const float* bias;
+    float slope;
+    int act;
+    int num_kblocks;
+    int linear_k;
+    int tiles_w, tiles_h, tiles_n;
+    int tile_w, tile_h, tile_n;
+    int n_tiles;          // cout_total / BLOCK_N
+    int n_tiles_per_out;  // n-tiles per output map (CONVT: C_out / BLOCK_N; NHWC: n_tiles)
+    int store_full, store_pool;
+    uint32_t kblk[B2R_MAX_KBLOCKS];
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+    static constexpr int kBStageBytes = BLOCK_N * 128;
+    static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+    static constexpr int kStages = BLOCK_N == 64 ? 6 : (BLOCK_N == 128 ? 5 : 3);
+    static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
+    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * (kStagingFull + kStagingPool) +
+                                      BLOCK_N * 4 /*bias*/ + 256 /*barriers + tmem ptr*/;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act, float slope) {
+    if (act == B2R_ACT_RELU) return fmaxf(x, 0.f);
+    if (act == B2R_ACT_PRELU) return x >= 0.f ? x : x * slope;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
+    __nv_bfloat162 y = *reinterpret_cast<__nv_bfloat162*>(&b);
+    __nv_bfloat162 r = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr uint32_t kIdesc = make_idesc_bf16_f32(kBlockM, BLOCK_N);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stages = smem;
+    uint8_t* staging = smem + kStages * Cfg::kStageBytes;
+    float* bias_s = reinterpret_cast<float*>(staging + 2 * (kStagingFull + kStagingPool));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + BLOCK_N);
+    uint64_t* full_bar = bars;                       // [kStages]
+    uint64_t* empty_bar = bars + kStages;            // [kStages]
+    uint64_t* tmem_full_bar = bars + 2 * kStages;    // [2]
+    uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // [2]
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int total_tiles = num_m_tiles * p.n_tiles;
+
+    if (warp_idx == 0 && lane == 0) {
+        for (int i = 0; i < B2R_MAX_SRC; ++i) tma_prefetch_desc(&p.a_map[i]);
+        tma_prefetch_desc(&p.b_map);
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.out_map[i]);
+        tma_prefetch_desc(&p.pool_map);
+    }
+    if (warp_idx == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kStages; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], 4);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp_idx == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                const int m = tile / p.n_tiles;
+                const int w0 = (m % p.tiles_w) * p.tile_w;
+                const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.tile_h;
+                const int n0 = (m / (p.tiles_w * p.tiles_h)) * p.tile_n;
+                for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                    int src = 0, dh = 0, dw = 0, c0 = kb * kBlockK;
+                    if (!p.linear_k) {
+                        const uint32_t e = p.kblk[kb];
+                        src = e & 3;
+                        dh = int((e >> 2) & 3) - 1;
+                        dw = int((e >> 4) & 3) - 1;
+                        c0 = int(e >> 8) * kBlockK;
+                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    uint8_t* sa = stages + stage * Cfg::kStageBytes;
+                    tma_load_4d(sa, &p.a_map[src], &full_bar[stage], c0, w0 + dw, h0 + dh, n0);
+                    tma_load_2d(sa + kAStageBytes, &p.b_map, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================================== MMA issuer =====================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + uint32_t(acc * BLOCK_N);
+                for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stages + stage * Cfg::kStageBytes);
+                    const uint64_t adesc = make_sdesc_sw128(sa, 1024);
+                    const uint64_t bdesc = make_sdesc_sw128(sa + kAStageBytes, 1024);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // advance 32 B (16 bf16) along K inside the 128-B swizzle row: +2 in the >>4 address field
+                        umma_bf16_ss(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc,
+                                     (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs have read it
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===================================== epilogue =====================================
+        const int quarter = warp_idx & 3;          // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;       // tile row (pixel) == TMEM lane
+        const int epi_tid = row;                   // 0..127
+        const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t chunk_counter = 0;
+        const int tw = p.tile_w, th = p.tile_h;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.n_tiles;
+            const int m = tile / p.n_tiles;
+            const int w0 = (m % p.tiles_w) * p.tile_w;
+            const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.tile_h;
+            const int n0 = (m / (p.tiles_w * p.tiles_h)) * p.tile_n;
+            const int out_idx = n_tile / p.n_tiles_per_out;
+            const int ch_tile0 = (n_tile % p.n_tiles_per_out) * BLOCK_N;
+
+            // bias of this n-tile -> smem (previous tile's readers are past their last named barrier)
+            for (int i = epi_tid; i < BLOCK_N; i += kEpiThreads) bias_s[i] = p.bias[n_tile * BLOCK_N + i];
+
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 64; ++c) {
+                const int buf = chunk_counter & 1;
+                ++chunk_counter;
+                uint8_t* sfull = staging + buf * (kStagingFull + kStagingPool);
+                uint8_t* spool = sfull + kStagingFull;
+                if (epi_tid == 0) tma_store_wait_read<1>();  // the store that last read `buf` has drained
+                named_barrier_sync(1, kEpiThreads);
+
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * BLOCK_N + c * 64 + half * 32), v);
+                    tmem_ld_wait();
+                    const float* bs = bias_s + c * 64 + half * 32;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = q * 8 + e * 2;
+                            const float x0 = apply_act(__uint_as_float(v[j]) + bs[j], p.act, p.slope);
+                            const float x1 = apply_act(__uint_as_float(v[j + 1]) + bs[j + 1], p.act, p.slope);
+                            o[e] = pack_bf16x2(x0, x1);
+                        }
+                        const int jj = half * 4 + q;  // 16-byte chunk index within the 128-byte row
+                        const uint32_t addr = smem_u32(sfull) + uint32_t(row * 128 + ((jj ^ (row & 7)) << 4));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]),
+                                     "r"(o[2]), "r"(o[3])
+                                     : "memory");
+                    }
+                }
+                if (c == BLOCK_N / 64 - 1) {
+                    // all of this warp's TMEM reads of the accumulator are done -> hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                fence_proxy_async_smem();
+                named_barrier_sync(1, kEpiThreads);
+
+                if (p.store_pool) {
+                    // 2x2 max-pool of the staged tile: thread -> pooled pixel rp = tid/4, 16 channels (2 chunks)
+                    const int rp = epi_tid >> 2;
+                    const int cg = epi_tid & 3;
+                    const int pw = tw >> 1, ph = th >> 1;
+                    const int wp = rp % pw;
+                    const int hp = (rp / pw) % ph;
+                    const int nl = rp / (pw * ph);
+                    const int r00 = (nl * th + 2 * hp) * tw + 2 * wp;
+                    const int rr[4] = {r00, r00 + 1, r00 + tw, r00 + tw + 1};
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int jj = cg * 2 + cc;
+                        uint32_t mx[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t a = smem_u32(sfull) + uint32_t(rr[k] * 128 + ((jj ^ (rr[k] & 7)) << 4));
+                            uint32_t t0, t1, t2, t3;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3)
+                                         : "r"(a));
+                            if (k == 0) {
+                                mx[0] = t0; mx[1] = t1; mx[2] = t2; mx[3] = t3;
+                            } else {
+                                mx[0] = bf16x2_max(mx[0], t0);
+                                mx[1] = bf16x2_max(mx[1], t1);
+                                mx[2] = bf16x2_max(mx[2], t2);
+                                mx[3] = bf16x2_max(mx[3], t3);
+                            }
+                        }
+                        const uint32_t d = smem_u32(spool) + uint32_t(rp * 128 + ((jj ^ (rp & 7)) << 4));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(mx[0]), "r"(mx[1]),
+                                     "r"(mx[2]), "r"(mx[3])
+                                     : "memory");
+                    }
+                    fence_proxy_async_smem();
+                    named_barrier_sync(1, kEpiThreads);
+                }
+
+                if (epi_tid == 0) {
+                    const int ch0 = ch_tile0 + c * 64;
+                    if (p.store_full) tma_store_4d(&p.out_map[out_idx], sfull, ch0, w0, h0, n0);
+                    if (p.store_pool) tma_store_4d(&p.pool_map, spool, ch0, w0 >> 1, h0 >> 1, n0);
+                    tma_store_commit();
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (epi_tid == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        __syncwarp();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+static int next_pow2(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// Pick (tw, th, tn), powers of two with product 128, minimising the number of tiles, then the halo area.
+// Pass 0 keeps every box dimension within the next power of two of the tensor dimension; pass 1 (tiny tensors,
+// e.g. a batch of one row through a Linear layer) drops that restriction and relies on TMA clipping.
+static void choose_tile(int N, int H, int W, bool pool, bool spatial_taps, int* tw_o, int* th_o, int* tn_o) {
+    for (int pass = 0; pass < 2; ++pass) {
+        long best_tiles = -1, best_halo = 0;
+        for (int tw = 128; tw >= 1; tw >>= 1) {
+            for (int th = 128 / tw; th >= 1; th >>= 1) {
+                const int tn = 128 / (tw * th);
+                if (pass == 0 && (tw > next_pow2(W) || th > next_pow2(H) || tn > next_pow2(N))) continue;
+                if (pool && (tw < 2 || th < 2)) continue;
+                const long tiles = (long)ceil_div(W, tw) * ceil_div(H, th) * ceil_div(N, tn);
+                const long halo = spatial_taps ? (long)(tw + 2) * (th + 2) * tn : 0;
+                if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && halo < best_halo)) {
+                    best_tiles = tiles;
+                    best_halo = halo;
+                    *tw_o = tw;
+                    *th_o = th;
+                    *tn_o = tn;
+                }
+            }
+        }
+        if (best_tiles >= 0) return;
+    }
+}
+
+template <int BLOCK_N>
+static int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    B2R_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        B2R_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Cfg::kSmemBytes));
+        if (dev < 64) attr_set[dev] = true;
+    }
+    conv_gemm_kernel<BLOCK_N><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
+}  // namespace b2r
+
+extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
+    using namespace b2r;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    B2R_REQUIRE(d != nullptr, "desc is null");
+    B2R_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, "bad shape N=%d H=%d W=%d", d->N, d->H, d->W);
+    B2R_REQUIRE(d->num_src >= 1 && d->num_src <= B2R_MAX_SRC, "num_src=%d", d->num_src);
+    B2R_REQUIRE(d->weights && d->bias, "weights/bias null");
+    B2R_REQUIRE(d->cout_total > 0 && d->cout_total % 64 == 0, "cout_total=%d must be a multiple of 64", d->cout_total);
+    B2R_REQUIRE(d->num_kblocks >= 1, "num_kblocks=%d", d->num_kblocks);
+    B2R_REQUIRE(d->kblocks_host == nullptr || d->num_kblocks <= B2R_MAX_KBLOCKS, "num_kblocks=%d > %d", d->num_kblocks,
+                B2R_MAX_KBLOCKS);
+    B2R_REQUIRE(d->out || d->out_pool, "no output");
+    B2R_REQUIRE(d->out_C > 0 && d->out_C % 64 == 0, "out_C=%d must be a multiple of 64", d->out_C);
+    B2R_REQUIRE(d->act >= B2R_ACT_NONE && d->act <= B2R_ACT_PRELU, "act=%d", d->act);
+    const bool convt = d->out_mode == B2R_OUT_CONVT2X2;
+    B2R_REQUIRE(convt || d->out_mode == B2R_OUT_NHWC, "out_mode=%d", d->out_mode);
+    B2R_REQUIRE(!(convt && d->out_pool), "pooling is not available with CONVT2X2");
+    B2R_REQUIRE(!convt || d->cout_total % 4 == 0, "CONVT2X2 needs cout_total = 4*C_out");
+    const int cout = convt ? d->cout_total / 4 : d->cout_total;
+    B2R_REQUIRE(cout % 64 == 0 && cout <= d->out_C, "C_out=%d vs out_C=%d", cout, d->out_C);
+    if (d->out_pool) B2R_REQUIRE(d->H % 2 == 0 && d->W % 2 == 0, "fused pool needs even H, W (got %d x %d)", d->H, d->W);
+
+    bool spatial = false;
+    for (int i = 0; i < d->num_src; ++i) {
+        B2R_REQUIRE(d->src[i] != nullptr, "src[%d] is null", i);
+        B2R_REQUIRE(d->src_C[i] > 0 && d->src_C[i] % 64 == 0, "src_C[%d]=%d must be a multiple of 64", i, d->src_C[i]);
+    }
+    if (d->kblocks_host) {
+        for (int kb = 0; kb < d->num_kblocks; ++kb) {
+            const uint32_t e = d->kblocks_host[kb];
+            const int src = e & 3, dh = int((e >> 2) & 3) - 1, dw = int((e >> 4) & 3) - 1, c64 = int(e >> 8);
+            B2R_REQUIRE(src < d->num_src, "kblock %d: source %d >= num_src", kb, src);
+            B2R_REQUIRE(dh >= -1 && dh <= 1 && dw >= -1 && dw <= 1, "kblock %d: bad offset", kb);
+            B2R_REQUIRE((c64 + 1) * 64 <= d->src_C[src], "kblock %d: channel chunk %d outside source %d (C=%d)", kb, c64,
+                        src, d->src_C[src]);
+            if (dh != 0 || dw != 0) spatial = true;
+        }
+    } else {
+        B2R_REQUIRE(d->num_kblocks * 64 <= d->src_C[0], "linear K: %d kblocks vs src_C=%d", d->num_kblocks, d->src_C[0]);
+    }
+
+    // ---- tile geometry
+    int block_n = d->block_n;
+    if (block_n == 0) block_n = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
+    B2R_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "block_n=%d", block_n);
+    B2R_REQUIRE(cout % block_n == 0, "C_out=%d not a multiple of block_n=%d", cout, block_n);
+    int tw = d->tile_w, th = d->tile_h, tn = d->tile_n;
+    if (tw == 0 && th == 0 && tn == 0) choose_tile(d->N, d->H, d->W, d->out_pool != nullptr, spatial, &tw, &th, &tn);
+    B2R_REQUIRE(tw > 0 && th > 0 && tn > 0 && tw * th * tn == kBlockM, "tile %dx%dx%d must cover 128 pixels", tw, th, tn);
+    B2R_REQUIRE(tw <= 256 && th <= 256 && tn <= 256, "tile dims must be <= 256");
+    if (d->out_pool) B2R_REQUIRE(tw % 2 == 0 && th % 2 == 0, "fused pool needs even tile_w, tile_h");
+
+    static thread_local ConvGemmParams tp;  // ~1.6 KB, passed by value as the __grid_constant__ kernel parameter
+    ConvGemmParams& P = tp;
+    memset(&P, 0, sizeof(P));
+
+    const uint64_t N = d->N, H = d->H, W = d->W;
+    for (int i = 0; i < B2R_MAX_SRC; ++i) {
+        const int s = i < d->num_src ? i : 0;  // unused slots alias source 0 so that prefetch sees a valid map
+        const uint64_t C = d->src_C[s];
+        const uint64_t dims[4] = {C, W, H, N};
+        const uint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+        const uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+        int rc = encode_tmap_bf16(&P.a_map[i], d->src[s], 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t K = (uint64_t)d->num_kblocks * 64;
+        const uint64_t dims[2] = {K, (uint64_t)d->cout_total};
+        const uint64_t strides[1] = {K * 2};
+        const uint32_t box[2] = {64, (uint32_t)block_n};
+        int rc = encode_tmap_bf16(&P.b_map, d->weights, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    const uint64_t OC = d->out_C;
+    const uint32_t obox[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+    if (convt) {
+        B2R_REQUIRE(d->out != nullptr, "CONVT2X2 needs out");
+        for (int q = 0; q < 4; ++q) {
+            const int i = q >> 1, j = q & 1;
+            const uint8_t* base = static_cast<const uint8_t*>(d->out) + ((uint64_t)i * 2 * W + j) * OC * 2;
+            const uint64_t dims[4] = {OC, W, H, N};
+            const uint64_t strides[3] = {2 * OC * 2, 2 * (2 * W) * OC * 2, (2 * H) * (2 * W) * OC * 2};
+            int rc = encode_tmap_bf16(&P.out_map[q], base, 4, dims, strides, obox);
+            if (rc) return rc;
+        }
+    } else {
+        const void* obase = d->out ? d->out : d->out_pool;  // placeholder map when only the pooled output is stored
+        const uint64_t dims[4] = {OC, W, H, N};
+        const uint64_t strides[3] = {OC * 2, W * OC * 2, H * W * OC * 2};
+        if (d->out) {
+            int rc = encode_tmap_bf16(&P.out_map[0], obase, 4, dims, strides, obox);
+            if (rc) return rc;
+        } else {
+            const uint64_t pd[4] = {OC, W / 2, H / 2, N};
+            const uint64_t ps[3] = {OC * 2, (W / 2) * OC * 2, (H / 2) * (W / 2) * OC * 2};
+            const uint32_t pb[4] = {64, (uint32_t)(tw / 2), (uint32_t)(th / 2), (uint32_t)tn};
+            int rc = encode_tmap_bf16(&P.out_map[0], obase, 4, pd, ps, pb);
+            if (rc) return rc;
+        }
+        for (int q = 1; q < 4; ++q) P.out_map[q] = P.out_map[0];
+    }
+    if (d->out_pool) {
+        const uint64_t pd[4] = {OC, W / 2, H / 2, N};
+        const uint64_t ps[3] = {OC * 2, (W / 2) * OC * 2, (H / 2) * (W / 2) * OC * 2};
+        const uint32_t pb[4] = {64, (uint32_t)(tw / 2), (uint32_t)(th / 2), (uint32_t)tn};
+        int rc = encode_tmap_bf16(&P.pool_map, d->out_pool, 4, pd, ps, pb);
+        if (rc) return rc;
+    } else {
+        P.pool_map = P.out_map[0];
+    }
+
+    P.bias = d->bias;
+    P.slope = d->slope;
+    P.act = d->act;
+    P.num_kblocks = d->num_kblocks;
+    P.linear_k = d->kblocks_host == nullptr;
+    if (d->kblocks_host) memcpy(P.kblk, d->kblocks_host, sizeof(uint32_t) * d->num_kblocks);
+    P.tile_w = tw;
+    P.tile_h = th;
+    P.tile_n = tn;
+    P.tiles_w = ceil_div(d->W, tw);
+    P.tiles_h = ceil_div(d->H, th);
+    P.tiles_n = ceil_div(d->N, tn);
+    P.n_tiles = d->cout_total / block_n;
+    P.n_tiles_per_out = convt ? cout / block_n : P.n_tiles;
+    P.store_full = d->out != nullptr;
+    P.store_pool = d->out_pool != nullptr;
+
+    int sms = 0;
+    int rc = device_sm_count(&sms);
+    if (rc) return rc;
+    const long total_tiles = (long)P.tiles_w * P.tiles_h * P.tiles_n * P.n_tiles;
+    B2R_REQUIRE(total_tiles < (1L << 31), "too many tiles");
+    int grid = d->max_ctas > 0 ? d->max_ctas : sms;
+    if (grid > total_tiles) grid = (int)total_tiles;
+
+    switch (block_n) {
+        case 64: return launch<64>(P, grid, stream);
+        case 128: return launch<128>(P, grid, stream);
+        default: return launch<256>(P, grid, stream);
+    }
+}

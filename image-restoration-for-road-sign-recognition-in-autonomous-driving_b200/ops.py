@@ -1,0 +1,228 @@
+"""Tensor-level wrappers over the C-ABI: argument checking, raw pointers, current CUDA stream.
+
+PyTorch is used here for device memory and streams only; every computation below is one libb2r.so kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)   # 18_test_unified_benchmark.py:31
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise L.B2RError(f"{name}: tensor must live on a CUDA device (there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise L.B2RError(f"{name}: dtype {t.dtype}, expected {dtype}")
+    if not t.is_contiguous():
+        raise L.B2RError(f"{name}: tensor must be contiguous")
+    if ndim is not None and t.dim() != ndim:
+        raise L.B2RError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def kblock(src: int, dh: int, dw: int, c64: int) -> int:
+    """B2R_KBLOCK from include/b2r.h."""
+    return src | ((dh + 1) << 2) | ((dw + 1) << 4) | (c64 << 8)
+
+
+def conv_gemm(srcs: Sequence[torch.Tensor], weights: torch.Tensor, bias: torch.Tensor,
+              kblocks: Optional[Sequence[int]], act: int = L.B2R_ACT_NONE, slope: float = 0.0,
+              out: Optional[torch.Tensor] = None, out_pool: Optional[torch.Tensor] = None,
+              out_mode: int = L.B2R_OUT_NHWC, tile=(0, 0, 0), block_n: int = 0, max_ctas: int = 0) -> None:
+    """One fused tensor-core layer (b2r_conv_gemm).  srcs: NHWC bf16 [N,H,W,C_i]; weights bf16 [cout_total, K]."""
+    n, h, w = srcs[0].shape[:3]
+    d = L.ConvGemmDesc()
+    d.N, d.H, d.W = int(n), int(h), int(w)
+    d.num_src = len(srcs)
+    for i, s in enumerate(srcs):
+        _chk(s, torch.bfloat16, f"src[{i}]", 4)
+        if tuple(s.shape[:3]) != (n, h, w):
+            raise L.B2RError(f"src[{i}] shape {tuple(s.shape)} does not match the pixel grid {(n, h, w)}")
+        d.src[i] = s.data_ptr()
+        d.src_C[i] = int(s.shape[3])
+    _chk(weights, torch.bfloat16, "weights", 2)
+    _chk(bias, torch.float32, "bias", 1)
+    d.weights = weights.data_ptr()
+    d.bias = bias.data_ptr()
+    d.cout_total = int(weights.shape[0])
+    if bias.numel() != d.cout_total:
+        raise L.B2RError(f"bias has {bias.numel()} entries, weights have {d.cout_total} rows")
+    if weights.shape[1] % 64 != 0:
+        raise L.B2RError(f"weights K={weights.shape[1]} is not a multiple of 64")
+    d.num_kblocks = int(weights.shape[1]) // 64
+    arr = None
+    if kblocks is not None:
+        if len(kblocks) != d.num_kblocks:
+            raise L.B2RError(f"{len(kblocks)} k-blocks for a weight matrix with K={weights.shape[1]}")
+        arr = (C.c_uint32 * len(kblocks))(*kblocks)
+        d.kblocks_host = C.cast(arr, C.POINTER(C.c_uint32))
+    d.act, d.slope, d.out_mode = int(act), float(slope), int(out_mode)
+    oc = 0
+    if out is not None:
+        _chk(out, torch.bfloat16, "out", 4)
+        exp = (n, 2 * h, 2 * w) if out_mode == L.B2R_OUT_CONVT2X2 else (n, h, w)
+        if tuple(out.shape[:3]) != exp:
+            raise L.B2RError(f"out shape {tuple(out.shape)} != expected {exp} + (C,)")
+        d.out = out.data_ptr()
+        oc = int(out.shape[3])
+    if out_pool is not None:
+        _chk(out_pool, torch.bfloat16, "out_pool", 4)
+        if tuple(out_pool.shape[:3]) != (n, h // 2, w // 2):
+            raise L.B2RError(f"out_pool shape {tuple(out_pool.shape)} != {(n, h // 2, w // 2)} + (C,)")
+        if oc and int(out_pool.shape[3]) != oc:
+            raise L.B2RError("out and out_pool must have the same channel count")
+        d.out_pool = out_pool.data_ptr()
+        oc = int(out_pool.shape[3])
+    d.out_C = oc
+    d.tile_w, d.tile_h, d.tile_n = (int(x) for x in tile)
+    d.block_n, d.max_ctas = int(block_n), int(max_ctas)
+    L.check(L.load().b2r_conv_gemm(C.byref(d), _stream()))
+    del arr
+
+
+def conv3x3_c3(x: torch.Tensor, weights: torch.Tensor, bias: torch.Tensor, act: int, slope: float = 0.0,
+               normalize: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """First layer.  x: f32 [N,3,H,W] or u8 [N,H,W,3]; returns bf16 NHWC [N,H,W,64]."""
+    if x.dtype == torch.uint8:
+        _chk(x, torch.uint8, "x", 4)
+        n, h, w, c = x.shape
+        fmt = L.B2R_IN_U8_NHWC
+    else:
+        _chk(x, torch.float32, "x", 4)
+        n, c, h, w = x.shape
+        fmt = L.B2R_IN_F32_NCHW
+    if c != 3:
+        raise L.B2RError(f"conv3x3_c3 needs 3 input channels, got {c}")
+    _chk(weights, torch.float32, "weights", 4)
+    _chk(bias, torch.float32, "bias", 1)
+    if tuple(weights.shape) != (64, 3, 3, 3) or bias.numel() != 64:
+        raise L.B2RError(f"conv3x3_c3 weights must be [64,3,3,3], got {tuple(weights.shape)}")
+    if out is None:
+        out = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=x.device)
+    _chk(out, torch.bfloat16, "out", 4)
+    mean = std = None
+    if normalize:
+        if fmt != L.B2R_IN_U8_NHWC:
+            raise L.B2RError("normalize=True is the u8 judge hand-off; f32 input is taken as is")
+        mean = (C.c_float * 3)(*IMAGENET_MEAN)
+        std = (C.c_float * 3)(*IMAGENET_STD)
+    L.check(L.load().b2r_conv3x3_c3(x.data_ptr(), fmt, mean, std, weights.data_ptr(), bias.data_ptr(), int(act),
+                                    float(slope), out.data_ptr(), int(n), int(h), int(w), _stream()))
+    return out
+
+
+def final_conv1x1(x: torch.Tensor, weights: torch.Tensor, bias: torch.Tensor, want_f32: bool = True,
+                  want_u8: bool = False):
+    """64 -> 3 head.  x: bf16 NHWC [N,H,W,64]; returns (f32 [N,3,H,W] | None, u8 [N,H,W,3] | None)."""
+    _chk(x, torch.bfloat16, "x", 4)
+    n, h, w, c = x.shape
+    if c != 64:
+        raise L.B2RError(f"final_conv1x1 needs 64 channels, got {c}")
+    _chk(weights, torch.float32, "weights")
+    _chk(bias, torch.float32, "bias", 1)
+    if weights.numel() != 192 or bias.numel() != 3:
+        raise L.B2RError("final_conv1x1 weights must hold 3x64 values")
+    o32 = torch.empty((n, 3, h, w), dtype=torch.float32, device=x.device) if want_f32 else None
+    o8 = torch.empty((n, h, w, 3), dtype=torch.uint8, device=x.device) if want_u8 else None
+    L.check(L.load().b2r_final_conv1x1(x.data_ptr(), weights.data_ptr(), bias.data_ptr(), _ptr(o32), _ptr(o8), int(n),
+                                       int(h), int(w), _stream()))
+    return o32, o8
+
+
+def maxpool2x2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(x, torch.bfloat16, "x", 4)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
+    _chk(out, torch.bfloat16, "out", 4)
+    L.check(L.load().b2r_maxpool2x2(x.data_ptr(), out.data_ptr(), int(n), int(h), int(w), int(c), _stream()))
+    return out
+
+
+def adaptive_avgpool7(x: torch.Tensor) -> torch.Tensor:
+    _chk(x, torch.bfloat16, "x", 4)
+    n, h, w, c = x.shape
+    out = torch.empty((n, 7, 7, c), dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().b2r_adaptive_avgpool7(x.data_ptr(), out.data_ptr(), int(n), int(h), int(w), int(c), _stream()))
+    return out
+
+
+def linear_f32out(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _chk(x, torch.bfloat16, "x", 2)
+    _chk(w, torch.bfloat16, "w", 2)
+    _chk(b, torch.float32, "b", 1)
+    bsz, k = x.shape
+    o = w.shape[0]
+    if w.shape[1] != k or b.numel() != o:
+        raise L.B2RError(f"linear shapes: x {tuple(x.shape)}, w {tuple(w.shape)}, b {tuple(b.shape)}")
+    out = torch.empty((bsz, o), dtype=torch.float32, device=x.device)
+    L.check(L.load().b2r_linear_f32out(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), int(bsz), int(k),
+                                       int(o), _stream()))
+    return out
+
+
+def argmax_count(logits: torch.Tensor, labels: Optional[torch.Tensor] = None,
+                 counts: Optional[torch.Tensor] = None, want_conf: bool = False):
+    """Top-1 (+ softmax confidence) and the running (correct, total) counters.  Returns (pred int64 [N], conf|None)."""
+    _chk(logits, torch.float32, "logits", 2)
+    n, c = logits.shape
+    pred = torch.empty((n,), dtype=torch.int64, device=logits.device)
+    conf = torch.empty((n,), dtype=torch.float32, device=logits.device) if want_conf else None
+    if labels is not None:
+        _chk(labels, torch.int64, "labels", 1)
+        if labels.numel() != n:
+            raise L.B2RError("labels length does not match logits rows")
+    if counts is not None:
+        _chk(counts, torch.int64, "counts", 1)
+        if counts.numel() != 2:
+            raise L.B2RError("counts must be int64[2] = (correct, total)")
+    L.check(L.load().b2r_argmax_count(logits.data_ptr(), _ptr(labels), pred.data_ptr(), _ptr(conf), _ptr(counts),
+                                      int(n), int(c), _stream()))
+    return pred, conf
+
+
+def degrade(images: torch.Tensor, ksize: Optional[torch.Tensor], taps: Optional[torch.Tensor],
+            fog_on: Optional[torch.Tensor], fog_t: Optional[torch.Tensor], fog_add: Optional[torch.Tensor],
+            sigma: Optional[torch.Tensor], noise: Optional[torch.Tensor] = None, seed: int = 0,
+            image_index0: int = 0, order: int = L.B2R_ORDER_BLUR_FOG_NOISE, flags: int = 0,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """b2r_degrade on u8 NHWC [N,H,W,3] with per-image parameter tensors on the same device."""
+    _chk(images, torch.uint8, "images", 4)
+    n, h, w, c = images.shape
+    if c != 3:
+        raise L.B2RError("images must be NHWC with 3 channels")
+    if out is None:
+        out = torch.empty_like(images)
+    _chk(out, torch.uint8, "out", 4)
+    for t, dt, nm in ((ksize, torch.int32, "ksize"), (taps, torch.float32, "taps"), (fog_on, torch.int32, "fog_on"),
+                      (fog_t, torch.float32, "fog_t"), (fog_add, torch.float32, "fog_add"),
+                      (sigma, torch.float32, "sigma"), (noise, torch.float64, "noise")):
+        if t is not None:
+            _chk(t, dt, nm)
+    if taps is not None and taps.numel() != n * 225:
+        raise L.B2RError(f"taps must hold N*225 floats, got {taps.numel()}")
+    for t, nm in ((ksize, "ksize"), (fog_on, "fog_on"), (fog_t, "fog_t"), (fog_add, "fog_add"), (sigma, "sigma")):
+        if t is not None and t.numel() != n:
+            raise L.B2RError(f"{nm} must have one entry per image")
+    if noise is not None and tuple(noise.shape) != (n, h, w, 3):
+        raise L.B2RError(f"noise must be f64 {(n, h, w, 3)}, got {tuple(noise.shape)}")
+    L.check(L.load().b2r_degrade(images.data_ptr(), out.data_ptr(), int(n), int(h), int(w), _ptr(taps), _ptr(ksize),
+                                 _ptr(fog_t), _ptr(fog_add), _ptr(fog_on), _ptr(sigma), _ptr(noise),
+                                 int(seed) & (2 ** 64 - 1), int(image_index0), int(order), int(flags), _stream()))
+    return out

@@ -1,0 +1,91 @@
+"""Weight re-packing from the reference's state_dict layouts to the layouts the sm_100a kernels read.
+
+Done once at `load_state_dict` time (or first forward): eval-mode BatchNorm folded into the preceding conv
+(14_train_unified_advanced.py:100-104, eps = 1e-5), OIHW -> [C_out, K] bf16 with K ordered by k-block
+(source, tap, 64-channel chunk), ConvTranspose2d [C_in, C_out, 2, 2] -> four stacked 1x1 matrices, VGG16
+classifier[0] columns permuted from the NCHW flatten order (c*49 + h*7 + w) to the NHWC order the activations use.
+Pure tensor reshuffling on whatever device the parameters live on; no arithmetic beyond the BN fold.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from .ops import kblock
+
+BN_EPS = 1e-5  # nn.BatchNorm2d default, used by ResidualBlock (14_train_unified_advanced.py:100)
+
+
+def fold_bn(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
+            mean: torch.Tensor, var: torch.Tensor, eps: float = BN_EPS) -> Tuple[torch.Tensor, torch.Tensor]:
+    """BN(conv(x)) in eval mode == conv'(x) with w' = w * s[co], b' = (b - mean) * s + beta, s = gamma / sqrt(var+eps)."""
+    w = w.double()
+    s = gamma.double() / torch.sqrt(var.double() + eps)
+    b0 = b.double() if b is not None else torch.zeros_like(s)
+    w2 = w * s.view(-1, *([1] * (w.dim() - 1)))
+    b2 = (b0 - mean.double()) * s + beta.double()
+    return w2.float(), b2.float()
+
+
+class KPlan:
+    """Accumulates the K dimension of one fused layer: weight column groups + the matching k-block list."""
+
+    def __init__(self, cout: int):
+        self.cout = cout
+        self.cols: List[torch.Tensor] = []
+        self.kblocks: List[int] = []
+
+    def add_conv3x3(self, src: int, w: torch.Tensor, c_offset: int = 0) -> "KPlan":
+        """w: [C_out, C_in_slice, 3, 3] applied to channels [c_offset, c_offset + C_in_slice) of source `src`."""
+        co, ci, kh, kw = w.shape
+        assert co == self.cout and kh == 3 and kw == 3 and ci % 64 == 0 and c_offset % 64 == 0
+        for i in range(3):
+            for j in range(3):
+                for c in range(ci // 64):
+                    self.cols.append(w[:, c * 64:(c + 1) * 64, i, j])
+                    self.kblocks.append(kblock(src, i - 1, j - 1, c_offset // 64 + c))
+        return self
+
+    def add_1x1(self, src: int, w: torch.Tensor, c_offset: int = 0) -> "KPlan":
+        """w: [C_out, C_in_slice] (centre tap only) on channels [c_offset, ...) of source `src`."""
+        co, ci = w.shape[:2]
+        w = w.reshape(co, ci)
+        assert co == self.cout and ci % 64 == 0 and c_offset % 64 == 0
+        for c in range(ci // 64):
+            self.cols.append(w[:, c * 64:(c + 1) * 64])
+            self.kblocks.append(kblock(src, 0, 0, c_offset // 64 + c))
+        return self
+
+    def finish(self, device=None) -> Tuple[torch.Tensor, List[int]]:
+        wmat = torch.cat(self.cols, dim=1).to(torch.bfloat16).contiguous()
+        if device is not None:
+            wmat = wmat.to(device)
+        return wmat, list(self.kblocks)
+
+
+def pack_conv3x3(w: torch.Tensor, splits: Optional[Sequence[int]] = None):
+    """Plain conv3x3 over one source, or over a channel concat of several sources (splits = channels per source)."""
+    co, ci = w.shape[:2]
+    splits = list(splits) if splits else [ci]
+    assert sum(splits) == ci
+    plan = KPlan(co)
+    off = 0
+    for s, n in enumerate(splits):
+        plan.add_conv3x3(s, w[:, off:off + n])
+        off += n
+    return plan.finish()
+
+
+def pack_convT2x2(w: torch.Tensor, b: torch.Tensor):
+    """ConvTranspose2d(k=2, s=2) weight [C_in, C_out, 2, 2] -> [4*C_out, C_in] (quadrant q = 2*i + j major)."""
+    ci, co = w.shape[:2]
+    wm = w.permute(2, 3, 1, 0).reshape(4 * co, ci)  # [(i, j, co), ci]
+    bias = b.repeat(4)
+    return wm.to(torch.bfloat16).contiguous(), bias.float().contiguous()
+
+
+def pack_fc_from_nchw_flatten(w: torch.Tensor, c: int, h: int, wd: int) -> torch.Tensor:
+    """Linear weight whose columns index an NCHW flatten -> columns for the NHWC flatten of the same tensor."""
+    o = w.shape[0]
+    return w.reshape(o, c, h, wd).permute(0, 2, 3, 1).reshape(o, h * wd * c).to(torch.bfloat16).contiguous()

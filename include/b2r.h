@@ -1,0 +1,182 @@
+/* b2r.h — C-ABI of libb2r.so, the sm_100a (B200) kernels behind the degrade -> restore -> classify path.
+ *
+ * The reference (LordTARN1SHED/Image-Restoration-for-Road-Sign-Recognition-in-Autonomous-Driving) has no FFI of
+ * its own: its boundary for this path is the PyTorch module contract (`nn.Module.forward`, `load_state_dict`)
+ * and a handful of NumPy/OpenCV functions.  Each entry point below names the reference call site it replaces
+ * (file:line relative to the reference root).  The Python host in
+ * `image-restoration-for-road-sign-recognition-in-autonomous-driving_b200/` binds these with ctypes and keeps
+ * the reference's module surface on top (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its comment says "host".
+ *   - the library never allocates or frees device memory and never keeps a pointer after a call returns.
+ *   - all work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*).
+ *   - return value: 0 = ok, negative = error (B2R_E*); `b2r_last_error()` gives the message (thread-local).
+ *   - activations between layers: NHWC bf16.  There is no CPU fallback anywhere in this library.
+ */
+#ifndef B2R_H_
+#define B2R_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_VERSION 100
+
+#define B2R_OK 0
+#define B2R_EINVAL (-22)   /* bad argument (shape, alignment, null pointer) */
+#define B2R_ECUDA (-5)     /* a CUDA runtime / driver call failed */
+#define B2R_ENODEV (-19)   /* no sm_100 device */
+
+/* activation codes */
+#define B2R_ACT_NONE 0
+#define B2R_ACT_RELU 1
+#define B2R_ACT_PRELU 2 /* single shared slope, nn.PReLU() default (14_train_unified_advanced.py:101) */
+
+int b2r_version(void);
+const char* b2r_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (1) Fused compound degradation: motion blur (+) fog (+) AWGN, u8 NHWC in -> u8 NHWC out, one launch.
+ *
+ * Replaces apply_compound_distortion (16_gen_compound_data.py:14-37, order Blur->Fog->Noise),
+ * apply_random_distortions (14_train_unified_advanced.py:31-64, order Fog->Noise->Blur),
+ * make_compound_distortion (15_test_unified.py:93-120) and the single degradations
+ * add_gaussian_noise (02_gen_noise.py:12-27), apply_motion_blur (03_gen_blur.py:11-30, without the min-max
+ * renormalisation) and add_fog (04_gen_fog.py:12-31).
+ *
+ * Per-image parameters (device arrays of length N):
+ *   ksize[i]   blur kernel side d (0 or 1 = no blur, else 2..15); taps[i*225 + ky*d + kx] row-major d x d f32,
+ *              correlation with anchor d/2 and BORDER_REFLECT_101, f32 accumulation over the non-zero taps in
+ *              row-major order, round-half-even + saturate to u8 (cv2.filter2D on u8).
+ *   fog_on[i]  0 skips the fog stage; fog_t[i] = transmission t; fog_add[i] = float32(A*(1-t)), the airlight term
+ *              evaluated by the host in double precision exactly as Python evaluates `A * (1 - t)`:
+ *              I = fl32(fl32(J*t) + fog_add).
+ *   sigma[i]   AWGN standard deviation on the [0,1] scale; 0 skips the noise stage.
+ * order: B2R_ORDER_BLUR_FOG_NOISE = chain(blur(in)) (script 16); B2R_ORDER_FOG_NOISE_BLUR = blur(chain(in))
+ *        (scripts 14/15), with chain(v) = quant(noise(fog(v/255))).
+ * flags: B2R_DEG_CLIP_AFTER_NOISE clips to [0,1] right after the noise is added (15:108).  Every float -> u8 step
+ *        is clip(x*255, 0, 255) followed by truncation, as in the reference.
+ * Noise: if `noise` is non-null it is an f64 NHWC tensor of the noise values themselves (what
+ *        np.random.normal(0, sigma, shape) returned), added in float64 like NumPy does: the parity path ("AWGN is
+ *        compared by injecting the same noise tensor").  Otherwise Philox4x32-10 keyed by `seed`,
+ *        counter = (pixel index, image_index0 + i), Box-Muller, scaled by sigma[i].
+ * ------------------------------------------------------------------------------------------------------------- */
+#define B2R_ORDER_BLUR_FOG_NOISE 0
+#define B2R_ORDER_FOG_NOISE_BLUR 1
+#define B2R_DEG_CLIP_AFTER_NOISE 1
+#define B2R_MAX_BLUR 15
+
+int b2r_degrade(const uint8_t* in_nhwc, uint8_t* out_nhwc, int N, int H, int W,
+                const float* taps /* [N,225] or NULL when no image blurs */, const int32_t* ksize,
+                const float* fog_t, const float* fog_add, const int32_t* fog_on, const float* sigma,
+                const double* noise /* [N,H,W,3] or NULL */, uint64_t seed, uint64_t image_index0, int order,
+                int flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (2) First conv layer (C_in = 3), bias + activation fused, output NHWC bf16 [N,H,W,64].
+ *
+ * Replaces SimpleUNet.enc1[0..1] (07_train_restoration.py:80), ResUNet.enc1 (14_train_unified_advanced.py:122)
+ * and VGG16 features[0..1] (torchvision vgg16, used at 18_test_unified_benchmark.py:58) together with the tensor
+ * hand-off that precedes each of them: ToTensor (17_run_unified_inference.py:66) or ToTensor + Normalize
+ * (18_test_unified_benchmark.py:28-32).
+ *   in_fmt B2R_IN_F32_NCHW: `in` is f32 [N,3,H,W] (the nn.Module.forward argument)
+ *   in_fmt B2R_IN_U8_NHWC : `in` is u8 [N,H,W,3]; x = u8/255, then (x - mean[c]) / std[c] when `mean`/`std` are
+ *                           non-null (host pointers to 3 floats).
+ * weights: f32 [64][3][3][3] (OIHW, as in the state_dict), bias f32 [64].
+ * ------------------------------------------------------------------------------------------------------------- */
+#define B2R_IN_F32_NCHW 0
+#define B2R_IN_U8_NHWC 1
+
+int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host, const float* std_host, const float* weights,
+                   const float* bias, int act, float slope, void* out_nhwc_bf16, int N, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (3) Implicit-GEMM convolution on tcgen05 tensor cores (TMA-staged NHWC bf16 tiles, TMEM f32 accumulators).
+ *
+ * One call = one fused layer:  out = act( sum_kblocks  A_kb * W_kb  + bias ), optionally followed by a fused
+ * 2x2 max-pool (second output), with the M dimension = output pixels (128 per tile) and N = output channels.
+ * The K loop is a list of "k-blocks": 64 input channels of one source tensor at one spatial offset.  That single
+ * mechanism gives
+ *   - conv3x3, padding 1 (nine offsets per 64-channel chunk; zero padding = TMA out-of-bounds fill);
+ *   - concat-free decoder convs: torch.cat((up, skip), 1) (07:112, 14:171) is two sources in one K loop;
+ *   - the ResidualBlock shortcut (14:107-115): the 1x1 conv (or identity) on the block input is one more centre
+ *     k-block group, so BN(conv(.)) + shortcut(x) and the ReLU happen in one accumulator / one epilogue;
+ *   - ConvTranspose2d(k=2, s=2) (07:91, 14:140): a 1x1 GEMM with 4*C_out rows of weights, each quadrant stored
+ *     through its own strided output view (out_mode B2R_OUT_CONVT2X2);
+ *   - nn.Linear (VGG16 classifier): H = 1, W = batch rows, one source.
+ * Eval-mode BatchNorm (14:101,104) is folded into `weights`/`bias` by the host at load time.
+ *
+ * Replaces the nn.Conv2d / nn.ConvTranspose2d / nn.BatchNorm2d / nn.ReLU / nn.PReLU / nn.MaxPool2d / torch.cat /
+ * nn.Linear calls inside SimpleUNet.forward (07_train_restoration.py:99-120), ResidualBlock.forward and
+ * ResUNet.forward (14_train_unified_advanced.py:114-115, 151-186) and torchvision VGG16.forward
+ * (18_test_unified_benchmark.py:46).
+ * ------------------------------------------------------------------------------------------------------------- */
+#define B2R_MAX_SRC 3
+#define B2R_MAX_KBLOCKS 96
+#define B2R_OUT_NHWC 0
+#define B2R_OUT_CONVT2X2 1
+
+/* k-block encoding: bits [0,2) source index, [2,4) dh+1, [4,6) dw+1, [8,24) first channel / 64 */
+#define B2R_KBLOCK(src, dh, dw, c64) \
+    ((uint32_t)(src) | ((uint32_t)((dh) + 1) << 2) | ((uint32_t)((dw) + 1) << 4) | ((uint32_t)(c64) << 8))
+
+typedef struct b2r_conv_gemm_desc {
+    int32_t N, H, W;                 /* pixel grid of the sources (and of `out` for B2R_OUT_NHWC) */
+    int32_t num_src;
+    const void* src[B2R_MAX_SRC];    /* bf16 NHWC [N,H,W,src_C[i]] */
+    int32_t src_C[B2R_MAX_SRC];      /* multiples of 64 */
+    const void* weights;             /* bf16 [cout_total][64*num_kblocks], K order = k-block order */
+    const float* bias;               /* f32 [cout_total] */
+    int32_t cout_total;              /* multiple of 64; for CONVT2X2 = 4*C_out, quadrant-major (q = 2*i + j) */
+    int32_t num_kblocks;
+    const uint32_t* kblocks_host;    /* HOST pointer, num_kblocks entries; NULL = source 0, centre tap, c = 64*kb */
+    int32_t act;
+    float slope;
+    int32_t out_mode;
+    void* out;                       /* bf16 NHWC; NHWC mode: [N,H,W,out_C]; CONVT: [N,2H,2W,out_C]; may be NULL */
+    void* out_pool;                  /* bf16 NHWC [N,H/2,W/2,out_C] (2x2 max-pool of the activated output) or NULL */
+    int32_t out_C;                   /* channel pitch of out / out_pool */
+    int32_t tile_w, tile_h, tile_n;  /* pixels per tile along W, H, N (product 128); 0,0,0 = choose */
+    int32_t block_n;                 /* 64 / 128 / 256; 0 = choose */
+    int32_t max_ctas;                /* 0 = one per SM */
+} b2r_conv_gemm_desc;
+
+int b2r_conv_gemm(const b2r_conv_gemm_desc* desc /* host */, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (4) Output head of the restorers: final 1x1 conv 64 -> 3 (07:97, 14:149) + the reference's post-processing.
+ *   out_f32_nchw (optional): raw f32 [N,3,H,W] — the nn.Module.forward result, unclamped.
+ *   out_u8_nhwc  (optional): clamp(0,1) -> x*255 -> truncation to u8, [N,H,W,3]
+ *                            (17_run_unified_inference.py:86-92, 08_run_inference.py:96-98, 15_test_unified.py:186-188).
+ * weights f32 [3][64], bias f32 [3].
+ * ------------------------------------------------------------------------------------------------------------- */
+int b2r_final_conv1x1(const void* in_nhwc_bf16, const float* weights, const float* bias, float* out_f32_nchw,
+                      uint8_t* out_u8_nhwc, int N, int H, int W, void* stream);
+
+/* 2x2/2 max-pool on NHWC bf16 (nn.MaxPool2d(2,2): 07:81, 14:124) — standalone form of the fused epilogue. */
+int b2r_maxpool2x2(const void* in_nhwc_bf16, void* out_nhwc_bf16, int N, int H, int W, int C, void* stream);
+
+/* AdaptiveAvgPool2d((7,7)) of torchvision VGG16 on NHWC bf16 [N,H,W,C] -> [N,7,7,C] (identity at H=W=7). */
+int b2r_adaptive_avgpool7(const void* in_nhwc_bf16, void* out_nhwc_bf16, int N, int H, int W, int C, void* stream);
+
+/* Small-N linear layer with f32 output: out[b][o] = sum_k in[b][k] * w[o][k] + bias[o]
+ * (VGG16 classifier[6] = nn.Linear(4096, 43): 18_test_unified_benchmark.py:59).  in bf16 [B,K], w bf16 [O,K]. */
+int b2r_linear_f32out(const void* in_bf16, const void* w_bf16, const float* bias, float* out, int B, int K, int O,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (5) Top-1 + correct count: torch.max(outputs, 1) and (predicted == labels).sum()
+ * (18_test_unified_benchmark.py:47-49, 06_test_baseline.py:53-55).  Lowest index wins ties, like torch.max.
+ * pred (optional) int64 [N]; conf (optional) f32 [N] = softmax probability of the arg-max (15_test_unified.py:125-129);
+ * labels (optional) int64 [N]; counts (optional) int64[2] += {correct, N} (accumulated with one atomic per block).
+ * ------------------------------------------------------------------------------------------------------------- */
+int b2r_argmax_count(const float* logits, const int64_t* labels, int64_t* pred, float* conf, int64_t* counts, int N,
+                     int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2R_H_ */

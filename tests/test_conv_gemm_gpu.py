@@ -1,0 +1,203 @@
+"""GPU parity of the tcgen05 implicit-GEMM conv (b2r_conv_gemm) against PyTorch fp32 convs on the same bf16-rounded
+operands.  Floating point: the comparator is torch fp32 (TF32 off); tolerance = bf16 output rounding (2^-8 relative)
+plus fp32 accumulation-order noise, stated per test.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _ops():
+    from b200restore import ops, packing, _lib
+    return ops, packing, _lib
+
+
+def nhwc_bf16(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def to_nchw_f32(x_nhwc):
+    return x_nhwc.float().permute(0, 3, 1, 2).contiguous()
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def assert_close_bf16(got, ref, what, rel=2.0 ** -7, abs_=2e-2):
+    """|got - ref| <= abs_ + rel*|ref| elementwise; bf16 rounding of the output alone is 2^-9 relative."""
+    err = (got - ref).abs()
+    bound = abs_ + rel * ref.abs()
+    bad = err > bound
+    assert not bad.any(), (f"{what}: {int(bad.sum())} / {bad.numel()} outside tolerance; max err "
+                           f"{float(err.max()):.4g} at ref {float(ref.flatten()[err.argmax()]):.4g}")
+
+
+@pytest.mark.parametrize("n,h,w,ci,co,block_n,tile", [
+    (2, 16, 32, 64, 64, 0, (0, 0, 0)),       # smallest: K = 9 blocks, one N tile
+    (1, 24, 40, 128, 128, 0, (16, 8, 1)),    # partial tiles at the right / bottom edge
+    (3, 8, 8, 64, 256, 256, (8, 8, 2)),      # images packed into one M tile, odd batch (clipped in N)
+    (8, 4, 4, 128, 64, 0, (4, 4, 8)),        # tiny maps: 8 images per tile
+    (2, 14, 14, 256, 512, 256, (0, 0, 0)),   # VGG conv5-like 14x14, K = 36 blocks, two N tiles
+    (1, 16, 16, 512, 128, 128, (16, 8, 1)),  # K = 72 blocks
+    (1, 32, 32, 64, 128, 64, (0, 0, 0)),     # block_n smaller than C_out -> several N tiles
+])
+def test_conv3x3_relu(n, h, w, ci, co, block_n, tile):
+    ops, packing, L = _ops()
+    x = rnd(n, ci, h, w, seed=1)
+    wt = rnd(co, ci, 3, 3, scale=(2.0 / (9 * ci)) ** 0.5, seed=2)
+    b = rnd(co, scale=0.1, seed=3)
+    xb = nhwc_bf16(x)
+    wm, kbl = packing.pack_conv3x3(wt)
+    out = torch.full((n, h, w, co), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.conv_gemm([xb], wm.cuda(), b, kbl, act=L.B2R_ACT_RELU, out=out, block_n=block_n, tile=tile)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(to_nchw_f32(xb), wt.to(torch.bfloat16).float(), b, padding=1))
+    assert_close_bf16(to_nchw_f32(out), ref, "conv3x3+relu")
+
+
+def test_conv3x3_two_sources_prelu_pool():
+    """Concat-free decoder conv: cat((a, s), 1) -> conv3x3 -> PReLU, with the fused 2x2 max-pool second output."""
+    ops, packing, L = _ops()
+    n, h, w = 2, 16, 32
+    a = rnd(n, 64, h, w, seed=4)
+    s = rnd(n, 128, h, w, seed=5)
+    wt = rnd(128, 192, 3, 3, scale=(2.0 / (9 * 192)) ** 0.5, seed=6)
+    b = rnd(128, scale=0.1, seed=7)
+    ab, sb = nhwc_bf16(a), nhwc_bf16(s)
+    wm, kbl = packing.pack_conv3x3(wt, splits=[64, 128])
+    out = torch.full((n, h, w, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
+    pool = torch.full((n, h // 2, w // 2, 128), float("nan"), dtype=torch.bfloat16, device="cuda")
+    slope = 0.25
+    ops.conv_gemm([ab, sb], wm.cuda(), b, kbl, act=L.B2R_ACT_PRELU, slope=slope, out=out, out_pool=pool)
+    torch.cuda.synchronize()
+    xin = torch.cat((to_nchw_f32(ab), to_nchw_f32(sb)), 1)
+    ref = F.prelu(F.conv2d(xin, wt.to(torch.bfloat16).float(), b, padding=1), torch.tensor([slope], device="cuda"))
+    assert_close_bf16(to_nchw_f32(out), ref, "two-source conv")
+    # the pooled output must be exactly the max-pool of the stored full-resolution output
+    ref_pool = F.max_pool2d(to_nchw_f32(out), 2, 2)
+    assert torch.equal(to_nchw_f32(pool), ref_pool)
+
+
+def test_pool_only_output():
+    ops, packing, L = _ops()
+    n, h, w = 1, 16, 16
+    x = rnd(n, 64, h, w, seed=8)
+    wt = rnd(64, 64, 3, 3, scale=(2.0 / 576) ** 0.5, seed=9)
+    b = rnd(64, scale=0.1, seed=10)
+    xb = nhwc_bf16(x)
+    wm, kbl = packing.pack_conv3x3(wt)
+    pool = torch.full((n, h // 2, w // 2, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.conv_gemm([xb], wm.cuda(), b, kbl, act=L.B2R_ACT_RELU, out_pool=pool)
+    torch.cuda.synchronize()
+    ref = F.max_pool2d(F.relu(F.conv2d(to_nchw_f32(xb), wt.to(torch.bfloat16).float(), b, padding=1)), 2, 2)
+    assert_close_bf16(to_nchw_f32(pool), ref, "pool-only conv")
+
+
+def test_residual_block_second_conv():
+    """relu(conv3x3(y) + conv1x1(x) + bias): the ResidualBlock tail as one K loop over two sources."""
+    ops, packing, L = _ops()
+    n, h, w = 2, 8, 16
+    y = rnd(n, 128, h, w, seed=11)
+    x = rnd(n, 64, h, w, seed=12)
+    w2 = rnd(128, 128, 3, 3, scale=(1.0 / (9 * 128)) ** 0.5, seed=13)
+    ws = rnd(128, 64, 1, 1, scale=(1.0 / 64) ** 0.5, seed=14)
+    b = rnd(128, scale=0.1, seed=15)
+    yb, xb = nhwc_bf16(y), nhwc_bf16(x)
+    plan = packing.KPlan(128).add_conv3x3(0, w2).add_1x1(1, ws)
+    wm, kbl = plan.finish()
+    out = torch.empty((n, h, w, 128), dtype=torch.bfloat16, device="cuda")
+    ops.conv_gemm([yb, xb], wm.cuda(), b, kbl, act=L.B2R_ACT_RELU, out=out)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(to_nchw_f32(yb), w2.to(torch.bfloat16).float(), b, padding=1)
+                 + F.conv2d(to_nchw_f32(xb), ws.to(torch.bfloat16).float()))
+    assert_close_bf16(to_nchw_f32(out), ref, "residual tail")
+
+
+def test_identity_shortcut_is_exact_add():
+    """An identity 1x1 k-block adds the bf16 block input exactly (fp32 accumulate)."""
+    ops, packing, L = _ops()
+    n, h, w = 1, 8, 16
+    x = rnd(n, 64, h, w, seed=16)
+    xb = nhwc_bf16(x)
+    zero3 = torch.zeros(64, 64, 3, 3, device="cuda")
+    plan = packing.KPlan(64).add_conv3x3(0, zero3).add_1x1(0, torch.eye(64, device="cuda"))
+    wm, kbl = plan.finish()
+    out = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device="cuda")
+    ops.conv_gemm([xb], wm.cuda(), torch.zeros(64, device="cuda"), kbl, act=L.B2R_ACT_NONE, out=out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, xb)
+
+
+@pytest.mark.parametrize("n,h,w,ci,co", [(2, 8, 16, 256, 128), (1, 4, 4, 64, 64), (3, 14, 14, 128, 64)])
+def test_conv_transpose_2x2(n, h, w, ci, co):
+    ops, packing, L = _ops()
+    x = rnd(n, ci, h, w, seed=17)
+    wt = rnd(ci, co, 2, 2, scale=(1.0 / ci) ** 0.5, seed=18)
+    b = rnd(co, scale=0.1, seed=19)
+    xb = nhwc_bf16(x)
+    wm, bias4 = packing.pack_convT2x2(wt, b)
+    out = torch.full((n, 2 * h, 2 * w, co), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.conv_gemm([xb], wm.cuda(), bias4.cuda(), None, act=L.B2R_ACT_NONE, out=out, out_mode=L.B2R_OUT_CONVT2X2)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(to_nchw_f32(xb), wt.to(torch.bfloat16).float(), b, stride=2)
+    assert_close_bf16(to_nchw_f32(out), ref, "convT 2x2")
+
+
+@pytest.mark.parametrize("bsz,k,o", [(200, 512, 256), (64, 25088, 128), (1, 4096, 64)])
+def test_linear_as_conv(bsz, k, o):
+    ops, packing, L = _ops()
+    x = rnd(bsz, k, seed=20)
+    wt = rnd(o, k, scale=(1.0 / k) ** 0.5, seed=21)
+    b = rnd(o, scale=0.1, seed=22)
+    xb = x.to(torch.bfloat16).contiguous()
+    out = torch.full((1, 1, bsz, o), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.conv_gemm([xb.view(1, 1, bsz, k)], wt.to(torch.bfloat16).contiguous(), b, None, act=L.B2R_ACT_RELU, out=out)
+    torch.cuda.synchronize()
+    ref = F.relu(xb.float() @ wt.to(torch.bfloat16).float().t() + b)
+    assert_close_bf16(out.view(bsz, o).float(), ref, "linear")
+
+
+def test_many_tiles_persistent_loop():
+    """More tiles than SMs, several waves, both accumulator stages and all smem stages wrap many times."""
+    ops, packing, L = _ops()
+    n, h, w, ci, co = 16, 64, 64, 64, 64
+    x = rnd(n, ci, h, w, seed=23)
+    wt = rnd(co, ci, 3, 3, scale=(2.0 / 576) ** 0.5, seed=24)
+    b = rnd(co, scale=0.1, seed=25)
+    xb = nhwc_bf16(x)
+    wm, kbl = packing.pack_conv3x3(wt)
+    out = torch.empty((n, h, w, co), dtype=torch.bfloat16, device="cuda")
+    pool = torch.empty((n, h // 2, w // 2, co), dtype=torch.bfloat16, device="cuda")
+    ops.conv_gemm([xb], wm.cuda(), b, kbl, act=L.B2R_ACT_RELU, out=out, out_pool=pool)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(to_nchw_f32(xb), wt.to(torch.bfloat16).float(), b, padding=1))
+    assert_close_bf16(to_nchw_f32(out), ref, "many tiles")
+    assert torch.equal(to_nchw_f32(pool), F.max_pool2d(to_nchw_f32(out), 2, 2))
+
+
+def test_argument_errors():
+    ops, packing, L = _ops()
+    xb = torch.zeros((1, 8, 16, 64), dtype=torch.bfloat16, device="cuda")
+    wm = torch.zeros((64, 576), dtype=torch.bfloat16, device="cuda")
+    b = torch.zeros(64, device="cuda")
+    _, kbl = packing.pack_conv3x3(torch.zeros(64, 64, 3, 3))
+    with pytest.raises(L.B2RError):
+        ops.conv_gemm([xb.cpu()], wm, b, kbl, out=torch.empty_like(xb))           # CPU tensor: no fallback
+    with pytest.raises(L.B2RError):
+        ops.conv_gemm([xb], wm, b, kbl)                                            # no output
+    with pytest.raises(L.B2RError):
+        ops.conv_gemm([xb], wm, b, kbl, out=torch.empty_like(xb), tile=(16, 4, 1))  # tile != 128 pixels
+    with pytest.raises(L.B2RError):
+        odd = torch.zeros((1, 7, 16, 64), dtype=torch.bfloat16, device="cuda")
+        ops.conv_gemm([odd], wm, b, kbl, out_pool=torch.empty((1, 3, 8, 64), dtype=torch.bfloat16, device="cuda"))
