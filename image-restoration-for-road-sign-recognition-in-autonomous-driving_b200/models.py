@@ -1,0 +1,444 @@
+"""Drop-in inference modules: same constructors, attribute names and `state_dict` schema as the reference's
+`SimpleUNet` (07_train_restoration.py:75-120), `ResidualBlock` / `ResUNet` (14_train_unified_advanced.py:96-186)
+and the VGG16-43 judge (torchvision `vgg16` + head swap, 18_test_unified_benchmark.py:58-59), so
+`model.load_state_dict(torch.load('restoration_*.pth'))` works unchanged — but `forward` runs the sm_100a
+kernels of libb2r.so (NHWC bf16 activations, fp32 accumulation) instead of ATen.
+
+The nn.Conv2d / nn.BatchNorm2d / ... children exist only as parameter containers that give the state_dict its
+keys; they are never called.  Packed device-layout weights are rebuilt automatically whenever a parameter tensor
+is replaced or modified in place (load_state_dict, .to(), classifier[6] swap).
+
+Inference only: eval-mode BatchNorm (running statistics), no autograd.  No CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops, packing
+
+DEFAULT_MICRO_BATCH = 128
+
+
+class _Workspace:
+    """Named activation buffers reused across calls (PyTorch owns the memory; the kernels only see pointers)."""
+
+    def __init__(self):
+        self._bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, shape, device, dtype=torch.bfloat16) -> torch.Tensor:
+        t = self._bufs.get(name)
+        shape = tuple(int(s) for s in shape)
+        if t is None or tuple(t.shape) != shape or t.device != device or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            self._bufs[name] = t
+        return t
+
+    def clear(self):
+        self._bufs.clear()
+
+
+class _B200Module(nn.Module):
+    """Shared plumbing: pack cache keyed on parameter identity/version, micro-batching, argument checks."""
+
+    micro_batch: int = DEFAULT_MICRO_BATCH
+
+    def __init__(self):
+        super().__init__()
+        object.__setattr__(self, "_pack", None)
+        object.__setattr__(self, "_pack_sig", None)
+        object.__setattr__(self, "_ws", _Workspace())
+
+    # -- pack cache -------------------------------------------------------------------------------------------
+    def _signature(self):
+        return tuple((k, v.data_ptr(), v._version, v.device) for k, v in self.state_dict(keep_vars=True).items())
+
+    def _packed(self):
+        sig = self._signature()
+        if self._pack is None or sig != self._pack_sig:
+            with torch.no_grad():
+                pack = self._build_pack({k: v.detach() for k, v in self.state_dict(keep_vars=True).items()})
+            object.__setattr__(self, "_pack", pack)
+            object.__setattr__(self, "_pack_sig", sig)
+        return self._pack
+
+    def _build_pack(self, sd):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    # -- checks -----------------------------------------------------------------------------------------------
+    def _check_input(self, x: torch.Tensor, div: int) -> None:
+        if self.training:
+            raise L.B2RError(f"{type(self).__name__} is inference-only (eval-mode BatchNorm); call .eval() first, as "
+                             "the reference drivers do (17_run_unified_inference.py:64)")
+        if not isinstance(x, torch.Tensor) or x.dim() != 4:
+            raise L.B2RError("expected a 4-D tensor")
+        if not x.is_cuda:
+            raise L.B2RError("input must be a CUDA tensor: this build has no CPU fallback")
+        dev = next(self.parameters()).device
+        if dev != x.device:
+            raise L.B2RError(f"module parameters are on {dev}, input on {x.device}; call .to(device) first")
+        h, w = (x.shape[1], x.shape[2]) if x.dtype == torch.uint8 else (x.shape[2], x.shape[3])
+        if h % div or w % div:
+            raise L.B2RError(f"H and W must be multiples of {div} (got {h}x{w}); the reference's F.interpolate "
+                             "re-alignment branch (14_train_unified_advanced.py:169-183) is not implemented")
+
+    @staticmethod
+    def _chunks(n: int, mb: int):
+        for s in range(0, n, mb):
+            yield s, min(mb, n - s)
+
+
+def _conv(ci: int, co: int, k: int = 3) -> nn.Conv2d:
+    return nn.Conv2d(ci, co, k, padding=k // 2)
+
+
+def _double_conv(ci: int, co: int) -> nn.Sequential:
+    return nn.Sequential(_conv(ci, co), nn.ReLU(), _conv(co, co), nn.ReLU())
+
+
+# =================================================================================================================
+# SimpleUNet
+# =================================================================================================================
+class SimpleUNet(_B200Module):
+    """Two-level U-Net, f32 [N,3,H,W] in [0,1] -> f32 [N,3,H,W] (unclamped), H and W multiples of 4."""
+
+    def __init__(self):
+        super().__init__()
+        self.enc1 = _double_conv(3, 64)
+        self.pool1 = nn.MaxPool2d(2, 2)
+        self.enc2 = _double_conv(64, 128)
+        self.pool2 = nn.MaxPool2d(2, 2)
+        self.bottleneck = _double_conv(128, 256)
+        self.up2 = nn.ConvTranspose2d(256, 128, 2, stride=2)
+        self.dec2 = _double_conv(256, 128)
+        self.up1 = nn.ConvTranspose2d(128, 64, 2, stride=2)
+        self.dec1 = _double_conv(128, 64)
+        self.final = nn.Conv2d(64, 3, 1)
+
+    def _build_pack(self, sd):
+        dev = sd["final.weight"].device
+        P = {}
+
+        def conv(name, key, splits=None):
+            w, kb = packing.pack_conv3x3(sd[key + ".weight"].float(), splits)
+            P[name] = (w.to(dev), sd[key + ".bias"].float().contiguous(), kb)
+
+        P["enc1.0"] = (sd["enc1.0.weight"].float().contiguous(), sd["enc1.0.bias"].float().contiguous())
+        conv("enc1.2", "enc1.2")
+        conv("enc2.0", "enc2.0")
+        conv("enc2.2", "enc2.2")
+        conv("bottleneck.0", "bottleneck.0")
+        conv("bottleneck.2", "bottleneck.2")
+        conv("dec2.0", "dec2.0", [128, 128])  # torch.cat((up2(b), e2), 1)  (07:112)
+        conv("dec2.2", "dec2.2")
+        conv("dec1.0", "dec1.0", [64, 64])    # torch.cat((up1(d2), e1), 1) (07:116)
+        conv("dec1.2", "dec1.2")
+        for up in ("up2", "up1"):
+            w, b = packing.pack_convT2x2(sd[up + ".weight"].float(), sd[up + ".bias"].float())
+            P[up] = (w.to(dev), b.to(dev))
+        P["final"] = (sd["final.weight"].float().reshape(3, 64).contiguous(), sd["final.bias"].float().contiguous())
+        return P
+
+    def _run(self, x, out_f32, out_u8):
+        """x: f32 [n,3,H,W] or u8 [n,H,W,3] slice; writes the requested outputs."""
+        P, ws = self._packed(), self._ws
+        u8_in = x.dtype == torch.uint8
+        n = x.shape[0]
+        H, W = (x.shape[1], x.shape[2]) if u8_in else (x.shape[2], x.shape[3])
+        dev = x.device
+        R = L.B2R_ACT_RELU
+        g = lambda name, h, w, c: ws.get(name, (n, h, w, c), dev)  # noqa: E731
+
+        a = ops.conv3x3_c3(x, *P["enc1.0"], act=R, out=g("a", H, W, 64))
+        e1, p1 = g("e1", H, W, 64), g("p1", H // 2, W // 2, 64)
+        ops.conv_gemm([a], *P["enc1.2"], act=R, out=e1, out_pool=p1)
+        t = g("e2a", H // 2, W // 2, 128)
+        ops.conv_gemm([p1], *P["enc2.0"], act=R, out=t)
+        e2, p2 = g("e2", H // 2, W // 2, 128), g("p2", H // 4, W // 4, 128)
+        ops.conv_gemm([t], *P["enc2.2"], act=R, out=e2, out_pool=p2)
+        b1, b2 = g("b1", H // 4, W // 4, 256), g("b2", H // 4, W // 4, 256)
+        ops.conv_gemm([p2], *P["bottleneck.0"], act=R, out=b1)
+        ops.conv_gemm([b1], *P["bottleneck.2"], act=R, out=b2)
+        u2 = g("u2", H // 2, W // 2, 128)
+        ops.conv_gemm([b2], *P["up2"], None, out=u2, out_mode=L.B2R_OUT_CONVT2X2)
+        d2a, d2 = g("e2a", H // 2, W // 2, 128), g("d2", H // 2, W // 2, 128)
+        ops.conv_gemm([u2, e2], *P["dec2.0"], act=R, out=d2a)
+        ops.conv_gemm([d2a], *P["dec2.2"], act=R, out=d2)
+        u1 = g("u1", H, W, 64)
+        ops.conv_gemm([d2], *P["up1"], None, out=u1, out_mode=L.B2R_OUT_CONVT2X2)
+        d1a, d1 = g("a", H, W, 64), g("d1", H, W, 64)
+        ops.conv_gemm([u1, e1], *P["dec1.0"], act=R, out=d1a)
+        ops.conv_gemm([d1a], *P["dec1.2"], act=R, out=d1)
+        L.check(L.load().b2r_final_conv1x1(d1.data_ptr(), P["final"][0].data_ptr(), P["final"][1].data_ptr(),
+                                           ops._ptr(out_f32), ops._ptr(out_u8), n, H, W, ops._stream()))
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return _restorer_forward(self, x, 4, want_f32=True, want_u8=False)[0]
+
+    @torch.no_grad()
+    def restore_u8(self, x: torch.Tensor) -> torch.Tensor:
+        """u8 NHWC (or f32 NCHW) in -> clamp(0,1)*255 truncated to u8 NHWC (17_run_unified_inference.py:86-92)."""
+        return _restorer_forward(self, x, 4, want_f32=False, want_u8=True)[1]
+
+
+def _restorer_forward(m, x, div, want_f32, want_u8):
+    m._check_input(x, div)
+    if x.dtype not in (torch.float32, torch.uint8):
+        raise L.B2RError(f"input dtype {x.dtype}; expected float32 NCHW (nn.Module contract) or uint8 NHWC")
+    x = x.contiguous()
+    u8_in = x.dtype == torch.uint8
+    n = x.shape[0]
+    H, W = (x.shape[1], x.shape[2]) if u8_in else (x.shape[2], x.shape[3])
+    if (x.shape[3] if u8_in else x.shape[1]) != 3:
+        raise L.B2RError("expected 3 image channels")
+    o32 = torch.empty((n, 3, H, W), dtype=torch.float32, device=x.device) if want_f32 else None
+    o8 = torch.empty((n, H, W, 3), dtype=torch.uint8, device=x.device) if want_u8 else None
+    for s, c in m._chunks(n, m.micro_batch):
+        m._run(x[s:s + c], None if o32 is None else o32[s:s + c], None if o8 is None else o8[s:s + c])
+    return o32, o8
+
+
+# =================================================================================================================
+# ResUNet
+# =================================================================================================================
+class ResidualBlock(nn.Module):
+    """Parameter container with the reference's key layout: conv_block.{0,1,2,3,4}, shortcut.{0,1} (14:96-112)."""
+
+    def __init__(self, in_c: int, out_c: int):
+        super().__init__()
+        self.conv_block = nn.Sequential(_conv(in_c, out_c), nn.BatchNorm2d(out_c), nn.PReLU(),
+                                        _conv(out_c, out_c), nn.BatchNorm2d(out_c))
+        self.shortcut = nn.Sequential()
+        if in_c != out_c:
+            self.shortcut = nn.Sequential(nn.Conv2d(in_c, out_c, 1), nn.BatchNorm2d(out_c))
+        self.in_c, self.out_c = in_c, out_c
+
+    def forward(self, x):  # never used by ResUNet.forward; kept so the container is not silently callable
+        raise L.B2RError("ResidualBlock is a parameter container here; call ResUNet.forward")
+
+
+class ResUNet(_B200Module):
+    """Three-level residual U-Net, f32 [N,3,H,W] -> f32 [N,3,H,W] (unclamped), H and W multiples of 8."""
+
+    # (attribute path, C_in split over the concat sources, C_out)
+    _BLOCKS = (("res1", (64,), 64), ("res2", (64,), 128), ("res3", (128,), 256),
+               ("bottleneck.0", (256,), 512), ("bottleneck.1", (512,), 512), ("bottleneck.2", (512,), 256),
+               ("dec3", (128, 256), 128), ("dec2", (64, 128), 64), ("dec1", (64, 64), 64))
+
+    def __init__(self):
+        super().__init__()
+        self.enc1 = nn.Sequential(_conv(3, 64), nn.PReLU())
+        self.res1 = ResidualBlock(64, 64)
+        self.pool1 = nn.MaxPool2d(2, 2)
+        self.res2 = ResidualBlock(64, 128)
+        self.pool2 = nn.MaxPool2d(2, 2)
+        self.res3 = ResidualBlock(128, 256)
+        self.pool3 = nn.MaxPool2d(2, 2)
+        self.bottleneck = nn.Sequential(ResidualBlock(256, 512), ResidualBlock(512, 512), ResidualBlock(512, 256))
+        self.up3 = nn.ConvTranspose2d(256, 128, 2, stride=2)
+        self.dec3 = ResidualBlock(256 + 128, 128)
+        self.up2 = nn.ConvTranspose2d(128, 64, 2, stride=2)
+        self.dec2 = ResidualBlock(128 + 64, 64)
+        self.up1 = nn.ConvTranspose2d(64, 64, 2, stride=2)
+        self.dec1 = ResidualBlock(64 + 64, 64)
+        self.final = nn.Conv2d(64, 3, 1)
+
+    def _build_pack(self, sd):
+        dev = sd["final.weight"].device
+        P = {}
+        P["enc1"] = (sd["enc1.0.weight"].float().contiguous(), sd["enc1.0.bias"].float().contiguous(),
+                     float(sd["enc1.1.weight"].float().reshape(-1)[0]))
+        for name, splits, co in self._BLOCKS:
+            cb = name + ".conv_block."
+            bn = lambda i: (sd[cb + f"{i}.weight"], sd[cb + f"{i}.bias"], sd[cb + f"{i}.running_mean"],  # noqa: E731
+                            sd[cb + f"{i}.running_var"])
+            w1, b1 = packing.fold_bn(sd[cb + "0.weight"], sd[cb + "0.bias"], *bn(1))
+            w2, b2 = packing.fold_bn(sd[cb + "3.weight"], sd[cb + "3.bias"], *bn(4))
+            slope = float(sd[cb + "2.weight"].float().reshape(-1)[0])
+            ci = sum(splits)
+            # conv 1 over the (virtual) concat of the block's input sources
+            wm1, kb1 = packing.pack_conv3x3(w1, splits)
+            # conv 2 over y (source 0) + the shortcut over the block input (sources 1..)
+            plan = packing.KPlan(co).add_conv3x3(0, w2)
+            if ci != co:
+                sc = name + ".shortcut."
+                ws_, bs_ = packing.fold_bn(sd[sc + "0.weight"], sd[sc + "0.bias"], sd[sc + "1.weight"],
+                                           sd[sc + "1.bias"], sd[sc + "1.running_mean"], sd[sc + "1.running_var"])
+                ws_ = ws_.reshape(co, ci)
+                b2 = b2 + bs_
+            else:
+                ws_ = torch.eye(co, device=w2.device)  # nn.Sequential() shortcut == identity (14:106)
+            off = 0
+            for s, c in enumerate(splits):
+                plan.add_1x1(1 + s, ws_[:, off:off + c])
+                off += c
+            wm2, kb2 = plan.finish()
+            P[name] = (wm1.to(dev), b1.to(dev).contiguous(), kb1, slope, wm2.to(dev), b2.to(dev).contiguous(), kb2)
+        for up in ("up3", "up2", "up1"):
+            w, b = packing.pack_convT2x2(sd[up + ".weight"].float(), sd[up + ".bias"].float())
+            P[up] = (w.to(dev), b.to(dev))
+        P["final"] = (sd["final.weight"].float().reshape(3, 64).contiguous(), sd["final.bias"].float().contiguous())
+        return P
+
+    def _block(self, name, srcs, y, out, out_pool=None):
+        wm1, b1, kb1, slope, wm2, b2, kb2 = self._packed()[name]
+        ops.conv_gemm(srcs, wm1, b1, kb1, act=L.B2R_ACT_PRELU, slope=slope, out=y)
+        ops.conv_gemm([y] + list(srcs), wm2, b2, kb2, act=L.B2R_ACT_RELU, out=out, out_pool=out_pool)
+
+    def _run(self, x, out_f32, out_u8):
+        P, ws = self._packed(), self._ws
+        u8_in = x.dtype == torch.uint8
+        n = x.shape[0]
+        H, W = (x.shape[1], x.shape[2]) if u8_in else (x.shape[2], x.shape[3])
+        dev = x.device
+        g = lambda name, h, w, c: ws.get(name, (n, h, w, c), dev)  # noqa: E731
+        H2, W2, H4, W4, H8, W8 = H // 2, W // 2, H // 4, W // 4, H // 8, W // 8
+
+        w0, b0, s0 = P["enc1"]
+        e1 = ops.conv3x3_c3(x, w0, b0, act=L.B2R_ACT_PRELU, slope=s0, out=g("e1", H, W, 64))
+        r1, p1 = g("r1", H, W, 64), g("p1", H2, W2, 64)
+        self._block("res1", [e1], g("y1", H, W, 64), r1, p1)
+        r2, p2 = g("r2", H2, W2, 128), g("p2", H4, W4, 128)
+        self._block("res2", [p1], g("y2", H2, W2, 128), r2, p2)
+        r3, p3 = g("r3", H4, W4, 256), g("p3", H8, W8, 256)
+        self._block("res3", [p2], g("y3", H4, W4, 256), r3, p3)
+        bt0, bt1, bt2 = g("bt0", H8, W8, 512), g("bt1", H8, W8, 512), g("bt2", H8, W8, 256)
+        self._block("bottleneck.0", [p3], g("yb0", H8, W8, 512), bt0)
+        self._block("bottleneck.1", [bt0], g("yb1", H8, W8, 512), bt1)
+        self._block("bottleneck.2", [bt1], g("yb2", H8, W8, 256), bt2)
+        u3 = g("u3", H4, W4, 128)
+        ops.conv_gemm([bt2], *P["up3"], None, out=u3, out_mode=L.B2R_OUT_CONVT2X2)
+        d3 = g("d3", H4, W4, 128)
+        self._block("dec3", [u3, r3], g("yd3", H4, W4, 128), d3)      # cat((d3, r3), 1) (14:171)
+        u2 = g("u2", H2, W2, 64)
+        ops.conv_gemm([d3], *P["up2"], None, out=u2, out_mode=L.B2R_OUT_CONVT2X2)
+        d2 = g("d2", H2, W2, 64)
+        self._block("dec2", [u2, r2], g("yd2", H2, W2, 64), d2)       # cat((d2, r2), 1) (14:177)
+        u1 = g("u1", H, W, 64)
+        ops.conv_gemm([d2], *P["up1"], None, out=u1, out_mode=L.B2R_OUT_CONVT2X2)
+        d1 = g("d1", H, W, 64)
+        self._block("dec1", [u1, r1], g("y1", H, W, 64), d1)          # cat((d1, r1), 1) (14:183)
+        L.check(L.load().b2r_final_conv1x1(d1.data_ptr(), P["final"][0].data_ptr(), P["final"][1].data_ptr(),
+                                           ops._ptr(out_f32), ops._ptr(out_u8), n, H, W, ops._stream()))
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return _restorer_forward(self, x, 8, want_f32=True, want_u8=False)[0]
+
+    @torch.no_grad()
+    def restore_u8(self, x: torch.Tensor) -> torch.Tensor:
+        return _restorer_forward(self, x, 8, want_f32=False, want_u8=True)[1]
+
+
+# =================================================================================================================
+# VGG16 judge
+# =================================================================================================================
+_VGG_CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M")
+
+
+class VGG16Judge(_B200Module):
+    """torchvision `vgg16` layout (features.N / classifier.N keys) with a `num_classes` head — the reference builds
+    it as `models.vgg16(...)` followed by `model.classifier[6] = nn.Linear(4096, 43)` (05_train_baseline.py:47-54,
+    06_test_baseline.py:65-67); assigning a new `classifier[6]` on this class works the same way.
+
+    forward(x): x = ImageNet-normalised f32 [N,3,H,W] (the reference's transform, 18:28-32) -> f32 logits [N,43];
+    forward_u8(x): x = u8 NHWC, ToTensor + Normalize fused into the first conv.  H, W multiples of 32.
+    """
+
+    def __init__(self, num_classes: int = 43):
+        super().__init__()
+        layers: List[nn.Module] = []
+        c = 3
+        for v in _VGG_CFG:
+            if v == "M":
+                layers.append(nn.MaxPool2d(2, 2))
+            else:
+                layers += [_conv(c, v), nn.ReLU(inplace=True)]
+                c = v
+        self.features = nn.Sequential(*layers)
+        self.avgpool = nn.AdaptiveAvgPool2d((7, 7))
+        self.classifier = nn.Sequential(nn.Linear(512 * 7 * 7, 4096), nn.ReLU(True), nn.Dropout(),
+                                        nn.Linear(4096, 4096), nn.ReLU(True), nn.Dropout(),
+                                        nn.Linear(4096, num_classes))
+
+    def _conv_indices(self) -> List[Tuple[int, bool]]:
+        """[(features index of conv, followed-by-pool?)] for the 13 convs."""
+        mods = list(self.features)
+        out = []
+        for i, m in enumerate(mods):
+            if isinstance(m, nn.Conv2d):
+                pooled = i + 2 < len(mods) and isinstance(mods[i + 2], nn.MaxPool2d)
+                out.append((i, pooled))
+        return out
+
+    def _build_pack(self, sd):
+        dev = sd["classifier.6.weight"].device
+        P = {"convs": []}
+        for i, pooled in self._conv_indices():
+            w, b = sd[f"features.{i}.weight"].float(), sd[f"features.{i}.bias"].float().contiguous()
+            if w.shape[1] == 3:
+                P["first"] = (w.contiguous(), b)
+            else:
+                wm, kb = packing.pack_conv3x3(w)
+                P["convs"].append((wm.to(dev), b, kb, pooled, int(w.shape[0])))
+        P["fc1"] = (packing.pack_fc_from_nchw_flatten(sd["classifier.0.weight"].float(), 512, 7, 7).to(dev),
+                    sd["classifier.0.bias"].float().contiguous())
+        P["fc2"] = (sd["classifier.3.weight"].to(torch.bfloat16).contiguous(), sd["classifier.3.bias"].float().contiguous())
+        P["fc3"] = (sd["classifier.6.weight"].to(torch.bfloat16).contiguous(), sd["classifier.6.bias"].float().contiguous())
+        return P
+
+    def _run(self, x, normalize_u8: bool) -> torch.Tensor:
+        P, ws = self._packed(), self._ws
+        u8_in = x.dtype == torch.uint8
+        n = x.shape[0]
+        H, W = (x.shape[1], x.shape[2]) if u8_in else (x.shape[2], x.shape[3])
+        dev = x.device
+        R = L.B2R_ACT_RELU
+        cur = ops.conv3x3_c3(x, *P["first"], act=R, normalize=u8_in and normalize_u8,
+                             out=ws.get("c0", (n, H, W, 64), dev))
+        h, w = H, W
+        for li, (wm, b, kb, pooled, co) in enumerate(P["convs"]):
+            if pooled:
+                nxt = ws.get(f"c{li + 1}", (n, h // 2, w // 2, co), dev)
+                ops.conv_gemm([cur], wm, b, kb, act=R, out_pool=nxt)
+                h, w = h // 2, w // 2
+            else:
+                nxt = ws.get(f"c{li + 1}", (n, h, w, co), dev)
+                ops.conv_gemm([cur], wm, b, kb, act=R, out=nxt)
+            cur = nxt
+        if (h, w) != (7, 7):
+            cur = ops.adaptive_avgpool7(cur)  # identity at 224x224
+        flat = cur.view(1, 1, n, 7 * 7 * 512)
+        f1 = ws.get("f1", (1, 1, n, 4096), dev)
+        ops.conv_gemm([flat], *P["fc1"], None, act=R, out=f1)
+        f2 = ws.get("f2", (1, 1, n, 4096), dev)
+        ops.conv_gemm([f1], *P["fc2"], None, act=R, out=f2)   # Dropout is the identity in eval mode
+        return ops.linear_f32out(f2.view(n, 4096), *P["fc3"])
+
+    def _forward(self, x: torch.Tensor, normalize_u8: bool) -> torch.Tensor:
+        self._check_input(x, 32)
+        x = x.contiguous()
+        n = x.shape[0]
+        outs = [self._run(x[s:s + c], normalize_u8) for s, c in self._chunks(n, self.micro_batch)]
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dtype != torch.float32:
+            raise L.B2RError("VGG16Judge.forward takes the normalised float32 NCHW tensor; use forward_u8 for u8 NHWC")
+        return self._forward(x, False)
+
+    @torch.no_grad()
+    def forward_u8(self, x: torch.Tensor) -> torch.Tensor:
+        """u8 NHWC [N,H,W,3] -> logits; ToTensor + Normalize(ImageNet) (18_test_unified_benchmark.py:28-32) fused."""
+        if x.dtype != torch.uint8:
+            raise L.B2RError("forward_u8 takes uint8 NHWC")
+        return self._forward(x, True)
+
+
+def vgg16(num_classes: int = 43) -> VGG16Judge:
+    return VGG16Judge(num_classes)
