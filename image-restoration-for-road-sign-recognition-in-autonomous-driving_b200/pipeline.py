@@ -1,0 +1,141 @@
+"""degrade -> restore -> classify -> count, on-device, one process per GPU.
+
+The reference runs this path as three scripts joined by PNG files on disk (16_gen_compound_data.py ->
+17_run_unified_inference.py -> 18_test_unified_benchmark.py); the only in-memory composition is the single-image
+demo 15_test_unified.py:170-200, which fixes the semantics kept here:
+
+    u8 image --degrade--> u8 --ToTensor--> restorer --clamp(0,1)*255, truncate--> u8 --ToTensor+Normalize--> VGG16
+       --torch.max(outputs, 1)--> predicted;  correct += (predicted == labels).sum()      (18:47-49)
+
+Every arrow is a libb2r.so kernel; images never leave HBM between stages.  Multi-GPU: images are independent, so
+each rank takes a contiguous block of the global index range, noise is keyed by the global image index (results
+do not depend on the world size) and the only collective is one all-reduce of the int64 (correct, total) pair.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from . import degrade as D
+from . import ops
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of the global image index range owned by `rank`."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_reduce_counts(counts: torch.Tensor) -> torch.Tensor:
+    """Sum the int64 (correct, total) pair over all ranks: the single collective of the path (NCCL on GPUs)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    return counts
+
+
+class RestoreClassifyPipeline:
+    """Holds a restorer (SimpleUNet / ResUNet) and the VGG16 judge on one device and streams batches through them."""
+
+    def __init__(self, restorer, judge, micro_batch: int = 128):
+        self.restorer = restorer.eval()
+        self.judge = judge.eval()
+        self.micro_batch = int(micro_batch)
+        self.device = next(judge.parameters()).device
+        if self.device.type != "cuda":
+            raise L.B2RError("RestoreClassifyPipeline needs its modules on a CUDA device (no CPU fallback)")
+        self._div = 8 if type(restorer).__name__ == "ResUNet" else 4
+        self._bufs = {}
+
+    def _buf(self, name, shape, dtype):
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    @torch.no_grad()
+    def run_micro_batch(self, clean_u8: torch.Tensor, labels: Optional[torch.Tensor], params, seed: int,
+                        image_index0: int, counts: Optional[torch.Tensor], noise: Optional[torch.Tensor] = None,
+                        keep: bool = False):
+        """One resident micro-batch through all stages.  Returns (pred int64 [n], extras dict when keep=True)."""
+        n, h, w, _ = clean_u8.shape
+        degraded = D.degrade(clean_u8, params, seed=seed, image_index0=image_index0, noise=noise,
+                             out=self._buf("deg", (n, h, w, 3), torch.uint8)) if params is not None else clean_u8
+        restored = self._buf("rest", (n, h, w, 3), torch.uint8)
+        self.restorer._check_input(degraded, self._div)
+        self.restorer._run(degraded, None, restored)
+        self.judge._check_input(restored, 32)
+        logits = self.judge._run(restored, True)
+        pred, _ = ops.argmax_count(logits, labels, counts)
+        if keep:
+            return pred, {"degraded": degraded.clone(), "restored": restored.clone(), "logits": logits.clone()}
+        return pred, None
+
+    @torch.no_grad()
+    def run(self, clean_u8: torch.Tensor, labels: torch.Tensor, params, seed: int = 0, image_index0: int = 0):
+        """Device-resident batch [N,H,W,3] u8 -> (pred int64 [N], counts int64 [2] = (correct, total))."""
+        n = clean_u8.shape[0]
+        counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        preds = torch.empty(n, dtype=torch.int64, device=self.device)
+        dparams = params.to(self.device) if isinstance(params, D.DegradeParams) else params
+        for s in range(0, n, self.micro_batch):
+            c = min(self.micro_batch, n - s)
+            sub = _slice_params(dparams, s, c) if dparams is not None else None
+            p, _ = self.run_micro_batch(clean_u8[s:s + c], labels[s:s + c], sub, seed, image_index0 + s, counts)
+            preds[s:s + c] = p
+        return preds, counts
+
+    @torch.no_grad()
+    def run_from_host(self, clean_u8_pinned: torch.Tensor, labels_pinned: torch.Tensor, params, seed: int = 0,
+                      image_index0: int = 0):
+        """End-to-end call with HOST buffers: per micro-batch H2D copy of the images/labels from pinned memory on a
+        copy stream (double-buffered, overlapped with compute), D2H read of the (correct, total) pair at the end.
+        Returns (counts as a Python tuple, h2d_bytes, d2h_bytes)."""
+        n, h, w, _ = clean_u8_pinned.shape
+        mb = self.micro_batch
+        counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        dparams = params.to(self.device) if isinstance(params, D.DegradeParams) else params
+        copy_stream = self._bufs.get("_copy_stream") or torch.cuda.Stream(device=self.device)
+        self._bufs["_copy_stream"] = copy_stream
+        main = torch.cuda.current_stream(self.device)
+        stage = [(self._buf(f"h2d_img{i}", (mb, h, w, 3), torch.uint8), self._buf(f"h2d_lab{i}", (mb,), torch.int64))
+                 for i in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        h2d = 0
+        chunks = [(s, min(mb, n - s)) for s in range(0, n, mb)]
+
+        def issue(i):
+            s, c = chunks[i]
+            b = i & 1
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(freed[b])
+                stage[b][0][:c].copy_(clean_u8_pinned[s:s + c], non_blocking=True)
+                stage[b][1][:c].copy_(labels_pinned[s:s + c], non_blocking=True)
+                ready[b].record(copy_stream)
+
+        if chunks:
+            issue(0)
+        for i, (s, c) in enumerate(chunks):
+            if i + 1 < len(chunks):
+                issue(i + 1)
+            b = i & 1
+            main.wait_event(ready[b])
+            sub = _slice_params(dparams, s, c) if dparams is not None else None
+            self.run_micro_batch(stage[b][0][:c], stage[b][1][:c], sub, seed, image_index0 + s, counts)
+            freed[b].record(main)
+            h2d += c * h * w * 3 + c * 8
+        host_counts = counts.cpu()           # the device -> host read of the step's result (synchronises)
+        return (int(host_counts[0]), int(host_counts[1])), h2d, host_counts.numel() * 8
+
+
+def _slice_params(p: "D.DeviceDegradeParams", s: int, c: int) -> "D.DeviceDegradeParams":
+    if s == 0 and c == p.n:
+        return p
+    return D.DeviceDegradeParams(c, p.order, p.flags, p.ksize[s:s + c], p.taps[s:s + c], p.fog_on[s:s + c],
+                                 p.fog_t[s:s + c], p.fog_add[s:s + c], p.sigma[s:s + c], p.any_blur)

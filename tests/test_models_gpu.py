@@ -1,0 +1,149 @@
+"""GPU parity of the drop-in modules against the fp32 oracle (oracle/models_oracle.py, itself pinned to the
+reference classes) on identical inputs and identical seeded checkpoints.
+
+Floating point, bf16 activations with fp32 accumulation vs an fp32 reference: the tolerance is stated per test as
+max-abs / PSNR on the f32 output (BASELINE.json north_star: "fp32-accumulated restorations must match within a
+stated max-abs/PSNR tolerance").  The comparator runs on the same GPU in fp32 with TF32 disabled.
+"""
+import io
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from _util import golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def psnr(a, b, peak=1.0):
+    mse = float(((a.double() - b.double()) ** 2).mean())
+    return 99.0 if mse == 0 else 10 * math.log10(peak * peak / mse)
+
+
+def _load(arch, seed):
+    from b200restore import models, synth
+    sd = synth.synthetic_state_dict(arch, seed)
+    m = {"simple_unet": models.SimpleUNet, "resunet": models.ResUNet, "vgg16": models.VGG16Judge}[arch]()
+    m.load_state_dict(sd)
+    return m.cuda().eval(), {k: v.cuda() for k, v in sd.items()}
+
+
+RESTORER_TOL = {"psnr_db": 45.0, "max_abs": 3e-2}
+
+
+@pytest.mark.parametrize("arch,shape", [("simple_unet", (2, 3, 64, 96)), ("simple_unet", (3, 3, 224, 224)),
+                                        ("resunet", (2, 3, 64, 96)), ("resunet", (3, 3, 224, 224))])
+def test_restorer_forward_vs_oracle(arch, shape):
+    from oracle import models_oracle as O
+    m, sd = _load(arch, 21)
+    fn = O.simple_unet_forward if arch == "simple_unet" else O.resunet_forward
+    from b200restore import synth
+    img, _ = synth.sign_like_images(shape[0], shape[2], shape[3], seed=1)
+    x = O.to_tensor_u8(img).cuda()
+    y = m(x)
+    with torch.no_grad():
+        ref = fn(sd, x)
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    p, mx = psnr(y, ref), float((y - ref).abs().max())
+    print(f"\n[{arch} {shape}] PSNR {p:.1f} dB, max-abs {mx:.4g}, ref range [{float(ref.min()):.3f}, {float(ref.max()):.3f}]")
+    assert p >= RESTORER_TOL["psnr_db"] and mx <= RESTORER_TOL["max_abs"]
+
+
+def test_restorer_matches_committed_reference_output():
+    """Directly against the reference classes' outputs stored by tests/golden/make_golden.py (same seed 11)."""
+    g = golden("models_ref.npz")
+    for arch in ("simple_unet", "resunet"):
+        m, _ = _load(arch, 11)
+        x = torch.from_numpy(g[arch + "_x"]).cuda()
+        ref = torch.from_numpy(g[arch + "_y"]).cuda()
+        y = m(x)
+        p, mx = psnr(y, ref), float((y - ref).abs().max())
+        print(f"\n[{arch} golden] PSNR {p:.1f} dB, max-abs {mx:.4g}")
+        assert p >= RESTORER_TOL["psnr_db"] and mx <= RESTORER_TOL["max_abs"]
+
+
+def test_restore_u8_is_truncation_of_forward():
+    from oracle import models_oracle as O
+    from b200restore import synth
+    m, _ = _load("simple_unet", 22)
+    img, _ = synth.sign_like_images(2, 64, 64, seed=2)
+    img = img.cuda()
+    y = m(O.to_tensor_u8(img))
+    u8_from_f32 = m.restore_u8(O.to_tensor_u8(img))
+    assert torch.equal(u8_from_f32, O.quantize_restored(y))
+    # u8 NHWC input (ToTensor fused into the first conv) gives the same bytes as the f32 NCHW entry
+    assert torch.equal(m.restore_u8(img), u8_from_f32)
+
+
+def test_micro_batching_is_invisible():
+    from oracle import models_oracle as O
+    from b200restore import synth
+    m, _ = _load("resunet", 23)
+    img, _ = synth.sign_like_images(5, 32, 32, seed=3)
+    x = O.to_tensor_u8(img).cuda()
+    m.micro_batch = 128
+    a = m(x)
+    m.micro_batch = 2
+    b = m(x)
+    assert torch.equal(a, b)
+
+
+def test_repack_on_load_and_head_swap():
+    from b200restore import models, synth
+    m, _ = _load("simple_unet", 24)
+    x = torch.rand((1, 3, 32, 32), generator=torch.Generator().manual_seed(0)).cuda()
+    y1 = m(x)
+    buf = io.BytesIO()
+    torch.save(synth.synthetic_state_dict("simple_unet", 25), buf)
+    buf.seek(0)
+    m.load_state_dict(torch.load(buf, map_location="cuda"))          # 17_run_unified_inference.py:63
+    y2 = m(x)
+    assert not torch.equal(y1, y2)
+    j, _ = _load("vgg16", 26)
+    xi = torch.randn((1, 3, 64, 64), generator=torch.Generator().manual_seed(1)).cuda()
+    l1 = j(xi)
+    j.classifier[6] = torch.nn.Linear(4096, 10).cuda()               # the reference's head swap (06:65-67)
+    assert j(xi).shape == (1, 10) and l1.shape == (1, 43)
+
+
+JUDGE_TOL = {"rel_to_logit_std": 0.03}
+
+
+@pytest.mark.parametrize("hw", [(224, 224), (64, 64), (256, 256)])
+def test_vgg16_logits_vs_oracle(hw):
+    from oracle import models_oracle as O
+    from b200restore import synth
+    j, sd = _load("vgg16", 27)
+    img, _ = synth.sign_like_images(4, hw[0], hw[1], seed=4)
+    img = img.cuda()
+    x = O.normalize_imagenet(O.to_tensor_u8(img))
+    with torch.no_grad():
+        ref = O.vgg16_forward(sd, x)
+    got = j(x)
+    got_u8 = j.forward_u8(img)
+    err = float((got - ref).abs().max())
+    scale = float(ref.std())
+    print(f"\n[vgg16 {hw}] max logit err {err:.4g}, logit std {scale:.4g}, ratio {err / scale:.4g}")
+    assert got.shape == (4, 43)
+    assert err <= JUDGE_TOL["rel_to_logit_std"] * scale
+    # the fused u8 entry (ToTensor + Normalize inside the first conv) == the f32 entry up to bf16 rounding of layer 1
+    assert float((got_u8 - got).abs().max()) <= JUDGE_TOL["rel_to_logit_std"] * scale
+
+
+def test_vgg16_matches_committed_torchvision_output():
+    g = golden("models_ref.npz")
+    j, _ = _load("vgg16", 13)
+    ref = torch.from_numpy(g["vgg16_y"]).cuda()
+    got = j(torch.from_numpy(g["vgg16_x"]).cuda())
+    err, scale = float((got - ref).abs().max()), float(ref.std())
+    print(f"\n[vgg16 golden] max err {err:.4g} vs logit std {scale:.4g}")
+    assert err <= JUDGE_TOL["rel_to_logit_std"] * scale
