@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — images/s of the degrade -> restore -> VGG16 classify -> top-1 count path (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--batch B]
+
+One "step" = one pass of the hot path over one batch of B synthetic GTSRB-shaped images per GPU (weak scaling: every
+rank owns a contiguous block of the global image index range; the only collective is the all-reduce of the int64
+(correct, total) pair at the end of the step).  For N > 1 launch under torchrun (one rank per GPU, NCCL).
+
+Prints ONE JSON line on rank 0:
+  value      images/s with the batch already resident in HBM when the timed region starts (CUDA events, max over ranks)
+  e2e        same metric through the public API with HOST buffers (pinned H2D of every micro-batch + D2H of the counts
+             inside the timed region)
+  roofline   the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs / summed CUDA-event duration of its
+             launches inside the timed region, against MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference path timed on this box's host cores (bounded sample, rank 0, N = 1)
+
+`--impl reference` times the reference's CPU implementation of the same path (oracle port: the reference is Python and
+cannot travel to the GPU box; oracle/ is pinned to it bit-for-bit by tests/test_oracle_*.py) with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (restorer arch, degradation recipe, classify?)
+    "degrade16_resunet_vgg16_top1": ("resunet", "compound16", True),      # BASELINE configs[3] per-GPU shard
+    "degrade16_unet_vgg16_top1": ("simple_unet", "compound16", True),
+    "degrade_fog_blur_unet": ("simple_unet", "compound16", False),        # BASELINE configs[1]
+    "degrade_random_resunet": ("resunet", "random14", False),             # BASELINE configs[2]
+}
+GFLOP_PER_IMAGE_224 = {"simple_unet": 38.831, "resunet": 55.992, "vgg16": 30.933}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="degrade16_resunet_vgg16_top1", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=4096, help="images per GPU per step")
+    ap.add_argument("--micro-batch", type=int, default=128)
+    ap.add_argument("--hw", type=int, default=224)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline sample (0 = choose)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi polled every 200 ms during the timed region (B200_PROFILING.md 'clocks' line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference / CPU baseline (oracle port; the ONLY place bench.py executes oracle/)
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference_images_per_s(workload: str, hw: int, sample: int, repeats: int, warmup: int = 1):
+    """Time the oracle port of the reference path on the host cores: script-16 degradation per image (as the
+    reference runs it, one image per call), then ToTensor -> restorer -> clamp/u8 -> Normalize -> VGG16 -> arg-max in
+    fp32 PyTorch with all threads.  Returns (images/s, cores, seconds per sample)."""
+    import numpy as np
+    import torch
+    from b200restore import synth
+    from oracle import degrade_oracle as DO, models_oracle as MO
+    arch, recipe, classify = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sdr = synth.synthetic_state_dict(arch, 31)
+    sdj = synth.synthetic_state_dict("vgg16", 32) if classify else None
+    fn = MO.simple_unet_forward if arch == "simple_unet" else MO.resunet_forward
+    imgs, labels = synth.sign_like_images(sample, hw, hw, seed=7)
+    imgs_np = imgs.numpy()
+    rng = np.random.default_rng(0)
+
+    def one_pass():
+        deg = []
+        for i in range(sample):
+            noise = rng.normal(0, 0.02 ** 0.5, imgs_np[i].shape)
+            if recipe == "compound16":
+                deg.append(DO.compound_16(imgs_np[i], noise))
+            else:
+                deg.append(DO.random_14(imgs_np[i], 0.5, noise, 10, 45))
+        deg = torch.from_numpy(np.stack(deg))
+        with torch.no_grad():
+            if classify:
+                _, _, pred = MO.restore_then_classify(fn, sdr, sdj, deg)
+                return int((pred == labels).sum())
+            out = fn(sdr, MO.to_tensor_u8(deg))
+            return int(MO.quantize_restored(out).sum() > 0)
+
+    for _ in range(warmup):
+        one_pass()
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        one_pass()
+        times.append(time.perf_counter() - t0)
+    dt = statistics.median(times)
+    return sample / dt, cores, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample or (16 if cores <= 16 else 32)
+    t0 = time.perf_counter()
+    ips, cores, dt = cpu_reference_images_per_s(args.workload, args.hw, sample, repeats=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": "images/sec restore->VGG16 classify", "value": ips, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "hw": args.hw, "images_per_step": sample,
+                   "note": "reference CPU path (oracle port, pinned to the reference's classes), host cores only"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} images of {args.hw}x{args.hw} per step, median of {args.steps} steps"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import b200restore as B
+    from b200restore import degrade as D, models, ops, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: libb2r has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+
+    arch, recipe, classify = WORKLOADS[args.workload]
+    B_, hw, mb = args.batch, args.hw, args.micro_batch
+    lo = rank * B_                                   # weak scaling: rank r owns global images [r*B, (r+1)*B)
+
+    restorer = (models.SimpleUNet if arch == "simple_unet" else models.ResUNet)()
+    restorer.load_state_dict(synth.synthetic_state_dict(arch, 31))
+    restorer = restorer.to(dev).eval()
+    judge = models.VGG16Judge()
+    judge.load_state_dict(synth.synthetic_state_dict("vgg16", 32))
+    judge = judge.to(dev).eval()
+    pipe = B.RestoreClassifyPipeline(restorer, judge, micro_batch=mb)
+
+    # synthetic GTSRB-shaped batch, generated in chunks on the host into pinned memory, then copied once to HBM
+    host_imgs = torch.empty((B_, hw, hw, 3), dtype=torch.uint8).pin_memory()
+    host_labels = torch.empty((B_,), dtype=torch.int64).pin_memory()
+    for s in range(0, B_, 512):
+        c = min(512, B_ - s)
+        im, lb = synth.sign_like_images(c, hw, hw, seed=7, index0=lo + s)
+        host_imgs[s:s + c] = im
+        host_labels[s:s + c] = lb
+    dev_imgs = host_imgs.to(dev)
+    dev_labels = host_labels.to(dev)
+    params = (D.compound_params(B_) if recipe == "compound16"
+              else D.random_params(B_, np.random.default_rng(2 + rank), order=0)).to(dev)
+
+    def step_device():
+        if classify:
+            _, counts = pipe.run(dev_imgs, dev_labels, params, seed=2, image_index0=lo)
+        else:
+            counts = torch.zeros(2, dtype=torch.int64, device=dev)
+            for s in range(0, B_, mb):
+                c = min(mb, B_ - s)
+                sub = B.pipeline._slice_params(params, s, c)
+                deg = D.degrade(dev_imgs[s:s + c], sub, seed=2, image_index0=lo + s)
+                restorer.restore_u8(deg)
+            counts[1] = B_
+        B.all_reduce_counts(counts)
+        return counts
+
+    def step_host():
+        (correct, total), h2d, d2h = pipe.run_from_host(host_imgs, host_labels, params, seed=2, image_index0=lo)
+        c = torch.tensor([correct, total], dtype=torch.int64, device=dev)
+        B.all_reduce_counts(c)
+        return c, h2d, d2h
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = None
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), res
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, per-launch events on the dominant kernel, clocks sampled
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    timer = ops.KernelTimer(kinds=("conv_gemm",))
+    launches0 = ops.STATS["launches"]
+    with ops.timing(timer):
+        total_ms, counts = timed(step_device, args.steps)
+    launches = ops.STATS["launches"] - launches0
+    ksum = timer.summary().get("conv_gemm", {"launches": 0, "work": 0.0, "ms": 1e-9})
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end (host buffers) : same K steps
+    e2e = None
+    if classify:
+        step_host()
+        e2e_ms, (c2, h2d, d2h) = timed(step_host, args.steps)
+        e2e = {"value": B_ * world * args.steps / (e2e_ms / 1e3), "unit": "images/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained"
+    conv_tf = ksum["work"] / (ksum["ms"] * 1e-3) / 1e12
+    ips = B_ * world * args.steps / (total_ms / 1e3)
+    gflop_img = GFLOP_PER_IMAGE_224[arch] + (GFLOP_PER_IMAGE_224["vgg16"] if classify else 0.0)
+    line = {
+        "metric": "images/sec restore->VGG16 classify", "value": ips, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "images_per_gpu_per_step": B_, "hw": hw, "micro_batch": mb,
+                   "restorer": arch, "judge": "vgg16-43" if classify else None, "degradation": recipe,
+                   "weights": "seeded synthetic state_dicts in the shipped schemas",
+                   "l2": "inputs (%.0f MB/step) larger than L2; no flush needed" % (B_ * hw * hw * 3 / 1e6),
+                   "parallelism": f"dp{world} (batch sharded, one int64[2] all-reduce per step)"},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM)",
+                     "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
+                     "peak_source": peak_src, "traffic": None,
+                     "launches": ksum["launches"], "kernel_ms_per_step": ksum["ms"] / args.steps,
+                     "share_of_step": ksum["ms"] / total_ms,
+                     "pipeline_tflops": ips / world * gflop_img / 1e3 if hw == 224 else None},
+        "counts": [int(counts[0]), int(counts[1])],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample or (16 if cores <= 16 else 32)
+        v, cores, dt = cpu_reference_images_per_s(args.workload, hw, sample, repeats=1, warmup=1)
+        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"{sample} images of {hw}x{hw}, one timed pass after one warm-up pass "
+                                          f"({dt:.1f} s); oracle port of scripts 16 -> 17 -> 18 in fp32 PyTorch"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -174,6 +174,7 @@ class SimpleUNet(_B200Module):
         ops.conv_gemm([d1a], *P["dec1.2"], act=R, out=d1)
         L.check(L.load().b2r_final_conv1x1(d1.data_ptr(), P["final"][0].data_ptr(), P["final"][1].data_ptr(),
                                            ops._ptr(out_f32), ops._ptr(out_u8), n, H, W, ops._stream()))
+        ops.STATS["launches"] += 1
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -277,7 +278,9 @@ class ResUNet(_B200Module):
                 plan.add_1x1(1 + s, ws_[:, off:off + c])
                 off += c
             wm2, kb2 = plan.finish()
-            P[name] = (wm1.to(dev), b1.to(dev).contiguous(), kb1, slope, wm2.to(dev), b2.to(dev).contiguous(), kb2)
+            alg_k2 = int(wm2.shape[1]) - (0 if ci != co else co)   # the identity block is not algorithmic work
+            P[name] = (wm1.to(dev), b1.to(dev).contiguous(), kb1, slope, wm2.to(dev), b2.to(dev).contiguous(), kb2,
+                       alg_k2)
         for up in ("up3", "up2", "up1"):
             w, b = packing.pack_convT2x2(sd[up + ".weight"].float(), sd[up + ".bias"].float())
             P[up] = (w.to(dev), b.to(dev))
@@ -285,9 +288,9 @@ class ResUNet(_B200Module):
         return P
 
     def _block(self, name, srcs, y, out, out_pool=None):
-        wm1, b1, kb1, slope, wm2, b2, kb2 = self._packed()[name]
+        wm1, b1, kb1, slope, wm2, b2, kb2, alg_k2 = self._packed()[name]
         ops.conv_gemm(srcs, wm1, b1, kb1, act=L.B2R_ACT_PRELU, slope=slope, out=y)
-        ops.conv_gemm([y] + list(srcs), wm2, b2, kb2, act=L.B2R_ACT_RELU, out=out, out_pool=out_pool)
+        ops.conv_gemm([y] + list(srcs), wm2, b2, kb2, act=L.B2R_ACT_RELU, out=out, out_pool=out_pool, alg_k=alg_k2)
 
     def _run(self, x, out_f32, out_u8):
         P, ws = self._packed(), self._ws
@@ -324,6 +327,7 @@ class ResUNet(_B200Module):
         self._block("dec1", [u1, r1], g("y1", H, W, 64), d1)          # cat((d1, r1), 1) (14:183)
         L.check(L.load().b2r_final_conv1x1(d1.data_ptr(), P["final"][0].data_ptr(), P["final"][1].data_ptr(),
                                            ops._ptr(out_f32), ops._ptr(out_u8), n, H, W, ops._stream()))
+        ops.STATS["launches"] += 1
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -14,6 +14,62 @@ from . import _lib as L
 IMAGENET_MEAN = (0.485, 0.456, 0.406)   # 18_test_unified_benchmark.py:31
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
+# launch accounting: every C-ABI call below is exactly one kernel launch of libb2r.so
+STATS = {"launches": 0}
+
+
+class KernelTimer:
+    """Optional per-launch CUDA-event timing on the launching stream (used by bench.py for the roofline numbers).
+
+    `with ops.timing(timer):` brackets every launch of the kinds in `kinds` with an event pair and records the
+    algorithmic work (FLOPs or bytes) the caller states for it; `summary()` synchronises and sums."""
+
+    def __init__(self, kinds=("conv_gemm",)):
+        self.kinds = set(kinds)
+        self.records = []   # (kind, work, start_event, end_event)
+
+    def start(self, kind):
+        if kind not in self.kinds:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        return e
+
+    def stop(self, kind, work, e0):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record(torch.cuda.current_stream())
+        self.records.append((kind, float(work), e0, e1))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, work, e0, e1 in self.records:
+            d = out.setdefault(kind, {"launches": 0, "work": 0.0, "ms": 0.0})
+            d["launches"] += 1
+            d["work"] += work
+            d["ms"] += e0.elapsed_time(e1)
+        return out
+
+
+_TIMER: Optional[KernelTimer] = None
+
+
+class timing:
+    def __init__(self, timer: Optional[KernelTimer]):
+        self.timer = timer
+
+    def __enter__(self):
+        global _TIMER
+        self._prev, _TIMER = _TIMER, self.timer
+        return self.timer
+
+    def __exit__(self, *a):
+        global _TIMER
+        _TIMER = self._prev
+        return False
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -44,8 +100,10 @@ def kblock(src: int, dh: int, dw: int, c64: int) -> int:
 def conv_gemm(srcs: Sequence[torch.Tensor], weights: torch.Tensor, bias: torch.Tensor,
               kblocks: Optional[Sequence[int]], act: int = L.B2R_ACT_NONE, slope: float = 0.0,
               out: Optional[torch.Tensor] = None, out_pool: Optional[torch.Tensor] = None,
-              out_mode: int = L.B2R_OUT_NHWC, tile=(0, 0, 0), block_n: int = 0, max_ctas: int = 0) -> None:
-    """One fused tensor-core layer (b2r_conv_gemm).  srcs: NHWC bf16 [N,H,W,C_i]; weights bf16 [cout_total, K]."""
+              out_mode: int = L.B2R_OUT_NHWC, tile=(0, 0, 0), block_n: int = 0, max_ctas: int = 0,
+              alg_k: Optional[int] = None) -> None:
+    """One fused tensor-core layer (b2r_conv_gemm).  srcs: NHWC bf16 [N,H,W,C_i]; weights bf16 [cout_total, K].
+    `alg_k`: K elements that are algorithmic work (excludes e.g. an identity-shortcut block); accounting only."""
     n, h, w = srcs[0].shape[:3]
     d = L.ConvGemmDesc()
     d.N, d.H, d.W = int(n), int(h), int(w)
@@ -92,7 +150,12 @@ def conv_gemm(srcs: Sequence[torch.Tensor], weights: torch.Tensor, bias: torch.T
     d.out_C = oc
     d.tile_w, d.tile_h, d.tile_n = (int(x) for x in tile)
     d.block_n, d.max_ctas = int(block_n), int(max_ctas)
+    e0 = _TIMER.start("conv_gemm") if _TIMER is not None else None
     L.check(L.load().b2r_conv_gemm(C.byref(d), _stream()))
+    STATS["launches"] += 1
+    if e0 is not None:
+        k_alg = int(weights.shape[1]) if alg_k is None else int(alg_k)
+        _TIMER.stop("conv_gemm", 2.0 * n * h * w * d.cout_total * k_alg, e0)
     del arr
 
 
@@ -124,6 +187,7 @@ def conv3x3_c3(x: torch.Tensor, weights: torch.Tensor, bias: torch.Tensor, act: 
         std = (C.c_float * 3)(*IMAGENET_STD)
     L.check(L.load().b2r_conv3x3_c3(x.data_ptr(), fmt, mean, std, weights.data_ptr(), bias.data_ptr(), int(act),
                                     float(slope), out.data_ptr(), int(n), int(h), int(w), _stream()))
+    STATS["launches"] += 1
     return out
 
 
@@ -142,6 +206,7 @@ def final_conv1x1(x: torch.Tensor, weights: torch.Tensor, bias: torch.Tensor, wa
     o8 = torch.empty((n, h, w, 3), dtype=torch.uint8, device=x.device) if want_u8 else None
     L.check(L.load().b2r_final_conv1x1(x.data_ptr(), weights.data_ptr(), bias.data_ptr(), _ptr(o32), _ptr(o8), int(n),
                                        int(h), int(w), _stream()))
+    STATS["launches"] += 1
     return o32, o8
 
 
@@ -152,6 +217,7 @@ def maxpool2x2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
         out = torch.empty((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
     _chk(out, torch.bfloat16, "out", 4)
     L.check(L.load().b2r_maxpool2x2(x.data_ptr(), out.data_ptr(), int(n), int(h), int(w), int(c), _stream()))
+    STATS["launches"] += 1
     return out
 
 
@@ -160,6 +226,7 @@ def adaptive_avgpool7(x: torch.Tensor) -> torch.Tensor:
     n, h, w, c = x.shape
     out = torch.empty((n, 7, 7, c), dtype=torch.bfloat16, device=x.device)
     L.check(L.load().b2r_adaptive_avgpool7(x.data_ptr(), out.data_ptr(), int(n), int(h), int(w), int(c), _stream()))
+    STATS["launches"] += 1
     return out
 
 
@@ -174,6 +241,7 @@ def linear_f32out(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Te
     out = torch.empty((bsz, o), dtype=torch.float32, device=x.device)
     L.check(L.load().b2r_linear_f32out(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), int(bsz), int(k),
                                        int(o), _stream()))
+    STATS["launches"] += 1
     return out
 
 
@@ -194,6 +262,7 @@ def argmax_count(logits: torch.Tensor, labels: Optional[torch.Tensor] = None,
             raise L.B2RError("counts must be int64[2] = (correct, total)")
     L.check(L.load().b2r_argmax_count(logits.data_ptr(), _ptr(labels), pred.data_ptr(), _ptr(conf), _ptr(counts),
                                       int(n), int(c), _stream()))
+    STATS["launches"] += 1
     return pred, conf
 
 
@@ -225,4 +294,5 @@ def degrade(images: torch.Tensor, ksize: Optional[torch.Tensor], taps: Optional[
     L.check(L.load().b2r_degrade(images.data_ptr(), out.data_ptr(), int(n), int(h), int(w), _ptr(taps), _ptr(ksize),
                                  _ptr(fog_t), _ptr(fog_add), _ptr(fog_on), _ptr(sigma), _ptr(noise),
                                  int(seed) & (2 ** 64 - 1), int(image_index0), int(order), int(flags), _stream()))
+    STATS["launches"] += 1
     return out

@@ -27,15 +27,20 @@ def _fill(name: str, t: torch.Tensor, g: torch.Generator) -> torch.Tensor:
     if t.dim() == 1:
         if ".conv_block.1." in name or ".conv_block.4." in name or ".shortcut.1." in name:
             if name.endswith("weight"):                      # BN gamma
-                return torch.rand(shape, generator=g) + 0.5
+                gamma = torch.rand(shape, generator=g) + 0.5
+                # the two branches that are summed in a ResidualBlock are damped (x0.6, tuned on the oracle) so the
+                # activation RMS stays ~constant through the nine blocks instead of doubling per block
+                return gamma if ".conv_block.1." in name else gamma * 0.6
             return torch.randn(shape, generator=g) * 0.1     # BN beta
+        if name == "final.bias":                             # restorer outputs centred inside [0, 1]
+            return 0.5 + torch.randn(shape, generator=g) * 0.05
         return torch.randn(shape, generator=g) * 0.05        # conv / linear bias
     if t.dim() == 4:
         if name.startswith("up"):                            # ConvTranspose2d [C_in, C_out, 2, 2]: one tap per output
             fan_in = shape[0]
             return torch.randn(shape, generator=g) * (1.0 / fan_in) ** 0.5
         fan_in = shape[1] * shape[2] * shape[3]
-        gain = 1.0 if name.startswith("final") or ".shortcut." in name else 2.0
+        gain = 0.1 if name.startswith("final") else (1.0 if ".shortcut." in name else 2.0)
         return torch.randn(shape, generator=g) * (gain / fan_in) ** 0.5
     if t.dim() == 2:                                         # nn.Linear
         return torch.randn(shape, generator=g) * (2.0 / shape[1]) ** 0.5

@@ -37,7 +37,8 @@ def _load(arch, seed):
     return m.cuda().eval(), {k: v.cuda() for k, v in sd.items()}
 
 
-RESTORER_TOL = {"psnr_db": 45.0, "max_abs": 3e-2}
+# observed on B200: PSNR 59-63 dB, max-abs 3e-3 .. 7e-3 on outputs spanning about [0, 1]
+RESTORER_TOL = {"psnr_db": 50.0, "max_abs": 2e-2}
 
 
 @pytest.mark.parametrize("arch,shape", [("simple_unet", (2, 3, 64, 96)), ("simple_unet", (3, 3, 224, 224)),
@@ -115,7 +116,8 @@ def test_repack_on_load_and_head_swap():
     assert j(xi).shape == (1, 10) and l1.shape == (1, 43)
 
 
-JUDGE_TOL = {"rel_to_logit_std": 0.03}
+# bf16 activations through 13 convs + 2 FC layers: observed max |logit error| = 2-3 % of the logit standard deviation
+JUDGE_TOL = {"rel_to_logit_std": 0.05}
 
 
 @pytest.mark.parametrize("hw", [(224, 224), (64, 64), (256, 256)])
