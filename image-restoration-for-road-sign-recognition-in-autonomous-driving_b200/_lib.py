@@ -16,6 +16,7 @@ B2R_DEG_CLIP_AFTER_NOISE = 1
 B2R_IN_F32_NCHW, B2R_IN_U8_NHWC = 0, 1
 B2R_OUT_NHWC, B2R_OUT_CONVT2X2 = 0, 1
 B2R_MAX_SRC, B2R_MAX_KBLOCKS, B2R_MAX_BLUR = 3, 96, 15
+B2R_CONV_GENERIC_ONLY = 1
 
 # every symbol include/b2r.h declares (tests/test_abi.py checks the list against the header and the .so)
 SYMBOLS = (
@@ -45,6 +46,7 @@ class ConvGemmDesc(C.Structure):
         ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("tile_n", C.c_int32),
         ("block_n", C.c_int32),
         ("max_ctas", C.c_int32),
+        ("flags", C.c_int32),
     ]
 
 

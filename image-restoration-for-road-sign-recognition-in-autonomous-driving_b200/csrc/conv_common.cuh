@@ -1,0 +1,113 @@
+// Shared between conv_gemm.cu (generic) and conv_n64.cu (C_out = 64): epilogue helpers and parameter blocks.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/b2r.h"
+#include "ptx_sm100.cuh"
+
+namespace b2r {
+
+constexpr int kEpiThreadsC = 128;
+constexpr int kN64MaxRing = 8;
+constexpr int kN64MaxSlots = 40;
+constexpr int kN64MaxSmem = 227 * 1024;
+
+// conv_n64 ring-slot encoding: [0,2) source | [2] centre (1 tap) | [4,6) dw+1 | [8,20) channel chunk | [20,32) first k-block
+struct alignas(64) ConvN64Params {
+    CUtensorMap a3_map[B2R_MAX_SRC];  // box 64 ch x TW x (TH+2) x 1
+    CUtensorMap a1_map[B2R_MAX_SRC];  // box 64 ch x TW x TH x 1
+    CUtensorMap b_map;                // weights [64][K], box 64 x 64
+    CUtensorMap out_map, pool_map;
+    const float* bias;
+    float slope;
+    int act;
+    int num_slots, num_kblocks;
+    int ring_slots, slot_bytes;
+    int tiles_w, tiles_h, n_img;
+    int tile_w, tile_h;
+    int store_full, store_pool;
+    uint32_t slot[kN64MaxSlots];
+};
+
+int launch_conv_n64(const ConvN64Params& p, int grid, size_t smem_bytes, cudaStream_t stream);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float apply_act(float x, int act, float slope) {
+    if (act == B2R_ACT_RELU) return fmaxf(x, 0.f);
+    if (act == B2R_ACT_PRELU) return x >= 0.f ? x : x * slope;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
+    __nv_bfloat162 y = *reinterpret_cast<__nv_bfloat162*>(&b);
+    __nv_bfloat162 r = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// 32 fp32 accumulator columns of this thread's pixel row -> +bias, activation, bf16 -> four 16-byte chunks of the
+// 128-byte staging row, written with the 128B TMA swizzle (chunk index XOR row & 7).
+__device__ __forceinline__ void epilogue_store_half(const uint32_t (&v)[32], const float* bias32, int act, float slope,
+                                                    uint8_t* sfull, int row, int half) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = q * 8 + e * 2;
+            const float x0 = apply_act(__uint_as_float(v[j]) + bias32[j], act, slope);
+            const float x1 = apply_act(__uint_as_float(v[j + 1]) + bias32[j + 1], act, slope);
+            o[e] = pack_bf16x2(x0, x1);
+        }
+        const int jj = half * 4 + q;
+        const uint32_t addr = smem_u32(sfull) + uint32_t(row * 128 + ((jj ^ (row & 7)) << 4));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                     : "memory");
+    }
+}
+
+// 2x2 max-pool of a staged 128-pixel x 64-channel tile (tw x th x tn pixels) into the 32-pixel pooled staging tile.
+// Thread -> pooled pixel tid/4, 16 channels (two 16-byte chunks).
+__device__ __forceinline__ void epilogue_pool_chunk(const uint8_t* sfull, uint8_t* spool, int epi_tid, int tw, int th) {
+    const int rp = epi_tid >> 2;
+    const int cg = epi_tid & 3;
+    const int pw = tw >> 1, ph = th >> 1;
+    const int wp = rp % pw;
+    const int hp = (rp / pw) % ph;
+    const int nl = rp / (pw * ph);
+    const int r00 = (nl * th + 2 * hp) * tw + 2 * wp;
+    const int rr[4] = {r00, r00 + 1, r00 + tw, r00 + tw + 1};
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        const int jj = cg * 2 + cc;
+        uint32_t mx[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t a = smem_u32(sfull) + uint32_t(rr[k] * 128 + ((jj ^ (rr[k] & 7)) << 4));
+            uint32_t t0, t1, t2, t3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(a));
+            if (k == 0) {
+                mx[0] = t0; mx[1] = t1; mx[2] = t2; mx[3] = t3;
+            } else {
+                mx[0] = bf16x2_max(mx[0], t0);
+                mx[1] = bf16x2_max(mx[1], t1);
+                mx[2] = bf16x2_max(mx[2], t2);
+                mx[3] = bf16x2_max(mx[3], t3);
+            }
+        }
+        const uint32_t d = smem_u32(spool) + uint32_t(rp * 128 + ((jj ^ (rp & 7)) << 4));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(mx[0]), "r"(mx[1]), "r"(mx[2]), "r"(mx[3])
+                     : "memory");
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace b2r

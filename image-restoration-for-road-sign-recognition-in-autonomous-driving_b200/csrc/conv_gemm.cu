@@ -17,9 +17,11 @@
 // Reference semantics replaced: nn.Conv2d(3x3, pad 1) / ConvTranspose2d(2,2) / BatchNorm2d(eval) / ReLU / PReLU /
 // MaxPool2d(2,2) / torch.cat / the ResidualBlock add, as used by SimpleUNet.forward (07_train_restoration.py:99-120),
 // ResUNet.forward (14_train_unified_advanced.py:151-186) and torchvision VGG16 (18_test_unified_benchmark.py:46).
+#include <cstdlib>
 #include <cstring>
 
 #include "b2r_internal.h"
+#include "conv_common.cuh"
 #include "ptx_sm100.cuh"
 
 namespace b2r {
@@ -59,24 +61,6 @@ struct GemmCfg {
     static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * (kStagingFull + kStagingPool) +
                                       BLOCK_N * 4 /*bias*/ + 256 /*barriers + tmem ptr*/;
 };
-
-__device__ __forceinline__ float apply_act(float x, int act, float slope) {
-    if (act == B2R_ACT_RELU) return fmaxf(x, 0.f);
-    if (act == B2R_ACT_PRELU) return x >= 0.f ? x : x * slope;
-    return x;
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-
-__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
-    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
-    __nv_bfloat162 y = *reinterpret_cast<__nv_bfloat162*>(&b);
-    __nv_bfloat162 r = __hmax2(x, y);
-    return *reinterpret_cast<uint32_t*>(&r);
-}
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -233,23 +217,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * BLOCK_N + c * 64 + half * 32), v);
                     tmem_ld_wait();
-                    const float* bs = bias_s + c * 64 + half * 32;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t o[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int j = q * 8 + e * 2;
-                            const float x0 = apply_act(__uint_as_float(v[j]) + bs[j], p.act, p.slope);
-                            const float x1 = apply_act(__uint_as_float(v[j + 1]) + bs[j + 1], p.act, p.slope);
-                            o[e] = pack_bf16x2(x0, x1);
-                        }
-                        const int jj = half * 4 + q;  // 16-byte chunk index within the 128-byte row
-                        const uint32_t addr = smem_u32(sfull) + uint32_t(row * 128 + ((jj ^ (row & 7)) << 4));
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]),
-                                     "r"(o[2]), "r"(o[3])
-                                     : "memory");
-                    }
+                    epilogue_store_half(v, bias_s + c * 64 + half * 32, p.act, p.slope, sfull, row, half);
                 }
                 if (c == BLOCK_N / 64 - 1) {
                     // all of this warp's TMEM reads of the accumulator are done -> hand it back to the MMA warp
@@ -261,40 +229,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 named_barrier_sync(1, kEpiThreads);
 
                 if (p.store_pool) {
-                    // 2x2 max-pool of the staged tile: thread -> pooled pixel rp = tid/4, 16 channels (2 chunks)
-                    const int rp = epi_tid >> 2;
-                    const int cg = epi_tid & 3;
-                    const int pw = tw >> 1, ph = th >> 1;
-                    const int wp = rp % pw;
-                    const int hp = (rp / pw) % ph;
-                    const int nl = rp / (pw * ph);
-                    const int r00 = (nl * th + 2 * hp) * tw + 2 * wp;
-                    const int rr[4] = {r00, r00 + 1, r00 + tw, r00 + tw + 1};
-#pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int jj = cg * 2 + cc;
-                        uint32_t mx[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t a = smem_u32(sfull) + uint32_t(rr[k] * 128 + ((jj ^ (rr[k] & 7)) << 4));
-                            uint32_t t0, t1, t2, t3;
-                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3)
-                                         : "r"(a));
-                            if (k == 0) {
-                                mx[0] = t0; mx[1] = t1; mx[2] = t2; mx[3] = t3;
-                            } else {
-                                mx[0] = bf16x2_max(mx[0], t0);
-                                mx[1] = bf16x2_max(mx[1], t1);
-                                mx[2] = bf16x2_max(mx[2], t2);
-                                mx[3] = bf16x2_max(mx[3], t3);
-                            }
-                        }
-                        const uint32_t d = smem_u32(spool) + uint32_t(rp * 128 + ((jj ^ (rp & 7)) << 4));
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(mx[0]), "r"(mx[1]),
-                                     "r"(mx[2]), "r"(mx[3])
-                                     : "memory");
-                    }
+                    epilogue_pool_chunk(sfull, spool, epi_tid, tw, th);
                     fence_proxy_async_smem();
                     named_barrier_sync(1, kEpiThreads);
                 }
@@ -358,6 +293,131 @@ static void choose_tile(int N, int H, int W, bool pool, bool spatial_taps, int* 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// dispatch to the C_out = 64 specialisation (conv_n64.cu) when the layer has its shape
+// ------------------------------------------------------------------------------------------------------------
+static bool n64_disabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B2R_DISABLE_N64");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+// returns B2R_OK and sets *handled when the layer was launched on the specialised kernel
+static int try_conv_n64(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    if (n64_disabled() || (d->flags & B2R_CONV_GENERIC_ONLY) || d->out_mode != B2R_OUT_NHWC || d->cout_total != 64 || d->kblocks_host == nullptr) return B2R_OK;
+    if (d->block_n != 0 && d->block_n != 64) return B2R_OK;
+    if (d->tile_n > 1) return B2R_OK;
+    const int nk = d->num_kblocks;
+    uint32_t slots[kN64MaxSlots];
+    int ns = 0;
+    for (int i = 0; i < nk;) {
+        const uint32_t e = d->kblocks_host[i];
+        const int src = e & 3, dh = int((e >> 2) & 3) - 1, dw = int((e >> 4) & 3) - 1, c64 = int(e >> 8);
+        bool group = (i + 9 <= nk);
+        for (int t = 0; group && t < 9; ++t)  // dw-major, dh-minor: k-block i+t is tap (dh = t%3 - 1, dw = t/3 - 1)
+            group = d->kblocks_host[i + t] == B2R_KBLOCK(src, t % 3 - 1, t / 3 - 1, c64);
+        if (group) {
+            if (ns + 3 > kN64MaxSlots) return B2R_OK;
+            for (int j = 0; j < 3; ++j)
+                slots[ns++] = uint32_t(src) | (uint32_t(j) << 4) | (uint32_t(c64) << 8) | (uint32_t(i + 3 * j) << 20);
+            i += 9;
+        } else if (dh == 0 && dw == 0) {
+            if (ns + 1 > kN64MaxSlots) return B2R_OK;
+            slots[ns++] = uint32_t(src) | (1u << 2) | (1u << 4) | (uint32_t(c64) << 8) | (uint32_t(i) << 20);
+            i += 1;
+        } else {
+            return B2R_OK;  // some other tap order: the generic kernel handles it
+        }
+    }
+    // tile: one image per tile, 8 x 16 or 16 x 8 pixels (W x H)
+    int tw = d->tile_w, th = d->tile_h;
+    if (tw == 0 && th == 0) {
+        const long t_a = (long)ceil_div(d->W, 8) * ceil_div(d->H, 16);
+        const long t_b = (long)ceil_div(d->W, 16) * ceil_div(d->H, 8);
+        if (t_a <= t_b) { tw = 8; th = 16; } else { tw = 16; th = 8; }
+    }
+    if (!((tw == 8 && th == 16) || (tw == 16 && th == 8))) return B2R_OK;
+    const int slot_bytes = (th + 2) * tw * 128;
+    const long fixed = 1024 + (long)nk * 8192 + 16384 + 4096 + 256 + 256;
+    int ring = int((kN64MaxSmem - fixed) / slot_bytes);
+    if (ring > kN64MaxRing) ring = kN64MaxRing;
+    if (ring < 3) return B2R_OK;  // weights too large to keep resident next to a useful ring
+
+    static thread_local ConvN64Params tp;
+    ConvN64Params& P = tp;
+    memset(&P, 0, sizeof(P));
+    const uint64_t N = d->N, H = d->H, W = d->W;
+    for (int i = 0; i < B2R_MAX_SRC; ++i) {
+        const int s = i < d->num_src ? i : 0;
+        const uint64_t C = d->src_C[s];
+        const uint64_t dims[4] = {C, W, H, N};
+        const uint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+        const uint32_t box3[4] = {64, (uint32_t)tw, (uint32_t)(th + 2), 1};
+        const uint32_t box1[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
+        int rc = encode_tmap_bf16(&P.a3_map[i], d->src[s], 4, dims, strides, box3);
+        if (rc) return rc;
+        rc = encode_tmap_bf16(&P.a1_map[i], d->src[s], 4, dims, strides, box1);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t K = (uint64_t)nk * 64;
+        const uint64_t dims[2] = {K, 64};
+        const uint64_t strides[1] = {K * 2};
+        const uint32_t box[2] = {64, 64};
+        int rc = encode_tmap_bf16(&P.b_map, d->weights, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    const uint64_t OC = d->out_C;
+    const uint64_t pd[4] = {OC, W / 2, H / 2, N};
+    const uint64_t ps[3] = {OC * 2, (W / 2) * OC * 2, (H / 2) * (W / 2) * OC * 2};
+    const uint32_t pb[4] = {64, (uint32_t)(tw / 2), (uint32_t)(th / 2), 1};
+    if (d->out) {
+        const uint64_t dims[4] = {OC, W, H, N};
+        const uint64_t strides[3] = {OC * 2, W * OC * 2, H * W * OC * 2};
+        const uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
+        int rc = encode_tmap_bf16(&P.out_map, d->out, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    if (d->out_pool) {
+        int rc = encode_tmap_bf16(&P.pool_map, d->out_pool, 4, pd, ps, pb);
+        if (rc) return rc;
+    }
+    if (!d->out) P.out_map = P.pool_map;
+    if (!d->out_pool) P.pool_map = P.out_map;
+    P.bias = d->bias;
+    P.slope = d->slope;
+    P.act = d->act;
+    P.num_slots = ns;
+    P.num_kblocks = nk;
+    P.ring_slots = ring;
+    P.slot_bytes = slot_bytes;
+    P.tile_w = tw;
+    P.tile_h = th;
+    P.tiles_w = ceil_div(d->W, tw);
+    P.tiles_h = ceil_div(d->H, th);
+    P.n_img = d->N;
+    P.store_full = d->out != nullptr;
+    P.store_pool = d->out_pool != nullptr;
+    memcpy(P.slot, slots, sizeof(uint32_t) * ns);
+    int sms = 0;
+    int rc = device_sm_count(&sms);
+    if (rc) return rc;
+    const long total_tiles = (long)P.tiles_w * P.tiles_h * P.n_img;
+    if (total_tiles >= (1L << 31)) return B2R_OK;
+    int grid = d->max_ctas > 0 ? d->max_ctas : sms;
+    if (grid > total_tiles) grid = (int)total_tiles;
+    const size_t smem = size_t(fixed) + size_t(ring) * slot_bytes;
+    rc = launch_conv_n64(P, grid, smem, stream);
+    if (rc) return rc;
+    *handled = true;
+    return B2R_OK;
+}
+
 template <int BLOCK_N>
 static int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
     using Cfg = GemmCfg<BLOCK_N>;
@@ -415,6 +475,12 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
         }
     } else {
         B2R_REQUIRE(d->num_kblocks * 64 <= d->src_C[0], "linear K: %d kblocks vs src_C=%d", d->num_kblocks, d->src_C[0]);
+    }
+
+    {
+        bool handled = false;
+        int rc = try_conv_n64(d, stream, &handled);
+        if (rc || handled) return rc;
     }
 
     // ---- tile geometry

@@ -40,9 +40,12 @@ class KPlan:
         """w: [C_out, C_in_slice, 3, 3] applied to channels [c_offset, c_offset + C_in_slice) of source `src`."""
         co, ci, kh, kw = w.shape
         assert co == self.cout and kh == 3 and kw == 3 and ci % 64 == 0 and c_offset % 64 == 0
-        for i in range(3):
+        # group order: 64-channel chunk outermost, then dw (kernel column), then dh (kernel row) — nine consecutive
+        # k-blocks share one (source, chunk), which is the shape csrc/conv_n64.cu recognises (three column-shifted
+        # halo loads feed nine taps) and also keeps the generic kernel's nine shifted reads of a tile adjacent in L2
+        for c in range(ci // 64):
             for j in range(3):
-                for c in range(ci // 64):
+                for i in range(3):
                     self.cols.append(w[:, c * 64:(c + 1) * 64, i, j])
                     self.kblocks.append(kblock(src, i - 1, j - 1, c_offset // 64 + c))
         return self

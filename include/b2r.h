@@ -119,6 +119,10 @@ int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host, const flo
 #define B2R_OUT_NHWC 0
 #define B2R_OUT_CONVT2X2 1
 
+/* flags: B2R_CONV_GENERIC_ONLY keeps the layer on the generic kernel even when the C_out = 64 specialisation
+ * (resident weights + column-shifted halo boxes, csrc/conv_n64.cu) applies; used by the A/B parity test. */
+#define B2R_CONV_GENERIC_ONLY 1
+
 /* k-block encoding: bits [0,2) source index, [2,4) dh+1, [4,6) dw+1, [8,24) first channel / 64 */
 #define B2R_KBLOCK(src, dh, dw, c64) \
     ((uint32_t)(src) | ((uint32_t)((dh) + 1) << 2) | ((uint32_t)((dw) + 1) << 4) | ((uint32_t)(c64) << 8))
@@ -142,6 +146,7 @@ typedef struct b2r_conv_gemm_desc {
     int32_t tile_w, tile_h, tile_n;  /* pixels per tile along W, H, N (product 128); 0,0,0 = choose */
     int32_t block_n;                 /* 64 / 128 / 256; 0 = choose */
     int32_t max_ctas;                /* 0 = one per SM */
+    int32_t flags;                   /* B2R_CONV_* */
 } b2r_conv_gemm_desc;
 
 int b2r_conv_gemm(const b2r_conv_gemm_desc* desc /* host */, void* stream);

@@ -201,3 +201,77 @@ def test_argument_errors():
     with pytest.raises(L.B2RError):
         odd = torch.zeros((1, 7, 16, 64), dtype=torch.bfloat16, device="cuda")
         ops.conv_gemm([odd], wm, b, kbl, out_pool=torch.empty((1, 3, 8, 64), dtype=torch.bfloat16, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# C_out = 64 specialisation (csrc/conv_n64.cu): resident weights + column-shifted halo boxes
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,h,w,splits,shortcut,pool,tile", [
+    (2, 32, 32, (64,), None, False, (0, 0, 0)),          # plain 64 -> 64
+    (1, 224, 224, (64,), None, True, (0, 0, 0)),         # VGG conv1_2 shape with the fused pool
+    (3, 40, 24, (64,), None, False, (0, 0, 0)),          # partial tiles on both edges
+    (2, 48, 64, (64, 64), None, False, (16, 8, 1)),      # dec1.c1: cat of two sources, 16 x 8 tile
+    (2, 32, 48, (64,), "identity", True, (0, 0, 0)),     # res1.c2: conv + identity shortcut + pool
+    (2, 32, 32, (64,), (64, 128), False, (8, 16, 1)),    # dec2.c2: conv(y) + 1x1 shortcut over cat(64, 128)
+])
+def test_conv_n64_specialisation_equals_generic_kernel(n, h, w, splits, shortcut, pool, tile):
+    """Same k-block order => same accumulation order: the specialised kernel must reproduce the generic kernel's
+    bf16 output bit for bit, and both must match the fp32 torch reference within bf16 tolerance."""
+    ops, packing, L = _ops()
+    srcs = [nhwc_bf16(rnd(n, c, h, w, seed=40 + i)) for i, c in enumerate(splits)]
+    ci = sum(splits)
+    wt = rnd(64, ci, 3, 3, scale=(2.0 / (9 * ci)) ** 0.5, seed=50)
+    b = rnd(64, scale=0.1, seed=51)
+    plan = packing.KPlan(64)
+    off = 0
+    for s, c in enumerate(splits):
+        plan.add_conv3x3(s, wt[:, off:off + c])
+        off += c
+    ref = F.conv2d(torch.cat([to_nchw_f32(s) for s in srcs], 1), wt.to(torch.bfloat16).float(), b, padding=1)
+    all_srcs = list(srcs)
+    if shortcut == "identity":
+        plan.add_1x1(len(all_srcs), torch.eye(64, device="cuda"))
+        xs = nhwc_bf16(rnd(n, 64, h, w, seed=52))
+        all_srcs.append(xs)
+        ref = ref + to_nchw_f32(xs)
+    elif shortcut is not None:
+        ws = rnd(64, sum(shortcut), 1, 1, scale=(1.0 / sum(shortcut)) ** 0.5, seed=53)
+        off = 0
+        sc_in = []
+        for c in shortcut:
+            xs = nhwc_bf16(rnd(n, c, h, w, seed=54 + c))
+            plan.add_1x1(len(all_srcs), ws[:, off:off + c])
+            all_srcs.append(xs)
+            sc_in.append(to_nchw_f32(xs))
+            off += c
+        ref = ref + F.conv2d(torch.cat(sc_in, 1), ws.to(torch.bfloat16).float())
+    ref = F.relu(ref)
+    wm, kbl = plan.finish()
+    wm = wm.cuda()
+    outs = []
+    for flags in (0, L.B2R_CONV_GENERIC_ONLY):
+        out = torch.full((n, h, w, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+        pl = torch.full((n, h // 2, w // 2, 64), float("nan"), dtype=torch.bfloat16, device="cuda") if pool else None
+        ops.conv_gemm(all_srcs, wm, b, kbl, act=L.B2R_ACT_RELU, out=out, out_pool=pl,
+                      tile=tile if flags == 0 else (0, 0, 0), flags=flags)
+        torch.cuda.synchronize()
+        outs.append((out, pl))
+    assert_close_bf16(to_nchw_f32(outs[0][0]), ref, "n64 kernel vs torch")
+    assert torch.equal(outs[0][0], outs[1][0]), "specialised and generic kernels disagree"
+    if pool:
+        assert torch.equal(outs[0][1], outs[1][1])
+        assert torch.equal(to_nchw_f32(outs[0][1]), F.max_pool2d(to_nchw_f32(outs[0][0]), 2, 2))
+
+
+def test_conv_n64_many_tiles_and_ring_wraps():
+    ops, packing, L = _ops()
+    n, h, w = 24, 112, 112
+    x = nhwc_bf16(rnd(n, 64, h, w, seed=60))
+    wt = rnd(64, 64, 3, 3, scale=(2.0 / 576) ** 0.5, seed=61)
+    b = rnd(64, scale=0.1, seed=62)
+    wm, kbl = packing.pack_conv3x3(wt)
+    out = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device="cuda")
+    ops.conv_gemm([x], wm.cuda(), b, kbl, act=L.B2R_ACT_RELU, out=out)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(to_nchw_f32(x), wt.to(torch.bfloat16).float(), b, padding=1))
+    assert_close_bf16(to_nchw_f32(out), ref, "n64 many tiles")
