@@ -16,7 +16,7 @@ B2R_DEG_CLIP_AFTER_NOISE = 1
 B2R_IN_F32_NCHW, B2R_IN_U8_NHWC = 0, 1
 B2R_OUT_NHWC, B2R_OUT_CONVT2X2 = 0, 1
 B2R_MAX_SRC, B2R_MAX_KBLOCKS, B2R_MAX_BLUR = 3, 96, 15
-B2R_CONV_GENERIC_ONLY = 1
+B2R_CONV_GENERIC_ONLY, B2R_CONV_NO_W3 = 1, 2
 
 # every symbol include/b2r.h declares (tests/test_abi.py checks the list against the header and the .so)
 SYMBOLS = (
@@ -33,6 +33,7 @@ class ConvGemmDesc(C.Structure):
         ("src", C.c_void_p * B2R_MAX_SRC),
         ("src_C", C.c_int32 * B2R_MAX_SRC),
         ("weights", C.c_void_p),
+        ("weights_w3", C.c_void_p),
         ("bias", C.c_void_p),
         ("cout_total", C.c_int32),
         ("num_kblocks", C.c_int32),

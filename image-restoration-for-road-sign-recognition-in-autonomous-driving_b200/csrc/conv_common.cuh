@@ -34,6 +34,24 @@ struct alignas(64) ConvN64Params {
 
 int launch_conv_n64(const ConvN64Params& p, int grid, size_t smem_bytes, cudaStream_t stream);
 
+// conv_w3 group encoding: [0,2) source | [2] centre (one k-step, kernel row 1) | [8,20) channel chunk | [20,32) first k-step
+constexpr int kW3MaxGroups = 24;
+struct alignas(64) ConvW3Params {
+    CUtensorMap a_map[B2R_MAX_SRC];  // box 64 ch x 16 x 10 x 1
+    CUtensorMap b_map;               // wide weights [192][64 * num_ksteps], box 64 x 192
+    CUtensorMap out_map, pool_map;   // boxes 64 x 14 x 8 x 1 and 64 x 7 x 4 x 1
+    const float* bias;
+    float slope;
+    int act;
+    int num_groups, num_ksteps, ring_slots;
+    int tiles_w, tiles_h, n_img;
+    int store_full, store_pool;
+    uint32_t group[kW3MaxGroups];
+};
+
+size_t conv_w3_smem_bytes(int num_ksteps, int ring_slots);
+int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream);
+
 #ifdef __CUDACC__
 __device__ __forceinline__ float apply_act(float x, int act, float slope) {
     if (act == B2R_ACT_RELU) return fmaxf(x, 0.f);

@@ -418,6 +418,105 @@ static int try_conv_n64(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* 
     return B2R_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// dispatch to the tap-folded C_out = 64 kernel (conv_w3.cu) when the caller supplied the wide weight layout
+// ------------------------------------------------------------------------------------------------------------
+static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* handled) {
+    *handled = false;
+    if (d->weights_w3 == nullptr || (d->flags & (B2R_CONV_GENERIC_ONLY | B2R_CONV_NO_W3))) return B2R_OK;
+    if (d->out_mode != B2R_OUT_NHWC || d->cout_total != 64 || d->kblocks_host == nullptr) return B2R_OK;
+    if (d->block_n != 0 && d->block_n != 64) return B2R_OK;
+    if (d->tile_w != 0 || d->tile_h != 0 || d->tile_n != 0) return B2R_OK;  // explicit tiles belong to the other kernels
+    const int nk = d->num_kblocks;
+    uint32_t groups[kW3MaxGroups];
+    int ng = 0, nsteps = 0;
+    for (int i = 0; i < nk;) {
+        const uint32_t e = d->kblocks_host[i];
+        const int src = e & 3, dh = int((e >> 2) & 3) - 1, dw = int((e >> 4) & 3) - 1, c64 = int(e >> 8);
+        bool group = (i + 9 <= nk);
+        for (int t = 0; group && t < 9; ++t)
+            group = d->kblocks_host[i + t] == B2R_KBLOCK(src, t % 3 - 1, t / 3 - 1, c64);
+        if (ng >= kW3MaxGroups) return B2R_OK;
+        if (group) {
+            groups[ng++] = uint32_t(src) | (uint32_t(c64) << 8) | (uint32_t(nsteps) << 20);
+            nsteps += 3;
+            i += 9;
+        } else if (dh == 0 && dw == 0) {
+            groups[ng++] = uint32_t(src) | (1u << 2) | (uint32_t(c64) << 8) | (uint32_t(nsteps) << 20);
+            nsteps += 1;
+            i += 1;
+        } else {
+            return B2R_OK;
+        }
+    }
+    int ring = 4;
+    while (ring >= 2 && conv_w3_smem_bytes(nsteps, ring) > (size_t)kN64MaxSmem) --ring;
+    if (ring < 2) return B2R_OK;  // weights too large to stay resident: other kernels take the layer
+
+    static thread_local ConvW3Params tp;
+    ConvW3Params& P = tp;
+    memset(&P, 0, sizeof(P));
+    const uint64_t N = d->N, H = d->H, W = d->W;
+    for (int i = 0; i < B2R_MAX_SRC; ++i) {
+        const int s = i < d->num_src ? i : 0;
+        const uint64_t C = d->src_C[s];
+        const uint64_t dims[4] = {C, W, H, N};
+        const uint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+        const uint32_t box[4] = {64, 16, 10, 1};
+        int rc = encode_tmap_bf16(&P.a_map[i], d->src[s], 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t K = (uint64_t)nsteps * 64;
+        const uint64_t dims[2] = {K, 192};
+        const uint64_t strides[1] = {K * 2};
+        const uint32_t box[2] = {64, 192};
+        int rc = encode_tmap_bf16(&P.b_map, d->weights_w3, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    const uint64_t OC = d->out_C;
+    if (d->out) {
+        const uint64_t dims[4] = {OC, W, H, N};
+        const uint64_t strides[3] = {OC * 2, W * OC * 2, H * W * OC * 2};
+        const uint32_t box[4] = {64, 14, 8, 1};
+        int rc = encode_tmap_bf16(&P.out_map, d->out, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    if (d->out_pool) {
+        const uint64_t pd[4] = {OC, W / 2, H / 2, N};
+        const uint64_t ps[3] = {OC * 2, (W / 2) * OC * 2, (H / 2) * (W / 2) * OC * 2};
+        const uint32_t pb[4] = {64, 7, 4, 1};
+        int rc = encode_tmap_bf16(&P.pool_map, d->out_pool, 4, pd, ps, pb);
+        if (rc) return rc;
+    }
+    if (!d->out) P.out_map = P.pool_map;
+    if (!d->out_pool) P.pool_map = P.out_map;
+    P.bias = d->bias;
+    P.slope = d->slope;
+    P.act = d->act;
+    P.num_groups = ng;
+    P.num_ksteps = nsteps;
+    P.ring_slots = ring;
+    P.tiles_w = ceil_div(d->W, 14);
+    P.tiles_h = ceil_div(d->H, 8);
+    P.n_img = d->N;
+    P.store_full = d->out != nullptr;
+    P.store_pool = d->out_pool != nullptr;
+    memcpy(P.group, groups, sizeof(uint32_t) * ng);
+    int sms = 0;
+    int rc = device_sm_count(&sms);
+    if (rc) return rc;
+    const long total_tiles = (long)P.tiles_w * P.tiles_h * P.n_img;
+    if (total_tiles >= (1L << 31)) return B2R_OK;
+    int grid = d->max_ctas > 0 ? d->max_ctas : sms;
+    if (grid > total_tiles) grid = (int)total_tiles;
+    rc = launch_conv_w3(P, grid, stream);
+    if (rc) return rc;
+    *handled = true;
+    return B2R_OK;
+}
+
 template <int BLOCK_N>
 static int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
     using Cfg = GemmCfg<BLOCK_N>;
@@ -479,7 +578,9 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
 
     {
         bool handled = false;
-        int rc = try_conv_n64(d, stream, &handled);
+        int rc = try_conv_w3(d, stream, &handled);
+        if (rc || handled) return rc;
+        rc = try_conv_n64(d, stream, &handled);
         if (rc || handled) return rc;
     }
 

@@ -1,0 +1,237 @@
+// tcgen05 conv3x3 for C_out = 64 with the three horizontal taps folded into the MMA N dimension (N = 192).
+//
+// Measured on B200 (tools/exp/mma_rate.cu, profiles/r01_mma_rate.md): one tcgen05.mma 128 x N x 16 with both
+// operands in shared memory takes max(75.6, N/2) cycles.  With N = C_out = 64 the tensor pipe can therefore never
+// exceed 32/75.6 = 42 % of its peak, however the operands are staged (csrc/conv_n64.cu reaches 96 % of that floor).
+// This kernel makes N = 3 x 64: the B operand of one k-step holds the weights of the three taps (kh, kw = 0..2)
+// of one kernel row for 64 input channels, so ONE MMA produces the three partial sums
+//     D_kw[(h, c)] = sum_ci in[h + kh - 1][c][ci] * W[co][ci][kh][kw],        c = input column inside the tile,
+// at the ideal 96 cycles, and the shift along W moves from the operand side to the epilogue:
+//     out[h][w] = D_0[(h, w)] + D_1[(h, w + 1)] + D_2[(h, w + 2)]
+// which is two warp shuffles per value because a tile row (16 columns) lives in 16 adjacent lanes.  A tile is
+// 8 rows x 16 input columns -> 8 x 14 outputs (224 = 16 * 14, 112 = 8 * 14: no waste at the sizes that matter;
+// 12.5 % of the MMA rows are halo).  Per (source, 64-channel chunk) the producer loads ONE box
+// 64 ch x 16 x (8 + 2) (20 KB) that feeds the three kernel rows (12 MMAs, 1152 cycles): 11x less L2->SM traffic
+// than the generic kernel.  The weights [192][K/3] stay resident in shared memory.  1x1 centre groups (ResidualBlock
+// shortcut / identity) are k-steps whose kw = 0 and kw = 2 weight rows are zero.
+#include <cstring>
+
+#include "b2r_internal.h"
+#include "conv_common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace b2r {
+
+constexpr int kW3Threads = 192;
+constexpr int kW3BStep = 192 * 128;      // weights of one k-step: 192 rows x 128 B
+constexpr int kW3Slot = 10 * 16 * 128;   // one halo box: (8 + 2) rows x 16 columns x 128 B
+constexpr int kW3Staging = 14336;        // 8 x 14 pixels x 128 B
+constexpr int kW3StagingPool = 4096;     // 4 x 7 pixels x 128 B, padded
+
+__global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_constant__ ConvW3Params p) {
+    constexpr uint32_t kIdesc = make_idesc_bf16_f32(128, 192);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* b_res = smem;
+    uint8_t* ring = b_res + p.num_ksteps * kW3BStep;
+    uint8_t* sfull = ring + p.ring_slots * kW3Slot;
+    uint8_t* spool = sfull + kW3Staging;
+    float* bias_s = reinterpret_cast<float*>(spool + kW3StagingPool);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 64);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kN64MaxRing;
+    uint64_t* tmem_full_bar = bars + 2 * kN64MaxRing;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint64_t* b_full_bar = tmem_empty_bar + 2;
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(b_full_bar + 1);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const int total_tiles = tiles_per_img * p.n_img;
+    const int R = p.ring_slots;
+
+    if (warp_idx == 0 && lane == 0) {
+        for (int i = 0; i < B2R_MAX_SRC; ++i) tma_prefetch_desc(&p.a_map[i]);
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.out_map);
+        tma_prefetch_desc(&p.pool_map);
+    }
+    if (warp_idx == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < R; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], 4);
+            }
+            mbar_init(b_full_bar, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(tmem_ptr_s);   // 2 accumulator stages x 192 columns (power-of-two allocation)
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 128) bias_s[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp_idx == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(b_full_bar, uint32_t(p.num_ksteps) * kW3BStep);
+            for (int ks = 0; ks < p.num_ksteps; ++ks)
+                tma_load_2d(b_res + ks * kW3BStep, &p.b_map, b_full_bar, ks * 64, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n0 = tile / tiles_per_img;
+                const int t = tile - n0 * tiles_per_img;
+                const int w0 = (t % p.tiles_w) * 14;
+                const int h0 = (t / p.tiles_w) * 8;
+                for (int g = 0; g < p.num_groups; ++g) {
+                    const uint32_t e = p.group[g];
+                    const int src = e & 3;
+                    const int c0 = int((e >> 8) & 0xFFF) * 64;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], kW3Slot);
+                    tma_load_4d(ring + stage * kW3Slot, &p.a_map[src], &full_bar[stage], c0, w0 - 1, h0 - 1, n0);
+                    if (++stage == R) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================================== MMA issuer =====================================
+        if (lane == 0) {
+            mbar_wait(b_full_bar, 0);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(b_res);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + uint32_t(acc * 256);
+                uint32_t first = 1;
+                for (int g = 0; g < p.num_groups; ++g) {
+                    const uint32_t e = p.group[g];
+                    const int center = (e >> 2) & 1;
+                    const int ks0 = int(e >> 20);
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(ring + stage * kW3Slot);
+                    const int nk = center ? 1 : 3;
+                    for (int t = 0; t < nk; ++t) {
+                        const int kh = center ? 1 : t;   // kernel row: A = buffer rows kh .. kh+7 (16 columns each)
+                        const uint64_t adesc = make_sdesc_sw128(sa + uint32_t(kh) * 2048u, 1024);
+                        const uint64_t bdesc = make_sdesc_sw128(b_base + uint32_t(ks0 + t) * kW3BStep, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_bf16_ss(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == R) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===================================== epilogue =====================================
+        const int quarter = warp_idx & 3;
+        const int epi_tid = quarter * 32 + lane;
+        const int hh = quarter * 2 + (lane >> 4);  // tile row of this lane's pixel
+        const int cc = lane & 15;                  // buffer column; output column w = cc is valid for cc < 14
+        const int srow = hh * 14 + cc;             // row of the 8 x 14 staging tile
+        const bool valid = cc < 14;
+        const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n0 = tile / tiles_per_img;
+            const int t = tile - n0 * tiles_per_img;
+            const int w0 = (t % p.tiles_w) * 14;
+            const int h0 = (t / p.tiles_w) * 8;
+
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            if (epi_tid == 0) tma_store_wait_read<0>();
+            named_barrier_sync(1, kEpiThreadsC);
+            const uint32_t tacc = tmem_base + lane_base + uint32_t(acc * 256);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t d0[32], d1[32], d2[32];
+                tmem_ld_32x32(tacc + uint32_t(half * 32), d0);         // kw = 0 partial sums, channels half*32 ..
+                tmem_ld_32x32(tacc + uint32_t(64 + half * 32), d1);    // kw = 1
+                tmem_ld_32x32(tacc + uint32_t(128 + half * 32), d2);   // kw = 2
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[j]), 1);
+                    const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[j]), 2);
+                    d0[j] = __float_as_uint((__uint_as_float(d0[j]) + a1) + a2);
+                }
+                if (valid) epilogue_store_half(d0, bias_s + half * 32, p.act, p.slope, sfull, srow, half);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            fence_proxy_async_smem();
+            named_barrier_sync(1, kEpiThreadsC);
+            if (p.store_pool) {
+                if (epi_tid < 28 * 4) epilogue_pool_chunk(sfull, spool, epi_tid, 14, 8);
+                fence_proxy_async_smem();
+                named_barrier_sync(1, kEpiThreadsC);
+            }
+            if (epi_tid == 0) {
+                if (p.store_full) tma_store_4d(&p.out_map, sfull, 0, w0, h0, n0);
+                if (p.store_pool) tma_store_4d(&p.pool_map, spool, 0, w0 >> 1, h0 >> 1, n0);
+                tma_store_commit();
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (epi_tid == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        __syncwarp();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+size_t conv_w3_smem_bytes(int num_ksteps, int ring_slots) {
+    return 1024 + size_t(num_ksteps) * kW3BStep + size_t(ring_slots) * kW3Slot + kW3Staging + kW3StagingPool + 256 + 256;
+}
+
+int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    B2R_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        B2R_CUDA(cudaFuncSetAttribute(conv_w3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
+        if (dev < 64) attr_set[dev] = true;
+    }
+    conv_w3_kernel<<<grid, kW3Threads, conv_w3_smem_bytes(p.num_ksteps, p.ring_slots), stream>>>(p);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
+}  // namespace b2r

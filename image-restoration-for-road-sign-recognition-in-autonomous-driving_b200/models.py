@@ -123,8 +123,10 @@ class SimpleUNet(_B200Module):
         P = {}
 
         def conv(name, key, splits=None):
-            w, kb = packing.pack_conv3x3(sd[key + ".weight"].float(), splits)
-            P[name] = (w.to(dev), sd[key + ".bias"].float().contiguous(), kb)
+            plan = packing.plan_conv3x3(sd[key + ".weight"].float(), splits)
+            w, kb = plan.finish(dev)
+            P[name] = dict(weights=w, bias=sd[key + ".bias"].float().contiguous(), kblocks=kb,
+                           weights_w3=plan.finish_w3(dev))
 
         P["enc1.0"] = (sd["enc1.0.weight"].float().contiguous(), sd["enc1.0.bias"].float().contiguous())
         conv("enc1.2", "enc1.2")
@@ -154,24 +156,24 @@ class SimpleUNet(_B200Module):
 
         a = ops.conv3x3_c3(x, *P["enc1.0"], act=R, out=g("a", H, W, 64))
         e1, p1 = g("e1", H, W, 64), g("p1", H // 2, W // 2, 64)
-        ops.conv_gemm([a], *P["enc1.2"], act=R, out=e1, out_pool=p1)
+        ops.conv_gemm([a], **P["enc1.2"], act=R, out=e1, out_pool=p1)
         t = g("e2a", H // 2, W // 2, 128)
-        ops.conv_gemm([p1], *P["enc2.0"], act=R, out=t)
+        ops.conv_gemm([p1], **P["enc2.0"], act=R, out=t)
         e2, p2 = g("e2", H // 2, W // 2, 128), g("p2", H // 4, W // 4, 128)
-        ops.conv_gemm([t], *P["enc2.2"], act=R, out=e2, out_pool=p2)
+        ops.conv_gemm([t], **P["enc2.2"], act=R, out=e2, out_pool=p2)
         b1, b2 = g("b1", H // 4, W // 4, 256), g("b2", H // 4, W // 4, 256)
-        ops.conv_gemm([p2], *P["bottleneck.0"], act=R, out=b1)
-        ops.conv_gemm([b1], *P["bottleneck.2"], act=R, out=b2)
+        ops.conv_gemm([p2], **P["bottleneck.0"], act=R, out=b1)
+        ops.conv_gemm([b1], **P["bottleneck.2"], act=R, out=b2)
         u2 = g("u2", H // 2, W // 2, 128)
         ops.conv_gemm([b2], *P["up2"], None, out=u2, out_mode=L.B2R_OUT_CONVT2X2)
         d2a, d2 = g("e2a", H // 2, W // 2, 128), g("d2", H // 2, W // 2, 128)
-        ops.conv_gemm([u2, e2], *P["dec2.0"], act=R, out=d2a)
-        ops.conv_gemm([d2a], *P["dec2.2"], act=R, out=d2)
+        ops.conv_gemm([u2, e2], **P["dec2.0"], act=R, out=d2a)
+        ops.conv_gemm([d2a], **P["dec2.2"], act=R, out=d2)
         u1 = g("u1", H, W, 64)
         ops.conv_gemm([d2], *P["up1"], None, out=u1, out_mode=L.B2R_OUT_CONVT2X2)
         d1a, d1 = g("a", H, W, 64), g("d1", H, W, 64)
-        ops.conv_gemm([u1, e1], *P["dec1.0"], act=R, out=d1a)
-        ops.conv_gemm([d1a], *P["dec1.2"], act=R, out=d1)
+        ops.conv_gemm([u1, e1], **P["dec1.0"], act=R, out=d1a)
+        ops.conv_gemm([d1a], **P["dec1.2"], act=R, out=d1)
         L.check(L.load().b2r_final_conv1x1(d1.data_ptr(), P["final"][0].data_ptr(), P["final"][1].data_ptr(),
                                            ops._ptr(out_f32), ops._ptr(out_u8), n, H, W, ops._stream()))
         ops.STATS["launches"] += 1
@@ -262,7 +264,8 @@ class ResUNet(_B200Module):
             slope = float(sd[cb + "2.weight"].float().reshape(-1)[0])
             ci = sum(splits)
             # conv 1 over the (virtual) concat of the block's input sources
-            wm1, kb1 = packing.pack_conv3x3(w1, splits)
+            plan1 = packing.plan_conv3x3(w1, splits)
+            wm1, kb1 = plan1.finish()
             # conv 2 over y (source 0) + the shortcut over the block input (sources 1..)
             plan = packing.KPlan(co).add_conv3x3(0, w2)
             if ci != co:
@@ -279,8 +282,10 @@ class ResUNet(_B200Module):
                 off += c
             wm2, kb2 = plan.finish()
             alg_k2 = int(wm2.shape[1]) - (0 if ci != co else co)   # the identity block is not algorithmic work
-            P[name] = (wm1.to(dev), b1.to(dev).contiguous(), kb1, slope, wm2.to(dev), b2.to(dev).contiguous(), kb2,
-                       alg_k2)
+            P[name] = (dict(weights=wm1.to(dev), bias=b1.to(dev).contiguous(), kblocks=kb1,
+                            weights_w3=plan1.finish_w3(dev)), slope,
+                       dict(weights=wm2.to(dev), bias=b2.to(dev).contiguous(), kblocks=kb2,
+                            weights_w3=plan.finish_w3(dev), alg_k=alg_k2))
         for up in ("up3", "up2", "up1"):
             w, b = packing.pack_convT2x2(sd[up + ".weight"].float(), sd[up + ".bias"].float())
             P[up] = (w.to(dev), b.to(dev))
@@ -288,9 +293,9 @@ class ResUNet(_B200Module):
         return P
 
     def _block(self, name, srcs, y, out, out_pool=None):
-        wm1, b1, kb1, slope, wm2, b2, kb2, alg_k2 = self._packed()[name]
-        ops.conv_gemm(srcs, wm1, b1, kb1, act=L.B2R_ACT_PRELU, slope=slope, out=y)
-        ops.conv_gemm([y] + list(srcs), wm2, b2, kb2, act=L.B2R_ACT_RELU, out=out, out_pool=out_pool, alg_k=alg_k2)
+        c1, slope, c2 = self._packed()[name]
+        ops.conv_gemm(srcs, **c1, act=L.B2R_ACT_PRELU, slope=slope, out=y)
+        ops.conv_gemm([y] + list(srcs), **c2, act=L.B2R_ACT_RELU, out=out, out_pool=out_pool)
 
     def _run(self, x, out_f32, out_u8):
         P, ws = self._packed(), self._ws
@@ -387,8 +392,10 @@ class VGG16Judge(_B200Module):
             if w.shape[1] == 3:
                 P["first"] = (w.contiguous(), b)
             else:
-                wm, kb = packing.pack_conv3x3(w)
-                P["convs"].append((wm.to(dev), b, kb, pooled, int(w.shape[0])))
+                plan = packing.plan_conv3x3(w)
+                wm, kb = plan.finish(dev)
+                P["convs"].append((dict(weights=wm, bias=b, kblocks=kb, weights_w3=plan.finish_w3(dev)), pooled,
+                                   int(w.shape[0])))
         P["fc1"] = (packing.pack_fc_from_nchw_flatten(sd["classifier.0.weight"].float(), 512, 7, 7).to(dev),
                     sd["classifier.0.bias"].float().contiguous())
         P["fc2"] = (sd["classifier.3.weight"].to(torch.bfloat16).contiguous(), sd["classifier.3.bias"].float().contiguous())
@@ -405,14 +412,14 @@ class VGG16Judge(_B200Module):
         cur = ops.conv3x3_c3(x, *P["first"], act=R, normalize=u8_in and normalize_u8,
                              out=ws.get("c0", (n, H, W, 64), dev))
         h, w = H, W
-        for li, (wm, b, kb, pooled, co) in enumerate(P["convs"]):
+        for li, (cv, pooled, co) in enumerate(P["convs"]):
             if pooled:
                 nxt = ws.get(f"c{li + 1}", (n, h // 2, w // 2, co), dev)
-                ops.conv_gemm([cur], wm, b, kb, act=R, out_pool=nxt)
+                ops.conv_gemm([cur], **cv, act=R, out_pool=nxt)
                 h, w = h // 2, w // 2
             else:
                 nxt = ws.get(f"c{li + 1}", (n, h, w, co), dev)
-                ops.conv_gemm([cur], wm, b, kb, act=R, out=nxt)
+                ops.conv_gemm([cur], **cv, act=R, out=nxt)
             cur = nxt
         if (h, w) != (7, 7):
             cur = ops.adaptive_avgpool7(cur)  # identity at 224x224

@@ -101,7 +101,7 @@ def conv_gemm(srcs: Sequence[torch.Tensor], weights: torch.Tensor, bias: torch.T
               kblocks: Optional[Sequence[int]], act: int = L.B2R_ACT_NONE, slope: float = 0.0,
               out: Optional[torch.Tensor] = None, out_pool: Optional[torch.Tensor] = None,
               out_mode: int = L.B2R_OUT_NHWC, tile=(0, 0, 0), block_n: int = 0, max_ctas: int = 0,
-              alg_k: Optional[int] = None, flags: int = 0) -> None:
+              alg_k: Optional[int] = None, flags: int = 0, weights_w3: Optional[torch.Tensor] = None) -> None:
     """One fused tensor-core layer (b2r_conv_gemm).  srcs: NHWC bf16 [N,H,W,C_i]; weights bf16 [cout_total, K].
     `alg_k`: K elements that are algorithmic work (excludes e.g. an identity-shortcut block); accounting only."""
     n, h, w = srcs[0].shape[:3]
@@ -117,6 +117,11 @@ def conv_gemm(srcs: Sequence[torch.Tensor], weights: torch.Tensor, bias: torch.T
     _chk(weights, torch.bfloat16, "weights", 2)
     _chk(bias, torch.float32, "bias", 1)
     d.weights = weights.data_ptr()
+    if weights_w3 is not None:
+        _chk(weights_w3, torch.bfloat16, "weights_w3", 2)
+        if weights_w3.shape[0] != 192 or weights_w3.shape[1] % 64 != 0:
+            raise L.B2RError(f"weights_w3 must be [192, 64*k-steps], got {tuple(weights_w3.shape)}")
+        d.weights_w3 = weights_w3.data_ptr()
     d.bias = bias.data_ptr()
     d.cout_total = int(weights.shape[0])
     if bias.numel() != d.cout_total:

@@ -29,24 +29,31 @@ def fold_bn(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, bet
 
 
 class KPlan:
-    """Accumulates the K dimension of one fused layer: weight column groups + the matching k-block list."""
+    """Accumulates the K dimension of one fused layer: weight column groups + the matching k-block list.
+
+    `finish()` gives the generic layout bf16 [C_out][K] (K = 64 x k-blocks).  For C_out = 64 layers `finish_w3()`
+    additionally gives the tap-folded layout bf16 [192][64 x k-steps] read by csrc/conv_w3.cu: one k-step per
+    (3x3 group, kernel row kh) whose rows are (kw, co), and one per centre block with the kw = 0, 2 rows zero."""
 
     def __init__(self, cout: int):
         self.cout = cout
         self.cols: List[torch.Tensor] = []
         self.kblocks: List[int] = []
+        self._groups: List[Tuple[str, torch.Tensor]] = []   # ("3x3", w[co,64,3,3]) | ("1x1", w[co,64])
 
     def add_conv3x3(self, src: int, w: torch.Tensor, c_offset: int = 0) -> "KPlan":
         """w: [C_out, C_in_slice, 3, 3] applied to channels [c_offset, c_offset + C_in_slice) of source `src`."""
         co, ci, kh, kw = w.shape
         assert co == self.cout and kh == 3 and kw == 3 and ci % 64 == 0 and c_offset % 64 == 0
         # group order: 64-channel chunk outermost, then dw (kernel column), then dh (kernel row) — nine consecutive
-        # k-blocks share one (source, chunk), which is the shape csrc/conv_n64.cu recognises (three column-shifted
-        # halo loads feed nine taps) and also keeps the generic kernel's nine shifted reads of a tile adjacent in L2
+        # k-blocks share one (source, chunk), which is the shape csrc/conv_n64.cu and csrc/conv_w3.cu recognise and
+        # which keeps the generic kernel's nine shifted reads of a tile adjacent in L2
         for c in range(ci // 64):
+            wc = w[:, c * 64:(c + 1) * 64]
+            self._groups.append(("3x3", wc))
             for j in range(3):
                 for i in range(3):
-                    self.cols.append(w[:, c * 64:(c + 1) * 64, i, j])
+                    self.cols.append(wc[:, :, i, j])
                     self.kblocks.append(kblock(src, i - 1, j - 1, c_offset // 64 + c))
         return self
 
@@ -56,7 +63,9 @@ class KPlan:
         w = w.reshape(co, ci)
         assert co == self.cout and ci % 64 == 0 and c_offset % 64 == 0
         for c in range(ci // 64):
-            self.cols.append(w[:, c * 64:(c + 1) * 64])
+            wc = w[:, c * 64:(c + 1) * 64]
+            self._groups.append(("1x1", wc))
+            self.cols.append(wc)
             self.kblocks.append(kblock(src, 0, 0, c_offset // 64 + c))
         return self
 
@@ -66,9 +75,30 @@ class KPlan:
             wmat = wmat.to(device)
         return wmat, list(self.kblocks)
 
+    def finish_w3(self, device=None) -> Optional[torch.Tensor]:
+        if self.cout != 64:
+            return None
+        steps = []
+        for kind, wc in self._groups:
+            if kind == "3x3":
+                for kh in range(3):                              # rows (kw, co), columns ci
+                    steps.append(wc[:, :, kh, :].permute(2, 0, 1).reshape(192, 64))
+            else:
+                z = torch.zeros_like(wc)
+                steps.append(torch.cat((z, wc, z), dim=0))       # only the kw = 1 (centre column) rows are non-zero
+        w3 = torch.cat(steps, dim=1).to(torch.bfloat16).contiguous()
+        return w3.to(device) if device is not None else w3
+
 
 def pack_conv3x3(w: torch.Tensor, splits: Optional[Sequence[int]] = None):
     """Plain conv3x3 over one source, or over a channel concat of several sources (splits = channels per source)."""
+    co, ci = w.shape[:2]
+    splits = list(splits) if splits else [ci]
+    assert sum(splits) == ci
+    return plan_conv3x3(w, splits).finish()
+
+
+def plan_conv3x3(w: torch.Tensor, splits: Optional[Sequence[int]] = None) -> KPlan:
     co, ci = w.shape[:2]
     splits = list(splits) if splits else [ci]
     assert sum(splits) == ci
@@ -77,7 +107,7 @@ def pack_conv3x3(w: torch.Tensor, splits: Optional[Sequence[int]] = None):
     for s, n in enumerate(splits):
         plan.add_conv3x3(s, w[:, off:off + n])
         off += n
-    return plan.finish()
+    return plan
 
 
 def pack_convT2x2(w: torch.Tensor, b: torch.Tensor):

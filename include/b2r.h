@@ -122,6 +122,7 @@ int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host, const flo
 /* flags: B2R_CONV_GENERIC_ONLY keeps the layer on the generic kernel even when the C_out = 64 specialisation
  * (resident weights + column-shifted halo boxes, csrc/conv_n64.cu) applies; used by the A/B parity test. */
 #define B2R_CONV_GENERIC_ONLY 1
+#define B2R_CONV_NO_W3 2 /* skip the tap-folded kernel (csrc/conv_w3.cu) even if weights_w3 is given */
 
 /* k-block encoding: bits [0,2) source index, [2,4) dh+1, [4,6) dw+1, [8,24) first channel / 64 */
 #define B2R_KBLOCK(src, dh, dw, c64) \
@@ -133,6 +134,10 @@ typedef struct b2r_conv_gemm_desc {
     const void* src[B2R_MAX_SRC];    /* bf16 NHWC [N,H,W,src_C[i]] */
     int32_t src_C[B2R_MAX_SRC];      /* multiples of 64 */
     const void* weights;             /* bf16 [cout_total][64*num_kblocks], K order = k-block order */
+    const void* weights_w3;          /* optional, C_out = 64 only: the same weights as bf16 [192][64*num_ksteps] for the
+                                        tap-folded kernel (csrc/conv_w3.cu): one k-step per (3x3 group, kernel row kh)
+                                        with rows (kw, co), and one per centre block with rows kw = 0, 2 zero; NULL =
+                                        use the [64][K] layout only */
     const float* bias;               /* f32 [cout_total] */
     int32_t cout_total;              /* multiple of 64; for CONVT2X2 = 4*C_out, quadrant-major (q = 2*i + j) */
     int32_t num_kblocks;

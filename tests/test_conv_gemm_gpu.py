@@ -247,20 +247,46 @@ def test_conv_n64_specialisation_equals_generic_kernel(n, h, w, splits, shortcut
         ref = ref + F.conv2d(torch.cat(sc_in, 1), ws.to(torch.bfloat16).float())
     ref = F.relu(ref)
     wm, kbl = plan.finish()
-    wm = wm.cuda()
+    wm, w3 = wm.cuda(), plan.finish_w3().cuda()
     outs = []
-    for flags in (0, L.B2R_CONV_GENERIC_ONLY):
+    for flags in (L.B2R_CONV_NO_W3, L.B2R_CONV_GENERIC_ONLY, 0):
         out = torch.full((n, h, w, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
         pl = torch.full((n, h // 2, w // 2, 64), float("nan"), dtype=torch.bfloat16, device="cuda") if pool else None
-        ops.conv_gemm(all_srcs, wm, b, kbl, act=L.B2R_ACT_RELU, out=out, out_pool=pl,
-                      tile=tile if flags == 0 else (0, 0, 0), flags=flags)
+        ops.conv_gemm(all_srcs, wm, b, kbl, act=L.B2R_ACT_RELU, out=out, out_pool=pl, weights_w3=w3,
+                      tile=tile if flags == L.B2R_CONV_NO_W3 else (0, 0, 0), flags=flags)
         torch.cuda.synchronize()
         outs.append((out, pl))
     assert_close_bf16(to_nchw_f32(outs[0][0]), ref, "n64 kernel vs torch")
-    assert torch.equal(outs[0][0], outs[1][0]), "specialised and generic kernels disagree"
+    assert torch.equal(outs[0][0], outs[1][0]), "resident-weight (n64) and generic kernels disagree"
+    # tap-folded kernel (conv_w3.cu): different fp32 summation order (three kw partial sums added in the epilogue),
+    # so equal to the others only up to one bf16 rounding of the output
+    assert_close_bf16(to_nchw_f32(outs[2][0]), ref, "w3 kernel vs torch")
+    d = (outs[2][0].float() - outs[0][0].float()).abs()
+    assert bool((d <= 2.0 ** -7 * outs[0][0].float().abs() + 1e-3).all()), float(d.max())
     if pool:
         assert torch.equal(outs[0][1], outs[1][1])
-        assert torch.equal(to_nchw_f32(outs[0][1]), F.max_pool2d(to_nchw_f32(outs[0][0]), 2, 2))
+        for o, pl in outs:
+            assert torch.equal(to_nchw_f32(pl), F.max_pool2d(to_nchw_f32(o), 2, 2))
+
+
+def test_conv_w3_full_size_and_odd_widths():
+    """224 x 224 (16 x 28 tiles of 14 x 8, no waste) and widths that are not multiples of 14 (clipped tiles)."""
+    ops, packing, L = _ops()
+    for n, h, w in ((2, 224, 224), (1, 40, 30), (3, 16, 100), (1, 8, 14)):
+        x = nhwc_bf16(rnd(n, 64, h, w, seed=70))
+        wt = rnd(64, 64, 3, 3, scale=(2.0 / 576) ** 0.5, seed=71)
+        b = rnd(64, scale=0.1, seed=72)
+        plan = packing.plan_conv3x3(wt)
+        wm, kbl = plan.finish()
+        out = torch.full((n, h, w, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+        pl = torch.full((n, h // 2, w // 2, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+        ops.conv_gemm([x], wm.cuda(), b, kbl, act=L.B2R_ACT_PRELU, slope=0.3, out=out, out_pool=pl,
+                      weights_w3=plan.finish_w3().cuda())
+        torch.cuda.synchronize()
+        ref = F.prelu(F.conv2d(to_nchw_f32(x), wt.to(torch.bfloat16).float(), b, padding=1),
+                      torch.tensor([0.3], device="cuda"))
+        assert_close_bf16(to_nchw_f32(out), ref, f"w3 {n}x{h}x{w}")
+        assert torch.equal(to_nchw_f32(pl), F.max_pool2d(to_nchw_f32(out), 2, 2))
 
 
 def test_conv_n64_many_tiles_and_ring_wraps():

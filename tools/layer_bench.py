@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--only", default=None)
     ap.add_argument("--json", default=None)
     ap.add_argument("--block-n", type=int, default=0)
+    ap.add_argument("--no-w3", action="store_true")
     args = ap.parse_args()
     from b200restore import ops, packing, _lib as L
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
@@ -66,7 +67,7 @@ def main():
         if kind == "convT":
             w = torch.randn((ci, co, 2, 2), generator=g) * (1.0 / ci) ** 0.5
             wm, bias = packing.pack_convT2x2(w, torch.zeros(co))
-            kbl, mode = None, L.B2R_OUT_CONVT2X2
+            kbl, mode, w3 = None, L.B2R_OUT_CONVT2X2, None
             out = torch.empty((n, 2 * hw, 2 * hw, co), dtype=torch.bfloat16, device=dev)
             alg_k = ci
         else:
@@ -81,14 +82,16 @@ def main():
                 srcs = srcs + [srcs[0].clone()]
                 plan.add_1x1(len(srcs) - 1, torch.eye(co))
             wm, kbl = plan.finish()
+            w3 = plan.finish_w3()
             bias, mode = torch.zeros(co), L.B2R_OUT_NHWC
             out = torch.empty((n, hw, hw, co), dtype=torch.bfloat16, device=dev)
         pool = torch.empty((n, hw // 2, hw // 2, co), dtype=torch.bfloat16, device=dev) if pooled else None
         wm, bias = wm.to(dev), bias.to(dev)
+        w3 = w3.to(dev) if (w3 is not None and not args.no_w3) else None
         flops = 2.0 * n * hw * hw * wm.shape[0] * alg_k
 
         def run():
-            ops.conv_gemm(srcs, wm, bias, kbl, act=L.B2R_ACT_RELU, out=out, out_pool=pool, out_mode=mode,
+            ops.conv_gemm(srcs, wm, bias, kbl, act=L.B2R_ACT_RELU, out=out, out_pool=pool, out_mode=mode, weights_w3=w3,
                           block_n=args.block_n if args.block_n and co % args.block_n == 0 else 0)
 
         for _ in range(3):
