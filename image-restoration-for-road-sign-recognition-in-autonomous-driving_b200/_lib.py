@@ -48,6 +48,7 @@ class ConvGemmDesc(C.Structure):
         ("block_n", C.c_int32),
         ("max_ctas", C.c_int32),
         ("flags", C.c_int32),
+        ("debug_timeline", C.c_void_p),
     ]
 
 

@@ -46,6 +46,7 @@ struct alignas(64) ConvW3Params {
     int num_groups, num_ksteps, ring_slots;
     int tiles_w, tiles_h, n_img;
     int store_full, store_pool;
+    long long* dbg;                  // optional [B2R_DBG_TILES][8] clock64 stamps written by CTA 0
     uint32_t group[kW3MaxGroups];
 };
 

@@ -495,6 +495,7 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
     P.bias = d->bias;
     P.slope = d->slope;
     P.act = d->act;
+    P.dbg = reinterpret_cast<long long*>(d->debug_timeline);
     P.num_groups = ng;
     P.num_ksteps = nsteps;
     P.ring_slots = ring;

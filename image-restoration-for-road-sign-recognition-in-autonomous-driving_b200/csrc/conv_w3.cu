@@ -22,7 +22,8 @@
 
 namespace b2r {
 
-constexpr int kW3Threads = 192;
+constexpr int kW3Threads = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kW3EpiThreads = 256;
 constexpr int kW3BStep = 192 * 128;      // weights of one k-step: 192 rows x 128 B
 constexpr int kW3Slot = 10 * 16 * 128;   // one halo box: (8 + 2) rows x 16 columns x 128 B
 constexpr int kW3Staging = 14336;        // 8 x 14 pixels x 128 B
@@ -50,6 +51,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     const int tiles_per_img = p.tiles_w * p.tiles_h;
     const int total_tiles = tiles_per_img * p.n_img;
     const int R = p.ring_slots;
+    // role timeline (debug): CTA 0 stamps clock64() for its first B2R_DBG_TILES tiles
+#define B2R_STAMP(iter, slot) \
+    do { if (p.dbg != nullptr && blockIdx.x == 0 && (iter) < B2R_DBG_TILES) p.dbg[(iter) * 8 + (slot)] = clock64(); } while (0)
 
     if (warp_idx == 0 && lane == 0) {
         for (int i = 0; i < B2R_MAX_SRC; ++i) tma_prefetch_desc(&p.a_map[i]);
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
-                mbar_init(&tmem_empty_bar[s], 4);
+                mbar_init(&tmem_empty_bar[s], 8);
             }
             mbar_init(b_full_bar, 1);
             fence_mbar_init();
@@ -87,7 +91,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 tma_load_2d(b_res + ks * kW3BStep, &p.b_map, b_full_bar, ks * 64, 0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
                 const int n0 = tile / tiles_per_img;
                 const int t = tile - n0 * tiles_per_img;
                 const int w0 = (t % p.tiles_w) * 14;
@@ -97,6 +102,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                     const int src = e & 3;
                     const int c0 = int((e >> 8) & 0xFFF) * 64;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (g == 0) B2R_STAMP(iter, 0);
                     mbar_arrive_expect_tx(&full_bar[stage], kW3Slot);
                     tma_load_4d(ring + stage * kW3Slot, &p.a_map[src], &full_bar[stage], c0, w0 - 1, h0 - 1, n0);
                     if (++stage == R) {
@@ -116,9 +122,11 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
+                B2R_STAMP(iter, 1);
                 const uint32_t tmem_d = tmem_base + uint32_t(acc * 256);
                 uint32_t first = 1;
                 for (int g = 0; g < p.num_groups; ++g) {
@@ -146,14 +154,19 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                     }
                 }
                 umma_commit(&tmem_full_bar[acc]);
+                B2R_STAMP(iter, 2);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
         }
     } else {
         // ===================================== epilogue =====================================
+        // Eight warps: warp w may touch TMEM lanes 32*(w%4).. only, so each lane quarter is shared by two warps that
+        // split the 64 output channels (half 0 / half 1): two warps per SM sub-partition hide each other's
+        // tcgen05.ld / shuffle latency (profiles/r01_w3_timeline.md: with four warps the drain paced the tile).
         const int quarter = warp_idx & 3;
-        const int epi_tid = quarter * 32 + lane;
+        const int half = (warp_idx - 2) >> 2;
+        const int epi_tid = (warp_idx - 2) * 32 + lane;
         const int hh = quarter * 2 + (lane >> 4);  // tile row of this lane's pixel
         const int cc = lane & 15;                  // buffer column; output column w = cc is valid for cc < 14
         const int srow = hh * 14 + cc;             // row of the 8 x 14 staging tile
@@ -161,7 +174,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             const int n0 = tile / tiles_per_img;
             const int t = tile - n0 * tiles_per_img;
             const int w0 = (t % p.tiles_w) * 14;
@@ -169,16 +183,22 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
+            if (epi_tid == 0) B2R_STAMP(iter, 3);
             if (epi_tid == 0) tma_store_wait_read<0>();
-            named_barrier_sync(1, kEpiThreadsC);
+            named_barrier_sync(1, kW3EpiThreads);
+            if (epi_tid == 0) B2R_STAMP(iter, 4);
             const uint32_t tacc = tmem_base + lane_base + uint32_t(acc * 256);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            {
                 uint32_t d0[32], d1[32], d2[32];
                 tmem_ld_32x32(tacc + uint32_t(half * 32), d0);         // kw = 0 partial sums, channels half*32 ..
                 tmem_ld_32x32(tacc + uint32_t(64 + half * 32), d1);    // kw = 1
                 tmem_ld_32x32(tacc + uint32_t(128 + half * 32), d2);   // kw = 2
                 tmem_ld_wait();
+                // the accumulator now lives in registers: hand the TMEM stage back to the MMA warp BEFORE the shift-add,
+                // activation and staging, so the next-but-one tile's MMAs overlap all of that
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[j]), 1);
@@ -187,20 +207,19 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 }
                 if (valid) epilogue_store_half(d0, bias_s + half * 32, p.act, p.slope, sfull, srow, half);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (epi_tid == 0) B2R_STAMP(iter, 5);
             fence_proxy_async_smem();
-            named_barrier_sync(1, kEpiThreadsC);
+            named_barrier_sync(1, kW3EpiThreads);
             if (p.store_pool) {
                 if (epi_tid < 28 * 4) epilogue_pool_chunk(sfull, spool, epi_tid, 14, 8);
                 fence_proxy_async_smem();
-                named_barrier_sync(1, kEpiThreadsC);
+                named_barrier_sync(1, kW3EpiThreads);
             }
             if (epi_tid == 0) {
                 if (p.store_full) tma_store_4d(&p.out_map, sfull, 0, w0, h0, n0);
                 if (p.store_pool) tma_store_4d(&p.pool_map, spool, 0, w0 >> 1, h0 >> 1, n0);
                 tma_store_commit();
+                B2R_STAMP(iter, 6);
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;

@@ -101,7 +101,8 @@ def conv_gemm(srcs: Sequence[torch.Tensor], weights: torch.Tensor, bias: torch.T
               kblocks: Optional[Sequence[int]], act: int = L.B2R_ACT_NONE, slope: float = 0.0,
               out: Optional[torch.Tensor] = None, out_pool: Optional[torch.Tensor] = None,
               out_mode: int = L.B2R_OUT_NHWC, tile=(0, 0, 0), block_n: int = 0, max_ctas: int = 0,
-              alg_k: Optional[int] = None, flags: int = 0, weights_w3: Optional[torch.Tensor] = None) -> None:
+              alg_k: Optional[int] = None, flags: int = 0, weights_w3: Optional[torch.Tensor] = None,
+              debug_timeline: Optional[torch.Tensor] = None) -> None:
     """One fused tensor-core layer (b2r_conv_gemm).  srcs: NHWC bf16 [N,H,W,C_i]; weights bf16 [cout_total, K].
     `alg_k`: K elements that are algorithmic work (excludes e.g. an identity-shortcut block); accounting only."""
     n, h, w = srcs[0].shape[:3]
@@ -155,6 +156,11 @@ def conv_gemm(srcs: Sequence[torch.Tensor], weights: torch.Tensor, bias: torch.T
     d.out_C = oc
     d.tile_w, d.tile_h, d.tile_n = (int(x) for x in tile)
     d.block_n, d.max_ctas, d.flags = int(block_n), int(max_ctas), int(flags)
+    if debug_timeline is not None:
+        _chk(debug_timeline, torch.int64, "debug_timeline")
+        if debug_timeline.numel() < 64 * 8:
+            raise L.B2RError("debug_timeline must hold 64 x 8 int64")
+        d.debug_timeline = debug_timeline.data_ptr()
     e0 = _TIMER.start("conv_gemm") if _TIMER is not None else None
     L.check(L.load().b2r_conv_gemm(C.byref(d), _stream()))
     STATS["launches"] += 1

@@ -114,6 +114,7 @@ int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host, const flo
  * ResUNet.forward (14_train_unified_advanced.py:114-115, 151-186) and torchvision VGG16.forward
  * (18_test_unified_benchmark.py:46).
  * ------------------------------------------------------------------------------------------------------------- */
+#define B2R_DBG_TILES 64
 #define B2R_MAX_SRC 3
 #define B2R_MAX_KBLOCKS 96
 #define B2R_OUT_NHWC 0
@@ -152,6 +153,8 @@ typedef struct b2r_conv_gemm_desc {
     int32_t block_n;                 /* 64 / 128 / 256; 0 = choose */
     int32_t max_ctas;                /* 0 = one per SM */
     int32_t flags;                   /* B2R_CONV_* */
+    int64_t* debug_timeline;         /* optional device buffer int64[B2R_DBG_TILES][8]: CTA 0 records clock64() stamps of
+                                        its first tiles per warp role (tools/role_timeline.py); NULL = off */
 } b2r_conv_gemm_desc;
 
 int b2r_conv_gemm(const b2r_conv_gemm_desc* desc /* host */, void* stream);
