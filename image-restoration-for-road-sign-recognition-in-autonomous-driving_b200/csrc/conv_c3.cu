@@ -1,0 +1,321 @@
+// First conv layer (C_in = 3 -> 64) on tcgen05: im2col built on the fly by producer warps.
+//
+// K = 27 is far too small for TMA-staged k-blocks, and on CUDA cores the layer costs 1728 FMA per pixel (it was 11 %
+// of the whole pipeline, profiles/r01_launches_v1_summary.md).  Here four producer warps (one thread per output
+// pixel of the 8 x 16 tile) gather the 27 inputs of their pixel straight from global memory (through L1; the next
+// tile's values are prefetched into registers), convert them and write one 128-byte row of the A operand directly in
+// the SWIZZLE_128B K-major layout the MMA reads.  K is laid out as 27 (hi, lo) bf16 pairs: x = hi + lo carries ~16
+// mantissa bits of the fp32 activation, and the packed weight matrix repeats each weight for both halves, so the
+// activation side of this layer stays near fp32 accuracy at no cost (K = 54 <= 64, four MMAs of N = 64 per tile).
+// For u8 input the ToTensor / Normalize arithmetic (u8/255, then (x - mean)/std, IEEE division as PyTorch does on the
+// CPU) is evaluated once per block into a 3 x 256 table of packed (hi, lo) pairs, so the hand-off is bit-faithful to
+// the reference's preprocessing (17_run_unified_inference.py:66, 18_test_unified_benchmark.py:28-32) and costs one
+// shared-memory load per value.  Zero padding is applied after the normalisation, as nn.Conv2d does.
+// Warp 4 loads the 8 KB weight tile once, allocates TMEM and issues the MMAs; warps 5..8 run the usual epilogue
+// (bias, ReLU / PReLU, bf16, swizzled staging, TMA store).  Persistent, one CTA per SM.
+#include <cstring>
+
+#include "b2r_internal.h"
+#include "conv_common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace b2r {
+
+constexpr int kC3Threads = 288;
+constexpr int kC3Stages = 3;
+
+struct alignas(64) ConvC3Params {
+    CUtensorMap b_map;    // packed weights bf16 [64][64], box 64 x 64
+    CUtensorMap out_map;  // NHWC bf16 [N,H,W,64], box 64 x 16 x 8 x 1
+    const void* in;
+    const float* bias;
+    float mean[3], stdv[3];
+    int normalize;
+    float slope;
+    int act;
+    int N, H, W;
+    int tiles_w, tiles_h;
+};
+
+__device__ __forceinline__ uint32_t split_hi_lo(float x) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    return uint32_t(__bfloat16_as_ushort(hi)) | (uint32_t(__bfloat16_as_ushort(lo)) << 16);
+}
+
+template <int IN_FMT>
+__global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_constant__ ConvC3Params p) {
+    constexpr uint32_t kIdesc = make_idesc_bf16_f32(128, 64);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_st = smem;                               // kC3Stages x 16 KB
+    uint8_t* b_s = a_st + kC3Stages * 16384;            // 8 KB
+    uint8_t* sfull = b_s + 8192;                        // 16 KB staging
+    uint32_t* lut = reinterpret_cast<uint32_t*>(sfull + 16384);  // [3][256] packed (hi, lo)
+    float* bias_s = reinterpret_cast<float*>(lut + 768);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 64);
+    uint64_t* full_bar = bars;                  // [kC3Stages], 128 producer arrivals
+    uint64_t* empty_bar = bars + kC3Stages;     // [kC3Stages]
+    uint64_t* tmem_full_bar = bars + 2 * kC3Stages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint64_t* b_full_bar = tmem_empty_bar + 2;
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(b_full_bar + 1);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const int total_tiles = tiles_per_img * p.N;
+    const int H = p.H, W = p.W;
+
+    if (warp_idx == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&p.b_map);
+            tma_prefetch_desc(&p.out_map);
+            for (int s = 0; s < kC3Stages; ++s) {
+                mbar_init(&full_bar[s], 128);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], 4);
+            }
+            mbar_init(b_full_bar, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc<128>(tmem_ptr_s);
+    }
+    if (IN_FMT == B2R_IN_U8_NHWC) {
+        for (int i = threadIdx.x; i < 768; i += kC3Threads) {
+            const int c = i >> 8, u = i & 255;
+            float v = __fdiv_rn(float(u), 255.0f);                                   // ToTensor
+            if (p.normalize) v = __fdiv_rn(v - p.mean[c], p.stdv[c]);                 // Normalize
+            lut[i] = split_hi_lo(v);
+        }
+    }
+    if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp_idx < 4) {
+        // ===================================== im2col producers =====================================
+        const int r = threadIdx.x;            // tile row == pixel (h = r / 16, w = r % 16)
+        const int ph = r >> 4, pw = r & 15;
+        uint32_t cur[27], nxt[27];
+
+        auto gather = [&](int tile, uint32_t (&v)[27]) {
+            const int n0 = tile / tiles_per_img;
+            const int t = tile - n0 * tiles_per_img;
+            const int w = (t % p.tiles_w) * 16 + pw;
+            const int h = (t / p.tiles_w) * 8 + ph;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int hh = h + kh - 1;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int ww = w + kw - 1;
+                    const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int idx = (kh * 3 + kw) * 3 + c;
+                        if (IN_FMT == B2R_IN_U8_NHWC) {
+                            // raw byte now, table lookup later (0x100 marks padding)
+                            v[idx] = ok ? uint32_t(__ldg(static_cast<const uint8_t*>(p.in) +
+                                                         ((size_t(n0) * H + hh) * W + ww) * 3 + c))
+                                        : 0x100u;
+                        } else {
+                            v[idx] = ok ? __float_as_uint(__ldg(static_cast<const float*>(p.in) +
+                                                                ((size_t(n0) * 3 + c) * H + hh) * W + ww))
+                                        : 0u;
+                        }
+                    }
+                }
+            }
+        };
+
+        int stage = 0;
+        uint32_t phase = 0;
+        int tile = blockIdx.x;
+        if (tile < total_tiles) gather(tile, cur);
+        for (; tile < total_tiles; tile += gridDim.x) {
+            const int next = tile + gridDim.x;
+            if (next < total_tiles) gather(next, nxt);   // prefetch: these loads complete while the row is built
+            uint32_t wrd[32];
+#pragma unroll
+            for (int i = 0; i < 27; ++i) {
+                if (IN_FMT == B2R_IN_U8_NHWC)
+                    wrd[i] = (cur[i] & 0x100u) ? 0u : lut[(i % 3) * 256 + cur[i]];
+                else
+                    wrd[i] = split_hi_lo(__uint_as_float(cur[i]));
+            }
+#pragma unroll
+            for (int i = 27; i < 32; ++i) wrd[i] = 0u;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            const uint32_t row_addr = smem_u32(a_st + stage * 16384) + uint32_t(r * 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t addr = row_addr + uint32_t((j ^ (r & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(wrd[4 * j]), "r"(wrd[4 * j + 1]),
+                             "r"(wrd[4 * j + 2]), "r"(wrd[4 * j + 3])
+                             : "memory");
+            }
+            fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == kC3Stages) {
+                stage = 0;
+                phase ^= 1;
+            }
+#pragma unroll
+            for (int i = 0; i < 27; ++i) cur[i] = nxt[i];
+        }
+    } else if (warp_idx == 4) {
+        // ===================================== weight load + MMA issuer =====================================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(b_full_bar, 8192);
+            tma_load_2d(b_s, &p.b_map, b_full_bar, 0, 0);
+            mbar_wait(b_full_bar, 0);
+            tc_fence_after();
+            const uint64_t bdesc = make_sdesc_sw128(smem_u32(b_s), 1024);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint64_t adesc = make_sdesc_sw128(smem_u32(a_st + stage * 16384), 1024);
+                const uint32_t tmem_d = tmem_base + uint32_t(acc * 64);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, k > 0 ? 1u : 0u);
+                umma_commit(&empty_bar[stage]);
+                umma_commit(&tmem_full_bar[acc]);
+                if (++stage == kC3Stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===================================== epilogue =====================================
+        const int quarter = warp_idx & 3;
+        const int row = quarter * 32 + lane;
+        const bool leader = (warp_idx == 5 && lane == 0);
+        const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n0 = tile / tiles_per_img;
+            const int t = tile - n0 * tiles_per_img;
+            const int w0 = (t % p.tiles_w) * 16;
+            const int h0 = (t / p.tiles_w) * 8;
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * 64), v0);
+            tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * 64 + 32), v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (leader) tma_store_wait_read<0>();   // previous tile's store has finished reading the staging tile
+            named_barrier_sync(1, kEpiThreadsC);
+            epilogue_store_half(v0, bias_s, p.act, p.slope, sfull, row, 0);
+            epilogue_store_half(v1, bias_s + 32, p.act, p.slope, sfull, row, 1);
+            fence_proxy_async_smem();
+            named_barrier_sync(1, kEpiThreadsC);
+            if (leader) {
+                tma_store_4d(&p.out_map, sfull, 0, w0, h0, n0);
+                tma_store_commit();
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (leader) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 4) {
+        tc_fence_after();
+        __syncwarp();
+        tmem_dealloc<128>(tmem_base);
+    }
+}
+
+}  // namespace b2r
+
+extern "C" int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host, const float* std_host,
+                              const void* weights_packed, const float* bias, int act, float slope, void* out, int N,
+                              int H, int W, void* stream_v) {
+    using namespace b2r;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    B2R_REQUIRE(in && weights_packed && bias && out, "null pointer");
+    B2R_REQUIRE(N > 0 && H > 0 && W > 0, "bad shape N=%d H=%d W=%d", N, H, W);
+    B2R_REQUIRE(in_fmt == B2R_IN_F32_NCHW || in_fmt == B2R_IN_U8_NHWC, "in_fmt=%d", in_fmt);
+    B2R_REQUIRE((mean_host == nullptr) == (std_host == nullptr), "mean/std must both be given or both be null");
+    B2R_REQUIRE(!(mean_host && in_fmt != B2R_IN_U8_NHWC), "normalisation is only defined for the u8 hand-off");
+    B2R_REQUIRE(act >= B2R_ACT_NONE && act <= B2R_ACT_PRELU, "act=%d", act);
+    static thread_local ConvC3Params P;
+    memset(&P, 0, sizeof(P));
+    {
+        const uint64_t dims[2] = {64, 64};
+        const uint64_t strides[1] = {128};
+        const uint32_t box[2] = {64, 64};
+        int rc = encode_tmap_bf16(&P.b_map, weights_packed, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        const uint64_t strides[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
+        const uint32_t box[4] = {64, 16, 8, 1};
+        int rc = encode_tmap_bf16(&P.out_map, out, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    P.in = in;
+    P.bias = bias;
+    P.normalize = mean_host != nullptr;
+    for (int c = 0; c < 3; ++c) {
+        P.mean[c] = mean_host ? mean_host[c] : 0.f;
+        P.stdv[c] = std_host ? std_host[c] : 1.f;
+    }
+    P.slope = slope;
+    P.act = act;
+    P.N = N;
+    P.H = H;
+    P.W = W;
+    P.tiles_w = (W + 15) / 16;
+    P.tiles_h = (H + 7) / 8;
+    const long total_tiles = (long)P.tiles_w * P.tiles_h * N;
+    B2R_REQUIRE(total_tiles < (1L << 31), "too many tiles");
+    int sms = 0;
+    int rc = device_sm_count(&sms);
+    if (rc) return rc;
+    const int grid = (int)(total_tiles < sms ? total_tiles : sms);
+    const size_t smem = 1024 + kC3Stages * 16384 + 8192 + 16384 + 768 * 4 + 256 + 256;
+    static bool attr_set[64][2] = {{false}};
+    int dev = 0;
+    B2R_CUDA(cudaGetDevice(&dev));
+    if (in_fmt == B2R_IN_U8_NHWC) {
+        if (dev >= 64 || !attr_set[dev][0]) {
+            B2R_CUDA(cudaFuncSetAttribute(conv_c3_kernel<B2R_IN_U8_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+            if (dev < 64) attr_set[dev][0] = true;
+        }
+        conv_c3_kernel<B2R_IN_U8_NHWC><<<grid, kC3Threads, smem, stream>>>(P);
+    } else {
+        if (dev >= 64 || !attr_set[dev][1]) {
+            B2R_CUDA(cudaFuncSetAttribute(conv_c3_kernel<B2R_IN_F32_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+            if (dev < 64) attr_set[dev][1] = true;
+        }
+        conv_c3_kernel<B2R_IN_F32_NCHW><<<grid, kC3Threads, smem, stream>>>(P);
+    }
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}

@@ -1,5 +1,4 @@
-// Small CUDA-core kernels around the tensor-core convs: the C_in = 3 first layer (with the ToTensor / Normalize
-// hand-off fused in), the 64 -> 3 output head with the clamp / truncating u8 quantiser, stand-alone pooling,
+// Small CUDA-core kernels around the tensor-core convs: the 64 -> 3 output head with the clamp / truncating u8 quantiser, stand-alone pooling,
 // the 43-way classifier row and the arg-max + correct-count reduction.  All are HBM- or latency-bound.
 #include <cstring>
 
@@ -25,89 +24,6 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
     for (int i = 0; i < 4; ++i) {
         f[2 * i] = __uint_as_float(w[i] << 16);
         f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// conv3x3, C_in = 3 -> 64, fp32 math, bf16 NHWC out.  16x16 pixel tile per 256-thread block.
-// ------------------------------------------------------------------------------------------------------------
-struct C3Norm {
-    float mean[3];
-    float inv_std_is_set;  // 0: no normalisation
-    float stdv[3];
-};
-
-template <int IN_FMT>
-__global__ void __launch_bounds__(256) conv3x3_c3_kernel(const void* __restrict__ in, C3Norm nrm,
-                                                         const float* __restrict__ weights,
-                                                         const float* __restrict__ bias, int act, float slope,
-                                                         __nv_bfloat16* __restrict__ out, int N, int H, int W) {
-    __shared__ float s_in[18][18][3];
-    __shared__ __align__(16) float s_w[27][64];  // [ci*9 + kh*3 + kw][co]
-    __shared__ __align__(16) float s_b[64];
-
-    const int tid = threadIdx.x;
-    const int n = blockIdx.z;
-    const int h0 = blockIdx.y * 16, w0 = blockIdx.x * 16;
-
-    for (int i = tid; i < 27 * 64; i += 256) {
-        const int co = i & 63, k = i >> 6;  // weights are OIHW: [co][ci][kh][kw] -> index co*27 + k
-        s_w[k][co] = weights[co * 27 + k];
-    }
-    if (tid < 64) s_b[tid] = bias[tid];
-    for (int i = tid; i < 18 * 18 * 3; i += 256) {
-        const int c = i % 3, x = (i / 3) % 18, y = i / 54;
-        const int h = h0 + y - 1, w = w0 + x - 1;
-        float v = 0.f;
-        if (h >= 0 && h < H && w >= 0 && w < W) {
-            if (IN_FMT == B2R_IN_F32_NCHW) {
-                v = static_cast<const float*>(in)[((size_t(n) * 3 + c) * H + h) * W + w];
-            } else {
-                const uint8_t u = static_cast<const uint8_t*>(in)[((size_t(n) * H + h) * W + w) * 3 + c];
-                v = __fdiv_rn(float(u), 255.0f);  // ToTensor
-                if (nrm.inv_std_is_set != 0.f) v = __fdiv_rn(v - nrm.mean[c], nrm.stdv[c]);  // Normalize
-            }
-        }
-        s_in[y][x][c] = v;
-    }
-    __syncthreads();
-
-    const int ty = tid >> 4, tx = tid & 15;
-    const int h = h0 + ty, w = w0 + tx;
-    float x[27];
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) x[c * 9 + kh * 3 + kw] = s_in[ty + kh][tx + kw][c];
-
-    if (h >= H || w >= W) return;
-    uint4* orow = reinterpret_cast<uint4*>(out + ((size_t(n) * H + h) * W + w) * 64);
-#pragma unroll 1
-    for (int g = 0; g < 8; ++g) {
-        float acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = s_b[g * 8 + j];
-#pragma unroll
-        for (int k = 0; k < 27; ++k) {
-            const float4 wa = *reinterpret_cast<const float4*>(&s_w[k][g * 8]);
-            const float4 wb = *reinterpret_cast<const float4*>(&s_w[k][g * 8 + 4]);
-            acc[0] = fmaf(x[k], wa.x, acc[0]);
-            acc[1] = fmaf(x[k], wa.y, acc[1]);
-            acc[2] = fmaf(x[k], wa.z, acc[2]);
-            acc[3] = fmaf(x[k], wa.w, acc[3]);
-            acc[4] = fmaf(x[k], wb.x, acc[4]);
-            acc[5] = fmaf(x[k], wb.y, acc[5]);
-            acc[6] = fmaf(x[k], wb.z, acc[6]);
-            acc[7] = fmaf(x[k], wb.w, acc[7]);
-        }
-        uint4 o;
-        o.x = pack2(act_fn(acc[0], act, slope), act_fn(acc[1], act, slope));
-        o.y = pack2(act_fn(acc[2], act, slope), act_fn(acc[3], act, slope));
-        o.z = pack2(act_fn(acc[4], act, slope), act_fn(acc[5], act, slope));
-        o.w = pack2(act_fn(acc[6], act, slope), act_fn(acc[7], act, slope));
-        orow[g] = o;
     }
 }
 
@@ -305,37 +221,6 @@ __global__ void __launch_bounds__(256) argmax_count_kernel(const float* __restri
 
 // ================================================================================================================
 extern "C" {
-
-int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host, const float* std_host, const float* weights,
-                   const float* bias, int act, float slope, void* out, int N, int H, int W, void* stream_v) {
-    using namespace b2r;
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    B2R_REQUIRE(in && weights && bias && out, "null pointer");
-    B2R_REQUIRE(N > 0 && H > 0 && W > 0, "bad shape N=%d H=%d W=%d", N, H, W);
-    B2R_REQUIRE(N <= 65535, "N=%d exceeds gridDim.z", N);
-    B2R_REQUIRE(in_fmt == B2R_IN_F32_NCHW || in_fmt == B2R_IN_U8_NHWC, "in_fmt=%d", in_fmt);
-    B2R_REQUIRE((mean_host == nullptr) == (std_host == nullptr), "mean/std must both be given or both be null");
-    B2R_REQUIRE(act >= B2R_ACT_NONE && act <= B2R_ACT_PRELU, "act=%d", act);
-    C3Norm nrm;
-    memset(&nrm, 0, sizeof(nrm));
-    if (mean_host) {
-        B2R_REQUIRE(in_fmt == B2R_IN_U8_NHWC, "normalisation is only defined for the u8 hand-off");
-        for (int c = 0; c < 3; ++c) {
-            nrm.mean[c] = mean_host[c];
-            nrm.stdv[c] = std_host[c];
-        }
-        nrm.inv_std_is_set = 1.f;
-    }
-    dim3 grid((W + 15) / 16, (H + 15) / 16, N);
-    if (in_fmt == B2R_IN_F32_NCHW)
-        conv3x3_c3_kernel<B2R_IN_F32_NCHW><<<grid, 256, 0, stream>>>(in, nrm, weights, bias, act, slope,
-                                                                    static_cast<__nv_bfloat16*>(out), N, H, W);
-    else
-        conv3x3_c3_kernel<B2R_IN_U8_NHWC><<<grid, 256, 0, stream>>>(in, nrm, weights, bias, act, slope,
-                                                                   static_cast<__nv_bfloat16*>(out), N, H, W);
-    B2R_CHECK_LAUNCH();
-    return B2R_OK;
-}
 
 int b2r_final_conv1x1(const void* in, const float* weights, const float* bias, float* out_f32, uint8_t* out_u8, int N,
                       int H, int W, void* stream_v) {

@@ -128,7 +128,7 @@ class SimpleUNet(_B200Module):
             P[name] = dict(weights=w, bias=sd[key + ".bias"].float().contiguous(), kblocks=kb,
                            weights_w3=plan.finish_w3(dev))
 
-        P["enc1.0"] = (sd["enc1.0.weight"].float().contiguous(), sd["enc1.0.bias"].float().contiguous())
+        P["enc1.0"] = (packing.pack_conv_c3(sd["enc1.0.weight"].float()), sd["enc1.0.bias"].float().contiguous())
         conv("enc1.2", "enc1.2")
         conv("enc2.0", "enc2.0")
         conv("enc2.2", "enc2.2")
@@ -253,7 +253,7 @@ class ResUNet(_B200Module):
     def _build_pack(self, sd):
         dev = sd["final.weight"].device
         P = {}
-        P["enc1"] = (sd["enc1.0.weight"].float().contiguous(), sd["enc1.0.bias"].float().contiguous(),
+        P["enc1"] = (packing.pack_conv_c3(sd["enc1.0.weight"].float()), sd["enc1.0.bias"].float().contiguous(),
                      float(sd["enc1.1.weight"].float().reshape(-1)[0]))
         for name, splits, co in self._BLOCKS:
             cb = name + ".conv_block."
@@ -390,7 +390,7 @@ class VGG16Judge(_B200Module):
         for i, pooled in self._conv_indices():
             w, b = sd[f"features.{i}.weight"].float(), sd[f"features.{i}.bias"].float().contiguous()
             if w.shape[1] == 3:
-                P["first"] = (w.contiguous(), b)
+                P["first"] = (packing.pack_conv_c3(w), b)
             else:
                 plan = packing.plan_conv3x3(w)
                 wm, kb = plan.finish(dev)

@@ -172,7 +172,8 @@ def conv_gemm(srcs: Sequence[torch.Tensor], weights: torch.Tensor, bias: torch.T
 
 def conv3x3_c3(x: torch.Tensor, weights: torch.Tensor, bias: torch.Tensor, act: int, slope: float = 0.0,
                normalize: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """First layer.  x: f32 [N,3,H,W] or u8 [N,H,W,3]; returns bf16 NHWC [N,H,W,64]."""
+    """First layer.  x: f32 [N,3,H,W] or u8 [N,H,W,3]; weights = packing.pack_conv_c3(...) bf16 [64,64]; returns bf16
+    NHWC [N,H,W,64]."""
     if x.dtype == torch.uint8:
         _chk(x, torch.uint8, "x", 4)
         n, h, w, c = x.shape
@@ -183,10 +184,10 @@ def conv3x3_c3(x: torch.Tensor, weights: torch.Tensor, bias: torch.Tensor, act: 
         fmt = L.B2R_IN_F32_NCHW
     if c != 3:
         raise L.B2RError(f"conv3x3_c3 needs 3 input channels, got {c}")
-    _chk(weights, torch.float32, "weights", 4)
+    _chk(weights, torch.bfloat16, "weights", 2)
     _chk(bias, torch.float32, "bias", 1)
-    if tuple(weights.shape) != (64, 3, 3, 3) or bias.numel() != 64:
-        raise L.B2RError(f"conv3x3_c3 weights must be [64,3,3,3], got {tuple(weights.shape)}")
+    if tuple(weights.shape) != (64, 64) or bias.numel() != 64:
+        raise L.B2RError(f"conv3x3_c3 weights must be the packed bf16 [64,64] matrix, got {tuple(weights.shape)}")
     if out is None:
         out = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=x.device)
     _chk(out, torch.bfloat16, "out", 4)

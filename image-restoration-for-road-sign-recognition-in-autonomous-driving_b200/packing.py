@@ -122,3 +122,14 @@ def pack_fc_from_nchw_flatten(w: torch.Tensor, c: int, h: int, wd: int) -> torch
     """Linear weight whose columns index an NCHW flatten -> columns for the NHWC flatten of the same tensor."""
     o = w.shape[0]
     return w.reshape(o, c, h, wd).permute(0, 2, 3, 1).reshape(o, h * wd * c).to(torch.bfloat16).contiguous()
+
+
+def pack_conv_c3(w: torch.Tensor) -> torch.Tensor:
+    """First-layer weights f32 [64, 3, 3, 3] (OIHW) -> bf16 [64, 64] for csrc/conv_c3.cu: column 2*t + j (j = 0, 1) holds
+    w[co][ci][kh][kw] with t = (kh*3 + kw)*3 + ci (each weight twice: the kernel feeds activations as hi/lo bf16 pairs)."""
+    assert tuple(w.shape) == (64, 3, 3, 3)
+    flat = w.permute(0, 2, 3, 1).reshape(64, 27)            # [co][(kh, kw, ci)]
+    out = torch.zeros((64, 64), dtype=torch.float32, device=w.device)
+    out[:, 0:54:2] = flat
+    out[:, 1:54:2] = flat
+    return out.to(torch.bfloat16).contiguous()

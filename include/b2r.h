@@ -85,13 +85,17 @@ int b2r_degrade(const uint8_t* in_nhwc, uint8_t* out_nhwc, int N, int H, int W,
  *   in_fmt B2R_IN_F32_NCHW: `in` is f32 [N,3,H,W] (the nn.Module.forward argument)
  *   in_fmt B2R_IN_U8_NHWC : `in` is u8 [N,H,W,3]; x = u8/255, then (x - mean[c]) / std[c] when `mean`/`std` are
  *                           non-null (host pointers to 3 floats).
- * weights: f32 [64][3][3][3] (OIHW, as in the state_dict), bias f32 [64].
+ * weights_packed: bf16 [64][64], row co, column 2*t + j (j = 0, 1) = w[co][ci][kh][kw] with t = (kh*3 + kw)*3 + ci,
+ *                 columns >= 54 zero: every weight appears twice because the kernel feeds each fp32 input as a
+ *                 (hi, lo) bf16 pair (csrc/conv_c3.cu); the host packs it from the state_dict's f32 OIHW tensor.
+ * bias f32 [64].  Runs on the tensor cores (tcgen05) with an im2col producer; H, W arbitrary.
  * ------------------------------------------------------------------------------------------------------------- */
 #define B2R_IN_F32_NCHW 0
 #define B2R_IN_U8_NHWC 1
 
-int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host, const float* std_host, const float* weights,
-                   const float* bias, int act, float slope, void* out_nhwc_bf16, int N, int H, int W, void* stream);
+int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host, const float* std_host,
+                   const void* weights_packed, const float* bias, int act, float slope, void* out_nhwc_bf16, int N,
+                   int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * (3) Implicit-GEMM convolution on tcgen05 tensor cores (TMA-staged NHWC bf16 tiles, TMEM f32 accumulators).

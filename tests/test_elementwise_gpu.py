@@ -27,11 +27,13 @@ def test_conv3x3_c3_f32_nchw(n, h, w):
     x = torch.rand((n, 3, h, w), generator=_g(0)).cuda()
     wt = (torch.randn((64, 3, 3, 3), generator=_g(1)) * 0.3).cuda()
     b = (torch.randn(64, generator=_g(2)) * 0.1).cuda()
-    out = ops.conv3x3_c3(x, wt, b, act=L.B2R_ACT_PRELU, slope=0.2)
-    ref = F.prelu(F.conv2d(x, wt, b, padding=1), torch.tensor([0.2], device="cuda"))
-    # fp32 math, bf16 output rounding only: 2^-9 relative (+ tiny absolute for values near zero)
+    from b200restore import packing
+    out = ops.conv3x3_c3(x, packing.pack_conv_c3(wt), b, act=L.B2R_ACT_PRELU, slope=0.2)
+    # the kernel feeds each fp32 input as a (hi, lo) bf16 pair (~16 mantissa bits) against bf16 weights, fp32 accumulate:
+    # vs torch fp32 on the SAME bf16-rounded weights only the output's bf16 rounding (2^-9) and ~1e-4 of input split remain
+    ref = F.prelu(F.conv2d(x, wt.to(torch.bfloat16).float(), b, padding=1), torch.tensor([0.2], device="cuda"))
     err = (nchw(out) - ref).abs()
-    assert bool((err <= 2.0 ** -8 * ref.abs() + 1e-5).all()), float(err.max())
+    assert bool((err <= 2.0 ** -8 * ref.abs() + 2e-4).all()), float(err.max())
 
 
 def test_conv3x3_c3_u8_normalized():
@@ -40,14 +42,16 @@ def test_conv3x3_c3_u8_normalized():
     u8 = torch.randint(0, 256, (2, 40, 48, 3), dtype=torch.uint8, generator=_g(3)).cuda()
     wt = (torch.randn((64, 3, 3, 3), generator=_g(4)) * 0.3).cuda()
     b = (torch.randn(64, generator=_g(5)) * 0.1).cuda()
-    out = ops.conv3x3_c3(u8, wt, b, act=L.B2R_ACT_RELU, normalize=True)
-    ref = F.relu(F.conv2d(O.normalize_imagenet(O.to_tensor_u8(u8)), wt, b, padding=1))
+    from b200restore import packing
+    wp, wr = packing.pack_conv_c3(wt), wt.to(torch.bfloat16).float()
+    out = ops.conv3x3_c3(u8, wp, b, act=L.B2R_ACT_RELU, normalize=True)
+    ref = F.relu(F.conv2d(O.normalize_imagenet(O.to_tensor_u8(u8)), wr, b, padding=1))
     err = (nchw(out) - ref).abs()
-    assert bool((err <= 2.0 ** -8 * ref.abs() + 2e-5).all()), float(err.max())
-    out2 = ops.conv3x3_c3(u8, wt, b, act=L.B2R_ACT_RELU, normalize=False)
-    ref2 = F.relu(F.conv2d(O.to_tensor_u8(u8), wt, b, padding=1))
+    assert bool((err <= 2.0 ** -8 * ref.abs() + 5e-4).all()), float(err.max())
+    out2 = ops.conv3x3_c3(u8, wp, b, act=L.B2R_ACT_RELU, normalize=False)
+    ref2 = F.relu(F.conv2d(O.to_tensor_u8(u8), wr, b, padding=1))
     err2 = (nchw(out2) - ref2).abs()
-    assert bool((err2 <= 2.0 ** -8 * ref2.abs() + 2e-5).all()), float(err2.max())
+    assert bool((err2 <= 2.0 ** -8 * ref2.abs() + 2e-4).all()), float(err2.max())
 
 
 def test_final_conv1x1_f32_and_quantised_u8():
