@@ -20,7 +20,7 @@ B2R_CONV_GENERIC_ONLY, B2R_CONV_NO_W3 = 1, 2
 
 # every symbol include/b2r.h declares (tests/test_abi.py checks the list against the header and the .so)
 SYMBOLS = (
-    "b2r_version", "b2r_last_error", "b2r_degrade", "b2r_conv3x3_c3", "b2r_conv_gemm", "b2r_final_conv1x1",
+    "b2r_version", "b2r_last_error", "b2r_debug_timeline", "b2r_degrade", "b2r_conv3x3_c3", "b2r_conv_gemm", "b2r_final_conv1x1",
     "b2r_maxpool2x2", "b2r_adaptive_avgpool7", "b2r_linear_f32out", "b2r_argmax_count",
 )
 
@@ -80,6 +80,8 @@ def load() -> C.CDLL:
     lib.b2r_version.argtypes = []
     lib.b2r_last_error.restype = C.c_char_p
     lib.b2r_last_error.argtypes = []
+    lib.b2r_debug_timeline.restype = None
+    lib.b2r_debug_timeline.argtypes = [vp]
     lib.b2r_degrade.restype = C.c_int
     lib.b2r_degrade.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, u64, u64, i32, i32, vp]
     lib.b2r_conv3x3_c3.restype = C.c_int

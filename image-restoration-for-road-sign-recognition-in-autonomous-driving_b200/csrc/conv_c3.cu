@@ -11,7 +11,7 @@
 // CPU) is evaluated once per block into a 3 x 256 table of packed (hi, lo) pairs, so the hand-off is bit-faithful to
 // the reference's preprocessing (17_run_unified_inference.py:66, 18_test_unified_benchmark.py:28-32) and costs one
 // shared-memory load per value.  Zero padding is applied after the normalisation, as nn.Conv2d does.
-// Warp 4 loads the 8 KB weight tile once, allocates TMEM and issues the MMAs; warps 5..8 run the usual epilogue
+// Warps 0..7 are the producers; warp 8 loads the 8 KB weight tile once, allocates TMEM and issues the MMAs; warps 9..12 run the usual epilogue
 // (bias, ReLU / PReLU, bf16, swizzled staging, TMA store).  Persistent, one CTA per SM.
 #include <cstring>
 
@@ -21,8 +21,11 @@
 
 namespace b2r {
 
-constexpr int kC3Threads = 288;
-constexpr int kC3Stages = 3;
+constexpr int kC3ProducerWarps = 8;   // two groups of 128 threads build alternate tiles (hides the gather latency)
+constexpr int kC3EpiWarps = 8;        // two warps per TMEM lane quarter, 32 channels each
+constexpr int kC3Threads = (kC3ProducerWarps + 1 + kC3EpiWarps) * 32;
+constexpr int kC3Stages = 4;
+constexpr int kC3AccStages = 4;       // TMEM accumulator stages (4 x 64 columns)
 
 struct alignas(64) ConvC3Params {
     CUtensorMap b_map;    // packed weights bf16 [64][64], box 64 x 64
@@ -35,7 +38,10 @@ struct alignas(64) ConvC3Params {
     int act;
     int N, H, W;
     int tiles_w, tiles_h;
+    long long* dbg;
 };
+
+static long long* g_c3_dbg = nullptr;
 
 __device__ __forceinline__ uint32_t split_hi_lo(float x) {
     const __nv_bfloat16 hi = __float2bfloat16_rn(x);
@@ -57,8 +63,8 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
     uint64_t* full_bar = bars;                  // [kC3Stages], 128 producer arrivals
     uint64_t* empty_bar = bars + kC3Stages;     // [kC3Stages]
     uint64_t* tmem_full_bar = bars + 2 * kC3Stages;
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-    uint64_t* b_full_bar = tmem_empty_bar + 2;
+    uint64_t* tmem_empty_bar = tmem_full_bar + kC3AccStages;
+    uint64_t* b_full_bar = tmem_empty_bar + kC3AccStages;
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(b_full_bar + 1);
 
     const int warp_idx = threadIdx.x >> 5;
@@ -66,8 +72,10 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
     const int tiles_per_img = p.tiles_w * p.tiles_h;
     const int total_tiles = tiles_per_img * p.N;
     const int H = p.H, W = p.W;
+#define C3_STAMP(iter, slot) \
+    do { if (p.dbg != nullptr && blockIdx.x == 0 && (iter) < B2R_DBG_TILES) p.dbg[(iter) * 8 + (slot)] = clock64(); } while (0)
 
-    if (warp_idx == 4) {
+    if (warp_idx == kC3ProducerWarps) {
         if (lane == 0) {
             tma_prefetch_desc(&p.b_map);
             tma_prefetch_desc(&p.out_map);
@@ -75,15 +83,15 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
                 mbar_init(&full_bar[s], 128);
                 mbar_init(&empty_bar[s], 1);
             }
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < kC3AccStages; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
-                mbar_init(&tmem_empty_bar[s], 4);
+                mbar_init(&tmem_empty_bar[s], kC3EpiWarps);
             }
             mbar_init(b_full_bar, 1);
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc<128>(tmem_ptr_s);
+        tmem_alloc<kC3AccStages * 64>(tmem_ptr_s);
     }
     if (IN_FMT == B2R_IN_U8_NHWC) {
         for (int i = threadIdx.x; i < 768; i += kC3Threads) {
@@ -99,9 +107,10 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
 
-    if (warp_idx < 4) {
+    if (warp_idx < kC3ProducerWarps) {
         // ===================================== im2col producers =====================================
-        const int r = threadIdx.x;            // tile row == pixel (h = r / 16, w = r % 16)
+        const int group = warp_idx >> 2;      // 0 / 1: this group builds tile iterations group, group + 2, ...
+        const int r = threadIdx.x & 127;      // tile row == pixel (h = r / 16, w = r % 16)
         const int ph = r >> 4, pw = r & 15;
         uint32_t cur[27], nxt[27];
 
@@ -135,24 +144,34 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
             }
         };
 
-        int stage = 0;
-        uint32_t phase = 0;
-        int tile = blockIdx.x;
-        if (tile < total_tiles) gather(tile, cur);
-        for (; tile < total_tiles; tile += gridDim.x) {
-            const int next = tile + gridDim.x;
-            if (next < total_tiles) gather(next, nxt);   // prefetch: these loads complete while the row is built
+        const long stride = 2L * gridDim.x;
+        long tile = (long)blockIdx.x + (long)group * gridDim.x;
+        int it = group;
+        if (tile < total_tiles) gather((int)tile, cur);
+        for (; tile < total_tiles; tile += stride, it += 2) {
+            const long next = tile + stride;
+            if (next < total_tiles) gather((int)next, nxt);   // prefetch: these loads complete while the row is built
             uint32_t wrd[32];
+            const uint32_t lut_addr = smem_u32(lut);
 #pragma unroll
             for (int i = 0; i < 27; ++i) {
-                if (IN_FMT == B2R_IN_U8_NHWC)
-                    wrd[i] = (cur[i] & 0x100u) ? 0u : lut[(i % 3) * 256 + cur[i]];
-                else
+                if (IN_FMT == B2R_IN_U8_NHWC) {
+                    // explicit ld.shared (a generic pointer into shared memory would compile to LD.E); entry 256 of
+                    // each channel's table row is not used: padding is resolved by the select below
+                    uint32_t e;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(e) : "r"(lut_addr + (uint32_t(i % 3) * 256u + (cur[i] & 0xFFu)) * 4u));
+                    wrd[i] = (cur[i] & 0x100u) ? 0u : e;
+                } else {
                     wrd[i] = split_hi_lo(__uint_as_float(cur[i]));
+                }
             }
 #pragma unroll
             for (int i = 27; i < 32; ++i) wrd[i] = 0u;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            const int stage = it % kC3Stages;
+            const uint32_t phase = uint32_t(it / kC3Stages) & 1u;
+            if (r == 0) C3_STAMP(it, 0);
+            mbar_wait_warp(&empty_bar[stage], phase ^ 1);
+            if (r == 0) C3_STAMP(it, 1);
             const uint32_t row_addr = smem_u32(a_st + stage * 16384) + uint32_t(r * 128);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -163,14 +182,11 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
             }
             fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
             mbar_arrive(&full_bar[stage]);
-            if (++stage == kC3Stages) {
-                stage = 0;
-                phase ^= 1;
-            }
+            if (r == 0) C3_STAMP(it, 2);
 #pragma unroll
             for (int i = 0; i < 27; ++i) cur[i] = nxt[i];
         }
-    } else if (warp_idx == 4) {
+    } else if (warp_idx == kC3ProducerWarps) {
         // ===================================== weight load + MMA issuer =====================================
         if (lane == 0) {
             mbar_arrive_expect_tx(b_full_bar, 8192);
@@ -182,10 +198,12 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
+                C3_STAMP(it, 3);
                 const uint64_t adesc = make_sdesc_sw128(smem_u32(a_st + stage * 16384), 1024);
                 const uint32_t tmem_d = tmem_base + uint32_t(acc * 64);
 #pragma unroll
@@ -197,58 +215,70 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
                     stage = 0;
                     phase ^= 1;
                 }
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                if (++acc == kC3AccStages) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
             }
         }
     } else {
         // ===================================== epilogue =====================================
         const int quarter = warp_idx & 3;
+        const int half = (warp_idx - (kC3ProducerWarps + 1)) >> 2;   // channels half*32 .. half*32+31
         const int row = quarter * 32 + lane;
-        const bool leader = (warp_idx == 5 && lane == 0);
+        const bool leader = (warp_idx == kC3ProducerWarps + 1 && lane == 0);
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+        float b32[32];
+        lds_bias32(bias_s + half * 32, b32);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int n0 = tile / tiles_per_img;
             const int t = tile - n0 * tiles_per_img;
             const int w0 = (t % p.tiles_w) * 16;
             const int h0 = (t / p.tiles_w) * 8;
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            mbar_wait_warp(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * 64), v0);
-            tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * 64 + 32), v1);
+            if (leader) C3_STAMP(it, 4);
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * 64 + half * 32), v);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (leader) C3_STAMP(it, 5);
             if (leader) tma_store_wait_read<0>();   // previous tile's store has finished reading the staging tile
-            named_barrier_sync(1, kEpiThreadsC);
-            epilogue_store_half(v0, bias_s, p.act, p.slope, sfull, row, 0);
-            epilogue_store_half(v1, bias_s + 32, p.act, p.slope, sfull, row, 1);
+            named_barrier_sync(1, kC3EpiWarps * 32);
+            if (leader) C3_STAMP(it, 6);
+            epilogue_store_half(v, b32, p.act, p.slope, sfull, row, half);
             fence_proxy_async_smem();
-            named_barrier_sync(1, kEpiThreadsC);
+            named_barrier_sync(1, kC3EpiWarps * 32);
             if (leader) {
                 tma_store_4d(&p.out_map, sfull, 0, w0, h0, n0);
                 tma_store_commit();
+                C3_STAMP(it, 7);
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (++acc == kC3AccStages) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
         }
         if (leader) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp_idx == 4) {
+    if (warp_idx == kC3ProducerWarps) {
         tc_fence_after();
         __syncwarp();
-        tmem_dealloc<128>(tmem_base);
+        tmem_dealloc<kC3AccStages * 64>(tmem_base);
     }
 }
 
 }  // namespace b2r
+
+extern "C" void b2r_debug_timeline(int64_t* device_buf) { b2r::g_c3_dbg = reinterpret_cast<long long*>(device_buf); }
 
 extern "C" int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host, const float* std_host,
                               const void* weights_packed, const float* bias, int act, float slope, void* out, int N,
@@ -278,6 +308,7 @@ extern "C" int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host
         if (rc) return rc;
     }
     P.in = in;
+    P.dbg = g_c3_dbg;
     P.bias = bias;
     P.normalize = mean_host != nullptr;
     for (int c = 0; c < 3; ++c) {

@@ -54,11 +54,12 @@ size_t conv_w3_smem_bytes(int num_ksteps, int ring_slots);
 int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream);
 
 #ifdef __CUDACC__
-__device__ __forceinline__ float apply_act(float x, int act, float slope) {
-    if (act == B2R_ACT_RELU) return fmaxf(x, 0.f);
-    if (act == B2R_ACT_PRELU) return x >= 0.f ? x : x * slope;
-    return x;
+// All three activations are y = max(x, 0) + ns * min(x, 0) with ns = 0 (ReLU), slope (PReLU), 1 (none): branch-free and
+// exact in each case (one of the two terms is always a signed zero).
+__device__ __forceinline__ float act_neg_slope(int act, float slope) {
+    return act == B2R_ACT_RELU ? 0.f : (act == B2R_ACT_PRELU ? slope : 1.f);
 }
+__device__ __forceinline__ float apply_act_ns(float x, float ns) { return fmaf(ns, fminf(x, 0.f), fmaxf(x, 0.f)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -74,16 +75,28 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 
 // 32 fp32 accumulator columns of this thread's pixel row -> +bias, activation, bf16 -> four 16-byte chunks of the
 // 128-byte staging row, written with the 128B TMA swizzle (chunk index XOR row & 7).
-__device__ __forceinline__ void epilogue_store_half(const uint32_t (&v)[32], const float* bias32, int act, float slope,
-                                                    uint8_t* sfull, int row, int half) {
+// 32 bias values from shared memory into registers with explicit ld.shared (a `const float*` into shared memory is a
+// GENERIC pointer: the compiler emits LD.E through the L1TEX path, ~10x the latency of LDS; profiles/r01_c3_epilogue.md)
+__device__ __forceinline__ void lds_bias32(const float* bias_smem, float (&b)[32]) {
+    const uint32_t a = smem_u32(bias_smem);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(b[4 * i]), "=f"(b[4 * i + 1]), "=f"(b[4 * i + 2]), "=f"(b[4 * i + 3])
+                     : "r"(a + 16 * i));
+}
+
+__device__ __forceinline__ void epilogue_store_half(const uint32_t (&v)[32], const float (&bias32)[32], int act,
+                                                    float slope, uint8_t* sfull, int row, int half) {
+    const float ns = act_neg_slope(act, slope);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint32_t o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int j = q * 8 + e * 2;
-            const float x0 = apply_act(__uint_as_float(v[j]) + bias32[j], act, slope);
-            const float x1 = apply_act(__uint_as_float(v[j + 1]) + bias32[j + 1], act, slope);
+            const float x0 = apply_act_ns(__uint_as_float(v[j]) + bias32[j], ns);
+            const float x1 = apply_act_ns(__uint_as_float(v[j + 1]) + bias32[j + 1], ns);
             o[e] = pack_bf16x2(x0, x1);
         }
         const int jj = half * 4 + q;

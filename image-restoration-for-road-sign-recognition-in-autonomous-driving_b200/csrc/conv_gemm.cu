@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             // bias of this n-tile -> smem (previous tile's readers are past their last named barrier)
             for (int i = epi_tid; i < BLOCK_N; i += kEpiThreads) bias_s[i] = p.bias[n_tile * BLOCK_N + i];
 
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            mbar_wait_warp(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
 
 #pragma unroll 1
@@ -217,7 +217,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * BLOCK_N + c * 64 + half * 32), v);
                     tmem_ld_wait();
-                    epilogue_store_half(v, bias_s + c * 64 + half * 32, p.act, p.slope, sfull, row, half);
+                    float b32[32];
+                    lds_bias32(bias_s + c * 64 + half * 32, b32);
+                    epilogue_store_half(v, b32, p.act, p.slope, sfull, row, half);
                 }
                 if (c == BLOCK_N / 64 - 1) {
                     // all of this warp's TMEM reads of the accumulator are done -> hand it back to the MMA warp

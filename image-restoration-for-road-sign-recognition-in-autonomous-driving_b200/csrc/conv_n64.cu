@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kN64Threads, 1) conv_n64_kernel(const __grid_c
             const int w0 = (t % p.tiles_w) * p.tile_w;
             const int h0 = (t / p.tiles_w) * p.tile_h;
 
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            mbar_wait_warp(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             if (epi_tid == 0) tma_store_wait_read<0>();  // single staging buffer: previous tile's store has read it
             named_barrier_sync(1, kEpiThreadsC);
@@ -181,7 +181,9 @@ __global__ void __launch_bounds__(kN64Threads, 1) conv_n64_kernel(const __grid_c
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * 64 + half * 32), v);
                 tmem_ld_wait();
-                epilogue_store_half(v, bias_s + half * 32, p.act, p.slope, sfull, row, half);
+                float b32[32];
+                lds_bias32(bias_s + half * 32, b32);
+                epilogue_store_half(v, b32, p.act, p.slope, sfull, row, half);
             }
             tc_fence_before();
             __syncwarp();

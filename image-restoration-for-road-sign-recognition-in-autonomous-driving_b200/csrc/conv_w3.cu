@@ -172,6 +172,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         const int srow = hh * 14 + cc;             // row of the 8 x 14 staging tile
         const bool valid = cc < 14;
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+        float b32[32];                             // this warp's 32 output channels never change: bias lives in registers
+        lds_bias32(bias_s + half * 32, b32);
         int acc = 0;
         uint32_t acc_phase = 0;
         int iter = 0;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             const int w0 = (t % p.tiles_w) * 14;
             const int h0 = (t / p.tiles_w) * 8;
 
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            mbar_wait_warp(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             if (epi_tid == 0) B2R_STAMP(iter, 3);
             if (epi_tid == 0) tma_store_wait_read<0>();
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                     const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[j]), 2);
                     d0[j] = __float_as_uint((__uint_as_float(d0[j]) + a1) + a2);
                 }
-                if (valid) epilogue_store_half(d0, bias_s + half * 32, p.act, p.slope, sfull, srow, half);
+                if (valid) epilogue_store_half(d0, b32, p.act, p.slope, sfull, srow, half);
             }
             if (epi_tid == 0) B2R_STAMP(iter, 5);
             fence_proxy_async_smem();

@@ -64,6 +64,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~`ns` nanoseconds
+// pass, instead of re-polling shared memory every few cycles.  Polling matters: mbarrier probes are shared-memory
+// accesses, and hundreds of spinning threads measurably starve the tensor core's operand reads
+// (profiles/r01_c3_timeline.md).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+
 // Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.
 #ifndef B2R_WAIT_TIMEOUT_CYCLES
 #define B2R_WAIT_TIMEOUT_CYCLES (4000000000LL)
@@ -71,12 +89,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
         if (clock64() - t0 > B2R_WAIT_TIMEOUT_CYCLES) {
             printf("b2r: mbarrier wait timeout block %d thread %d bar %u parity %u\n", (int)blockIdx.x,
                    (int)threadIdx.x, smem_u32(bar), parity);
             __trap();
         }
+    }
+}
+
+// Whole-warp wait: lane 0 does the waiting, the other 31 lanes park at the warp barrier and then observe the
+// completed phase with a single (non-spinning) probe each, which also gives every lane its own acquire.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
+    while (!mbar_try_wait(bar, parity)) {
     }
 }
 

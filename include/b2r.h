@@ -38,6 +38,10 @@ extern "C" {
 int b2r_version(void);
 const char* b2r_last_error(void);
 
+/* Debug facility (tools/role_timeline.py): device buffer int64[B2R_DBG_TILES][8] in which CTA 0 of the NEXT
+ * b2r_conv3x3_c3 launches records clock64() stamps per warp role; NULL switches it off (the default). */
+void b2r_debug_timeline(int64_t* device_buf);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * (1) Fused compound degradation: motion blur (+) fog (+) AWGN, u8 NHWC in -> u8 NHWC out, one launch.
  *
