@@ -8,19 +8,27 @@
 //   quant : np.clip(x*255, 0, 255).astype(np.uint8) — truncation         (16:37, 14:53, 14:64, 15:111)
 // chain(v) = quant(noise(fog(v/255)));  script 16 computes chain(blur(in)), scripts 14/15 compute blur(chain(in)).
 // (u8 -> f32/255 -> *255 -> truncate is the identity on 0..255, so the reference's intermediate re-quantisations
-//  that are not listed here are no-ops; tests/test_oracle_degrade.py checks that claim against the reference.)
+//  that are not listed here are no-ops; tests/test_oracle_degrade.py checks that claim.)
 //
-// Layout: one CTA = 32 image rows x full width of one image.  The pre-blur image (raw input for order 0, chain(in)
-// for order 1) is staged in shared memory with an 8-pixel REFLECT_101 halo; taps sit in shared memory; every
-// thread then produces whole pixels.  Noise is counter-based (Philox4x32-10 keyed by seed, counter = pixel index,
-// global image index) so results do not depend on tiling, launch shape or the number of GPUs.
+// Structure (v2).  One CTA = 16 image rows x full width of one image.
+//   stage 1  the pre-blur image (raw input, or chain(input) for the scripts-14/15 order) is staged in shared memory
+//            as three PLANAR fp32 planes with exactly the halo this image's kernel needs (REFLECT_101), so the u8->f32
+//            conversion is paid once per staged pixel instead of once per tap;
+//   stage 2  a work item is 4 consecutive pixels x 3 channels (12 accumulators).  For every kernel row that has
+//            non-zero taps the item slides a 4-wide register window along the row: ONE shared-memory load per plane
+//            per tap feeds 12 FMAs.  Taps inside a row's [first, last] non-zero span are applied in order, zeros
+//            included: fma(0, x, acc) == acc, so the result is bit-identical to OpenCV's "non-zero taps, row-major"
+//            engine (degree <= 11; larger kernels go through OpenCV's DFT path, see tests/test_degrade_gpu.py);
+//   stage 3  round-half-even to u8, then chain() for the script-16 order, and one aligned 12-byte store per item.
+// Noise: one Philox4x32-10 call per pixel keyed by (seed; pixel index, global image index) -> Box-Muller with the
+// hardware log2/sin/cos units -> three normals; fp32 chain.  When the caller injects the reference's own noise tensor
+// (parity path) the add is done in float64 exactly as NumPy promotes it.
 #include "b2r_internal.h"
 
 namespace b2r {
 
-constexpr int kDegRows = 32;
-constexpr int kDegHalo = 8;
-constexpr int kDegThreads = 256;
+constexpr int kDegRows = 16;
+constexpr int kDegThreads = 224;
 
 struct DegradeParams {
     const uint8_t* in;
@@ -62,13 +70,13 @@ __device__ __forceinline__ void pixel_normals(uint64_t seed, uint64_t image, uin
     const float k = 2.3283064365386963e-10f;  // 2^-32
     const float u0 = fmaf(float(r.x), k, 0.5f * k), u1 = fmaf(float(r.y), k, 0.5f * k);
     const float u2 = fmaf(float(r.z), k, 0.5f * k), u3 = fmaf(float(r.w), k, 0.5f * k);
-    const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+    // sqrt(-2 ln u) = sqrt(-2 ln2 * log2 u); sin/cos(2 pi u) on the SFU (abs error ~4e-7: far below one u8 LSB / sigma)
+    const float ra = sqrtf(-1.3862943611198906f * __log2f(u0)), rb = sqrtf(-1.3862943611198906f * __log2f(u2));
     float s, c;
-    sincospif(2.0f * u1, &s, &c);
+    __sincosf(6.283185307179586f * u1, &s, &c);
     z[0] = ra * s;
     z[1] = ra * c;
-    sincospif(2.0f * u3, &s, &c);
-    z[2] = rb * s;
+    z[2] = rb * __sinf(6.283185307179586f * u3);
 }
 
 struct ImgParams {
@@ -78,51 +86,65 @@ struct ImgParams {
     const double* noise;  // injected noise for this image or nullptr
 };
 
-// chain(v): quant(noise(fog(v / 255))) for the 3 channels of the pixel at linear index `pix`
-__device__ __forceinline__ void chain3(const ImgParams& ip, uint32_t pix, const uint8_t (&v)[3], uint8_t (&q)[3]) {
+// chain(v): quant(noise(fog(v / 255))) for the 3 channels of the pixel at linear index `pix`.
+// `unit` = shared-memory table of float(u)/255 (IEEE division, as NumPy computes `astype(float32) / 255.0`).
+__device__ __forceinline__ void chain3(const ImgParams& ip, const float* unit, uint32_t pix, const int (&v)[3],
+                                       int (&q)[3]) {
     float x[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        x[c] = __fdiv_rn(float(v[c]), 255.0f);
+        x[c] = unit[v[c]];
         if (ip.fog_on) x[c] = __fadd_rn(__fmul_rn(x[c], ip.t), ip.add);  // two roundings, like NumPy (no FMA)
     }
-    if (ip.noise_on) {
-        double nz[3];
-        if (ip.noise) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) nz[c] = ip.noise[size_t(pix) * 3 + c];
-        } else {
-            float z[3];
-            pixel_normals(ip.seed, ip.image, pix, z);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) nz[c] = double(ip.sigma * z[c]);
-        }
+    if (ip.noise_on && ip.noise != nullptr) {
+        // parity path: float32 image + float64 noise -> float64, exactly as NumPy promotes
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            double y = double(x[c]) + nz[c];  // float32 image + float64 noise -> float64
+            double y = double(x[c]) + ip.noise[size_t(pix) * 3 + c];
             if (ip.clip_after) y = fmin(fmax(y, 0.0), 1.0);
             y = fmin(fmax(y * 255.0, 0.0), 255.0);
-            q[c] = static_cast<uint8_t>(y);  // truncation
+            q[c] = int(y);  // truncation
         }
-    } else {
+        return;
+    }
+    if (ip.noise_on) {
+        float z[3];
+        pixel_normals(ip.seed, ip.image, pix, z);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float y = x[c];
-            if (ip.clip_after) y = fminf(fmaxf(y, 0.f), 1.f);
-            y = fminf(fmaxf(__fmul_rn(y, 255.0f), 0.f), 255.f);
-            q[c] = static_cast<uint8_t>(y);
-        }
+        for (int c = 0; c < 3; ++c) x[c] = fmaf(ip.sigma, z[c], x[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float y = x[c];
+        if (ip.clip_after) y = fminf(fmaxf(y, 0.f), 1.f);
+        y = fminf(fmaxf(__fmul_rn(y, 255.0f), 0.f), 255.f);
+        q[c] = int(y);
     }
 }
 
+// Planar staging layout.  Work items own 4 consecutive pixels, so lane i of a warp reads staged column 4*i + m for a
+// warp-uniform offset m: with a plain row-major plane that is a 16-byte lane stride = 4-way bank conflict on every
+// load.  Columns are therefore de-interleaved by 4: column col lives at  (col & 3) * quarter + (col >> 2)  within its
+// row, which makes those loads unit-stride; `quarter` (= pitch / 4) is chosen = 8 (mod 32) so that the staging
+// writes (consecutive lanes = consecutive columns) are conflict-free as well.
+__device__ __forceinline__ int deint(int col, int quarter) { return (col & 3) * quarter + (col >> 2); }
+
+static __host__ __device__ int degrade_quarter(int W) {
+    int q = (W + (B2R_MAX_BLUR - 1) + 8 + 3) / 4;   // staged columns + 8 columns of slack for the unrolled window
+    while ((q & 31) != 8) ++q;
+    return q;
+}
+
 __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParams P) {
-    extern __shared__ uint8_t s_tile[];  // [(rows + 2*halo)][pitch]
-    __shared__ float s_taps[B2R_MAX_BLUR * B2R_MAX_BLUR];
+    extern __shared__ __align__(16) float s_planes[];  // [3][srows][pitch], columns de-interleaved by 4
+    __shared__ float s_taps[B2R_MAX_BLUR][B2R_MAX_BLUR + 5];  // zero padded: rows are walked in steps of 4 taps
+    __shared__ float s_unit[256];
+    __shared__ int s_seg[B2R_MAX_BLUR][2];  // per kernel row: first non-zero tap / number of 4-tap steps (0: empty row)
 
     const int n = blockIdx.y;
     const int r0 = blockIdx.x * kDegRows;
-    const int rows = min(kDegRows, P.H - r0);
     const int H = P.H, W = P.W;
+    const int rows = min(kDegRows, H - r0);
     const int tid = threadIdx.x;
 
     int d = P.ksize ? P.ksize[n] : 0;
@@ -140,74 +162,231 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
 
     const uint8_t* img_in = P.in + size_t(n) * H * W * 3;
     uint8_t* img_out = P.out + size_t(n) * H * W * 3;
+    const bool rows_aligned = ((W * 3) & 3) == 0 && ((reinterpret_cast<uintptr_t>(img_in) | reinterpret_cast<uintptr_t>(img_out)) & 3) == 0;
+    const int groups = (W + 3) >> 2;
+
+    for (int i = tid; i < 256; i += kDegThreads) s_unit[i] = __fdiv_rn(float(i), 255.0f);
 
     if (d == 0) {
-        // no blur for this image: pure per-pixel chain, no staging
-        for (int i = tid; i < rows * W; i += kDegThreads) {
-            const uint32_t pix = uint32_t(r0 * W + i);
-            uint8_t v[3], q[3];
+        // no blur for this image: pure per-pixel chain on items of 4 pixels (three aligned 32-bit loads / stores)
+        __syncthreads();
+        for (int item = tid; item < rows * groups; item += kDegThreads) {
+            const int y = item / groups;
+            const int x0 = (item - y * groups) << 2;
+            const size_t off = (size_t(r0 + y) * W + x0) * 3;
+            const bool fast = rows_aligned && x0 + 4 <= W;
+            uint32_t bytes[3] = {0u, 0u, 0u};
+            if (fast) {
+                const uint32_t* s32 = reinterpret_cast<const uint32_t*>(img_in + off);
+                bytes[0] = __ldg(s32);
+                bytes[1] = __ldg(s32 + 1);
+                bytes[2] = __ldg(s32 + 2);
+            } else {
+                const int nb = min(4, W - x0) * 3;
+                for (int b = 0; b < nb; ++b) bytes[b >> 2] |= uint32_t(img_in[off + b]) << (8 * (b & 3));
+            }
+            uint32_t outb[3] = {0u, 0u, 0u};
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[c] = img_in[size_t(pix) * 3 + c];
-            chain3(ip, pix, v, q);
+            for (int j = 0; j < 4; ++j) {
+                int v[3], q[3] = {0, 0, 0};
 #pragma unroll
-            for (int c = 0; c < 3; ++c) img_out[size_t(pix) * 3 + c] = q[c];
+                for (int c = 0; c < 3; ++c) {
+                    const int b = 3 * j + c;
+                    v[c] = int((bytes[b >> 2] >> (8 * (b & 3))) & 0xFFu);
+                }
+                if (x0 + j < W) chain3(ip, s_unit, uint32_t((r0 + y) * W + x0 + j), v, q);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int b = 3 * j + c;
+                    outb[b >> 2] |= uint32_t(q[c]) << (8 * (b & 3));
+                }
+            }
+            if (fast) {
+                uint32_t* d32 = reinterpret_cast<uint32_t*>(img_out + off);
+                d32[0] = outb[0];
+                d32[1] = outb[1];
+                d32[2] = outb[2];
+            } else {
+                const int nb = min(4, W - x0) * 3;
+                for (int b = 0; b < nb; ++b) img_out[off + b] = uint8_t(outb[b >> 2] >> (8 * (b & 3)));
+            }
         }
         return;
     }
 
-    for (int i = tid; i < d * d; i += kDegThreads) s_taps[i] = P.taps[size_t(n) * (B2R_MAX_BLUR * B2R_MAX_BLUR) + i];
+    for (int i = tid; i < B2R_MAX_BLUR * (B2R_MAX_BLUR + 5); i += kDegThreads) {
+        const int ky = i / (B2R_MAX_BLUR + 5), kx = i - ky * (B2R_MAX_BLUR + 5);
+        s_taps[ky][kx] = (ky < d && kx < d) ? P.taps[size_t(n) * (B2R_MAX_BLUR * B2R_MAX_BLUR) + ky * d + kx] : 0.f;
+    }
+    if (tid < d) {
+        const float* tr = P.taps + size_t(n) * (B2R_MAX_BLUR * B2R_MAX_BLUR) + tid * d;
+        int first = d, last = -1;
+        for (int k = 0; k < d; ++k)
+            if (tr[k] != 0.f) {
+                if (first == d) first = k;
+                last = k;
+            }
+        s_seg[tid][0] = first;
+        s_seg[tid][1] = last < first ? 0 : (last - first + 4) >> 2;
+    }
 
-    const int SW = W + 2 * kDegHalo;
-    const int pitch = SW * 3;
-    const int srows = rows + 2 * kDegHalo;
+    // halo of THIS kernel: cv2 anchor = d/2, so taps reach a pixels up/left and d-1-a pixels down/right
+    const int a = d / 2;
+    const int hb = d - 1 - a;
+    const int srows = rows + a + hb;
+    const int quarter = degrade_quarter(W);
+    const int pitch = quarter * 4;
+    const int plane = srows * pitch;
     const bool chain_first = P.order == B2R_ORDER_FOG_NOISE_BLUR;
-    for (int i = tid; i < srows * SW; i += kDegThreads) {
-        const int sy = i / SW, sx = i - sy * SW;
-        const int h = reflect101(r0 - kDegHalo + sy, H);
-        const int w = reflect101(sx - kDegHalo, W);
-        const uint32_t pix = uint32_t(h * W + w);
-        uint8_t v[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = img_in[size_t(pix) * 3 + c];
-        if (chain_first) {
-            uint8_t q[3];
-            chain3(ip, pix, v, q);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) v[c] = q[c];
+    __syncthreads();  // s_unit
+
+    const int scols = W + a + hb;
+    // (a) interior columns: items of 4 pixels = three aligned, coalesced 32-bit loads (the staging loop is where the
+    //     kernel meets HBM latency, so it is unrolled to keep several loads per thread in flight)
+#pragma unroll 2
+    for (int it = tid; it < srows * groups; it += kDegThreads) {
+        const int sy = it / groups;
+        const int g = it - sy * groups;
+        const int x0 = g << 2;
+        const int h = reflect101(r0 - a + sy, H);
+        const size_t off = (size_t(h) * W + x0) * 3;
+        uint32_t bytes[3] = {0u, 0u, 0u};
+        if (rows_aligned && x0 + 4 <= W) {
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(img_in + off);
+            bytes[0] = __ldg(s32);
+            bytes[1] = __ldg(s32 + 1);
+            bytes[2] = __ldg(s32 + 2);
+        } else {
+            const int nb = min(4, W - x0) * 3;
+            for (int b2 = 0; b2 < nb; ++b2) bytes[b2 >> 2] |= uint32_t(img_in[off + b2]) << (8 * (b2 & 3));
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) s_tile[sy * pitch + sx * 3 + c] = v[c];
+        for (int j = 0; j < 4; ++j) {
+            if (x0 + j < W) {
+                int v[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int b2 = 3 * j + c;
+                    v[c] = int((bytes[b2 >> 2] >> (8 * (b2 & 3))) & 0xFFu);
+                }
+                if (chain_first) {
+                    int q[3];
+                    chain3(ip, s_unit, uint32_t(h * W + x0 + j), v, q);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[c] = q[c];
+                }
+                const int o = sy * pitch + deint(a + x0 + j, quarter);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) s_planes[c * plane + o] = float(v[c]);
+            }
+        }
+    }
+    // (b) the few halo columns left / right of the image (REFLECT_101) and the zero slack columns
+    const int hc = pitch - W;
+    for (int it = tid; it < srows * hc; it += kDegThreads) {
+        const int sy = it / hc;
+        const int k = it - sy * hc;
+        const int sx = k < a ? k : W + k;
+        float f[3] = {0.f, 0.f, 0.f};  // slack columns are zero so that padded (zero) taps never meet a NaN
+        if (sx < scols) {
+            const int h = reflect101(r0 - a + sy, H);
+            const int w = reflect101(sx - a, W);
+            const uint32_t pix = uint32_t(h * W + w);
+            int v[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = img_in[size_t(pix) * 3 + c];
+            if (chain_first) {
+                int q[3];
+                chain3(ip, s_unit, pix, v, q);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = q[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[c] = float(v[c]);
+        }
+        const int o = sy * pitch + deint(sx, quarter);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s_planes[c * plane + o] = f[c];
     }
     __syncthreads();
 
-    const int a = d / 2;  // cv2 default anchor (-1,-1) -> kernel centre d/2
-    for (int i = tid; i < rows * W; i += kDegThreads) {
-        const int y = i / W, x = i - y * W;
-        float acc[3] = {0.f, 0.f, 0.f};
+    for (int item = tid; item < rows * groups; item += kDegThreads) {
+        const int y = item / groups;
+        const int g = item - y * groups;   // staged column of (pixel 4g + j, tap kx) = 4g + j + kx
+        const int x0 = g << 2;
+        float acc[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
         for (int ky = 0; ky < d; ++ky) {
-            const uint8_t* srow = s_tile + (y + kDegHalo + ky - a) * pitch + (x + kDegHalo - a) * 3;
-            for (int kx = 0; kx < d; ++kx) {
-                const float k = s_taps[ky * d + kx];
-                if (k != 0.f) {  // OpenCV's 2-D filter engine visits non-zero taps only, in row-major order
-                    acc[0] = fmaf(k, float(srow[kx * 3 + 0]), acc[0]);
-                    acc[1] = fmaf(k, float(srow[kx * 3 + 1]), acc[1]);
-                    acc[2] = fmaf(k, float(srow[kx * 3 + 2]), acc[2]);
-                }
+            const int k0 = s_seg[ky][0], steps = s_seg[ky][1];
+            if (steps == 0) continue;                       // uniform: the whole CTA works on one image
+            const float* rowp = s_planes + (y + ky) * pitch + g;
+            const float* tp = &s_taps[ky][k0];
+            // window registers hold staged columns 4g + m .. 4g + m + 3; column 4g + m sits at (m & 3)*quarter + (m >> 2)
+            float w0[3], w1[3], w2[3], w3[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                w0[c] = rowp[c * plane + deint(k0, quarter)];
+                w1[c] = rowp[c * plane + deint(k0 + 1, quarter)];
+                w2[c] = rowp[c * plane + deint(k0 + 2, quarter)];
+            }
+            int m = k0 + 3;
+#define B2R_DEG_STEP(A, B, C, D_)                                        \
+    {                                                                    \
+        const float k = *tp++;                                           \
+        const int o = deint(m, quarter);                                 \
+        ++m;                                                             \
+        _Pragma("unroll") for (int c = 0; c < 3; ++c) {                  \
+            D_[c] = rowp[c * plane + o];                                 \
+            acc[c][0] = fmaf(k, A[c], acc[c][0]);                        \
+            acc[c][1] = fmaf(k, B[c], acc[c][1]);                        \
+            acc[c][2] = fmaf(k, C[c], acc[c][2]);                        \
+            acc[c][3] = fmaf(k, D_[c], acc[c][3]);                       \
+        }                                                                \
+    }
+            for (int s4 = 0; s4 < steps; ++s4) {
+                B2R_DEG_STEP(w0, w1, w2, w3)
+                B2R_DEG_STEP(w1, w2, w3, w0)
+                B2R_DEG_STEP(w2, w3, w0, w1)
+                B2R_DEG_STEP(w3, w0, w1, w2)
+            }
+#undef B2R_DEG_STEP
+        }
+        uint32_t bytes[3] = {0u, 0u, 0u};  // 12 output bytes: pixel j channel c -> byte 3*j + c
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int v[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = min(max(__float2int_rn(acc[c][j]), 0), 255);
+            if (!chain_first && x0 + j < W) {
+                int q[3];
+                chain3(ip, s_unit, uint32_t((r0 + y) * W + x0 + j), v, q);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = q[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int b = 3 * j + c;
+                bytes[b >> 2] |= uint32_t(v[c]) << (8 * (b & 3));
             }
         }
-        uint8_t v[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = static_cast<uint8_t>(min(max(__float2int_rn(acc[c]), 0), 255));
-        const uint32_t pix = uint32_t((r0 + y) * W + x);
-        if (!chain_first) {
-            uint8_t q[3];
-            chain3(ip, pix, v, q);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) v[c] = q[c];
+        uint8_t* dst = img_out + (size_t(r0 + y) * W + x0) * 3;
+        if (rows_aligned && x0 + 4 <= W) {
+            uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+            d32[0] = bytes[0];
+            d32[1] = bytes[1];
+            d32[2] = bytes[2];
+        } else {
+            const int nb = min(4, W - x0) * 3;
+            for (int b = 0; b < nb; ++b) dst[b] = uint8_t(bytes[b >> 2] >> (8 * (b & 3)));
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) img_out[size_t(pix) * 3 + c] = v[c];
     }
+}
+
+static size_t degrade_smem_bytes(int W) {
+    return size_t(3) * (kDegRows + B2R_MAX_BLUR - 1) * degrade_quarter(W) * 4 * sizeof(float);
 }
 
 }  // namespace b2r
@@ -226,8 +405,7 @@ extern "C" int b2r_degrade(const uint8_t* in, uint8_t* out, int N, int H, int W,
     B2R_REQUIRE((ksize == nullptr) == (taps == nullptr), "ksize and taps must both be given or both be null");
     B2R_REQUIRE(fog_on == nullptr || (fog_t && fog_add), "fog_on given without fog_t / fog_add");
     B2R_REQUIRE(!(noise && !sigma), "injected noise needs sigma[] as the per-image on/off switch");
-    const int pitch = (W + 2 * kDegHalo) * 3;
-    const size_t smem = size_t(kDegRows + 2 * kDegHalo) * pitch;
+    const size_t smem = ksize ? degrade_smem_bytes(W) : 0;
     B2R_REQUIRE(smem <= 200 * 1024, "W=%d too wide for the staged tile", W);
     static bool attr_set[64] = {false};
     int dev = 0;
