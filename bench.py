@@ -305,6 +305,10 @@ def run_ours(args):
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained"
     conv_tf = ksum["work"] / (ksum["ms"] * 1e-3) / 1e12
+    traffic = None
+    tj = ROOT / "profiles" / "r01_conv_traffic.json"      # dram bytes per launch of these kernels from one ncu capture
+    if tj.exists():
+        traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
     ips = B_ * world * args.steps / (total_ms / 1e3)
     gflop_img = GFLOP_PER_IMAGE_224[arch] + (GFLOP_PER_IMAGE_224["vgg16"] if classify else 0.0)
     line = {
@@ -319,9 +323,11 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM)",
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convs (conv_gemm_kernel<N>, conv_w3_kernel, conv_n64_kernel)",
                      "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
-                     "peak_source": peak_src, "traffic": None,
+                     "peak_source": peak_src, "traffic": traffic,
+                     "traffic_note": "dram__bytes_read+write per launch averaged over all tcgen05 conv launches of one "
+                                     "ncu capture (profiles/r01_launches_v5_summary.md), micro-batch 128",
                      "launches": ksum["launches"], "kernel_ms_per_step": ksum["ms"] / args.steps,
                      "share_of_step": ksum["ms"] / total_ms,
                      "pipeline_tflops": ips / world * gflop_img / 1e3 if hw == 224 else None},
