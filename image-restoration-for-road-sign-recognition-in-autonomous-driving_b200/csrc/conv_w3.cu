@@ -22,8 +22,9 @@
 
 namespace b2r {
 
-constexpr int kW3Threads = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
-constexpr int kW3EpiThreads = 256;
+constexpr int kW3EpiWarps = 16;         // four per TMEM lane quarter, 16 output channels each
+constexpr int kW3Threads = (2 + kW3EpiWarps) * 32;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+constexpr int kW3EpiThreads = kW3EpiWarps * 32;
 constexpr int kW3BStep = 192 * 128;      // weights of one k-step: 192 rows x 128 B
 constexpr int kW3Slot = 10 * 16 * 128;   // one halo box: (8 + 2) rows x 16 columns x 128 B
 constexpr int kW3Staging = 14336;        // 8 x 14 pixels x 128 B
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
-                mbar_init(&tmem_empty_bar[s], 8);
+                mbar_init(&tmem_empty_bar[s], kW3EpiWarps);
             }
             mbar_init(b_full_bar, 1);
             fence_mbar_init();
@@ -103,8 +104,12 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                     const int c0 = int((e >> 8) & 0xFFF) * 64;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (g == 0) B2R_STAMP(iter, 0);
-                    mbar_arrive_expect_tx(&full_bar[stage], kW3Slot);
-                    tma_load_4d(ring + stage * kW3Slot, &p.a_map[src], &full_bar[stage], c0, w0 - 1, h0 - 1, n0);
+                    if (p.dbg_flags & 4) {
+                        mbar_arrive(&full_bar[stage]);   // experiment: no A traffic at all
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], kW3Slot);
+                        tma_load_4d(ring + stage * kW3Slot, &p.a_map[src], &full_bar[stage], c0, w0 - 1, h0 - 1, n0);
+                    }
                     if (++stage == R) {
                         stage = 0;
                         phase ^= 1;
@@ -114,66 +119,94 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         }
     } else if (warp_idx == 1) {
         // ===================================== MMA issuer =====================================
-        if (lane == 0) {
-            mbar_wait(b_full_bar, 0);
+        // The whole warp runs this loop with warp-uniform control flow and ONE elected lane issues: descriptor
+        // arithmetic then stays on the uniform datapath (two adds per MMA).  It matters here because this warp shares
+        // its SM sub-partition's issue slots with four busy epilogue warps (profiles/r01_w3_timeline.md).
+        mbar_wait_warp(b_full_bar, 0);
+        tc_fence_after();
+        const uint64_t desc_hi = make_sdesc_sw128(0, 1024) & 0xFFFFFFFF00000000ull;   // SBO / version / swizzle bits
+        const uint32_t a_lo0 = ((smem_u32(ring) >> 4) & 0x3FFF) | (1u << 16);
+        const uint32_t b_lo0 = ((smem_u32(b_res) >> 4) & 0x3FFF) | (1u << 16);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            mbar_wait_warp(&tmem_empty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
-            const uint32_t b_base = smem_u32(b_res);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            int iter = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+            if (lane == 0) B2R_STAMP(iter, 1);
+            const uint32_t tmem_d = tmem_base + uint32_t(acc * 256);
+            uint32_t accum = 0;
+            for (int g = 0; g < p.num_groups; ++g) {
+                const uint32_t e = p.group[g];
+                const bool center = ((e >> 2) & 1) != 0;
+                const uint32_t b_lo = b_lo0 + (e >> 20) * uint32_t(kW3BStep >> 4);
+                mbar_wait_warp(&full_bar[stage], phase);
                 tc_fence_after();
-                B2R_STAMP(iter, 1);
-                const uint32_t tmem_d = tmem_base + uint32_t(acc * 256);
-                uint32_t first = 1;
-                for (int g = 0; g < p.num_groups; ++g) {
-                    const uint32_t e = p.group[g];
-                    const int center = (e >> 2) & 1;
-                    const int ks0 = int(e >> 20);
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(ring + stage * kW3Slot);
-                    const int nk = center ? 1 : 3;
-                    for (int t = 0; t < nk; ++t) {
-                        const int kh = center ? 1 : t;   // kernel row: A = buffer rows kh .. kh+7 (16 columns each)
-                        const uint64_t adesc = make_sdesc_sw128(sa + uint32_t(kh) * 2048u, 1024);
-                        const uint64_t bdesc = make_sdesc_sw128(b_base + uint32_t(ks0 + t) * kW3BStep, 1024);
+                const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(kW3Slot >> 4);
+                if (elect_one()) {
+                    if (p.dbg_flags & 8) {
+                        // experiment: no tensor work
+                    } else if (center) {
+                        // one k-step on kernel row 1: A = buffer rows 16 .. 143
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_bf16_ss(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, first ? 0u : 1u);
-                            first = 0;
+                            umma_bf16_ss(tmem_d, desc_hi | uint64_t(a_lo + 128u + 2u * k), desc_hi | uint64_t(b_lo + 2u * k),
+                                         kIdesc, accum);
+                            accum = 1;
+                        }
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {   // kernel row t: A = buffer rows 16 t .. 16 t + 127 (2048 B apart)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_bf16_ss(tmem_d, desc_hi | uint64_t(a_lo + 128u * t + 2u * k),
+                                             desc_hi | uint64_t(b_lo + uint32_t(kW3BStep >> 4) * t + 2u * k), kIdesc, accum);
+                                accum = 1;
+                            }
                         }
                     }
                     umma_commit(&empty_bar[stage]);
-                    if (++stage == R) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
                 }
-                umma_commit(&tmem_full_bar[acc]);
-                B2R_STAMP(iter, 2);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                __syncwarp();
+                accum = 1;
+                if (++stage == R) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
+            if (elect_one()) umma_commit(&tmem_full_bar[acc]);
+            __syncwarp();
+            if (lane == 0) B2R_STAMP(iter, 2);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
         }
     } else {
         // ===================================== epilogue =====================================
-        // Eight warps: warp w may touch TMEM lanes 32*(w%4).. only, so each lane quarter is shared by two warps that
-        // split the 64 output channels (half 0 / half 1): two warps per SM sub-partition hide each other's
-        // tcgen05.ld / shuffle latency (profiles/r01_w3_timeline.md: with four warps the drain paced the tile).
+        // Sixteen warps: warp w may touch TMEM lanes 32*(w%4).. only, so each lane quarter is shared by four warps that
+        // split the 64 output channels (16 each).  The epilogue costs ~9 instructions per output value (two shuffles
+        // and two adds for the kw shift, bias, activation, convert) and is latency-bound with few warps per SM
+        // sub-partition (profiles/r01_w3_timeline.md: 4 warps 1870 cycles, 8 warps 1180 cycles per tile).
         const int quarter = warp_idx & 3;
-        const int half = (warp_idx - 2) >> 2;
+        const int cq = (warp_idx - 2) >> 2;          // channels cq*16 .. cq*16+15
         const int epi_tid = (warp_idx - 2) * 32 + lane;
         const int hh = quarter * 2 + (lane >> 4);  // tile row of this lane's pixel
         const int cc = lane & 15;                  // buffer column; output column w = cc is valid for cc < 14
         const int srow = hh * 14 + cc;             // row of the 8 x 14 staging tile
         const bool valid = cc < 14;
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-        float b32[32];                             // this warp's 32 output channels never change: bias lives in registers
-        lds_bias32(bias_s + half * 32, b32);
+        float b16[16];                             // this warp's 16 output channels never change: bias lives in registers
+        {
+            const uint32_t ba = smem_u32(bias_s + cq * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(b16[4 * i]), "=f"(b16[4 * i + 1]), "=f"(b16[4 * i + 2]), "=f"(b16[4 * i + 3])
+                             : "r"(ba + 16 * i));
+        }
+        const bool relu_only = p.act == B2R_ACT_RELU;
+        const float ns = act_neg_slope(p.act, p.slope);
         int acc = 0;
         uint32_t acc_phase = 0;
         int iter = 0;
@@ -191,23 +224,46 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             if (epi_tid == 0) B2R_STAMP(iter, 4);
             const uint32_t tacc = tmem_base + lane_base + uint32_t(acc * 256);
             {
-                uint32_t d0[32], d1[32], d2[32];
-                tmem_ld_32x32(tacc + uint32_t(half * 32), d0);         // kw = 0 partial sums, channels half*32 ..
-                tmem_ld_32x32(tacc + uint32_t(64 + half * 32), d1);    // kw = 1
-                tmem_ld_32x32(tacc + uint32_t(128 + half * 32), d2);   // kw = 2
-                tmem_ld_wait();
+                uint32_t d0[16], d1[16], d2[16];
+                if (p.dbg_flags & 1) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) d0[j] = d1[j] = d2[j] = 0u;
+                } else {
+                    tmem_ld_32x16(tacc + uint32_t(cq * 16), d0);          // kw = 0 partial sums of this warp's channels
+                    tmem_ld_32x16(tacc + uint32_t(64 + cq * 16), d1);     // kw = 1
+                    tmem_ld_32x16(tacc + uint32_t(128 + cq * 16), d2);    // kw = 2
+                    tmem_ld_wait();
+                }
                 // the accumulator now lives in registers: hand the TMEM stage back to the MMA warp BEFORE the shift-add,
                 // activation and staging, so the next-but-one tile's MMAs overlap all of that
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                float x[16];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[j]), 1);
                     const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[j]), 2);
-                    d0[j] = __float_as_uint((__uint_as_float(d0[j]) + a1) + a2);
+                    x[j] = ((__uint_as_float(d0[j]) + a1) + a2) + b16[j];
                 }
-                if (valid) epilogue_store_half(d0, b32, p.act, p.slope, sfull, srow, half);
+                if (relu_only) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) x[j] = apply_act_ns(x[j], ns);
+                }
+                if (valid && !(p.dbg_flags & 2)) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const uint32_t o0 = pack_bf16x2(x[8 * q], x[8 * q + 1]), o1 = pack_bf16x2(x[8 * q + 2], x[8 * q + 3]);
+                        const uint32_t o2 = pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), o3 = pack_bf16x2(x[8 * q + 6], x[8 * q + 7]);
+                        const int jj = cq * 2 + q;   // 16-byte chunk of the 128-byte staging row
+                        const uint32_t addr = smem_u32(sfull) + uint32_t(srow * 128 + ((jj ^ (srow & 7)) << 4));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                                     : "memory");
+                    }
+                }
             }
             if (epi_tid == 0) B2R_STAMP(iter, 5);
             fence_proxy_async_smem();
@@ -218,7 +274,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 named_barrier_sync(1, kW3EpiThreads);
             }
             if (epi_tid == 0) {
-                if (p.store_full) tma_store_4d(&p.out_map, sfull, 0, w0, h0, n0);
+                if (p.store_full && !(p.dbg_flags & 2)) tma_store_4d(&p.out_map, sfull, 0, w0, h0, n0);
                 if (p.store_pool) tma_store_4d(&p.pool_map, spool, 0, w0 >> 1, h0 >> 1, n0);
                 tma_store_commit();
                 B2R_STAMP(iter, 6);
