@@ -47,7 +47,6 @@ struct alignas(64) ConvW3Params {
     int tiles_w, tiles_h, n_img;
     int store_full, store_pool;
     long long* dbg;                  // optional [B2R_DBG_TILES][8] clock64 stamps written by CTA 0
-    int dbg_flags;                   // B2R_W3_DEBUG env (experiments only): 1 skip TMEM drain, 2 skip staging + stores
     uint32_t group[kW3MaxGroups];
 };
 

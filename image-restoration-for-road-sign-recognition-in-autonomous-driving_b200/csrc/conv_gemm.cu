@@ -498,10 +498,6 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
     P.slope = d->slope;
     P.act = d->act;
     P.dbg = reinterpret_cast<long long*>(d->debug_timeline);
-    {
-        const char* e = getenv("B2R_W3_DEBUG");
-        P.dbg_flags = e ? atoi(e) : 0;
-    }
     P.num_groups = ng;
     P.num_ksteps = nsteps;
     P.ring_slots = ring;

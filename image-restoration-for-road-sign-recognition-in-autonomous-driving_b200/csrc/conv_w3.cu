@@ -104,12 +104,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                     const int c0 = int((e >> 8) & 0xFFF) * 64;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (g == 0) B2R_STAMP(iter, 0);
-                    if (p.dbg_flags & 4) {
-                        mbar_arrive(&full_bar[stage]);   // experiment: no A traffic at all
-                    } else {
-                        mbar_arrive_expect_tx(&full_bar[stage], kW3Slot);
-                        tma_load_4d(ring + stage * kW3Slot, &p.a_map[src], &full_bar[stage], c0, w0 - 1, h0 - 1, n0);
-                    }
+                    mbar_arrive_expect_tx(&full_bar[stage], kW3Slot);
+                    tma_load_4d(ring + stage * kW3Slot, &p.a_map[src], &full_bar[stage], c0, w0 - 1, h0 - 1, n0);
                     if (++stage == R) {
                         stage = 0;
                         phase ^= 1;
@@ -146,9 +142,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 tc_fence_after();
                 const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(kW3Slot >> 4);
                 if (elect_one()) {
-                    if (p.dbg_flags & 8) {
-                        // experiment: no tensor work
-                    } else if (center) {
+                    if (center) {
                         // one k-step on kernel row 1: A = buffer rows 16 .. 143
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -211,11 +205,6 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         uint32_t acc_phase = 0;
         int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-            const int n0 = tile / tiles_per_img;
-            const int t = tile - n0 * tiles_per_img;
-            const int w0 = (t % p.tiles_w) * 14;
-            const int h0 = (t / p.tiles_w) * 8;
-
             mbar_wait_warp(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             if (epi_tid == 0) B2R_STAMP(iter, 3);
@@ -225,15 +214,10 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             const uint32_t tacc = tmem_base + lane_base + uint32_t(acc * 256);
             {
                 uint32_t d0[16], d1[16], d2[16];
-                if (p.dbg_flags & 1) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) d0[j] = d1[j] = d2[j] = 0u;
-                } else {
-                    tmem_ld_32x16(tacc + uint32_t(cq * 16), d0);          // kw = 0 partial sums of this warp's channels
-                    tmem_ld_32x16(tacc + uint32_t(64 + cq * 16), d1);     // kw = 1
-                    tmem_ld_32x16(tacc + uint32_t(128 + cq * 16), d2);    // kw = 2
-                    tmem_ld_wait();
-                }
+                tmem_ld_32x16(tacc + uint32_t(cq * 16), d0);          // kw = 0 partial sums of this warp's channels
+                tmem_ld_32x16(tacc + uint32_t(64 + cq * 16), d1);     // kw = 1
+                tmem_ld_32x16(tacc + uint32_t(128 + cq * 16), d2);    // kw = 2
+                tmem_ld_wait();
                 // the accumulator now lives in registers: hand the TMEM stage back to the MMA warp BEFORE the shift-add,
                 // activation and staging, so the next-but-one tile's MMAs overlap all of that
                 tc_fence_before();
@@ -253,7 +237,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 16; ++j) x[j] = apply_act_ns(x[j], ns);
                 }
-                if (valid && !(p.dbg_flags & 2)) {
+                if (valid) {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const uint32_t o0 = pack_bf16x2(x[8 * q], x[8 * q + 1]), o1 = pack_bf16x2(x[8 * q + 2], x[8 * q + 3]);
@@ -274,7 +258,12 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 named_barrier_sync(1, kW3EpiThreads);
             }
             if (epi_tid == 0) {
-                if (p.store_full && !(p.dbg_flags & 2)) tma_store_4d(&p.out_map, sfull, 0, w0, h0, n0);
+                // only the issuing thread needs the tile coordinates (three integer divisions)
+                const int n0 = tile / tiles_per_img;
+                const int t = tile - n0 * tiles_per_img;
+                const int w0 = (t % p.tiles_w) * 14;
+                const int h0 = (t / p.tiles_w) * 8;
+                if (p.store_full) tma_store_4d(&p.out_map, sfull, 0, w0, h0, n0);
                 if (p.store_pool) tma_store_4d(&p.pool_map, spool, 0, w0 >> 1, h0 >> 1, n0);
                 tma_store_commit();
                 B2R_STAMP(iter, 6);

@@ -78,3 +78,85 @@ def test_run_and_run_from_host_agree_and_count():
     pipe.micro_batch = 3
     pred2, counts2 = pipe.run(imgs.cuda(), labels.cuda(), params, seed=5, image_index0=100)
     assert torch.equal(pred, pred2) and torch.equal(counts, counts2)
+
+
+def test_top1_agreement_with_a_locally_fitted_judge():
+    """BASELINE.json north_star: 'VGG16 top-1 labels must agree bit-exactly on >= 99.9 % of images' — meaningful only
+    for a judge with realistic margins.  A random-init VGG16 has nearly flat logits, so (as the north star allows:
+    'random-init (or locally fine-tuned) VGG16') the 43-way head is fitted here by ridge regression on the fp32
+    oracle's penultimate features of restored training images; agreement is then measured on fresh images between the
+    fp32 oracle pipeline and the bf16 sm_100a pipeline, degraded with the SAME injected noise."""
+    import torch.nn.functional as F
+    from b200restore import degrade, models, synth, RestoreClassifyPipeline
+    from oracle import degrade_oracle as DO, models_oracle as MO
+    dev = torch.device("cuda")
+    sdr = synth.synthetic_state_dict("resunet", 31)
+    sdj = synth.synthetic_state_dict("vgg16", 32)
+    sdr_d = {k: v.to(dev) for k, v in sdr.items()}
+    sdj_d = {k: v.to(dev) for k, v in sdj.items()}
+    hw, n_fit, n_eval = 224, 430, 1032
+
+    def oracle_degrade_restore(imgs, seed):
+        z = np.random.default_rng(seed).standard_normal((len(imgs), hw, hw, 3))
+        noise = (0.02 ** 0.5) * z
+        deg = np.stack([DO.compound_16(imgs[i].numpy(), noise[i]) for i in range(len(imgs))])
+        with torch.no_grad():
+            outs = []
+            for s in range(0, len(imgs), 64):
+                d = torch.from_numpy(deg[s:s + 64]).to(dev)
+                outs.append(MO.quantize_restored(MO.resunet_forward(sdr_d, MO.to_tensor_u8(d))))
+        return noise, torch.cat(outs)
+
+    def penultimate(restored_u8):
+        with torch.no_grad():
+            feats = []
+            for s in range(0, len(restored_u8), 64):
+                x = MO.normalize_imagenet(MO.to_tensor_u8(restored_u8[s:s + 64]))
+                x = torch.flatten(F.adaptive_avg_pool2d(MO.vgg16_features(sdj_d, x), (7, 7)), 1)
+                x = F.relu(F.linear(x, sdj_d["classifier.0.weight"], sdj_d["classifier.0.bias"]))
+                feats.append(F.relu(F.linear(x, sdj_d["classifier.3.weight"], sdj_d["classifier.3.bias"])))
+        return torch.cat(feats)
+
+    # ---- fit the head on the oracle's features of restored training images (fp64 ridge regression to +-1 targets)
+    imgs_fit, lab_fit = synth.sign_like_images(n_fit, hw, hw, seed=100)
+    _, rest_fit = oracle_degrade_restore(imgs_fit, 101)
+    Phi = penultimate(rest_fit).double()
+    Phi1 = torch.cat([Phi, torch.ones(len(Phi), 1, dtype=torch.float64, device=dev)], 1)
+    Y = -torch.ones((n_fit, 43), dtype=torch.float64, device=dev)
+    Y[torch.arange(n_fit), lab_fit.to(dev)] = 1.0
+    lam = 1e-3 * float((Phi1 * Phi1).sum() / len(Phi1))
+    G = Phi1 @ Phi1.t() + lam * torch.eye(n_fit, dtype=torch.float64, device=dev)
+    Wb = Phi1.t() @ torch.linalg.solve(G, Y)                    # [4097, 43]
+    scale = 8.0                                                  # logits of a trained classifier span several units
+    sdj_d["classifier.6.weight"] = (scale * Wb[:-1].t()).float().contiguous()
+    sdj_d["classifier.6.bias"] = (scale * Wb[-1]).float().contiguous()
+
+    # ---- fresh images through both pipelines
+    imgs, labels = synth.sign_like_images(n_eval, hw, hw, seed=200, index0=5000)
+    noise, rest_ref = oracle_degrade_restore(imgs, 201)
+    with torch.no_grad():
+        logits_ref = torch.cat([MO.vgg16_forward(sdj_d, MO.normalize_imagenet(MO.to_tensor_u8(rest_ref[s:s + 64])))
+                                for s in range(0, n_eval, 64)])
+    pred_ref = MO.top1(logits_ref)
+
+    r, j = models.ResUNet(), models.VGG16Judge()
+    r.load_state_dict(sdr)
+    j.load_state_dict({k: v.cpu() for k, v in sdj_d.items()})
+    pipe = RestoreClassifyPipeline(r.to(dev), j.to(dev), micro_batch=128)
+    preds = []
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    for s in range(0, n_eval, 128):
+        c = min(128, n_eval - s)
+        p, _ = pipe.run_micro_batch(imgs[s:s + c].to(dev), labels[s:s + c].to(dev), degrade.compound_params(c).to(dev),
+                                    0, s, counts, noise=torch.from_numpy(noise[s:s + c]).to(dev))
+        preds.append(p.clone())
+    pred = torch.cat(preds)
+    agree = float((pred == pred_ref).float().mean())
+    acc_ref = float((pred_ref.cpu() == labels).float().mean())
+    top2 = torch.topk(logits_ref, 2, dim=1)[0]
+    margin = top2[:, 0] - top2[:, 1]
+    print(f"\n[fitted judge] oracle accuracy {100 * acc_ref:.2f} %, top-1 agreement bf16 pipeline vs fp32 oracle "
+          f"{100 * agree:.3f} % on {n_eval} images; reference margins: min {float(margin.min()):.3f}, "
+          f"5th pct {float(margin.kthvalue(max(1, n_eval // 20))[0]):.3f}, median {float(margin.median()):.3f}")
+    assert agree >= 0.999, f"top-1 agreement {agree:.4f} < 0.999"
+    assert counts[1].item() == n_eval and counts[0].item() == int((pred.cpu() == labels).sum())
