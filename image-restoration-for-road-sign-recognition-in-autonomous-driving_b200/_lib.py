@@ -48,6 +48,10 @@ class ConvGemmDesc(C.Structure):
         ("block_n", C.c_int32),
         ("max_ctas", C.c_int32),
         ("flags", C.c_int32),
+        ("head_w", C.c_void_p),
+        ("head_b", C.c_void_p),
+        ("head_out_f32", C.c_void_p),
+        ("head_out_u8", C.c_void_p),
         ("debug_timeline", C.c_void_p),
     ]
 

@@ -47,6 +47,11 @@ struct alignas(64) ConvW3Params {
     int tiles_w, tiles_h, n_img;
     int store_full, store_pool;
     long long* dbg;                  // optional [B2R_DBG_TILES][8] clock64 stamps written by CTA 0
+    const float* head_w;             // fused 64 -> 3 head (nullptr: none)
+    const float* head_b;
+    float* head_f32;
+    uint8_t* head_u8;
+    int H, W;
     uint32_t group[kW3MaxGroups];
 };
 

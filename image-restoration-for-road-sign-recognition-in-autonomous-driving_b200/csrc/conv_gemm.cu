@@ -492,12 +492,23 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
         int rc = encode_tmap_bf16(&P.pool_map, d->out_pool, 4, pd, ps, pb);
         if (rc) return rc;
     }
-    if (!d->out) P.out_map = P.pool_map;
-    if (!d->out_pool) P.pool_map = P.out_map;
+    if (!d->out && !d->out_pool) {
+        P.out_map = P.a_map[0];   // never used for a store (store_full = store_pool = 0); keeps prefetch valid
+        P.pool_map = P.a_map[0];
+    } else {
+        if (!d->out) P.out_map = P.pool_map;
+        if (!d->out_pool) P.pool_map = P.out_map;
+    }
     P.bias = d->bias;
     P.slope = d->slope;
     P.act = d->act;
     P.dbg = reinterpret_cast<long long*>(d->debug_timeline);
+    P.head_w = d->head_w;
+    P.head_b = d->head_b;
+    P.head_f32 = d->head_out_f32;
+    P.head_u8 = d->head_out_u8;
+    P.H = d->H;
+    P.W = d->W;
     P.num_groups = ng;
     P.num_ksteps = nsteps;
     P.ring_slots = ring;
@@ -549,15 +560,21 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
     B2R_REQUIRE(d->num_kblocks >= 1, "num_kblocks=%d", d->num_kblocks);
     B2R_REQUIRE(d->kblocks_host == nullptr || d->num_kblocks <= B2R_MAX_KBLOCKS, "num_kblocks=%d > %d", d->num_kblocks,
                 B2R_MAX_KBLOCKS);
-    B2R_REQUIRE(d->out || d->out_pool, "no output");
-    B2R_REQUIRE(d->out_C > 0 && d->out_C % 64 == 0, "out_C=%d must be a multiple of 64", d->out_C);
+    const bool head = d->head_w != nullptr;
+    B2R_REQUIRE(d->out || d->out_pool || head, "no output");
+    B2R_REQUIRE(!head || (d->head_b && (d->head_out_f32 || d->head_out_u8)), "head_w given without head_b / a head output");
+    B2R_REQUIRE(!head || (d->weights_w3 && d->cout_total == 64 && d->out_mode == B2R_OUT_NHWC && !d->out_pool &&
+                          !(d->flags & (B2R_CONV_GENERIC_ONLY | B2R_CONV_NO_W3))),
+                "the fused 64->3 head needs a C_out = 64 NHWC layer with weights_w3 and no pooled output");
+    B2R_REQUIRE(!head || !d->out, "with a fused head the 64-channel tensor is not stored: out must be NULL");
+    B2R_REQUIRE(head || (d->out_C > 0 && d->out_C % 64 == 0), "out_C=%d must be a multiple of 64", d->out_C);
     B2R_REQUIRE(d->act >= B2R_ACT_NONE && d->act <= B2R_ACT_PRELU, "act=%d", d->act);
     const bool convt = d->out_mode == B2R_OUT_CONVT2X2;
     B2R_REQUIRE(convt || d->out_mode == B2R_OUT_NHWC, "out_mode=%d", d->out_mode);
     B2R_REQUIRE(!(convt && d->out_pool), "pooling is not available with CONVT2X2");
     B2R_REQUIRE(!convt || d->cout_total % 4 == 0, "CONVT2X2 needs cout_total = 4*C_out");
     const int cout = convt ? d->cout_total / 4 : d->cout_total;
-    B2R_REQUIRE(cout % 64 == 0 && cout <= d->out_C, "C_out=%d vs out_C=%d", cout, d->out_C);
+    B2R_REQUIRE(cout % 64 == 0 && (cout <= d->out_C || (head && !d->out)), "C_out=%d vs out_C=%d", cout, d->out_C);
     if (d->out_pool) B2R_REQUIRE(d->H % 2 == 0 && d->W % 2 == 0, "fused pool needs even H, W (got %d x %d)", d->H, d->W);
 
     bool spatial = false;
@@ -583,6 +600,8 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
         bool handled = false;
         int rc = try_conv_w3(d, stream, &handled);
         if (rc || handled) return rc;
+        B2R_REQUIRE(!head, "the fused head is only implemented on the tap-folded kernel, which rejected this layer "
+                           "(weights too large to stay resident in shared memory?)");
         rc = try_conv_n64(d, stream, &handled);
         if (rc || handled) return rc;
     }

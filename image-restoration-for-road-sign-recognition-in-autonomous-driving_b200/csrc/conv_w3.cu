@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     uint8_t* sfull = ring + p.ring_slots * kW3Slot;
     uint8_t* spool = sfull + kW3Staging;
     float* bias_s = reinterpret_cast<float*>(spool + kW3StagingPool);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 64);
+    float* head_s = bias_s + 64;                                   // [3][64] head weights + [3] head bias (+ pad)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(head_s + 200);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kN64MaxRing;
     uint64_t* tmem_full_bar = bars + 2 * kN64MaxRing;
@@ -79,6 +80,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         tmem_alloc<512>(tmem_ptr_s);   // 2 accumulator stages x 192 columns (power-of-two allocation)
     }
     if (threadIdx.x >= 64 && threadIdx.x < 128) bias_s[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
+    if (p.head_w != nullptr && threadIdx.x >= 128 && threadIdx.x < 128 + 195)
+        head_s[threadIdx.x - 128] = threadIdx.x - 128 < 192 ? p.head_w[threadIdx.x - 128] : p.head_b[threadIdx.x - 128 - 192];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                              : "=f"(b16[4 * i]), "=f"(b16[4 * i + 1]), "=f"(b16[4 * i + 2]), "=f"(b16[4 * i + 3])
                              : "r"(ba + 16 * i));
         }
+        const bool has_head = p.head_w != nullptr;
         const bool relu_only = p.act == B2R_ACT_RELU;
         const float ns = act_neg_slope(p.act, p.slope);
         int acc = 0;
@@ -237,7 +241,30 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 16; ++j) x[j] = apply_act_ns(x[j], ns);
                 }
-                if (valid) {
+                if (has_head) {
+                    // fused 64 -> 3 head on the fp32 activations: this warp's 16 channels -> 3 partial sums per pixel,
+                    // parked in the (otherwise unused) staging tile as [cq][o][pixel row]
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+                    const uint32_t ha = smem_u32(head_s + cq * 16);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        float w0[4], w1[4], w2[4];
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w0[0]), "=f"(w0[1]), "=f"(w0[2]), "=f"(w0[3]) : "r"(ha + 16 * j4));
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w1[0]), "=f"(w1[1]), "=f"(w1[2]), "=f"(w1[3]) : "r"(ha + 256 + 16 * j4));
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w2[0]), "=f"(w2[1]), "=f"(w2[2]), "=f"(w2[3]) : "r"(ha + 512 + 16 * j4));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            s0 = fmaf(x[4 * j4 + j], w0[j], s0);
+                            s1 = fmaf(x[4 * j4 + j], w1[j], s1);
+                            s2 = fmaf(x[4 * j4 + j], w2[j], s2);
+                        }
+                    }
+                    float* part = reinterpret_cast<float*>(sfull) + (cq * 3) * 128 + quarter * 32 + lane;
+                    part[0] = s0;
+                    part[128] = s1;
+                    part[256] = s2;
+                }
+                if (valid && (p.store_full | p.store_pool)) {   // the pooled output is computed from the staged tile
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const uint32_t o0 = pack_bf16x2(x[8 * q], x[8 * q + 1]), o1 = pack_bf16x2(x[8 * q + 2], x[8 * q + 3]);
@@ -252,6 +279,30 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             if (epi_tid == 0) B2R_STAMP(iter, 5);
             fence_proxy_async_smem();
             named_barrier_sync(1, kW3EpiThreads);
+            if (has_head && cq == 0) {
+                // one thread per pixel: add the four partial sums (fixed order) + bias, then the reference's outputs
+                const int n0 = tile / tiles_per_img;
+                const int t = tile - n0 * tiles_per_img;
+                const int w = (t % p.tiles_w) * 14 + cc;
+                const int h = (t / p.tiles_w) * 8 + hh;
+                if (valid && w < p.W && h < p.H) {
+                    const float* part = reinterpret_cast<const float*>(sfull) + quarter * 32 + lane;
+                    float v[3];
+#pragma unroll
+                    for (int o = 0; o < 3; ++o)
+                        v[o] = (((part[o * 128] + part[(3 + o) * 128]) + part[(6 + o) * 128]) + part[(9 + o) * 128]) + head_s[192 + o];
+                    const size_t hw = size_t(p.H) * p.W, pix = size_t(h) * p.W + w;
+                    if (p.head_f32) {
+#pragma unroll
+                        for (int o = 0; o < 3; ++o) p.head_f32[(size_t(n0) * 3 + o) * hw + pix] = v[o];
+                    }
+                    if (p.head_u8) {
+#pragma unroll
+                        for (int o = 0; o < 3; ++o)   // torch.clamp(x, 0, 1); (x * 255).astype(np.uint8): truncation (17:86-92)
+                            p.head_u8[(size_t(n0) * hw + pix) * 3 + o] = static_cast<uint8_t>(fminf(fmaxf(v[o], 0.f), 1.f) * 255.0f);
+                    }
+                }
+            }
             if (p.store_pool) {
                 if (epi_tid < 28 * 4) epilogue_pool_chunk(sfull, spool, epi_tid, 14, 8);
                 fence_proxy_async_smem();
@@ -284,7 +335,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 }
 
 size_t conv_w3_smem_bytes(int num_ksteps, int ring_slots) {
-    return 1024 + size_t(num_ksteps) * kW3BStep + size_t(ring_slots) * kW3Slot + kW3Staging + kW3StagingPool + 256 + 256;
+    return 1024 + size_t(num_ksteps) * kW3BStep + size_t(ring_slots) * kW3Slot + kW3Staging + kW3StagingPool + 256 + 800 + 256;
 }
 
 int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream) {

@@ -171,12 +171,11 @@ class SimpleUNet(_B200Module):
         ops.conv_gemm([d2a], **P["dec2.2"], act=R, out=d2)
         u1 = g("u1", H, W, 64)
         ops.conv_gemm([d2], *P["up1"], None, out=u1, out_mode=L.B2R_OUT_CONVT2X2)
-        d1a, d1 = g("a", H, W, 64), g("d1", H, W, 64)
+        d1a = g("a", H, W, 64)
         ops.conv_gemm([u1, e1], **P["dec1.0"], act=R, out=d1a)
-        ops.conv_gemm([d1a], **P["dec1.2"], act=R, out=d1)
-        L.check(L.load().b2r_final_conv1x1(d1.data_ptr(), P["final"][0].data_ptr(), P["final"][1].data_ptr(),
-                                           ops._ptr(out_f32), ops._ptr(out_u8), n, H, W, ops._stream()))
-        ops.STATS["launches"] += 1
+        # dec1[2] + ReLU + final 1x1 (64 -> 3) + clamp/quantise in ONE launch: the 64-channel d1 never goes to HBM
+        ops.conv_gemm([d1a], **P["dec1.2"], act=R, head_w=P["final"][0], head_b=P["final"][1],
+                      head_out_f32=out_f32, head_out_u8=out_u8)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -292,10 +291,10 @@ class ResUNet(_B200Module):
         P["final"] = (sd["final.weight"].float().reshape(3, 64).contiguous(), sd["final.bias"].float().contiguous())
         return P
 
-    def _block(self, name, srcs, y, out, out_pool=None):
+    def _block(self, name, srcs, y, out, out_pool=None, head=None):
         c1, slope, c2 = self._packed()[name]
         ops.conv_gemm(srcs, **c1, act=L.B2R_ACT_PRELU, slope=slope, out=y)
-        ops.conv_gemm([y] + list(srcs), **c2, act=L.B2R_ACT_RELU, out=out, out_pool=out_pool)
+        ops.conv_gemm([y] + list(srcs), **c2, act=L.B2R_ACT_RELU, out=out, out_pool=out_pool, **(head or {}))
 
     def _run(self, x, out_f32, out_u8):
         P, ws = self._packed(), self._ws
@@ -328,11 +327,9 @@ class ResUNet(_B200Module):
         self._block("dec2", [u2, r2], g("yd2", H2, W2, 64), d2)       # cat((d2, r2), 1) (14:177)
         u1 = g("u1", H, W, 64)
         ops.conv_gemm([d2], *P["up1"], None, out=u1, out_mode=L.B2R_OUT_CONVT2X2)
-        d1 = g("d1", H, W, 64)
-        self._block("dec1", [u1, r1], g("y1", H, W, 64), d1)          # cat((d1, r1), 1) (14:183)
-        L.check(L.load().b2r_final_conv1x1(d1.data_ptr(), P["final"][0].data_ptr(), P["final"][1].data_ptr(),
-                                           ops._ptr(out_f32), ops._ptr(out_u8), n, H, W, ops._stream()))
-        ops.STATS["launches"] += 1
+        # dec1 block; its second conv also applies `final` (64 -> 3) and the clamp/quantise: d1 never goes to HBM
+        self._block("dec1", [u1, r1], g("y1", H, W, 64), None,        # cat((d1, r1), 1) (14:183)
+                    head=dict(head_w=P["final"][0], head_b=P["final"][1], head_out_f32=out_f32, head_out_u8=out_u8))
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -102,7 +102,9 @@ def conv_gemm(srcs: Sequence[torch.Tensor], weights: torch.Tensor, bias: torch.T
               out: Optional[torch.Tensor] = None, out_pool: Optional[torch.Tensor] = None,
               out_mode: int = L.B2R_OUT_NHWC, tile=(0, 0, 0), block_n: int = 0, max_ctas: int = 0,
               alg_k: Optional[int] = None, flags: int = 0, weights_w3: Optional[torch.Tensor] = None,
-              debug_timeline: Optional[torch.Tensor] = None) -> None:
+              debug_timeline: Optional[torch.Tensor] = None, head_w: Optional[torch.Tensor] = None,
+              head_b: Optional[torch.Tensor] = None, head_out_f32: Optional[torch.Tensor] = None,
+              head_out_u8: Optional[torch.Tensor] = None) -> None:
     """One fused tensor-core layer (b2r_conv_gemm).  srcs: NHWC bf16 [N,H,W,C_i]; weights bf16 [cout_total, K].
     `alg_k`: K elements that are algorithmic work (excludes e.g. an identity-shortcut block); accounting only."""
     n, h, w = srcs[0].shape[:3]
@@ -154,6 +156,22 @@ def conv_gemm(srcs: Sequence[torch.Tensor], weights: torch.Tensor, bias: torch.T
         d.out_pool = out_pool.data_ptr()
         oc = int(out_pool.shape[3])
     d.out_C = oc
+    if head_w is not None:
+        _chk(head_w, torch.float32, "head_w")
+        _chk(head_b, torch.float32, "head_b")
+        if head_w.numel() != 192 or head_b.numel() != 3:
+            raise L.B2RError("head_w / head_b must hold 3x64 and 3 values")
+        d.head_w, d.head_b = head_w.data_ptr(), head_b.data_ptr()
+        if head_out_f32 is not None:
+            _chk(head_out_f32, torch.float32, "head_out_f32", 4)
+            if tuple(head_out_f32.shape) != (n, 3, h, w):
+                raise L.B2RError(f"head_out_f32 shape {tuple(head_out_f32.shape)} != {(n, 3, h, w)}")
+            d.head_out_f32 = head_out_f32.data_ptr()
+        if head_out_u8 is not None:
+            _chk(head_out_u8, torch.uint8, "head_out_u8", 4)
+            if tuple(head_out_u8.shape) != (n, h, w, 3):
+                raise L.B2RError(f"head_out_u8 shape {tuple(head_out_u8.shape)} != {(n, h, w, 3)}")
+            d.head_out_u8 = head_out_u8.data_ptr()
     d.tile_w, d.tile_h, d.tile_n = (int(x) for x in tile)
     d.block_n, d.max_ctas, d.flags = int(block_n), int(max_ctas), int(flags)
     if debug_timeline is not None:

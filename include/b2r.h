@@ -161,6 +161,16 @@ typedef struct b2r_conv_gemm_desc {
     int32_t block_n;                 /* 64 / 128 / 256; 0 = choose */
     int32_t max_ctas;                /* 0 = one per SM */
     int32_t flags;                   /* B2R_CONV_* */
+    /* Optional fused output head (C_out = 64 layers on the tap-folded kernel only): the restorers' final 1x1 conv
+     * 64 -> 3 (07_train_restoration.py:97,119; 14_train_unified_advanced.py:149,186) applied to this layer's activated
+     * fp32 output before it is rounded to bf16, plus the reference's post-processing, so the 64-channel tensor never
+     * goes to HBM.  head_w f32 [3][64], head_b f32 [3]; head_out_f32 = f32 NCHW [N,3,H,W] (module output, unclamped)
+     * and/or head_out_u8 = u8 NHWC [N,H,W,3] (clamp(0,1)*255 truncated, 17_run_unified_inference.py:86-92).
+     * With a head, `out` / `out_pool` may both be NULL. */
+    const float* head_w;
+    const float* head_b;
+    float* head_out_f32;
+    uint8_t* head_out_u8;
     int64_t* debug_timeline;         /* optional device buffer int64[B2R_DBG_TILES][8]: CTA 0 records clock64() stamps of
                                         its first tiles per warp role (tools/role_timeline.py); NULL = off */
 } b2r_conv_gemm_desc;
