@@ -64,7 +64,10 @@ _lib = None
 
 
 def lib_path() -> Path:
-    return _build.LIB_PATH
+    """In-tree libb2r.so; $B2R_LIB selects another build of the same ABI (A/B kernel experiments only)."""
+    import os
+    alt = os.environ.get("B2R_LIB")
+    return Path(alt) if alt else _build.LIB_PATH
 
 
 def load() -> C.CDLL:

@@ -30,6 +30,9 @@ constexpr int kW3Slot = 10 * 16 * 128;   // one halo box: (8 + 2) rows x 16 colu
 constexpr int kW3Staging = 14336;        // 8 x 14 pixels x 128 B
 constexpr int kW3StagingPool = 4096;     // 4 x 7 pixels x 128 B, padded
 
+// kHead = true adds the fused 64 -> 3 output head; it is a separate instantiation because even unused, the extra
+// epilogue code cost the plain layers ~5 % (A/B in one gpurun call, profiles/r01_w3_timeline.md).
+template <bool kHead>
 __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_constant__ ConvW3Params p) {
     constexpr uint32_t kIdesc = make_idesc_bf16_f32(128, 192);
     extern __shared__ uint8_t smem_raw[];
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         tmem_alloc<512>(tmem_ptr_s);   // 2 accumulator stages x 192 columns (power-of-two allocation)
     }
     if (threadIdx.x >= 64 && threadIdx.x < 128) bias_s[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
-    if (p.head_w != nullptr && threadIdx.x >= 128 && threadIdx.x < 128 + 195)
+    if (kHead && threadIdx.x >= 128 && threadIdx.x < 128 + 195)
         head_s[threadIdx.x - 128] = threadIdx.x - 128 < 192 ? p.head_w[threadIdx.x - 128] : p.head_b[threadIdx.x - 128 - 192];
     tc_fence_before();
     __syncthreads();
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                              : "=f"(b16[4 * i]), "=f"(b16[4 * i + 1]), "=f"(b16[4 * i + 2]), "=f"(b16[4 * i + 3])
                              : "r"(ba + 16 * i));
         }
-        const bool has_head = p.head_w != nullptr;
+        constexpr bool has_head = kHead;
         const bool relu_only = p.act == B2R_ACT_RELU;
         const float ns = act_neg_slope(p.act, p.slope);
         int acc = 0;
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                     part[128] = s1;
                     part[256] = s2;
                 }
-                if (valid && (p.store_full | p.store_pool)) {   // the pooled output is computed from the staged tile
+                if (valid && (!kHead || p.store_full)) {   // without a head the tile is always staged (store and/or pool)
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const uint32_t o0 = pack_bf16x2(x[8 * q], x[8 * q + 1]), o1 = pack_bf16x2(x[8 * q + 2], x[8 * q + 3]);
@@ -343,10 +346,15 @@ int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream) {
     int dev = 0;
     B2R_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        B2R_CUDA(cudaFuncSetAttribute(conv_w3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
+        B2R_CUDA(cudaFuncSetAttribute(conv_w3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
+        B2R_CUDA(cudaFuncSetAttribute(conv_w3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
         if (dev < 64) attr_set[dev] = true;
     }
-    conv_w3_kernel<<<grid, kW3Threads, conv_w3_smem_bytes(p.num_ksteps, p.ring_slots), stream>>>(p);
+    const size_t smem = conv_w3_smem_bytes(p.num_ksteps, p.ring_slots);
+    if (p.head_w != nullptr)
+        conv_w3_kernel<true><<<grid, kW3Threads, smem, stream>>>(p);
+    else
+        conv_w3_kernel<false><<<grid, kW3Threads, smem, stream>>>(p);
     B2R_CHECK_LAUNCH();
     return B2R_OK;
 }
