@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="degrade16_resunet_vgg16_top1", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=4096, help="images per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=128)
+    ap.add_argument("--micro-batch", type=int, default=256)
     ap.add_argument("--hw", type=int, default=224)
     ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline sample (0 = choose)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

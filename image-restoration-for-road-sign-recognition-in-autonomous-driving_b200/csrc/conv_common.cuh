@@ -44,6 +44,7 @@ struct alignas(64) ConvW3Params {
     float slope;
     int act;
     int num_groups, num_ksteps, ring_slots;
+    int b_slots;                     // 0: weights resident (num_ksteps x 24 KB); > 0: weights streamed through this many slots
     int tiles_w, tiles_h, n_img;
     int store_full, store_pool;
     long long* dbg;                  // optional [B2R_DBG_TILES][8] clock64 stamps written by CTA 0
@@ -55,7 +56,7 @@ struct alignas(64) ConvW3Params {
     uint32_t group[kW3MaxGroups];
 };
 
-size_t conv_w3_smem_bytes(int num_ksteps, int ring_slots);
+size_t conv_w3_smem_bytes(int b_blocks, int ring_slots);
 int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream);
 
 #ifdef __CUDACC__

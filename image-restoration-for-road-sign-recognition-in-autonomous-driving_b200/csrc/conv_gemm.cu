@@ -452,9 +452,16 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
             return B2R_OK;
         }
     }
-    int ring = 4;
+    int ring = 4, b_slots = 0;
     while (ring >= 2 && conv_w3_smem_bytes(nsteps, ring) > (size_t)kN64MaxSmem) --ring;
-    if (ring < 2) return B2R_OK;  // weights too large to stay resident: other kernels take the layer
+    if (ring < 2) {
+        // weights too large to stay resident (192 -> 64: 216 KB): stream the k-steps through a ring instead
+        if (d->head_w) return B2R_OK;
+        ring = 3;
+        b_slots = kN64MaxRing;
+        while (b_slots >= 3 && conv_w3_smem_bytes(b_slots, ring) > (size_t)kN64MaxSmem) --b_slots;
+        if (b_slots < 3) return B2R_OK;
+    }
 
     static thread_local ConvW3Params tp;
     ConvW3Params& P = tp;
@@ -512,6 +519,7 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
     P.num_groups = ng;
     P.num_ksteps = nsteps;
     P.ring_slots = ring;
+    P.b_slots = b_slots;
     P.tiles_w = ceil_div(d->W, 14);
     P.tiles_h = ceil_div(d->H, 8);
     P.n_img = d->N;

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* b_res = smem;
-    uint8_t* ring = b_res + p.num_ksteps * kW3BStep;
+    const int b_blocks = p.b_slots > 0 ? p.b_slots : p.num_ksteps;   // resident weights, or a ring of weight k-steps
+    uint8_t* ring = b_res + b_blocks * kW3BStep;
     uint8_t* sfull = ring + p.ring_slots * kW3Slot;
     uint8_t* spool = sfull + kW3Staging;
     float* bias_s = reinterpret_cast<float*>(spool + kW3StagingPool);
@@ -49,7 +50,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     uint64_t* tmem_full_bar = bars + 2 * kN64MaxRing;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint64_t* b_full_bar = tmem_empty_bar + 2;
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(b_full_bar + 1);
+    uint64_t* bs_full_bar = b_full_bar + 1;             // [kN64MaxRing] streamed-weights ring
+    uint64_t* bs_empty_bar = bs_full_bar + kN64MaxRing;  // [kN64MaxRing]
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bs_empty_bar + kN64MaxRing);
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -77,6 +80,10 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 mbar_init(&tmem_empty_bar[s], kW3EpiWarps);
             }
             mbar_init(b_full_bar, 1);
+            for (int s = 0; s < kN64MaxRing; ++s) {
+                mbar_init(&bs_full_bar[s], 1);
+                mbar_init(&bs_empty_bar[s], 1);
+            }
             fence_mbar_init();
         }
         __syncwarp();
@@ -93,11 +100,16 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     if (warp_idx == 0) {
         // ===================================== TMA producer =====================================
         if (lane == 0) {
-            mbar_arrive_expect_tx(b_full_bar, uint32_t(p.num_ksteps) * kW3BStep);
-            for (int ks = 0; ks < p.num_ksteps; ++ks)
-                tma_load_2d(b_res + ks * kW3BStep, &p.b_map, b_full_bar, ks * 64, 0);
+            const bool stream_b = p.b_slots > 0;
+            if (!stream_b) {
+                mbar_arrive_expect_tx(b_full_bar, uint32_t(p.num_ksteps) * kW3BStep);
+                for (int ks = 0; ks < p.num_ksteps; ++ks)
+                    tma_load_2d(b_res + ks * kW3BStep, &p.b_map, b_full_bar, ks * 64, 0);
+            }
             int stage = 0;
             uint32_t phase = 0;
+            int bs = 0;
+            uint32_t bphase = 0;
             int iter = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
                 const int n0 = tile / tiles_per_img;
@@ -116,6 +128,20 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                         stage = 0;
                         phase ^= 1;
                     }
+                    if (stream_b) {
+                        // weights too large to stay resident (e.g. 192 -> 64): this group's k-steps go through a ring
+                        const int nk = ((e >> 2) & 1) ? 1 : 3;
+                        const int ks0 = int(e >> 20);
+                        for (int k = 0; k < nk; ++k) {
+                            mbar_wait(&bs_empty_bar[bs], bphase ^ 1);
+                            mbar_arrive_expect_tx(&bs_full_bar[bs], kW3BStep);
+                            tma_load_2d(b_res + bs * kW3BStep, &p.b_map, &bs_full_bar[bs], (ks0 + k) * 64, 0);
+                            if (++bs == p.b_slots) {
+                                bs = 0;
+                                bphase ^= 1;
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -124,13 +150,16 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         // The whole warp runs this loop with warp-uniform control flow and ONE elected lane issues: descriptor
         // arithmetic then stays on the uniform datapath (two adds per MMA).  It matters here because this warp shares
         // its SM sub-partition's issue slots with four busy epilogue warps (profiles/r01_w3_timeline.md).
-        mbar_wait_warp(b_full_bar, 0);
+        const bool stream_b = p.b_slots > 0;
+        if (!stream_b) mbar_wait_warp(b_full_bar, 0);
         tc_fence_after();
         const uint64_t desc_hi = make_sdesc_sw128(0, 1024) & 0xFFFFFFFF00000000ull;   // SBO / version / swizzle bits
         const uint32_t a_lo0 = ((smem_u32(ring) >> 4) & 0x3FFF) | (1u << 16);
         const uint32_t b_lo0 = ((smem_u32(b_res) >> 4) & 0x3FFF) | (1u << 16);
         int stage = 0;
         uint32_t phase = 0;
+        int bs = 0;
+        uint32_t bphase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         int iter = 0;
@@ -143,33 +172,59 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             for (int g = 0; g < p.num_groups; ++g) {
                 const uint32_t e = p.group[g];
                 const bool center = ((e >> 2) & 1) != 0;
-                const uint32_t b_lo = b_lo0 + (e >> 20) * uint32_t(kW3BStep >> 4);
                 mbar_wait_warp(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(kW3Slot >> 4);
-                if (elect_one()) {
-                    if (center) {
-                        // one k-step on kernel row 1: A = buffer rows 16 .. 143
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_bf16_ss(tmem_d, desc_hi | uint64_t(a_lo + 128u + 2u * k), desc_hi | uint64_t(b_lo + 2u * k),
-                                         kIdesc, accum);
-                            accum = 1;
-                        }
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < 3; ++t) {   // kernel row t: A = buffer rows 16 t .. 16 t + 127 (2048 B apart)
+                if (!stream_b) {
+                    const uint32_t b_lo = b_lo0 + (e >> 20) * uint32_t(kW3BStep >> 4);
+                    if (elect_one()) {
+                        if (center) {
+                            // one k-step on kernel row 1: A = buffer rows 16 .. 143
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                umma_bf16_ss(tmem_d, desc_hi | uint64_t(a_lo + 128u * t + 2u * k),
-                                             desc_hi | uint64_t(b_lo + uint32_t(kW3BStep >> 4) * t + 2u * k), kIdesc, accum);
+                                umma_bf16_ss(tmem_d, desc_hi | uint64_t(a_lo + 128u + 2u * k), desc_hi | uint64_t(b_lo + 2u * k),
+                                             kIdesc, accum);
                                 accum = 1;
                             }
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 3; ++t) {   // kernel row t: A = buffer rows 16 t .. 16 t + 127 (2048 B apart)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    umma_bf16_ss(tmem_d, desc_hi | uint64_t(a_lo + 128u * t + 2u * k),
+                                                 desc_hi | uint64_t(b_lo + uint32_t(kW3BStep >> 4) * t + 2u * k), kIdesc, accum);
+                                    accum = 1;
+                                }
+                            }
+                        }
+                        umma_commit(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                } else {
+                    const int nk = center ? 1 : 3;
+                    for (int t = 0; t < nk; ++t) {
+                        mbar_wait_warp(&bs_full_bar[bs], bphase);
+                        tc_fence_after();
+                        const uint32_t kh = center ? 1u : uint32_t(t);
+                        const uint32_t b_lo = b_lo0 + uint32_t(bs) * uint32_t(kW3BStep >> 4);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_bf16_ss(tmem_d, desc_hi | uint64_t(a_lo + 128u * kh + 2u * k), desc_hi | uint64_t(b_lo + 2u * k),
+                                             kIdesc, accum);
+                                accum = 1;
+                            }
+                            umma_commit(&bs_empty_bar[bs]);
+                            if (t == nk - 1) umma_commit(&empty_bar[stage]);
+                        }
+                        __syncwarp();
+                        accum = 1;
+                        if (++bs == p.b_slots) {
+                            bs = 0;
+                            bphase ^= 1;
                         }
                     }
-                    umma_commit(&empty_bar[stage]);
                 }
-                __syncwarp();
                 accum = 1;
                 if (++stage == R) {
                     stage = 0;
@@ -337,8 +392,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     }
 }
 
-size_t conv_w3_smem_bytes(int num_ksteps, int ring_slots) {
-    return 1024 + size_t(num_ksteps) * kW3BStep + size_t(ring_slots) * kW3Slot + kW3Staging + kW3StagingPool + 256 + 800 + 256;
+size_t conv_w3_smem_bytes(int b_blocks, int ring_slots) {
+    return 1024 + size_t(b_blocks) * kW3BStep + size_t(ring_slots) * kW3Slot + kW3Staging + kW3StagingPool + 256 + 800 + 512;
 }
 
 int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream) {
@@ -350,7 +405,7 @@ int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream) {
         B2R_CUDA(cudaFuncSetAttribute(conv_w3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
         if (dev < 64) attr_set[dev] = true;
     }
-    const size_t smem = conv_w3_smem_bytes(p.num_ksteps, p.ring_slots);
+    const size_t smem = conv_w3_smem_bytes(p.b_slots > 0 ? p.b_slots : p.num_ksteps, p.ring_slots);
     if (p.head_w != nullptr)
         conv_w3_kernel<true><<<grid, kW3Threads, smem, stream>>>(p);
     else

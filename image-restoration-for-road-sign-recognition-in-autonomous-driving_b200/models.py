@@ -20,7 +20,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import ops, packing
 
-DEFAULT_MICRO_BATCH = 128
+DEFAULT_MICRO_BATCH = 256   # resident images per pass (ResUNet workspace ~12 GB at 224x224); +1.6 % over 128 (fewer tail waves)
 
 
 class _Workspace:

@@ -40,7 +40,7 @@ def all_reduce_counts(counts: torch.Tensor) -> torch.Tensor:
 class RestoreClassifyPipeline:
     """Holds a restorer (SimpleUNet / ResUNet) and the VGG16 judge on one device and streams batches through them."""
 
-    def __init__(self, restorer, judge, micro_batch: int = 128):
+    def __init__(self, restorer, judge, micro_batch: int = 256):
         self.restorer = restorer.eval()
         self.judge = judge.eval()
         self.micro_batch = int(micro_batch)

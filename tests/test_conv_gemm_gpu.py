@@ -213,6 +213,8 @@ def test_argument_errors():
     (2, 48, 64, (64, 64), None, False, (16, 8, 1)),      # dec1.c1: cat of two sources, 16 x 8 tile
     (2, 32, 48, (64,), "identity", True, (0, 0, 0)),     # res1.c2: conv + identity shortcut + pool
     (2, 32, 32, (64,), (64, 128), False, (8, 16, 1)),    # dec2.c2: conv(y) + 1x1 shortcut over cat(64, 128)
+    (2, 40, 56, (64, 128), None, False, (0, 0, 0)),      # dec2.c1: 192 -> 64, weights (216 KB) streamed through a ring
+    (1, 112, 112, (64, 128), None, True, (0, 0, 0)),     # same at the real size, with the fused pool
 ])
 def test_conv_n64_specialisation_equals_generic_kernel(n, h, w, splits, shortcut, pool, tile):
     """Same k-block order => same accumulation order: the specialised kernel must reproduce the generic kernel's
