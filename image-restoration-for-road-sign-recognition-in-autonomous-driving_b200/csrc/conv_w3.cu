@@ -270,18 +270,16 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             mbar_wait_warp(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             if (epi_tid == 0) B2R_STAMP(iter, 3);
-            if (epi_tid == 0) tma_store_wait_read<0>();
-            named_barrier_sync(1, kW3EpiThreads);
-            if (epi_tid == 0) B2R_STAMP(iter, 4);
             const uint32_t tacc = tmem_base + lane_base + uint32_t(acc * 256);
             {
+                // Drain first, synchronise later: the accumulator goes to registers and the TMEM stage is handed back
+                // to the MMA warp BEFORE this tile waits for the shared staging buffer, so neither the CTA-wide
+                // barrier nor the shift-add / activation / staging sit on the MMA <-> epilogue hand-off chain.
                 uint32_t d0[16], d1[16], d2[16];
                 tmem_ld_32x16(tacc + uint32_t(cq * 16), d0);          // kw = 0 partial sums of this warp's channels
                 tmem_ld_32x16(tacc + uint32_t(64 + cq * 16), d1);     // kw = 1
                 tmem_ld_32x16(tacc + uint32_t(128 + cq * 16), d2);    // kw = 2
                 tmem_ld_wait();
-                // the accumulator now lives in registers: hand the TMEM stage back to the MMA warp BEFORE the shift-add,
-                // activation and staging, so the next-but-one tile's MMAs overlap all of that
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -299,6 +297,10 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 16; ++j) x[j] = apply_act_ns(x[j], ns);
                 }
+                // only now is the shared staging tile needed: wait until the previous tile's TMA store has read it
+                if (epi_tid == 0) tma_store_wait_read<0>();
+                named_barrier_sync(1, kW3EpiThreads);
+                if (epi_tid == 0) B2R_STAMP(iter, 4);
                 if (has_head) {
                     // fused 64 -> 3 head on the fp32 activations: this warp's 16 channels -> 3 partial sums per pixel,
                     // parked in the (otherwise unused) staging tile as [cq][o][pixel row]
