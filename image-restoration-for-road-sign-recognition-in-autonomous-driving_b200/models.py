@@ -291,8 +291,8 @@ class ResUNet(_B200Module):
         P["final"] = (sd["final.weight"].float().reshape(3, 64).contiguous(), sd["final.bias"].float().contiguous())
         return P
 
-    def _block(self, name, srcs, y, out, out_pool=None, head=None):
-        c1, slope, c2 = self._packed()[name]
+    def _block(self, P, name, srcs, y, out, out_pool=None, head=None):
+        c1, slope, c2 = P[name]
         ops.conv_gemm(srcs, **c1, act=L.B2R_ACT_PRELU, slope=slope, out=y)
         ops.conv_gemm([y] + list(srcs), **c2, act=L.B2R_ACT_RELU, out=out, out_pool=out_pool, **(head or {}))
 
@@ -308,27 +308,27 @@ class ResUNet(_B200Module):
         w0, b0, s0 = P["enc1"]
         e1 = ops.conv3x3_c3(x, w0, b0, act=L.B2R_ACT_PRELU, slope=s0, out=g("e1", H, W, 64))
         r1, p1 = g("r1", H, W, 64), g("p1", H2, W2, 64)
-        self._block("res1", [e1], g("y1", H, W, 64), r1, p1)
+        self._block(P, "res1", [e1], g("y1", H, W, 64), r1, p1)
         r2, p2 = g("r2", H2, W2, 128), g("p2", H4, W4, 128)
-        self._block("res2", [p1], g("y2", H2, W2, 128), r2, p2)
+        self._block(P, "res2", [p1], g("y2", H2, W2, 128), r2, p2)
         r3, p3 = g("r3", H4, W4, 256), g("p3", H8, W8, 256)
-        self._block("res3", [p2], g("y3", H4, W4, 256), r3, p3)
+        self._block(P, "res3", [p2], g("y3", H4, W4, 256), r3, p3)
         bt0, bt1, bt2 = g("bt0", H8, W8, 512), g("bt1", H8, W8, 512), g("bt2", H8, W8, 256)
-        self._block("bottleneck.0", [p3], g("yb0", H8, W8, 512), bt0)
-        self._block("bottleneck.1", [bt0], g("yb1", H8, W8, 512), bt1)
-        self._block("bottleneck.2", [bt1], g("yb2", H8, W8, 256), bt2)
+        self._block(P, "bottleneck.0", [p3], g("yb0", H8, W8, 512), bt0)
+        self._block(P, "bottleneck.1", [bt0], g("yb1", H8, W8, 512), bt1)
+        self._block(P, "bottleneck.2", [bt1], g("yb2", H8, W8, 256), bt2)
         u3 = g("u3", H4, W4, 128)
         ops.conv_gemm([bt2], *P["up3"], None, out=u3, out_mode=L.B2R_OUT_CONVT2X2)
         d3 = g("d3", H4, W4, 128)
-        self._block("dec3", [u3, r3], g("yd3", H4, W4, 128), d3)      # cat((d3, r3), 1) (14:171)
+        self._block(P, "dec3", [u3, r3], g("yd3", H4, W4, 128), d3)      # cat((d3, r3), 1) (14:171)
         u2 = g("u2", H2, W2, 64)
         ops.conv_gemm([d3], *P["up2"], None, out=u2, out_mode=L.B2R_OUT_CONVT2X2)
         d2 = g("d2", H2, W2, 64)
-        self._block("dec2", [u2, r2], g("yd2", H2, W2, 64), d2)       # cat((d2, r2), 1) (14:177)
+        self._block(P, "dec2", [u2, r2], g("yd2", H2, W2, 64), d2)       # cat((d2, r2), 1) (14:177)
         u1 = g("u1", H, W, 64)
         ops.conv_gemm([d2], *P["up1"], None, out=u1, out_mode=L.B2R_OUT_CONVT2X2)
         # dec1 block; its second conv also applies `final` (64 -> 3) and the clamp/quantise: d1 never goes to HBM
-        self._block("dec1", [u1, r1], g("y1", H, W, 64), None,        # cat((d1, r1), 1) (14:183)
+        self._block(P, "dec1", [u1, r1], g("y1", H, W, 64), None,        # cat((d1, r1), 1) (14:183)
                     head=dict(head_w=P["final"][0], head_b=P["final"][1], head_out_f32=out_f32, head_out_u8=out_u8))
 
     @torch.no_grad()
