@@ -22,9 +22,8 @@
 
 namespace b2r {
 
-constexpr int kW3EpiWarps = 16;         // four per TMEM lane quarter, 16 output channels each
+constexpr int kW3EpiWarps = 16;         // two groups of eight (one group per TMEM stage); two warps per lane quarter
 constexpr int kW3Threads = (2 + kW3EpiWarps) * 32;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
-constexpr int kW3EpiThreads = kW3EpiWarps * 32;
 constexpr int kW3BStep = 192 * 128;      // weights of one k-step: 192 rows x 128 B
 constexpr int kW3Slot = 10 * 16 * 128;   // one halo box: (8 + 2) rows x 16 columns x 128 B
 constexpr int kW3Staging = 14336;        // 8 x 14 pixels x 128 B
@@ -41,8 +40,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     const int b_blocks = p.b_slots > 0 ? p.b_slots : p.num_ksteps;   // resident weights, or a ring of weight k-steps
     uint8_t* ring = b_res + b_blocks * kW3BStep;
     uint8_t* sfull = ring + p.ring_slots * kW3Slot;
-    uint8_t* spool = sfull + kW3Staging;
-    float* bias_s = reinterpret_cast<float*>(spool + kW3StagingPool);
+    float* bias_s = reinterpret_cast<float*>(sfull + 2 * (kW3Staging + kW3StagingPool));   // two epilogue groups, each with staging + pool tiles
     float* head_s = bias_s + 64;                                   // [3][64] head weights + [3] head bias (+ pad)
     uint64_t* bars = reinterpret_cast<uint64_t*>(head_s + 200);
     uint64_t* full_bar = bars;
@@ -77,7 +75,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
-                mbar_init(&tmem_empty_bar[s], kW3EpiWarps);
+                mbar_init(&tmem_empty_bar[s], kW3EpiWarps / 2);
             }
             mbar_init(b_full_bar, 1);
             for (int s = 0; s < kN64MaxRing; ++s) {
@@ -174,6 +172,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 const bool center = ((e >> 2) & 1) != 0;
                 mbar_wait_warp(&full_bar[stage], phase);
                 tc_fence_after();
+                if (g == 0 && lane == 0) B2R_STAMP(iter, 7);
                 const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(kW3Slot >> 4);
                 if (!stream_b) {
                     const uint32_t b_lo = b_lo0 + (e >> 20) * uint32_t(kW3BStep >> 4);
@@ -239,50 +238,59 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         }
     } else {
         // ===================================== epilogue =====================================
-        // Sixteen warps: warp w may touch TMEM lanes 32*(w%4).. only, so each lane quarter is shared by four warps that
-        // split the 64 output channels (16 each).  The epilogue costs ~9 instructions per output value (two shuffles
-        // and two adds for the kw shift, bias, activation, convert) and is latency-bound with few warps per SM
-        // sub-partition (profiles/r01_w3_timeline.md: 4 warps 1870 cycles, 8 warps 1180 cycles per tile).
+        // Two independent groups of eight warps; group g owns TMEM stage g, i.e. every other tile, and has its own
+        // staging tile, named barrier and TMA-store bookkeeping.  While one group is still shifting / activating /
+        // staging tile i the other already drains tile i+1, so the per-tile epilogue latency (~1600 cycles, it was the
+        // pacing term with one group: profiles/r01_w3_timeline.md) may span two tile periods.
+        // Within a group, warp w may touch TMEM lanes 32*(w%4).. only: two warps per lane quarter, 32 channels each,
+        // processed as two passes of 16 channels to keep the live accumulator registers at 48.
+        const int group = (warp_idx - 2) >> 3;             // 0 / 1 == TMEM stage
         const int quarter = warp_idx & 3;
-        const int cq = (warp_idx - 2) >> 2;          // channels cq*16 .. cq*16+15
-        const int epi_tid = (warp_idx - 2) * 32 + lane;
+        const int half = ((warp_idx - 2) >> 2) & 1;        // channels half*32 .. half*32+31
+        const int gtid = ((warp_idx - 2) & 7) * 32 + lane; // 0..255 within the group
+        const uint32_t bar_id = 1u + uint32_t(group);
+        uint8_t* sfull_g = sfull + group * (kW3Staging + kW3StagingPool);
+        uint8_t* spool_g = sfull_g + kW3Staging;
         const int hh = quarter * 2 + (lane >> 4);  // tile row of this lane's pixel
         const int cc = lane & 15;                  // buffer column; output column w = cc is valid for cc < 14
         const int srow = hh * 14 + cc;             // row of the 8 x 14 staging tile
         const bool valid = cc < 14;
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-        float b16[16];                             // this warp's 16 output channels never change: bias lives in registers
-        {
-            const uint32_t ba = smem_u32(bias_s + cq * 16);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(b16[4 * i]), "=f"(b16[4 * i + 1]), "=f"(b16[4 * i + 2]), "=f"(b16[4 * i + 3])
-                             : "r"(ba + 16 * i));
-        }
         constexpr bool has_head = kHead;
         const bool relu_only = p.act == B2R_ACT_RELU;
         const float ns = act_neg_slope(p.act, p.slope);
-        int acc = 0;
+        const uint32_t tacc = tmem_base + lane_base + uint32_t(group * 256);
         uint32_t acc_phase = 0;
-        int iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-            mbar_wait_warp(&tmem_full_bar[acc], acc_phase);
+        int iter = group;
+        for (long tile = (long)blockIdx.x + (long)group * gridDim.x; tile < total_tiles; tile += 2L * gridDim.x, iter += 2) {
+            mbar_wait_warp(&tmem_full_bar[group], acc_phase);
             tc_fence_after();
-            if (epi_tid == 0) B2R_STAMP(iter, 3);
-            const uint32_t tacc = tmem_base + lane_base + uint32_t(acc * 256);
-            {
-                // Drain first, synchronise later: the accumulator goes to registers and the TMEM stage is handed back
-                // to the MMA warp BEFORE this tile waits for the shared staging buffer, so neither the CTA-wide
-                // barrier nor the shift-add / activation / staging sit on the MMA <-> epilogue hand-off chain.
+            if (gtid == 0) B2R_STAMP(iter, 3);
+            uint32_t packed[16];   // 32 output channels of this lane's pixel as bf16 pairs
+            float hs0 = 0.f, hs1 = 0.f, hs2 = 0.f;
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+                const int ch0 = half * 32 + sub * 16;
                 uint32_t d0[16], d1[16], d2[16];
-                tmem_ld_32x16(tacc + uint32_t(cq * 16), d0);          // kw = 0 partial sums of this warp's channels
-                tmem_ld_32x16(tacc + uint32_t(64 + cq * 16), d1);     // kw = 1
-                tmem_ld_32x16(tacc + uint32_t(128 + cq * 16), d2);    // kw = 2
+                tmem_ld_32x16(tacc + uint32_t(ch0), d0);          // kw = 0 partial sums
+                tmem_ld_32x16(tacc + uint32_t(64 + ch0), d1);     // kw = 1
+                tmem_ld_32x16(tacc + uint32_t(128 + ch0), d2);    // kw = 2
                 tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                if (sub == 1) {
+                    // the accumulator is in registers: hand the TMEM stage back before any of the math below
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[group]);
+                }
+                float b16[16];
+                {
+                    const uint32_t ba = smem_u32(bias_s + ch0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(b16[4 * i]), "=f"(b16[4 * i + 1]), "=f"(b16[4 * i + 2]), "=f"(b16[4 * i + 3])
+                                     : "r"(ba + 16 * i));
+                }
                 float x[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -297,15 +305,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 16; ++j) x[j] = apply_act_ns(x[j], ns);
                 }
-                // only now is the shared staging tile needed: wait until the previous tile's TMA store has read it
-                if (epi_tid == 0) tma_store_wait_read<0>();
-                named_barrier_sync(1, kW3EpiThreads);
-                if (epi_tid == 0) B2R_STAMP(iter, 4);
                 if (has_head) {
-                    // fused 64 -> 3 head on the fp32 activations: this warp's 16 channels -> 3 partial sums per pixel,
-                    // parked in the (otherwise unused) staging tile as [cq][o][pixel row]
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-                    const uint32_t ha = smem_u32(head_s + cq * 16);
+                    // fused 64 -> 3 head on the fp32 activations: partial sums over this warp's channels
+                    const uint32_t ha = smem_u32(head_s + ch0);
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
                         float w0[4], w1[4], w2[4];
@@ -314,43 +316,50 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w2[0]), "=f"(w2[1]), "=f"(w2[2]), "=f"(w2[3]) : "r"(ha + 512 + 16 * j4));
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            s0 = fmaf(x[4 * j4 + j], w0[j], s0);
-                            s1 = fmaf(x[4 * j4 + j], w1[j], s1);
-                            s2 = fmaf(x[4 * j4 + j], w2[j], s2);
+                            hs0 = fmaf(x[4 * j4 + j], w0[j], hs0);
+                            hs1 = fmaf(x[4 * j4 + j], w1[j], hs1);
+                            hs2 = fmaf(x[4 * j4 + j], w2[j], hs2);
                         }
                     }
-                    float* part = reinterpret_cast<float*>(sfull) + (cq * 3) * 128 + quarter * 32 + lane;
-                    part[0] = s0;
-                    part[128] = s1;
-                    part[256] = s2;
                 }
-                if (valid && (!kHead || p.store_full)) {   // without a head the tile is always staged (store and/or pool)
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const uint32_t o0 = pack_bf16x2(x[8 * q], x[8 * q + 1]), o1 = pack_bf16x2(x[8 * q + 2], x[8 * q + 3]);
-                        const uint32_t o2 = pack_bf16x2(x[8 * q + 4], x[8 * q + 5]), o3 = pack_bf16x2(x[8 * q + 6], x[8 * q + 7]);
-                        const int jj = cq * 2 + q;   // 16-byte chunk of the 128-byte staging row
-                        const uint32_t addr = smem_u32(sfull) + uint32_t(srow * 128 + ((jj ^ (srow & 7)) << 4));
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
-                                     : "memory");
-                    }
+                for (int j = 0; j < 8; ++j) packed[sub * 8 + j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+            }
+            // only now is this group's staging tile needed: wait until its previous TMA store has read it
+            if (gtid == 0) tma_store_wait_read<0>();
+            named_barrier_sync(bar_id, 256);
+            if (gtid == 0) B2R_STAMP(iter, 4);
+            if (has_head) {
+                // partial sums parked in the (otherwise unused) staging tile as [half][o][pixel row]
+                float* part = reinterpret_cast<float*>(sfull_g) + (half * 3) * 128 + quarter * 32 + lane;
+                part[0] = hs0;
+                part[128] = hs1;
+                part[256] = hs2;
+            }
+            if (valid && (!kHead || p.store_full)) {   // without a head the tile is always staged (store and/or pool)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int jj = half * 4 + q;   // 16-byte chunk of the 128-byte staging row
+                    const uint32_t addr = smem_u32(sfull_g) + uint32_t(srow * 128 + ((jj ^ (srow & 7)) << 4));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * q]), "r"(packed[4 * q + 1]),
+                                 "r"(packed[4 * q + 2]), "r"(packed[4 * q + 3])
+                                 : "memory");
                 }
             }
-            if (epi_tid == 0) B2R_STAMP(iter, 5);
+            if (gtid == 0) B2R_STAMP(iter, 5);
             fence_proxy_async_smem();
-            named_barrier_sync(1, kW3EpiThreads);
-            if (has_head && cq == 0) {
-                // one thread per pixel: add the four partial sums (fixed order) + bias, then the reference's outputs
-                const int n0 = tile / tiles_per_img;
-                const int t = tile - n0 * tiles_per_img;
+            named_barrier_sync(bar_id, 256);
+            if (has_head && half == 0) {
+                // one thread per pixel: add the two partial sums + bias, then the reference's outputs
+                const int n0 = int(tile / tiles_per_img);
+                const int t = int(tile - (long)n0 * tiles_per_img);
                 const int w = (t % p.tiles_w) * 14 + cc;
                 const int h = (t / p.tiles_w) * 8 + hh;
                 if (valid && w < p.W && h < p.H) {
-                    const float* part = reinterpret_cast<const float*>(sfull) + quarter * 32 + lane;
+                    const float* part = reinterpret_cast<const float*>(sfull_g) + quarter * 32 + lane;
                     float v[3];
 #pragma unroll
-                    for (int o = 0; o < 3; ++o)
-                        v[o] = (((part[o * 128] + part[(3 + o) * 128]) + part[(6 + o) * 128]) + part[(9 + o) * 128]) + head_s[192 + o];
+                    for (int o = 0; o < 3; ++o) v[o] = (part[o * 128] + part[(3 + o) * 128]) + head_s[192 + o];
                     const size_t hw = size_t(p.H) * p.W, pix = size_t(h) * p.W + w;
                     if (p.head_f32) {
 #pragma unroll
@@ -364,25 +373,24 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 }
             }
             if (p.store_pool) {
-                if (epi_tid < 28 * 4) epilogue_pool_chunk(sfull, spool, epi_tid, 14, 8);
+                if (gtid < 28 * 4) epilogue_pool_chunk(sfull_g, spool_g, gtid, 14, 8);
                 fence_proxy_async_smem();
-                named_barrier_sync(1, kW3EpiThreads);
+                named_barrier_sync(bar_id, 256);
             }
-            if (epi_tid == 0) {
+            if (gtid == 0) {
                 // only the issuing thread needs the tile coordinates (three integer divisions)
-                const int n0 = tile / tiles_per_img;
-                const int t = tile - n0 * tiles_per_img;
+                const int n0 = int(tile / tiles_per_img);
+                const int t = int(tile - (long)n0 * tiles_per_img);
                 const int w0 = (t % p.tiles_w) * 14;
                 const int h0 = (t / p.tiles_w) * 8;
-                if (p.store_full) tma_store_4d(&p.out_map, sfull, 0, w0, h0, n0);
-                if (p.store_pool) tma_store_4d(&p.pool_map, spool, 0, w0 >> 1, h0 >> 1, n0);
+                if (p.store_full) tma_store_4d(&p.out_map, sfull_g, 0, w0, h0, n0);
+                if (p.store_pool) tma_store_4d(&p.pool_map, spool_g, 0, w0 >> 1, h0 >> 1, n0);
                 tma_store_commit();
                 B2R_STAMP(iter, 6);
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            acc_phase ^= 1;
         }
-        if (epi_tid == 0) tma_store_wait_all<0>();
+        if (gtid == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -395,7 +403,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 }
 
 size_t conv_w3_smem_bytes(int b_blocks, int ring_slots) {
-    return 1024 + size_t(b_blocks) * kW3BStep + size_t(ring_slots) * kW3Slot + kW3Staging + kW3StagingPool + 256 + 800 + 512;
+    return 1024 + size_t(b_blocks) * kW3BStep + size_t(ring_slots) * kW3Slot + 2 * (kW3Staging + kW3StagingPool) + 256 + 800 + 512;
 }
 
 int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream) {

@@ -35,9 +35,9 @@ def main():
         print(f"--- C_in {ci} pooled={pooled}: per tile (cycles), tiles 20..27 of CTA 0")
         print(" tile | tile period | mma issue span | acc ready->epi start wait | epi: wait staging | drain TMEM+shift+stage | pool+store issue")
         base = int(t[20, 1])
-        print(" raw stamps relative to MMA start of tile 20: [producer issue, mma start, mma issued, epi start, staging free, drained, stores issued]")
+        print(" raw stamps relative to MMA start of tile 20: [producer issue, mma start(tmem free), mma issued, epi start(acc ready), staging free, staged, stores issued, mma A-data ready]")
         for i in range(20, 26):
-            print(f"   tile {i}: " + " ".join(f"{int(t[i, k]) - base:7d}" for k in range(7)))
+            print(f"   tile {i}: " + " ".join(f"{int(t[i, k]) - base:7d}" for k in range(8)))
         for i in range(20, 28):
             period = int(t[i + 1, 3] - t[i, 3])
             print(f" {i:4d} | {period:11d} | {int(t[i, 2] - t[i, 1]):14d} | "
