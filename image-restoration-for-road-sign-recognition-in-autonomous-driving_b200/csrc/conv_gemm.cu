@@ -56,14 +56,18 @@ template <int BLOCK_N>
 struct GemmCfg {
     static constexpr int kBStageBytes = BLOCK_N * 128;
     static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
-    static constexpr int kStages = BLOCK_N == 64 ? 6 : (BLOCK_N == 128 ? 5 : 3);
+    // BLOCK_N = 128: two co-resident CTAs per SM (2 x 256 TMEM columns, 2 x 106 KB of shared memory) with two stages
+    // each beat one CTA with five stages by 5-12 % (A/B in one gpurun call): while one CTA's roles are handing off
+    // (commit -> epilogue wake -> release -> MMA wake), the other CTA keeps the tensor pipe busy.
+    static constexpr int kStages = BLOCK_N == 64 ? 6 : (BLOCK_N == 128 ? 2 : 3);
+    static constexpr int kCtasPerSm = BLOCK_N == 128 ? 2 : 1;
     static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
     static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * (kStagingFull + kStagingPool) +
                                       BLOCK_N * 4 /*bias*/ + 256 /*barriers + tmem ptr*/;
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+__global__ void __launch_bounds__(kNumThreads, GemmCfg<BLOCK_N>::kCtasPerSm) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     using Cfg = GemmCfg<BLOCK_N>;
     constexpr int kStages = Cfg::kStages;
     constexpr uint32_t kIdesc = make_idesc_bf16_f32(kBlockM, BLOCK_N);
@@ -309,10 +313,12 @@ static bool n64_disabled() {
 }
 
 // returns B2R_OK and sets *handled when the layer was launched on the specialised kernel
-static int try_conv_n64(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* handled) {
+// cout = 64: resident weights (conv_n64.cu).  (A C_out = 128 variant with streamed weights was tried and was slower than
+// the generic kernel with two CTAs per SM; it is not kept.)
+static int try_conv_halo(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* handled, int cout) {
     *handled = false;
-    if (n64_disabled() || (d->flags & B2R_CONV_GENERIC_ONLY) || d->out_mode != B2R_OUT_NHWC || d->cout_total != 64 || d->kblocks_host == nullptr) return B2R_OK;
-    if (d->block_n != 0 && d->block_n != 64) return B2R_OK;
+    if (n64_disabled() || (d->flags & B2R_CONV_GENERIC_ONLY) || d->out_mode != B2R_OUT_NHWC || d->cout_total != cout || d->kblocks_host == nullptr) return B2R_OK;
+    if (d->block_n != 0 && d->block_n != cout) return B2R_OK;
     if (d->tile_n > 1) return B2R_OK;
     const int nk = d->num_kblocks;
     uint32_t slots[kN64MaxSlots];
@@ -368,9 +374,9 @@ static int try_conv_n64(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* 
     }
     {
         const uint64_t K = (uint64_t)nk * 64;
-        const uint64_t dims[2] = {K, 64};
+        const uint64_t dims[2] = {K, (uint64_t)cout};
         const uint64_t strides[1] = {K * 2};
-        const uint32_t box[2] = {64, 64};
+        const uint32_t box[2] = {64, (uint32_t)cout};
         int rc = encode_tmap_bf16(&P.b_map, d->weights, 2, dims, strides, box);
         if (rc) return rc;
     }
@@ -550,7 +556,7 @@ static int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
                                       Cfg::kSmemBytes));
         if (dev < 64) attr_set[dev] = true;
     }
-    conv_gemm_kernel<BLOCK_N><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
+    conv_gemm_kernel<BLOCK_N><<<grid * Cfg::kCtasPerSm, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
     B2R_CHECK_LAUNCH();
     return B2R_OK;
 }
@@ -610,7 +616,7 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
         if (rc || handled) return rc;
         B2R_REQUIRE(!head, "the fused head is only implemented on the tap-folded kernel, which rejected this layer "
                            "(weights too large to stay resident in shared memory?)");
-        rc = try_conv_n64(d, stream, &handled);
+        rc = try_conv_halo(d, stream, &handled, 64);
         if (rc || handled) return rc;
     }
 
