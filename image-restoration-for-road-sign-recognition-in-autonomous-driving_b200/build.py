@@ -39,18 +39,25 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source into libb2r.so; returns the path."""
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: Path | None = None) -> Path:
+    """Compile every CUDA source into libb2r.so; returns the path.
+
+    `defines` / `out` build a VARIANT next to the product library (e.g. defines=("B2R_TIMELINE",) for the role
+    timelines of tools/role_timeline.py, loaded through $B2R_LIB); the product build takes neither."""
+    variant = bool(defines) or out is not None
+    lib_path = Path(out) if out is not None else LIB_PATH
+    if variant and out is None:
+        raise ValueError("a variant build needs its own output path")
+    if not variant and not force and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
-    objdir = PKG_DIR / "build"
-    objdir.mkdir(exist_ok=True)
+    objdir = PKG_DIR / "build" / ("variant_" + "_".join(defines) if variant else "")
+    objdir.mkdir(parents=True, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = objdir / (src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -62,14 +69,18 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *objs,
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib_path), *objs,
             "-cudart", "static"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    # python -m b200restore.build [--force] [-v] [--define NAME ... --out PATH]
+    argv = sys.argv[1:]
+    defs = tuple(argv[i + 1] for i, a in enumerate(argv) if a == "--define")
+    outp = next((Path(argv[i + 1]) for i, a in enumerate(argv) if a == "--out"), None)
+    path = build(force="--force" in argv, verbose="-v" in argv, defines=defs, out=outp)
     print(path)

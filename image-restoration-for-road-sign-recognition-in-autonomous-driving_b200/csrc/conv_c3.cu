@@ -1,9 +1,10 @@
 // First conv layer (C_in = 3 -> 64) on tcgen05: im2col built on the fly by producer warps.
 //
 // K = 27 is far too small for TMA-staged k-blocks, and on CUDA cores the layer costs 1728 FMA per pixel (it was 11 %
-// of the whole pipeline, profiles/r01_launches_v1_summary.md).  Here four producer warps (one thread per output
-// pixel of the 8 x 16 tile) gather the 27 inputs of their pixel straight from global memory (through L1; the next
-// tile's values are prefetched into registers), convert them and write one 128-byte row of the A operand directly in
+// of the whole pipeline, profiles/r01_launches_v1_summary.md).  Here producer warps (groups of four, one thread per
+// output pixel of the 8 x 16 tile) fetch the tile's 10 x 18 x 3 input halo once (<= 5 values per thread, prefetched a
+// tile ahead), convert it and park it in shared memory; each thread then reads the 27 values of its pixel from there
+// (no per-tap address arithmetic or bounds checks) and writes one 128-byte row of the A operand directly in
 // the SWIZZLE_128B K-major layout the MMA reads.  K is laid out as 27 (hi, lo) bf16 pairs: x = hi + lo carries ~16
 // mantissa bits of the fp32 activation, and the packed weight matrix repeats each weight for both halves, so the
 // activation side of this layer stays near fp32 accuracy at no cost (K = 54 <= 64, four MMAs of N = 64 per tile).
@@ -26,10 +27,14 @@ constexpr int kC3EpiWarps = 8;        // two warps per TMEM lane quarter, 32 cha
 constexpr int kC3Threads = (kC3ProducerWarps + 1 + kC3EpiWarps) * 32;
 constexpr int kC3Stages = 4;
 constexpr int kC3AccStages = 4;       // TMEM accumulator stages (4 x 64 columns)
+constexpr int kC3HaloRS = 80;         // words per halo row (54 used): RS % 32 == 16 keeps a warp's two pixel rows on disjoint banks
+constexpr int kC3HaloWords = 10 * kC3HaloRS;
+constexpr int kC3HaloPerThread = 5;   // ceil(10 * 18 * 3 / 128)
+constexpr size_t kC3Smem = 1024 + kC3Stages * 16384 + 8192 + kC3EpiWarps * 4096 + 768 * 4 + 4 * kC3HaloWords * 4 + 256 + 256;
 
 struct alignas(64) ConvC3Params {
     CUtensorMap b_map;    // packed weights bf16 [64][64], box 64 x 64
-    CUtensorMap out_map;  // NHWC bf16 [N,H,W,64], box 64 x 16 x 8 x 1
+    CUtensorMap out_map;  // NHWC bf16 [N,H,W,64], box 64 x 16 x 2 x 1
     const void* in;
     const float* bias;
     float mean[3], stdv[3];
@@ -56,9 +61,10 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_st = smem;                               // kC3Stages x 16 KB
     uint8_t* b_s = a_st + kC3Stages * 16384;            // 8 KB
-    uint8_t* sfull = b_s + 8192;                        // 16 KB staging
-    uint32_t* lut = reinterpret_cast<uint32_t*>(sfull + 16384);  // [3][256] packed (hi, lo)
-    float* bias_s = reinterpret_cast<float*>(lut + 768);
+    uint8_t* sfull = b_s + 8192;                        // kC3EpiWarps x 4 KB staging slabs (32 pixels x 64 ch each)
+    uint32_t* lut = reinterpret_cast<uint32_t*>(sfull + kC3EpiWarps * 4096);  // [3][256] packed (hi, lo)
+    uint32_t* halo = lut + 768;                         // [2 groups][2 buffers][10][kC3HaloRS] packed (hi, lo)
+    float* bias_s = reinterpret_cast<float*>(halo + 4 * kC3HaloWords);
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 64);
     uint64_t* full_bar = bars;                  // [kC3Stages], 128 producer arrivals
     uint64_t* empty_bar = bars + kC3Stages;     // [kC3Stages]
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
             }
             for (int s = 0; s < kC3AccStages; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
-                mbar_init(&tmem_empty_bar[s], kC3EpiWarps);
+                mbar_init(&tmem_empty_bar[s], 4);   // the four warps of one epilogue group
             }
             mbar_init(b_full_bar, 1);
             fence_mbar_init();
@@ -112,59 +118,95 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
         const int group = warp_idx >> 2;      // 0 / 1: this group builds tile iterations group, group + 2, ...
         const int r = threadIdx.x & 127;      // tile row == pixel (h = r / 16, w = r % 16)
         const int ph = r >> 4, pw = r & 15;
-        uint32_t cur[27], nxt[27];
+        // The 10 x 18 x 3 input halo of a tile (540 values) is fetched ONCE by the group (<= 5 values per thread,
+        // consecutive threads on consecutive addresses), converted to packed (hi, lo) words and parked in shared
+        // memory; every thread then reads the 27 words of its pixel from there.  The per-thread element assignment
+        // does not depend on the tile, so its decomposition is done once, here.
+        uint32_t e_meta[kC3HaloPerThread];    // row | px << 8 | c << 16 | valid << 24
+        uint32_t e_rel[kC3HaloPerThread];     // element offset from the halo's top-left input element
+#pragma unroll
+        for (int j = 0; j < kC3HaloPerThread; ++j) {
+            const int e = r + 128 * j;
+            int row, px, c;
+            if (IN_FMT == B2R_IN_U8_NHWC) {
+                row = e / 54;
+                px = (e % 54) / 3;
+                c = e % 3;
+                e_rel[j] = uint32_t(row * W * 3 + px * 3 + c);
+            } else {
+                c = e / 180;
+                row = (e % 180) / 18;
+                px = e % 18;
+                e_rel[j] = uint32_t((c * H + row) * W + px);
+            }
+            e_meta[j] = uint32_t(row) | uint32_t(px) << 8 | uint32_t(c) << 16 | uint32_t(e < 540) << 24;
+        }
+        const uint32_t halo_base = smem_u32(halo) + uint32_t(group * 2 * kC3HaloWords * 4);
+        const uint32_t lut_addr = smem_u32(lut);
+        uint32_t raw[kC3HaloPerThread];
 
-        auto gather = [&](int tile, uint32_t (&v)[27]) {
-            const int n0 = tile / tiles_per_img;
-            const int t = tile - n0 * tiles_per_img;
-            const int w = (t % p.tiles_w) * 16 + pw;
-            const int h = (t / p.tiles_w) * 8 + ph;
+        const long stride = 2L * gridDim.x;
+        long tile = (long)blockIdx.x + (long)group * gridDim.x;
+        TileWalk ti;   // the tile whose halo is fetched next
+        ti.init(tile, stride, p.tiles_w, p.tiles_h);
+
+        auto gather = [&]() {
+            const int n0 = ti.n;
+            const int w0 = ti.tw * 16 - 1;
+            const int h0 = ti.th * 8 - 1;
+            const long base = (IN_FMT == B2R_IN_U8_NHWC) ? ((long(n0) * H + h0) * W + w0) * 3
+                                                          : (long(n0) * 3 * H + h0) * W + w0;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-                const int hh = h + kh - 1;
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const int ww = w + kw - 1;
-                    const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const int idx = (kh * 3 + kw) * 3 + c;
-                        if (IN_FMT == B2R_IN_U8_NHWC) {
-                            // raw byte now, table lookup later (0x100 marks padding)
-                            v[idx] = ok ? uint32_t(__ldg(static_cast<const uint8_t*>(p.in) +
-                                                         ((size_t(n0) * H + hh) * W + ww) * 3 + c))
-                                        : 0x100u;
-                        } else {
-                            v[idx] = ok ? __float_as_uint(__ldg(static_cast<const float*>(p.in) +
-                                                                ((size_t(n0) * 3 + c) * H + hh) * W + ww))
-                                        : 0u;
-                        }
-                    }
+            for (int j = 0; j < kC3HaloPerThread; ++j) {
+                const int hh = h0 + int(e_meta[j] & 0xFFu);
+                const int ww = w0 + int((e_meta[j] >> 8) & 0xFFu);
+                const bool ok = (e_meta[j] >> 24) && hh >= 0 && hh < H && ww >= 0 && ww < W;
+                if (IN_FMT == B2R_IN_U8_NHWC) {
+                    // raw byte now, table lookup later (0x100 marks padding)
+                    raw[j] = ok ? uint32_t(__ldg(static_cast<const uint8_t*>(p.in) + base + e_rel[j])) : 0x100u;
+                } else {
+                    raw[j] = ok ? __float_as_uint(__ldg(static_cast<const float*>(p.in) + base + e_rel[j])) : 0u;
                 }
             }
         };
 
-        const long stride = 2L * gridDim.x;
-        long tile = (long)blockIdx.x + (long)group * gridDim.x;
         int it = group;
-        if (tile < total_tiles) gather((int)tile, cur);
-        for (; tile < total_tiles; tile += stride, it += 2) {
-            const long next = tile + stride;
-            if (next < total_tiles) gather((int)next, nxt);   // prefetch: these loads complete while the row is built
-            uint32_t wrd[32];
-            const uint32_t lut_addr = smem_u32(lut);
+        uint32_t par = 0;
+        if (tile < total_tiles) gather();
+        for (; tile < total_tiles; tile += stride, it += 2, par ^= 1u) {
+            // halo words of this tile -> shared memory.  Two buffers per group: a thread can only be here after the
+            // group barrier of the previous tile, i.e. after every thread finished reading the tile before that.
+            const uint32_t hb = halo_base + par * uint32_t(kC3HaloWords * 4);
 #pragma unroll
-            for (int i = 0; i < 27; ++i) {
+            for (int j = 0; j < kC3HaloPerThread; ++j) {
+                uint32_t word;
                 if (IN_FMT == B2R_IN_U8_NHWC) {
-                    // explicit ld.shared (a generic pointer into shared memory would compile to LD.E); entry 256 of
-                    // each channel's table row is not used: padding is resolved by the select below
+                    // explicit ld.shared (a generic pointer into shared memory would compile to LD.E)
                     uint32_t e;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(e) : "r"(lut_addr + (uint32_t(i % 3) * 256u + (cur[i] & 0xFFu)) * 4u));
-                    wrd[i] = (cur[i] & 0x100u) ? 0u : e;
+                    asm volatile("ld.shared.b32 %0, [%1];"
+                                 : "=r"(e)
+                                 : "r"(lut_addr + (((e_meta[j] >> 16) & 0xFFu) * 256u + (raw[j] & 0xFFu)) * 4u));
+                    word = (raw[j] & 0x100u) ? 0u : e;
                 } else {
-                    wrd[i] = split_hi_lo(__uint_as_float(cur[i]));
+                    word = split_hi_lo(__uint_as_float(raw[j]));
                 }
+                const uint32_t widx = (e_meta[j] & 0xFFu) * uint32_t(kC3HaloRS) + ((e_meta[j] >> 8) & 0xFFu) * 3u +
+                                      ((e_meta[j] >> 16) & 0xFFu);
+                if (e_meta[j] >> 24) asm volatile("st.shared.b32 [%0], %1;" ::"r"(hb + widx * 4u), "r"(word) : "memory");
             }
+            const long next = tile + stride;
+            ti.next(p.tiles_w, p.tiles_h);
+            if (next < total_tiles) gather();   // these loads complete while the row is built
+            named_barrier_sync(2 + group, 128);
+            uint32_t wrd[32];
+            const uint32_t px_addr = hb + uint32_t((ph * kC3HaloRS + pw * 3) * 4);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int i = 0; i < 9; ++i)   // i = kw * 3 + c: nine consecutive words of halo row ph + kh
+                    asm volatile("ld.shared.b32 %0, [%1];"
+                                 : "=r"(wrd[kh * 9 + i])
+                                 : "r"(px_addr + uint32_t((kh * kC3HaloRS + i) * 4)));
 #pragma unroll
             for (int i = 27; i < 32; ++i) wrd[i] = 0u;
             const int stage = it % kC3Stages;
@@ -183,8 +225,6 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
             fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
             mbar_arrive(&full_bar[stage]);
             if (r == 0) C3_STAMP(it, 2);
-#pragma unroll
-            for (int i = 0; i < 27; ++i) cur[i] = nxt[i];
         }
     } else if (warp_idx == kC3ProducerWarps) {
         // ===================================== weight load + MMA issuer =====================================
@@ -223,48 +263,50 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
         }
     } else {
         // ===================================== epilogue =====================================
-        const int quarter = warp_idx & 3;
-        const int half = (warp_idx - (kC3ProducerWarps + 1)) >> 2;   // channels half*32 .. half*32+31
-        const int row = quarter * 32 + lane;
+        // Every warp is on its own: it drains the 32 TMEM lanes (= 32 pixels = two tile rows) it may access, all 64
+        // channels, stages them in a private 4 KB slab and stores that slab with its own TMA box (64 ch x 16 x 2).
+        // No CTA-wide barrier anywhere; the two groups of four warps take alternate tiles (TMEM stages it % 4).
+        const int quarter = warp_idx & 3;                              // TMEM lane quarter == tile rows 2q, 2q + 1
+        const int group = (warp_idx - (kC3ProducerWarps + 1)) >> 2;
         const bool leader = (warp_idx == kC3ProducerWarps + 1 && lane == 0);
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-        float b32[32];
-        lds_bias32(bias_s + half * 32, b32);
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int n0 = tile / tiles_per_img;
-            const int t = tile - n0 * tiles_per_img;
-            const int w0 = (t % p.tiles_w) * 16;
-            const int h0 = (t / p.tiles_w) * 8;
+        uint8_t* slab = sfull + (group * 4 + quarter) * 4096;
+        const long stride = 2L * gridDim.x;
+        long tile = (long)blockIdx.x + (long)group * gridDim.x;
+        TileWalk ti;
+        ti.init(tile, stride, p.tiles_w, p.tiles_h);
+        for (int it = group; tile < total_tiles; tile += stride, it += 2, ti.next(p.tiles_w, p.tiles_h)) {
+            const int acc = it & (kC3AccStages - 1);
+            const uint32_t acc_phase = uint32_t(it / kC3AccStages) & 1u;
             mbar_wait_warp(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             if (leader) C3_STAMP(it, 4);
             uint32_t v[32];
-            tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * 64 + half * 32), v);
+            float b32[32];
+            tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * 64), v);
+            tmem_ld_wait();
+            if (lane == 0) tma_store_wait_read<0>();   // this warp's previous store has finished reading the slab
+            __syncwarp();
+            if (leader) C3_STAMP(it, 5);
+            lds_bias32(bias_s, b32);
+            epilogue_store_half(v, b32, p.act, p.slope, slab, lane, 0);
+            tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * 64 + 32), v);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-            if (leader) C3_STAMP(it, 5);
-            if (leader) tma_store_wait_read<0>();   // previous tile's store has finished reading the staging tile
-            named_barrier_sync(1, kC3EpiWarps * 32);
+            lds_bias32(bias_s + 32, b32);
+            epilogue_store_half(v, b32, p.act, p.slope, slab, lane, 1);
             if (leader) C3_STAMP(it, 6);
-            epilogue_store_half(v, b32, p.act, p.slope, sfull, row, half);
             fence_proxy_async_smem();
-            named_barrier_sync(1, kC3EpiWarps * 32);
-            if (leader) {
-                tma_store_4d(&p.out_map, sfull, 0, w0, h0, n0);
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_4d(&p.out_map, slab, 0, ti.tw * 16, ti.th * 8 + quarter * 2, ti.n);
                 tma_store_commit();
-                C3_STAMP(it, 7);
             }
-            if (++acc == kC3AccStages) {
-                acc = 0;
-                acc_phase ^= 1;
-            }
+            if (leader) C3_STAMP(it, 7);
         }
-        if (leader) tma_store_wait_all<0>();
+        if (lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -303,7 +345,7 @@ extern "C" int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host
     {
         const uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         const uint64_t strides[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
-        const uint32_t box[4] = {64, 16, 8, 1};
+        const uint32_t box[4] = {64, 16, 2, 1};   // one epilogue warp's slab: 32 pixels = two tile rows
         int rc = encode_tmap_bf16(&P.out_map, out, 4, dims, strides, box);
         if (rc) return rc;
     }
@@ -328,7 +370,7 @@ extern "C" int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host
     int rc = device_sm_count(&sms);
     if (rc) return rc;
     const int grid = (int)(total_tiles < sms ? total_tiles : sms);
-    const size_t smem = 1024 + kC3Stages * 16384 + 8192 + 16384 + 768 * 4 + 256 + 256;
+    const size_t smem = kC3Smem;
     static bool attr_set[64][2] = {{false}};
     int dev = 0;
     B2R_CUDA(cudaGetDevice(&dev));

@@ -60,6 +60,38 @@ size_t conv_w3_smem_bytes(int b_blocks, int ring_slots);
 int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream);
 
 #ifdef __CUDACC__
+// Walks tiles first, first + stride, ... as (image, tile row, tile column) without per-tile integer divisions: the two
+// divisions per tile were ~350 cycles of dependent latency, and the compiler sinks them into the single thread that
+// issues the TMA store, i.e. onto the epilogue's critical path (profiles/r01_c3_timeline.md).
+struct TileWalk {
+    int n, th, tw;
+    int dn, dth, dtw;
+    __device__ __forceinline__ void init(long first, long stride, int tiles_w, int tiles_h) {
+        const long per_img = long(tiles_w) * tiles_h;
+        n = int(first / per_img);
+        int t = int(first - n * per_img);
+        th = t / tiles_w;
+        tw = t - th * tiles_w;
+        dn = int(stride / per_img);
+        t = int(stride - dn * per_img);
+        dth = t / tiles_w;
+        dtw = t - dth * tiles_w;
+    }
+    __device__ __forceinline__ void next(int tiles_w, int tiles_h) {
+        tw += dtw;
+        th += dth;
+        n += dn;
+        if (tw >= tiles_w) {
+            tw -= tiles_w;
+            ++th;
+        }
+        if (th >= tiles_h) {
+            th -= tiles_h;
+            ++n;
+        }
+    }
+};
+
 // All three activations are y = max(x, 0) + ns * min(x, 0) with ns = 0 (ReLU), slope (PReLU), 1 (none): branch-free and
 // exact in each case (one of the two terms is always a signed zero).
 __device__ __forceinline__ float act_neg_slope(int act, float slope) {
@@ -101,9 +133,11 @@ __device__ __forceinline__ void epilogue_store_half(const uint32_t (&v)[32], con
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int j = q * 8 + e * 2;
-            const float x0 = apply_act_ns(__uint_as_float(v[j]) + bias32[j], ns);
-            const float x1 = apply_act_ns(__uint_as_float(v[j + 1]) + bias32[j + 1], ns);
-            o[e] = pack_bf16x2(x0, x1);
+            const float y0 = __uint_as_float(v[j]) + bias32[j], y1 = __uint_as_float(v[j + 1]) + bias32[j + 1];
+            if (act == B2R_ACT_RELU)   // warp-uniform; rounding is monotonic and max(+0, -0) = +0, so this is
+                o[e] = bf16x2_max(pack_bf16x2(y0, y1), 0u);   // bit-identical to rounding max(y, 0)
+            else
+                o[e] = pack_bf16x2(apply_act_ns(y0, ns), apply_act_ns(y1, ns));
         }
         const int jj = half * 4 + q;
         const uint32_t addr = smem_u32(sfull) + uint32_t(row * 128 + ((jj ^ (row & 7)) << 4));

@@ -22,12 +22,22 @@
 
 namespace b2r {
 
-constexpr int kW3EpiWarps = 16;         // two groups of eight (one group per TMEM stage); two warps per lane quarter
+constexpr int kW3EpiWarps = 16;         // four warps per TMEM lane quarter, 16 output channels each
 constexpr int kW3Threads = (2 + kW3EpiWarps) * 32;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int kW3BStep = 192 * 128;      // weights of one k-step: 192 rows x 128 B
 constexpr int kW3Slot = 10 * 16 * 128;   // one halo box: (8 + 2) rows x 16 columns x 128 B
 constexpr int kW3Staging = 14336;        // 8 x 14 pixels x 128 B
 constexpr int kW3StagingPool = 4096;     // 4 x 7 pixels x 128 B, padded
+
+// Role timeline (debug builds only: nvcc -DB2R_TIMELINE, see tools/role_timeline.py): CTA 0 stamps clock64() for its
+// first B2R_DBG_TILES tiles.  Compiled out of the product: even predicated off, each stamp cost the MMA warp ~10
+// instructions on its critical path.
+#ifdef B2R_TIMELINE
+#define B2R_STAMP(iter, slot) \
+    do { if (p.dbg != nullptr && blockIdx.x == 0 && (iter) < B2R_DBG_TILES) p.dbg[(iter) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define B2R_STAMP(iter, slot) do { } while (0)
+#endif
 
 // kHead = true adds the fused 64 -> 3 output head; it is a separate instantiation because even unused, the extra
 // epilogue code cost the plain layers ~5 % (A/B in one gpurun call, profiles/r01_w3_timeline.md).
@@ -39,10 +49,11 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     uint8_t* b_res = smem;
     const int b_blocks = p.b_slots > 0 ? p.b_slots : p.num_ksteps;   // resident weights, or a ring of weight k-steps
     uint8_t* ring = b_res + b_blocks * kW3BStep;
-    uint8_t* sfull = ring + p.ring_slots * kW3Slot;
-    float* bias_s = reinterpret_cast<float*>(sfull + 2 * (kW3Staging + kW3StagingPool));   // two epilogue groups, each with staging + pool tiles
+    uint8_t* sfull = ring + p.ring_slots * kW3Slot;                 // two (staging + pool) tile pairs, used by alternate tiles
+    float* bias_s = reinterpret_cast<float*>(sfull + 2 * (kW3Staging + kW3StagingPool));
     float* head_s = bias_s + 64;                                   // [3][64] head weights + [3] head bias (+ pad)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(head_s + 200);
+    uint32_t* group_s = reinterpret_cast<uint32_t*>(head_s + 200);  // [kW3MaxGroups] group words (shared-memory copy)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(group_s + kW3MaxGroups);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kN64MaxRing;
     uint64_t* tmem_full_bar = bars + 2 * kN64MaxRing;
@@ -54,12 +65,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tiles_per_img = p.tiles_w * p.tiles_h;
-    const int total_tiles = tiles_per_img * p.n_img;
+    const long total_tiles = long(p.tiles_w) * p.tiles_h * p.n_img;
     const int R = p.ring_slots;
-    // role timeline (debug): CTA 0 stamps clock64() for its first B2R_DBG_TILES tiles
-#define B2R_STAMP(iter, slot) \
-    do { if (p.dbg != nullptr && blockIdx.x == 0 && (iter) < B2R_DBG_TILES) p.dbg[(iter) * 8 + (slot)] = clock64(); } while (0)
+    const int G = p.num_groups;
 
     if (warp_idx == 0 && lane == 0) {
         for (int i = 0; i < B2R_MAX_SRC; ++i) tma_prefetch_desc(&p.a_map[i]);
@@ -75,7 +83,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
-                mbar_init(&tmem_empty_bar[s], kW3EpiWarps / 2);
+                mbar_init(&tmem_empty_bar[s], kW3EpiWarps);
             }
             mbar_init(b_full_bar, 1);
             for (int s = 0; s < kN64MaxRing; ++s) {
@@ -90,6 +98,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     if (threadIdx.x >= 64 && threadIdx.x < 128) bias_s[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
     if (kHead && threadIdx.x >= 128 && threadIdx.x < 128 + 195)
         head_s[threadIdx.x - 128] = threadIdx.x - 128 < 192 ? p.head_w[threadIdx.x - 128] : p.head_b[threadIdx.x - 128 - 192];
+    if (threadIdx.x >= 352 && threadIdx.x < 352 + kW3MaxGroups) group_s[threadIdx.x - 352] = p.group[threadIdx.x - 352];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -108,18 +117,15 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             uint32_t phase = 0;
             int bs = 0;
             uint32_t bphase = 0;
-            int iter = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-                const int n0 = tile / tiles_per_img;
-                const int t = tile - n0 * tiles_per_img;
-                const int w0 = (t % p.tiles_w) * 14;
-                const int h0 = (t / p.tiles_w) * 8;
-                for (int g = 0; g < p.num_groups; ++g) {
-                    const uint32_t e = p.group[g];
+            TileWalk tw;
+            tw.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h);
+            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw.next(p.tiles_w, p.tiles_h)) {
+                const int n0 = tw.n, w0 = tw.tw * 14, h0 = tw.th * 8;
+                for (int g = 0; g < G; ++g) {
+                    const uint32_t e = group_s[g];
                     const int src = e & 3;
                     const int c0 = int((e >> 8) & 0xFFF) * 64;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (g == 0) B2R_STAMP(iter, 0);
                     mbar_arrive_expect_tx(&full_bar[stage], kW3Slot);
                     tma_load_4d(ring + stage * kW3Slot, &p.a_map[src], &full_bar[stage], c0, w0 - 1, h0 - 1, n0);
                     if (++stage == R) {
@@ -145,11 +151,13 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         }
     } else if (warp_idx == 1) {
         // ===================================== MMA issuer =====================================
-        // The whole warp runs this loop with warp-uniform control flow and ONE elected lane issues: descriptor
-        // arithmetic then stays on the uniform datapath (two adds per MMA).  It matters here because this warp shares
-        // its SM sub-partition's issue slots with four busy epilogue warps (profiles/r01_w3_timeline.md).
+        // The tensor pipe's queue only covers a few hundred cycles, so every instruction this warp executes between
+        // the last MMA of a tile and the first MMA of the next is exposed (it was ~880 cycles of a 2100-cycle tile:
+        // profiles/r01_w3_timeline.md).  Hence: warp-uniform control flow with ONE elected lane issuing (descriptor
+        // arithmetic stays on the uniform datapath), single-probe waits, group words from shared memory fetched one
+        // group ahead, no debug code.
         const bool stream_b = p.b_slots > 0;
-        if (!stream_b) mbar_wait_warp(b_full_bar, 0);
+        if (!stream_b) mbar_wait_uniform(b_full_bar, 0);
         tc_fence_after();
         const uint64_t desc_hi = make_sdesc_sw128(0, 1024) & 0xFFFFFFFF00000000ull;   // SBO / version / swizzle bits
         const uint32_t a_lo0 = ((smem_u32(ring) >> 4) & 0x3FFF) | (1u << 16);
@@ -158,19 +166,20 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         uint32_t phase = 0;
         int bs = 0;
         uint32_t bphase = 0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        int iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-            mbar_wait_warp(&tmem_empty_bar[acc], acc_phase ^ 1);
+        uint32_t acc = 0, acc_phase = 0;
+        uint32_t e_next = group_s[0];
+        [[maybe_unused]] int iter = 0;
+        for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            mbar_wait_uniform(&tmem_empty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             if (lane == 0) B2R_STAMP(iter, 1);
-            const uint32_t tmem_d = tmem_base + uint32_t(acc * 256);
+            const uint32_t tmem_d = tmem_base + acc * 256u;
             uint32_t accum = 0;
-            for (int g = 0; g < p.num_groups; ++g) {
-                const uint32_t e = p.group[g];
+            for (int g = 0; g < G; ++g) {
+                const uint32_t e = e_next;
+                e_next = group_s[g + 1 == G ? 0 : g + 1];
                 const bool center = ((e >> 2) & 1) != 0;
-                mbar_wait_warp(&full_bar[stage], phase);
+                mbar_wait_uniform(&full_bar[stage], phase);
                 tc_fence_after();
                 if (g == 0 && lane == 0) B2R_STAMP(iter, 7);
                 const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(kW3Slot >> 4);
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 } else {
                     const int nk = center ? 1 : 3;
                     for (int t = 0; t < nk; ++t) {
-                        mbar_wait_warp(&bs_full_bar[bs], bphase);
+                        mbar_wait_uniform(&bs_full_bar[bs], bphase);
                         tc_fence_after();
                         const uint32_t kh = center ? 1u : uint32_t(t);
                         const uint32_t b_lo = b_lo0 + uint32_t(bs) * uint32_t(kW3BStep >> 4);
@@ -233,164 +242,152 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             if (elect_one()) umma_commit(&tmem_full_bar[acc]);
             __syncwarp();
             if (lane == 0) B2R_STAMP(iter, 2);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            acc ^= 1u;
+            acc_phase ^= (acc == 0u) ? 1u : 0u;
         }
     } else {
         // ===================================== epilogue =====================================
-        // Two independent groups of eight warps; group g owns TMEM stage g, i.e. every other tile, and has its own
-        // staging tile, named barrier and TMA-store bookkeeping.  While one group is still shifting / activating /
-        // staging tile i the other already drains tile i+1, so the per-tile epilogue latency (~1600 cycles, it was the
-        // pacing term with one group: profiles/r01_w3_timeline.md) may span two tile periods.
-        // Within a group, warp w may touch TMEM lanes 32*(w%4).. only: two warps per lane quarter, 32 channels each,
-        // processed as two passes of 16 channels to keep the live accumulator registers at 48.
-        const int group = (warp_idx - 2) >> 3;             // 0 / 1 == TMEM stage
+        // All 16 warps work on every tile: warp (quarter, cq) owns TMEM lanes 32 quarter.. (a warp may touch only the
+        // lanes 32 (warp_idx % 4)..) and output channels 16 cq.. .  Its slice of the accumulator is 3 x 16 columns, so
+        // it is drained with three loads issued back to back and the TMEM stage is handed back to the MMA warp BEFORE
+        // any of the shift / activation / staging work (~150 cycles after the accumulator became ready; with two
+        // passes per warp the release came ~700 cycles later and the MMA warp waited for it on every tile).
+        // Tiles alternate between two staging buffers; per tile there is ONE 512-thread barrier (staged -> store).
+        const int e = warp_idx - 2;
         const int quarter = warp_idx & 3;
-        const int half = ((warp_idx - 2) >> 2) & 1;        // channels half*32 .. half*32+31
-        const int gtid = ((warp_idx - 2) & 7) * 32 + lane; // 0..255 within the group
-        const uint32_t bar_id = 1u + uint32_t(group);
-        uint8_t* sfull_g = sfull + group * (kW3Staging + kW3StagingPool);
-        uint8_t* spool_g = sfull_g + kW3Staging;
-        const int hh = quarter * 2 + (lane >> 4);  // tile row of this lane's pixel
-        const int cc = lane & 15;                  // buffer column; output column w = cc is valid for cc < 14
-        const int srow = hh * 14 + cc;             // row of the 8 x 14 staging tile
+        const int cq = e >> 2;                         // channels cq*16 .. cq*16+15
+        const int etid = e * 32 + lane;                // 0..511
+        const int hh = quarter * 2 + (lane >> 4);      // tile row of this lane's pixel
+        const int cc = lane & 15;                      // buffer column; output column w = cc is valid for cc < 14
+        const int srow = hh * 14 + cc;                 // row of the 8 x 14 staging tile
         const bool valid = cc < 14;
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-        constexpr bool has_head = kHead;
         const bool relu_only = p.act == B2R_ACT_RELU;
         const float ns = act_neg_slope(p.act, p.slope);
-        const uint32_t tacc = tmem_base + lane_base + uint32_t(group * 256);
-        uint32_t acc_phase = 0;
-        int iter = group;
-        for (long tile = (long)blockIdx.x + (long)group * gridDim.x; tile < total_tiles; tile += 2L * gridDim.x, iter += 2) {
-            mbar_wait_warp(&tmem_full_bar[group], acc_phase);
+        float b16[16];
+        {
+            const uint32_t ba = smem_u32(bias_s + cq * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(b16[4 * i]), "=f"(b16[4 * i + 1]), "=f"(b16[4 * i + 2]), "=f"(b16[4 * i + 3])
+                             : "r"(ba + 16 * i));
+        }
+        TileWalk tw;
+        tw.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h);
+        int iter = 0;
+        for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter, tw.next(p.tiles_w, p.tiles_h)) {
+            const uint32_t acc = uint32_t(iter) & 1u;
+            mbar_wait_uniform(&tmem_full_bar[acc], (uint32_t(iter) >> 1) & 1u);
             tc_fence_after();
-            if (gtid == 0) B2R_STAMP(iter, 3);
-            uint32_t packed[16];   // 32 output channels of this lane's pixel as bf16 pairs
-            float hs0 = 0.f, hs1 = 0.f, hs2 = 0.f;
+            if (etid == 0) B2R_STAMP(iter, 3);
+            uint32_t d0[16], d1[16], d2[16];
+            const uint32_t tacc = tmem_base + lane_base + acc * 256u + uint32_t(cq * 16);
+            tmem_ld_32x16(tacc, d0);            // kw = 0 partial sums
+            tmem_ld_32x16(tacc + 64u, d1);      // kw = 1
+            tmem_ld_32x16(tacc + 128u, d2);     // kw = 2
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (etid == 0) B2R_STAMP(iter, 4);
+            float x[16];
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-                const int ch0 = half * 32 + sub * 16;
-                uint32_t d0[16], d1[16], d2[16];
-                tmem_ld_32x16(tacc + uint32_t(ch0), d0);          // kw = 0 partial sums
-                tmem_ld_32x16(tacc + uint32_t(64 + ch0), d1);     // kw = 1
-                tmem_ld_32x16(tacc + uint32_t(128 + ch0), d2);    // kw = 2
-                tmem_ld_wait();
-                if (sub == 1) {
-                    // the accumulator is in registers: hand the TMEM stage back before any of the math below
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[group]);
-                }
-                float b16[16];
-                {
-                    const uint32_t ba = smem_u32(bias_s + ch0);
+            for (int j = 0; j < 16; ++j) {
+                const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[j]), 1);
+                const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[j]), 2);
+                x[j] = ((__uint_as_float(d0[j]) + a1) + a2) + b16[j];
+            }
+            if (relu_only) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                     : "=f"(b16[4 * i]), "=f"(b16[4 * i + 1]), "=f"(b16[4 * i + 2]), "=f"(b16[4 * i + 3])
-                                     : "r"(ba + 16 * i));
-                }
-                float x[16];
+                for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+            } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[j]), 1);
-                    const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[j]), 2);
-                    x[j] = ((__uint_as_float(d0[j]) + a1) + a2) + b16[j];
-                }
-                if (relu_only) {
+                for (int j = 0; j < 16; ++j) x[j] = apply_act_ns(x[j], ns);
+            }
+            uint8_t* sfull_b = sfull + acc * (kW3Staging + kW3StagingPool);
+            uint8_t* spool_b = sfull_b + kW3Staging;
+            if (kHead) {
+                // fused 64 -> 3 head on the fp32 activations: partial sums over this warp's 16 channels, parked in the
+                // (otherwise unused: a fused head never stores the 64-channel tile) staging buffer as [cq][o][pixel row]
+                float hs0 = 0.f, hs1 = 0.f, hs2 = 0.f;
+                const uint32_t ha = smem_u32(head_s + cq * 16);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
-                } else {
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    float w0[4], w1[4], w2[4];
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w0[0]), "=f"(w0[1]), "=f"(w0[2]), "=f"(w0[3]) : "r"(ha + 16 * j4));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w1[0]), "=f"(w1[1]), "=f"(w1[2]), "=f"(w1[3]) : "r"(ha + 256 + 16 * j4));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w2[0]), "=f"(w2[1]), "=f"(w2[2]), "=f"(w2[3]) : "r"(ha + 512 + 16 * j4));
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) x[j] = apply_act_ns(x[j], ns);
-                }
-                if (has_head) {
-                    // fused 64 -> 3 head on the fp32 activations: partial sums over this warp's channels
-                    const uint32_t ha = smem_u32(head_s + ch0);
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        float w0[4], w1[4], w2[4];
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w0[0]), "=f"(w0[1]), "=f"(w0[2]), "=f"(w0[3]) : "r"(ha + 16 * j4));
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w1[0]), "=f"(w1[1]), "=f"(w1[2]), "=f"(w1[3]) : "r"(ha + 256 + 16 * j4));
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w2[0]), "=f"(w2[1]), "=f"(w2[2]), "=f"(w2[3]) : "r"(ha + 512 + 16 * j4));
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            hs0 = fmaf(x[4 * j4 + j], w0[j], hs0);
-                            hs1 = fmaf(x[4 * j4 + j], w1[j], hs1);
-                            hs2 = fmaf(x[4 * j4 + j], w2[j], hs2);
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        hs0 = fmaf(x[4 * j4 + j], w0[j], hs0);
+                        hs1 = fmaf(x[4 * j4 + j], w1[j], hs1);
+                        hs2 = fmaf(x[4 * j4 + j], w2[j], hs2);
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) packed[sub * 8 + j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
-            }
-            // only now is this group's staging tile needed: wait until its previous TMA store has read it
-            if (gtid == 0) tma_store_wait_read<0>();
-            named_barrier_sync(bar_id, 256);
-            if (gtid == 0) B2R_STAMP(iter, 4);
-            if (has_head) {
-                // partial sums parked in the (otherwise unused) staging tile as [half][o][pixel row]
-                float* part = reinterpret_cast<float*>(sfull_g) + (half * 3) * 128 + quarter * 32 + lane;
+                float* part = reinterpret_cast<float*>(sfull_b) + (cq * 3) * 128 + quarter * 32 + lane;
                 part[0] = hs0;
                 part[128] = hs1;
                 part[256] = hs2;
-            }
-            if (valid && (!kHead || p.store_full)) {   // without a head the tile is always staged (store and/or pool)
+            } else {
+                if (valid) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int jj = half * 4 + q;   // 16-byte chunk of the 128-byte staging row
-                    const uint32_t addr = smem_u32(sfull_g) + uint32_t(srow * 128 + ((jj ^ (srow & 7)) << 4));
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * q]), "r"(packed[4 * q + 1]),
-                                 "r"(packed[4 * q + 2]), "r"(packed[4 * q + 3])
-                                 : "memory");
-                }
-            }
-            if (gtid == 0) B2R_STAMP(iter, 5);
-            fence_proxy_async_smem();
-            named_barrier_sync(bar_id, 256);
-            if (has_head && half == 0) {
-                // one thread per pixel: add the two partial sums + bias, then the reference's outputs
-                const int n0 = int(tile / tiles_per_img);
-                const int t = int(tile - (long)n0 * tiles_per_img);
-                const int w = (t % p.tiles_w) * 14 + cc;
-                const int h = (t / p.tiles_w) * 8 + hh;
-                if (valid && w < p.W && h < p.H) {
-                    const float* part = reinterpret_cast<const float*>(sfull_g) + quarter * 32 + lane;
-                    float v[3];
-#pragma unroll
-                    for (int o = 0; o < 3; ++o) v[o] = (part[o * 128] + part[(3 + o) * 128]) + head_s[192 + o];
-                    const size_t hw = size_t(p.H) * p.W, pix = size_t(h) * p.W + w;
-                    if (p.head_f32) {
-#pragma unroll
-                        for (int o = 0; o < 3; ++o) p.head_f32[(size_t(n0) * 3 + o) * hw + pix] = v[o];
-                    }
-                    if (p.head_u8) {
-#pragma unroll
-                        for (int o = 0; o < 3; ++o)   // torch.clamp(x, 0, 1); (x * 255).astype(np.uint8): truncation (17:86-92)
-                            p.head_u8[(size_t(n0) * hw + pix) * 3 + o] = static_cast<uint8_t>(fminf(fmaxf(v[o], 0.f), 1.f) * 255.0f);
+                    for (int q = 0; q < 2; ++q) {
+                        const int jj = cq * 2 + q;   // 16-byte chunk of the 128-byte staging row
+                        const uint32_t addr = smem_u32(sfull_b) + uint32_t(srow * 128 + ((jj ^ (srow & 7)) << 4));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                                     "r"(pack_bf16x2(x[8 * q], x[8 * q + 1])), "r"(pack_bf16x2(x[8 * q + 2], x[8 * q + 3])),
+                                     "r"(pack_bf16x2(x[8 * q + 4], x[8 * q + 5])), "r"(pack_bf16x2(x[8 * q + 6], x[8 * q + 7]))
+                                     : "memory");
                     }
                 }
-            }
-            if (p.store_pool) {
-                if (gtid < 28 * 4) epilogue_pool_chunk(sfull_g, spool_g, gtid, 14, 8);
                 fence_proxy_async_smem();
-                named_barrier_sync(bar_id, 256);
+                // the store of the PREVIOUS tile (other buffer) has been read: after the barrier below that buffer is
+                // free for the next tile.  It was issued a whole tile ago, so this does not wait in steady state.
+                if (etid == 0) tma_store_wait_read<0>();
             }
-            if (gtid == 0) {
-                // only the issuing thread needs the tile coordinates (three integer divisions)
-                const int n0 = int(tile / tiles_per_img);
-                const int t = int(tile - (long)n0 * tiles_per_img);
-                const int w0 = (t % p.tiles_w) * 14;
-                const int h0 = (t / p.tiles_w) * 8;
-                if (p.store_full) tma_store_4d(&p.out_map, sfull_g, 0, w0, h0, n0);
-                if (p.store_pool) tma_store_4d(&p.pool_map, spool_g, 0, w0 >> 1, h0 >> 1, n0);
-                tma_store_commit();
-                B2R_STAMP(iter, 6);
+            if (etid == 0) B2R_STAMP(iter, 5);
+            named_barrier_sync(1, kW3EpiWarps * 32);
+            if (kHead) {
+                if (cq == 0) {
+                    // one thread per pixel: add the four partial sums + bias, then the reference's outputs
+                    const int w = tw.tw * 14 + cc;
+                    const int h = tw.th * 8 + hh;
+                    if (valid && w < p.W && h < p.H) {
+                        const float* part = reinterpret_cast<const float*>(sfull_b) + quarter * 32 + lane;
+                        float v[3];
+#pragma unroll
+                        for (int o = 0; o < 3; ++o)
+                            v[o] = ((part[o * 128] + part[(3 + o) * 128]) + (part[(6 + o) * 128] + part[(9 + o) * 128])) + head_s[192 + o];
+                        const size_t hw = size_t(p.H) * p.W, pix = size_t(h) * p.W + w;
+                        if (p.head_f32) {
+#pragma unroll
+                            for (int o = 0; o < 3; ++o) p.head_f32[(size_t(tw.n) * 3 + o) * hw + pix] = v[o];
+                        }
+                        if (p.head_u8) {
+#pragma unroll
+                            for (int o = 0; o < 3; ++o)   // torch.clamp(x, 0, 1); (x * 255).astype(np.uint8): truncation (17:86-92)
+                                p.head_u8[(size_t(tw.n) * hw + pix) * 3 + o] = static_cast<uint8_t>(fminf(fmaxf(v[o], 0.f), 1.f) * 255.0f);
+                        }
+                    }
+                }
+            } else if (e < 4) {
+                // warps 0..3 (128 threads, one small barrier of their own) pool the staged tile and issue the stores
+                if (p.store_pool) {
+                    if (etid < 28 * 4) epilogue_pool_chunk(sfull_b, spool_b, etid, 14, 8);
+                    fence_proxy_async_smem();
+                    named_barrier_sync(2, 128);
+                }
+                if (etid == 0) {
+                    const int w0 = tw.tw * 14, h0 = tw.th * 8;
+                    if (p.store_full) tma_store_4d(&p.out_map, sfull_b, 0, w0, h0, tw.n);
+                    if (p.store_pool) tma_store_4d(&p.pool_map, spool_b, 0, w0 >> 1, h0 >> 1, tw.n);
+                    tma_store_commit();
+                    B2R_STAMP(iter, 6);
+                }
             }
-            acc_phase ^= 1;
         }
-        if (gtid == 0) tma_store_wait_all<0>();
+        if (etid == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -403,7 +400,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 }
 
 size_t conv_w3_smem_bytes(int b_blocks, int ring_slots) {
-    return 1024 + size_t(b_blocks) * kW3BStep + size_t(ring_slots) * kW3Slot + 2 * (kW3Staging + kW3StagingPool) + 256 + 800 + 512;
+    return 1024 + size_t(b_blocks) * kW3BStep + size_t(ring_slots) * kW3Slot + 2 * (kW3Staging + kW3StagingPool) + 256 + 800 + 640;
 }
 
 int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream) {

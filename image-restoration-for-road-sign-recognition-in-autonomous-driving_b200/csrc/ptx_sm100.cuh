@@ -86,16 +86,41 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 #ifndef B2R_WAIT_TIMEOUT_CYCLES
 #define B2R_WAIT_TIMEOUT_CYCLES (4000000000LL)
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+// The slow path (hardware-suspended retries + the timeout report) is kept out of line: inlined at every wait it
+// bloated the role loops (instruction-cache misses showed up as no_inst stalls on the MMA warp).
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
     const long long t0 = clock64();
-    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity), "r"(20000u)
+            : "memory");
+        if (ok) return;
         if (clock64() - t0 > B2R_WAIT_TIMEOUT_CYCLES) {
             printf("b2r: mbarrier wait timeout block %d thread %d bar %u parity %u\n", (int)blockIdx.x,
-                   (int)threadIdx.x, smem_u32(bar), parity);
+                   (int)threadIdx.x, bar_addr, parity);
             __trap();
         }
     }
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(smem_u32(bar), parity);
+}
+
+// Warp-uniform wait for role loops that run with all 32 lanes (MMA issuer, epilogue): every lane probes in the same
+// instruction, so a completed phase costs one probe and one reconvergence point instead of lane-0-probe + warp
+// barrier + second probe.  The trailing __syncwarp matters: elect.sync after a divergent return would elect twice.
+__device__ __forceinline__ void mbar_wait_uniform(uint64_t* bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(smem_u32(bar), parity);
+    __syncwarp();
 }
 
 // Whole-warp wait: lane 0 does the waiting, the other 31 lanes park at the warp barrier and then observe the
