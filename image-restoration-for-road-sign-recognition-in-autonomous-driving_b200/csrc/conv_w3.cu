@@ -23,11 +23,15 @@
 namespace b2r {
 
 constexpr int kW3EpiWarps = 16;         // four warps per TMEM lane quarter, 16 output channels each
-constexpr int kW3Threads = (2 + kW3EpiWarps) * 32;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+constexpr int kW3Threads = (3 + kW3EpiWarps) * 32;   // warp 0 TMA, warps 1-2 MMA (alternate tiles), warps 3.. epilogue
 constexpr int kW3BStep = 192 * 128;      // weights of one k-step: 192 rows x 128 B
 constexpr int kW3Slot = 10 * 16 * 128;   // one halo box: (8 + 2) rows x 16 columns x 128 B
 constexpr int kW3Staging = 14336;        // 8 x 14 pixels x 128 B
 constexpr int kW3StagingPool = 4096;     // 4 x 7 pixels x 128 B, padded
+#ifndef B2R_W3_PREFETCH_TILES
+#define B2R_W3_PREFETCH_TILES 4
+#endif
+constexpr int kW3PrefetchTiles = B2R_W3_PREFETCH_TILES;   // L2 prefetch distance beyond the tile being loaded
 
 // Role timeline (debug builds only: nvcc -DB2R_TIMELINE, see tools/role_timeline.py): CTA 0 stamps clock64() for its
 // first B2R_DBG_TILES tiles.  Compiled out of the product: even predicated off, each stamp cost the MMA warp ~10
@@ -54,13 +58,17 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     float* head_s = bias_s + 64;                                   // [3][64] head weights + [3] head bias (+ pad)
     uint32_t* group_s = reinterpret_cast<uint32_t*>(head_s + 200);  // [kW3MaxGroups] group words (shared-memory copy)
     uint64_t* bars = reinterpret_cast<uint64_t*>(group_s + kW3MaxGroups);
-    uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + kN64MaxRing;
-    uint64_t* tmem_full_bar = bars + 2 * kN64MaxRing;
+    // "Data landed" barriers exist once per issuing warp: warp m only ever waits on full_bar[m][.], which the producer
+    // arms for tiles of parity m, so it observes EVERY phase of the barriers it waits on.  (With one shared set, a
+    // warp that skips the other warp's tile may skip a phase, and a parity wait cannot tell phase n from phase n - 2:
+    // it passes immediately on a slot whose previous fill has not even arrived.)
+    uint64_t* full_bar = bars;                          // [2][kN64MaxRing]
+    uint64_t* empty_bar = bars + 2 * kN64MaxRing;       // [kN64MaxRing]
+    uint64_t* tmem_full_bar = empty_bar + kN64MaxRing;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint64_t* b_full_bar = tmem_empty_bar + 2;
-    uint64_t* bs_full_bar = b_full_bar + 1;             // [kN64MaxRing] streamed-weights ring
-    uint64_t* bs_empty_bar = bs_full_bar + kN64MaxRing;  // [kN64MaxRing]
+    uint64_t* bs_full_bar = b_full_bar + 1;                  // [2][kN64MaxRing] streamed-weights ring
+    uint64_t* bs_empty_bar = bs_full_bar + 2 * kN64MaxRing;  // [kN64MaxRing]
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bs_empty_bar + kN64MaxRing);
 
     const int warp_idx = threadIdx.x >> 5;
@@ -79,6 +87,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         if (lane == 0) {
             for (int s = 0; s < R; ++s) {
                 mbar_init(&full_bar[s], 1);
+                mbar_init(&full_bar[kN64MaxRing + s], 1);
                 mbar_init(&empty_bar[s], 1);
             }
             for (int s = 0; s < 2; ++s) {
@@ -88,6 +97,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             mbar_init(b_full_bar, 1);
             for (int s = 0; s < kN64MaxRing; ++s) {
                 mbar_init(&bs_full_bar[s], 1);
+                mbar_init(&bs_full_bar[kN64MaxRing + s], 1);
                 mbar_init(&bs_empty_bar[s], 1);
             }
             fence_mbar_init();
@@ -119,15 +129,38 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             uint32_t bphase = 0;
             TileWalk tw;
             tw.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h);
-            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw.next(p.tiles_w, p.tiles_h)) {
+            // L2 prefetch cursor, kW3PrefetchTiles tiles ahead of the tile being loaded: the ring (2-4 slots, as few as
+            // one tile for 128 -> 64) cannot cover HBM latency under load; without this the MMA warps waited ~270-800
+            // cycles per tile for their first A box (profiles/r01_w3_timeline.md)
+            TileWalk pf;
+            long pf_tile = (long)blockIdx.x + (long)kW3PrefetchTiles * gridDim.x;
+            pf.init(pf_tile, gridDim.x, p.tiles_w, p.tiles_h);
+            int par = 0;   // which issuing warp consumes this tile
+            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw.next(p.tiles_w, p.tiles_h), par ^= 1) {
+#ifndef B2R_EXP_NO_PREFETCH
+                if (pf_tile < total_tiles) {
+                    for (int g = 0; g < G; ++g) {
+                        const uint32_t e = group_s[g];
+                        tma_prefetch_l2_4d(&p.a_map[e & 3], int((e >> 8) & 0xFFF) * 64, pf.tw * 14 - 1, pf.th * 8 - 1, pf.n);
+                    }
+                }
+                pf_tile += gridDim.x;
+                pf.next(p.tiles_w, p.tiles_h);
+#endif
                 const int n0 = tw.n, w0 = tw.tw * 14, h0 = tw.th * 8;
+                uint64_t* full_m = full_bar + par * kN64MaxRing;
+                uint64_t* bs_full_m = bs_full_bar + par * kN64MaxRing;
                 for (int g = 0; g < G; ++g) {
                     const uint32_t e = group_s[g];
                     const int src = e & 3;
                     const int c0 = int((e >> 8) & 0xFFF) * 64;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], kW3Slot);
-                    tma_load_4d(ring + stage * kW3Slot, &p.a_map[src], &full_bar[stage], c0, w0 - 1, h0 - 1, n0);
+#ifdef B2R_EXP_NO_LOAD   // experiment builds only (tools/exp/README.md): which role paces the tile?
+                    mbar_arrive(&full_m[stage]);
+#else
+                    mbar_arrive_expect_tx(&full_m[stage], kW3Slot);
+                    tma_load_4d(ring + stage * kW3Slot, &p.a_map[src], &full_m[stage], c0, w0 - 1, h0 - 1, n0);
+#endif
                     if (++stage == R) {
                         stage = 0;
                         phase ^= 1;
@@ -138,8 +171,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                         const int ks0 = int(e >> 20);
                         for (int k = 0; k < nk; ++k) {
                             mbar_wait(&bs_empty_bar[bs], bphase ^ 1);
-                            mbar_arrive_expect_tx(&bs_full_bar[bs], kW3BStep);
-                            tma_load_2d(b_res + bs * kW3BStep, &p.b_map, &bs_full_bar[bs], (ks0 + k) * 64, 0);
+                            mbar_arrive_expect_tx(&bs_full_m[bs], kW3BStep);
+                            tma_load_2d(b_res + bs * kW3BStep, &p.b_map, &bs_full_m[bs], (ks0 + k) * 64, 0);
                             if (++bs == p.b_slots) {
                                 bs = 0;
                                 bphase ^= 1;
@@ -149,37 +182,53 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp_idx == 1) {
-        // ===================================== MMA issuer =====================================
-        // The tensor pipe's queue only covers a few hundred cycles, so every instruction this warp executes between
-        // the last MMA of a tile and the first MMA of the next is exposed (it was ~880 cycles of a 2100-cycle tile:
-        // profiles/r01_w3_timeline.md).  Hence: warp-uniform control flow with ONE elected lane issuing (descriptor
-        // arithmetic stays on the uniform datapath), single-probe waits, group words from shared memory fetched one
-        // group ahead, no debug code.
+    } else if (warp_idx <= 2) {
+        // ===================================== MMA issuers =====================================
+        // TWO issuing warps, one per TMEM stage: warp 1 takes tiles 0, 2, 4, ... of this CTA, warp 2 tiles 1, 3, ...
+        // The tensor pipe's queue only covers a few hundred cycles, and a single issuer needed ~650-880 cycles of plain
+        // instructions (barrier probes, reconvergence, descriptor set-up; it competes with four busy epilogue warps for
+        // its sub-partition's issue slots) between the last MMA of a tile and the first MMA of the next, during which
+        // the pipe ran dry (profiles/r01_w3_timeline.md).  With two issuers that gap overlaps the other warp's MMAs.
+        // Each warp: warp-uniform control flow with ONE elected lane issuing (descriptor arithmetic stays on the uniform
+        // datapath), single-probe waits, group words from shared memory fetched one group ahead.
+        const int m = warp_idx - 1;
         const bool stream_b = p.b_slots > 0;
         if (!stream_b) mbar_wait_uniform(b_full_bar, 0);
         tc_fence_after();
         const uint64_t desc_hi = make_sdesc_sw128(0, 1024) & 0xFFFFFFFF00000000ull;   // SBO / version / swizzle bits
         const uint32_t a_lo0 = ((smem_u32(ring) >> 4) & 0x3FFF) | (1u << 16);
         const uint32_t b_lo0 = ((smem_u32(b_res) >> 4) & 0x3FFF) | (1u << 16);
-        int stage = 0;
-        uint32_t phase = 0;
-        int bs = 0;
-        uint32_t bphase = 0;
-        uint32_t acc = 0, acc_phase = 0;
+        // ring positions: a tile consumes G A-slots and num_ksteps B-slots; this warp starts m tiles in and then
+        // skips the other warp's tile after each of its own
+        int stage = 0, bs = 0;
+        uint32_t phase_bits = 0, bphase_bits = 0;   // bit s: parity of this warp's next wait on slot s of its own barrier set
+        uint64_t* full_m = full_bar + m * kN64MaxRing;
+        uint64_t* bs_full_m = bs_full_bar + m * kN64MaxRing;
+        auto skip_tile = [&]() {
+            stage += G;
+            while (stage >= R) stage -= R;
+            if (stream_b) {
+                bs += p.num_ksteps;
+                while (bs >= p.b_slots) bs -= p.b_slots;
+            }
+        };
+        if (m == 1) skip_tile();
+        const uint32_t acc = uint32_t(m);
+        const uint32_t tmem_d = tmem_base + acc * 256u;
+        uint32_t acc_phase = 0;
         uint32_t e_next = group_s[0];
-        [[maybe_unused]] int iter = 0;
-        for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        [[maybe_unused]] int iter = m;
+        for (long tile = (long)blockIdx.x + (long)m * gridDim.x; tile < total_tiles; tile += 2L * gridDim.x, iter += 2) {
             mbar_wait_uniform(&tmem_empty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             if (lane == 0) B2R_STAMP(iter, 1);
-            const uint32_t tmem_d = tmem_base + acc * 256u;
             uint32_t accum = 0;
             for (int g = 0; g < G; ++g) {
                 const uint32_t e = e_next;
                 e_next = group_s[g + 1 == G ? 0 : g + 1];
                 const bool center = ((e >> 2) & 1) != 0;
-                mbar_wait_uniform(&full_bar[stage], phase);
+                mbar_wait_uniform(&full_m[stage], (phase_bits >> stage) & 1u);
+                phase_bits ^= 1u << stage;
                 tc_fence_after();
                 if (g == 0 && lane == 0) B2R_STAMP(iter, 7);
                 const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(kW3Slot >> 4);
@@ -211,7 +260,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 } else {
                     const int nk = center ? 1 : 3;
                     for (int t = 0; t < nk; ++t) {
-                        mbar_wait_uniform(&bs_full_bar[bs], bphase);
+                        mbar_wait_uniform(&bs_full_m[bs], (bphase_bits >> bs) & 1u);
+                        bphase_bits ^= 1u << bs;
                         tc_fence_after();
                         const uint32_t kh = center ? 1u : uint32_t(t);
                         const uint32_t b_lo = b_lo0 + uint32_t(bs) * uint32_t(kW3BStep >> 4);
@@ -227,23 +277,17 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                         }
                         __syncwarp();
                         accum = 1;
-                        if (++bs == p.b_slots) {
-                            bs = 0;
-                            bphase ^= 1;
-                        }
+                        if (++bs == p.b_slots) bs = 0;
                     }
                 }
                 accum = 1;
-                if (++stage == R) {
-                    stage = 0;
-                    phase ^= 1;
-                }
+                if (++stage == R) stage = 0;
             }
             if (elect_one()) umma_commit(&tmem_full_bar[acc]);
             __syncwarp();
             if (lane == 0) B2R_STAMP(iter, 2);
-            acc ^= 1u;
-            acc_phase ^= (acc == 0u) ? 1u : 0u;
+            acc_phase ^= 1u;
+            skip_tile();   // the other issuer's tile
         }
     } else {
         // ===================================== epilogue =====================================
@@ -253,7 +297,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         // any of the shift / activation / staging work (~150 cycles after the accumulator became ready; with two
         // passes per warp the release came ~700 cycles later and the MMA warp waited for it on every tile).
         // Tiles alternate between two staging buffers; per tile there is ONE 512-thread barrier (staged -> store).
-        const int e = warp_idx - 2;
+        const int e = warp_idx - 3;
         const int quarter = warp_idx & 3;
         const int cq = e >> 2;                         // channels cq*16 .. cq*16+15
         const int etid = e * 32 + lane;                // 0..511
@@ -291,6 +335,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
             if (etid == 0) B2R_STAMP(iter, 4);
+#ifndef B2R_EXP_NO_STAGE
             float x[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -346,6 +391,11 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 // free for the next tile.  It was issued a whole tile ago, so this does not wait in steady state.
                 if (etid == 0) tma_store_wait_read<0>();
             }
+#else
+            uint8_t* sfull_b = sfull + acc * (kW3Staging + kW3StagingPool);
+            uint8_t* spool_b = sfull_b + kW3Staging;
+            (void)spool_b; (void)valid; (void)srow; (void)relu_only; (void)ns; (void)b16; (void)d0; (void)d1; (void)d2;
+#endif
             if (etid == 0) B2R_STAMP(iter, 5);
             named_barrier_sync(1, kW3EpiWarps * 32);
             if (kHead) {
@@ -378,6 +428,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                     fence_proxy_async_smem();
                     named_barrier_sync(2, 128);
                 }
+#ifndef B2R_EXP_NO_STAGE
                 if (etid == 0) {
                     const int w0 = tw.tw * 14, h0 = tw.th * 8;
                     if (p.store_full) tma_store_4d(&p.out_map, sfull_b, 0, w0, h0, tw.n);
@@ -385,6 +436,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                     tma_store_commit();
                     B2R_STAMP(iter, 6);
                 }
+#endif
             }
         }
         if (etid == 0) tma_store_wait_all<0>();

@@ -139,6 +139,15 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
 
+// L2 prefetch of a tensor-map box (no shared-memory destination, no completion tracking): used by the producers to
+// pull tiles several steps ahead of the shared-memory ring out of HBM, whose loaded latency (~2500 cycles) a ring of
+// 2-4 slots cannot cover.
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

@@ -5,15 +5,21 @@
 #include "ptx_sm100.cuh"
 using namespace b2r;
 
-__global__ void __launch_bounds__(128, 1) k(long long* out, int tiles, int ring, int same_b) {
+__global__ void __launch_bounds__(128, 1) k(long long* out, int tiles, int ring, int same_b, int random_data, int commits) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, dummy[2];
     __shared__ uint32_t tmem_ptr;
     const int total = 3 * 24576 + ring * 20480;
-    for (int i = threadIdx.x; i < total / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    for (int i = threadIdx.x; i < total / 4; i += 128) {
+        // zeros, or pseudo-random bf16 pairs in (-2, 2): operand toggling is what the tensor pipe's power depends on
+        uint32_t h = (uint32_t(i) * 2654435761u) ^ (blockIdx.x * 0x9E3779B9u);
+        h ^= h >> 15; h *= 0x85EBCA6Bu; h ^= h >> 13;
+        const uint32_t v = (h & 0x807F807Fu) | 0x3F003F00u | ((h >> 8) & 0x00800080u);
+        reinterpret_cast<uint32_t*>(smem)[i] = random_data ? v : 0u;
+    }
     if (threadIdx.x < 32) {
-        if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+        if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&dummy[0], 1); mbar_init(&dummy[1], 1); fence_mbar_init(); }
         __syncwarp();
         tmem_alloc<512>(&tmem_ptr);
     }
@@ -35,6 +41,9 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int tiles, int ring,
                     for (int kk = 0; kk < 4; ++kk)
                         umma_bf16_ss(tmd, hi | uint64_t(a_lo + 128u * r + 2u * kk),
                                      hi | uint64_t(b0 + (same_b ? 0u : 1536u * r) + 2u * kk), idesc, (r | kk) ? 1u : 0u);
+                // conv_w3 commits twice per tile (ring slot free, accumulator ready); nobody waits on these here
+                if (commits >= 1) umma_commit(&dummy[0]);
+                if (commits >= 2) umma_commit(&dummy[1]);
             }
             __syncwarp();
         }
@@ -53,11 +62,16 @@ int main() {
     const int ring = 4;
     size_t smem = 1024 + 3 * 24576 + ring * 20480;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int same_b = 0; same_b < 2; ++same_b) {
-        k<<<148, 128, smem>>>(d, 2000, ring, same_b);
+    // grid 1 vs 148 CTAs, zero vs random operands, short vs long run: separates the instruction's own rate from
+    // chip-level (power) throttling, which shows up as MORE SM CYCLES per MMA, not only as a lower clock
+    for (int commits = 0; commits < 3; ++commits) {
+        const int grid = 148, tiles = 20000;
+        k<<<grid, 128, smem>>>(d, tiles, ring, 0, 1, commits);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-        printf("w3 pattern, %s B: %.1f cycles per MMA (ideal 96)  [%s]\n", same_b ? "same" : "3 different", h[0] / (2000.0 * 12), cudaGetErrorString(e));
+        long long mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
+        printf("w3 pattern, %3d CTAs, random operands, %d tcgen05.commit per 12 MMAs: %.1f cycles per MMA (ideal 96)  [%s]\n", grid,
+               commits, mx / (double(tiles) * 12), cudaGetErrorString(e));
     }
     return 0;
 }

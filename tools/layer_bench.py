@@ -40,6 +40,33 @@ LAYERS = [
 ]
 
 
+class _NvmlSampler:
+    """Median SM clock and board power while the timed loop runs (use --iters >= 200 so there is something to sample)."""
+
+    def __init__(self):
+        import threading
+        import pynvml
+        pynvml.nvmlInit()
+        self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(0)
+        self.mhz, self.watts, self.go = [], [], True
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def _loop(self):
+        import time
+        while self.go:
+            self.mhz.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            self.watts.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            time.sleep(0.003)
+
+    def stop(self):
+        self.go = False
+        self.t.join()
+        k = len(self.mhz) // 2   # second half: the governor has settled
+        mhz, w = sorted(self.mhz[k:]), sorted(self.watts[k:])
+        return f"  | SM {mhz[len(mhz) // 2]} MHz, {w[len(w) // 2]:.0f} W ({len(self.mhz)} samples)"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=128)
@@ -48,6 +75,7 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--no-w3", action="store_true")
+    ap.add_argument("--clocks", action="store_true", help="sample SM clock / board power (NVML) during the timed loop")
     args = ap.parse_args()
     from b200restore import ops, packing, _lib as L
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
@@ -98,15 +126,17 @@ def main():
             run()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = _NvmlSampler() if args.clocks else None
         e0.record()
         for _ in range(args.iters):
             run()
         e1.record()
         torch.cuda.synchronize()
+        clk = sampler.stop() if sampler else ""
         ms = e0.elapsed_time(e1) / args.iters
         tf = flops / (ms * 1e-3) / 1e12
         print(f"{name:42s} {ms * 1e3:9.1f} us  {tf:7.1f} TFLOP/s  {100 * tf / burst:5.1f}% of burst  "
-              f"{100 * tf / sust:5.1f}% of sustained", flush=True)
+              f"{100 * tf / sust:5.1f}% of sustained{clk}", flush=True)
         results.append({"layer": name, "us": ms * 1e3, "tflops": tf, "frac_burst": tf / burst, "frac_sustained": tf / sust})
         del srcs, out, pool
         torch.cuda.empty_cache()

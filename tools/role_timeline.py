@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Per-role timeline of CTA 0 of the tap-folded conv kernel (debug_timeline field of b2r_conv_gemm_desc).
 
-Prints, for tiles in steady state, the cycles between the stamps: producer issue, MMA start / all MMAs issued,
-epilogue start (accumulator ready) / staging free / TMEM drained / stores issued.  Tells which role paces the tile."""
+Needs a library built with the stamps compiled in (they are not in the product build):
+    python -m b200restore.build --define B2R_TIMELINE --out tools/exp/libb2r_timeline.so
+    B2R_LIB=tools/exp/libb2r_timeline.so python tools/role_timeline.py
+Prints, for tiles in steady state, the MMA warp's and the epilogue's stamps: tells which role paces the tile."""
 import sys
 from pathlib import Path
 
@@ -31,19 +33,15 @@ def main():
                           weights_w3=w3, debug_timeline=dbg)
         torch.cuda.synchronize()
         t = dbg.cpu()
-        t0 = int(t[0, 1])
-        print(f"--- C_in {ci} pooled={pooled}: per tile (cycles), tiles 20..27 of CTA 0")
-        print(" tile | tile period | mma issue span | acc ready->epi start wait | epi: wait staging | drain TMEM+shift+stage | pool+store issue")
+        print(f"--- C_in {ci} pooled={pooled}: tiles 20..27 of CTA 0, cycles relative to the MMA warp's start of tile 20")
+        print(" stamps: [1 mma: tmem stage free, 7 mma: first A box ready, 2 mma: all MMAs issued + committed, "
+              "3 epi: accumulator ready, 4 epi: TMEM drained + released, 5 epi: staged, 6 epi: stores issued]")
         base = int(t[20, 1])
-        print(" raw stamps relative to MMA start of tile 20: [producer issue, mma start(tmem free), mma issued, epi start(acc ready), staging free, staged, stores issued, mma A-data ready]")
-        for i in range(20, 26):
-            print(f"   tile {i}: " + " ".join(f"{int(t[i, k]) - base:7d}" for k in range(8)))
         for i in range(20, 28):
-            period = int(t[i + 1, 3] - t[i, 3])
-            print(f" {i:4d} | {period:11d} | {int(t[i, 2] - t[i, 1]):14d} | "
-                  f"{int(t[i, 3] - t[i - 1, 6]):25d} | {int(t[i, 4] - t[i, 3]):17d} | {int(t[i, 5] - t[i, 4]):22d} | "
-                  f"{int(t[i, 6] - t[i, 5]):16d}")
-
+            r = [int(t[i, k]) - base for k in (1, 7, 2, 3, 4, 5, 6)]
+            print(f"   tile {i}: " + " ".join(f"{v:7d}" for v in r) + f"   | period {int(t[i + 1, 1] - t[i, 1]):5d}"
+                  f" | mma: wait A {r[1] - r[0]:4d}, issue {r[2] - r[1]:5d}, to next tile {int(t[i + 1, 1]) - base - r[2]:4d}"
+                  f" | epi: acc ready {r[3] - r[2]:4d} after last issue, drain {r[4] - r[3]:4d}, math+stage {r[5] - r[4]:4d}, store {r[6] - r[5]:4d}")
 
 if __name__ == "__main__":
     main()
