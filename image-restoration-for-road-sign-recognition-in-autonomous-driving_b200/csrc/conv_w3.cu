@@ -23,7 +23,7 @@
 namespace b2r {
 
 constexpr int kW3EpiWarps = 16;         // four warps per TMEM lane quarter, 16 output channels each
-constexpr int kW3Threads = (3 + kW3EpiWarps) * 32;   // warp 0 TMA, warps 1-2 MMA (alternate tiles), warps 3.. epilogue
+constexpr int kW3Threads = (4 + kW3EpiWarps) * 32;   // warp 0 TMA loads, warps 1-2 MMA (alternate tiles), warps 3..18 epilogue, warp 19 TMA stores
 constexpr int kW3BStep = 192 * 128;      // weights of one k-step: 192 rows x 128 B
 constexpr int kW3Slot = 10 * 16 * 128;   // one halo box: (8 + 2) rows x 16 columns x 128 B
 constexpr int kW3Staging = 14336;        // 8 x 14 pixels x 128 B
@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     uint64_t* b_full_bar = tmem_empty_bar + 2;
     uint64_t* bs_full_bar = b_full_bar + 1;                  // [2][kN64MaxRing] streamed-weights ring
     uint64_t* bs_empty_bar = bs_full_bar + 2 * kN64MaxRing;  // [kN64MaxRing]
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bs_empty_bar + kN64MaxRing);
+    uint64_t* staged_bar = bs_empty_bar + kN64MaxRing;   // [2] staging buffer written by all 16 epilogue warps
+    uint64_t* free_bar = staged_bar + 2;                 // [2] its TMA store has been read: reusable
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(free_bar + 2);
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -95,6 +97,10 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 mbar_init(&tmem_empty_bar[s], kW3EpiWarps);
             }
             mbar_init(b_full_bar, 1);
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&staged_bar[s], kW3EpiWarps);
+                mbar_init(&free_bar[s], 1);
+            }
             for (int s = 0; s < kN64MaxRing; ++s) {
                 mbar_init(&bs_full_bar[s], 1);
                 mbar_init(&bs_full_bar[kN64MaxRing + s], 1);
@@ -289,6 +295,31 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             acc_phase ^= 1u;
             skip_tile();   // the other issuer's tile
         }
+    } else if (warp_idx == 3 + kW3EpiWarps) {
+        // ===================================== TMA store issuer =====================================
+        // One thread: waits until all 16 epilogue warps have staged a tile, stores it, and hands the staging buffer
+        // back once the store has read it.  Keeping this off the epilogue warps removed the last CTA-wide barrier and
+        // ~340 cycles per tile from their critical path (profiles/r01_w3_timeline.md).
+        if (!kHead && lane == 0) {
+            TileWalk tw;
+            tw.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h);
+            int iter = 0;
+            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter, tw.next(p.tiles_w, p.tiles_h)) {
+                const int buf = iter & 1;
+                uint8_t* sfull_b = sfull + buf * (kW3Staging + kW3StagingPool);
+                mbar_wait(&staged_bar[buf], (uint32_t(iter) >> 1) & 1u);
+#ifndef B2R_EXP_NO_STAGE
+                const int w0 = tw.tw * 14, h0 = tw.th * 8;
+                if (p.store_full) tma_store_4d(&p.out_map, sfull_b, 0, w0, h0, tw.n);
+                if (p.store_pool) tma_store_4d(&p.pool_map, sfull_b + kW3Staging, 0, w0 >> 1, h0 >> 1, tw.n);
+                tma_store_commit();
+                tma_store_wait_read<0>();
+#endif
+                B2R_STAMP(iter, 6);
+                mbar_arrive(&free_bar[buf]);
+            }
+            tma_store_wait_all<0>();
+        }
     } else {
         // ===================================== epilogue =====================================
         // All 16 warps work on every tile: warp (quarter, cq) owns TMEM lanes 32 quarter.. (a warp may touch only the
@@ -296,7 +327,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         // it is drained with three loads issued back to back and the TMEM stage is handed back to the MMA warp BEFORE
         // any of the shift / activation / staging work (~150 cycles after the accumulator became ready; with two
         // passes per warp the release came ~700 cycles later and the MMA warp waited for it on every tile).
-        // Tiles alternate between two staging buffers; per tile there is ONE 512-thread barrier (staged -> store).
+        // The warps never synchronise with each other: each stages its 32 pixels x 16 channels (and, for pooled
+        // layers, the 2x2 maxima it can form with two lane exchanges: a warp holds tile rows 2q, 2q+1, i.e. complete
+        // pooling windows) and arrives on the staging buffer's mbarrier; the store warp does the rest.
         const int e = warp_idx - 3;
         const int quarter = warp_idx & 3;
         const int cq = e >> 2;                         // channels cq*16 .. cq*16+15
@@ -305,6 +338,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         const int cc = lane & 15;                      // buffer column; output column w = cc is valid for cc < 14
         const int srow = hh * 14 + cc;                 // row of the 8 x 14 staging tile
         const bool valid = cc < 14;
+        const int prow = quarter * 7 + (cc >> 1);      // row of the 4 x 7 pooled staging tile (lanes with even cc, lane < 16)
+        const bool pool_lane = lane < 14 && (lane & 1) == 0;
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
         const bool relu_only = p.act == B2R_ACT_RELU;
         const float ns = act_neg_slope(p.act, p.slope);
@@ -335,6 +370,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
             if (etid == 0) B2R_STAMP(iter, 4);
+            uint8_t* sfull_b = sfull + acc * (kW3Staging + kW3StagingPool);
+            uint8_t* spool_b = sfull_b + kW3Staging;
 #ifndef B2R_EXP_NO_STAGE
             float x[16];
 #pragma unroll
@@ -350,8 +387,6 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 16; ++j) x[j] = apply_act_ns(x[j], ns);
             }
-            uint8_t* sfull_b = sfull + acc * (kW3Staging + kW3StagingPool);
-            uint8_t* spool_b = sfull_b + kW3Staging;
             if (kHead) {
                 // fused 64 -> 3 head on the fp32 activations: partial sums over this warp's 16 channels, parked in the
                 // (otherwise unused: a fused head never stores the 64-channel tile) staging buffer as [cq][o][pixel row]
@@ -374,41 +409,17 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 part[0] = hs0;
                 part[128] = hs1;
                 part[256] = hs2;
-            } else {
-                if (valid) {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int jj = cq * 2 + q;   // 16-byte chunk of the 128-byte staging row
-                        const uint32_t addr = smem_u32(sfull_b) + uint32_t(srow * 128 + ((jj ^ (srow & 7)) << 4));
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                                     "r"(pack_bf16x2(x[8 * q], x[8 * q + 1])), "r"(pack_bf16x2(x[8 * q + 2], x[8 * q + 3])),
-                                     "r"(pack_bf16x2(x[8 * q + 4], x[8 * q + 5])), "r"(pack_bf16x2(x[8 * q + 6], x[8 * q + 7]))
-                                     : "memory");
-                    }
-                }
-                fence_proxy_async_smem();
-                // the store of the PREVIOUS tile (other buffer) has been read: after the barrier below that buffer is
-                // free for the next tile.  It was issued a whole tile ago, so this does not wait in steady state.
-                if (etid == 0) tma_store_wait_read<0>();
-            }
-#else
-            uint8_t* sfull_b = sfull + acc * (kW3Staging + kW3StagingPool);
-            uint8_t* spool_b = sfull_b + kW3Staging;
-            (void)spool_b; (void)valid; (void)srow; (void)relu_only; (void)ns; (void)b16; (void)d0; (void)d1; (void)d2;
-#endif
-            if (etid == 0) B2R_STAMP(iter, 5);
-            named_barrier_sync(1, kW3EpiWarps * 32);
-            if (kHead) {
+                named_barrier_sync(1, kW3EpiWarps * 32);   // the only cross-warp exchange: four partial sums per pixel
                 if (cq == 0) {
                     // one thread per pixel: add the four partial sums + bias, then the reference's outputs
                     const int w = tw.tw * 14 + cc;
                     const int h = tw.th * 8 + hh;
                     if (valid && w < p.W && h < p.H) {
-                        const float* part = reinterpret_cast<const float*>(sfull_b) + quarter * 32 + lane;
+                        const float* pr = reinterpret_cast<const float*>(sfull_b) + quarter * 32 + lane;
                         float v[3];
 #pragma unroll
                         for (int o = 0; o < 3; ++o)
-                            v[o] = ((part[o * 128] + part[(3 + o) * 128]) + (part[(6 + o) * 128] + part[(9 + o) * 128])) + head_s[192 + o];
+                            v[o] = ((pr[o * 128] + pr[(3 + o) * 128]) + (pr[(6 + o) * 128] + pr[(9 + o) * 128])) + head_s[192 + o];
                         const size_t hw = size_t(p.H) * p.W, pix = size_t(h) * p.W + w;
                         if (p.head_f32) {
 #pragma unroll
@@ -421,25 +432,53 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                         }
                     }
                 }
-            } else if (e < 4) {
-                // warps 0..3 (128 threads, one small barrier of their own) pool the staged tile and issue the stores
+            } else {
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+                // the store of this buffer's previous tile (two tiles ago) has been read
+                mbar_wait_uniform(&free_bar[acc], ((uint32_t(iter) >> 1) & 1u) ^ 1u);
+                if (p.store_full && valid) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int jj = cq * 2 + q;   // 16-byte chunk of the 128-byte staging row
+                        const uint32_t addr = smem_u32(sfull_b) + uint32_t(srow * 128 + ((jj ^ (srow & 7)) << 4));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                                     "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                                     : "memory");
+                    }
+                }
                 if (p.store_pool) {
-                    if (etid < 28 * 4) epilogue_pool_chunk(sfull_b, spool_b, etid, 14, 8);
-                    fence_proxy_async_smem();
-                    named_barrier_sync(2, 128);
+                    // 2x2 max-pool in registers: the window of pooled pixel (q, cc/2) is lanes {l, l+1, l+16, l+17}
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        pk[j] = bf16x2_max(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
+                        pk[j] = bf16x2_max(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 16));
+                    }
+                    if (pool_lane) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int jj = cq * 2 + q;
+                            const uint32_t addr = smem_u32(spool_b) + uint32_t(prow * 128 + ((jj ^ (prow & 7)) << 4));
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                                         "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                                         : "memory");
+                        }
+                    }
                 }
-#ifndef B2R_EXP_NO_STAGE
-                if (etid == 0) {
-                    const int w0 = tw.tw * 14, h0 = tw.th * 8;
-                    if (p.store_full) tma_store_4d(&p.out_map, sfull_b, 0, w0, h0, tw.n);
-                    if (p.store_pool) tma_store_4d(&p.pool_map, spool_b, 0, w0 >> 1, h0 >> 1, tw.n);
-                    tma_store_commit();
-                    B2R_STAMP(iter, 6);
-                }
+                fence_proxy_async_smem();
+            }
+#else
+            (void)valid; (void)srow; (void)relu_only; (void)ns; (void)b16; (void)d0; (void)d1; (void)d2; (void)spool_b; (void)sfull_b;
+            (void)prow; (void)pool_lane; (void)hh;
+            if (!kHead) mbar_wait_uniform(&free_bar[acc], ((uint32_t(iter) >> 1) & 1u) ^ 1u);
 #endif
+            if (etid == 0) B2R_STAMP(iter, 5);
+            if (!kHead) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&staged_bar[acc]);
             }
         }
-        if (etid == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
