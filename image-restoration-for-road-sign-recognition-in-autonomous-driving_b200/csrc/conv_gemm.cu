@@ -47,7 +47,7 @@ struct alignas(64) ConvGemmParams {
     int tiles_w, tiles_h, tiles_n;
     int tile_w, tile_h, tile_n;
     int n_tiles;          // cout_total / BLOCK_N
-    int n_tiles_per_out;  // n-tiles per output map (CONVT: C_out / BLOCK_N; NHWC: n_tiles)
+    int cout_per_out;     // channels per output map (CONVT2X2: C_out, four maps; NHWC: cout_total, one map)
     int store_full, store_pool;
     uint32_t kblk[B2R_MAX_KBLOCKS];
 };
@@ -198,8 +198,10 @@ __global__ void __launch_bounds__(kNumThreads, GemmCfg<BLOCK_N>::kCtasPerSm) con
             const int w0 = (m % p.tiles_w) * p.tile_w;
             const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.tile_h;
             const int n0 = (m / (p.tiles_w * p.tiles_h)) * p.tile_n;
-            const int out_idx = n_tile / p.n_tiles_per_out;
-            const int ch_tile0 = (n_tile % p.n_tiles_per_out) * BLOCK_N;
+            // first channel of this n-tile inside its output map (CONVT2X2: an n-tile may span several of the four
+            // maps, e.g. C_out = 64 with BLOCK_N = 256 covers all four taps in one tile)
+            int out_idx = (n_tile * BLOCK_N) / p.cout_per_out;
+            int ch_in_out = n_tile * BLOCK_N - out_idx * p.cout_per_out;
 
             // bias of this n-tile -> smem (previous tile's readers are past their last named barrier)
             for (int i = epi_tid; i < BLOCK_N; i += kEpiThreads) bias_s[i] = p.bias[n_tile * BLOCK_N + i];
@@ -241,10 +243,14 @@ __global__ void __launch_bounds__(kNumThreads, GemmCfg<BLOCK_N>::kCtasPerSm) con
                 }
 
                 if (epi_tid == 0) {
-                    const int ch0 = ch_tile0 + c * 64;
-                    if (p.store_full) tma_store_4d(&p.out_map[out_idx], sfull, ch0, w0, h0, n0);
-                    if (p.store_pool) tma_store_4d(&p.pool_map, spool, ch0, w0 >> 1, h0 >> 1, n0);
+                    if (p.store_full) tma_store_4d(&p.out_map[out_idx], sfull, ch_in_out, w0, h0, n0);
+                    if (p.store_pool) tma_store_4d(&p.pool_map, spool, ch_in_out, w0 >> 1, h0 >> 1, n0);
                     tma_store_commit();
+                }
+                ch_in_out += 64;
+                if (ch_in_out >= p.cout_per_out) {
+                    ch_in_out = 0;
+                    ++out_idx;
                 }
             }
             acc ^= 1;
@@ -622,9 +628,13 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
 
     // ---- tile geometry
     int block_n = d->block_n;
-    if (block_n == 0) block_n = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
+    // CONVT2X2: the four taps are four column blocks of ONE GEMM (cout_total = 4 C_out), so an n-tile may span taps:
+    // C_out = 64 runs as one 128 x 256 tile per 128 pixels instead of four 128 x 64 tiles that each re-load the input
+    const int n_span = convt ? d->cout_total : cout;
+    if (block_n == 0) block_n = (n_span % 256 == 0) ? 256 : (n_span % 128 == 0 ? 128 : 64);
     B2R_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "block_n=%d", block_n);
-    B2R_REQUIRE(cout % block_n == 0, "C_out=%d not a multiple of block_n=%d", cout, block_n);
+    B2R_REQUIRE(n_span % block_n == 0 && (cout % block_n == 0 || block_n % cout == 0),
+                "C_out=%d (cout_total=%d) incompatible with block_n=%d", cout, d->cout_total, block_n);
     int tw = d->tile_w, th = d->tile_h, tn = d->tile_n;
     if (tw == 0 && th == 0 && tn == 0) choose_tile(d->N, d->H, d->W, d->out_pool != nullptr, spatial, &tw, &th, &tn);
     B2R_REQUIRE(tw > 0 && th > 0 && tn > 0 && tw * th * tn == kBlockM, "tile %dx%dx%d must cover 128 pixels", tw, th, tn);
@@ -704,7 +714,7 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
     P.tiles_h = ceil_div(d->H, th);
     P.tiles_n = ceil_div(d->N, tn);
     P.n_tiles = d->cout_total / block_n;
-    P.n_tiles_per_out = convt ? cout / block_n : P.n_tiles;
+    P.cout_per_out = convt ? cout : d->cout_total;
     P.store_full = d->out != nullptr;
     P.store_pool = d->out_pool != nullptr;
 
