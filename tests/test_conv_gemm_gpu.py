@@ -303,3 +303,52 @@ def test_conv_n64_many_tiles_and_ring_wraps():
     torch.cuda.synchronize()
     ref = F.relu(F.conv2d(to_nchw_f32(x), wt.to(torch.bfloat16).float(), b, padding=1))
     assert_close_bf16(to_nchw_f32(out), ref, "n64 many tiles")
+
+
+def test_conv_w3_random_shapes_against_generic_kernel():
+    """Seeded sweep over ragged shapes / source splits / pooling for the tap-folded kernel (two MMA issuer warps, per-warp
+    staging, store warp): every output must agree with the generic kernel's within one bf16 rounding, pooled outputs
+    must be the exact 2x2 maxima of the stored tile, and nothing outside the tensors may be touched (NaN guards)."""
+    ops, packing, L = _ops()
+    g = torch.Generator().manual_seed(1234)
+    for case in range(10):
+        n = int(torch.randint(1, 5, (1,), generator=g))
+        h = 2 * int(torch.randint(1, 40, (1,), generator=g))
+        w = 2 * int(torch.randint(1, 60, (1,), generator=g))
+        splits = [(64,), (64, 64), (128,), (64, 128)][int(torch.randint(0, 4, (1,), generator=g))]
+        pool = bool(torch.randint(0, 2, (1,), generator=g))
+        store_full = bool(torch.randint(0, 2, (1,), generator=g)) or not pool
+        srcs = [nhwc_bf16(rnd(n, c, h, w, seed=300 + 7 * case + i)) for i, c in enumerate(splits)]
+        ci = sum(splits)
+        wt = rnd(64, ci, 3, 3, scale=(2.0 / (9 * ci)) ** 0.5, seed=400 + case)
+        b = rnd(64, scale=0.1, seed=500 + case)
+        plan = packing.KPlan(64)
+        off = 0
+        for s, c in enumerate(splits):
+            plan.add_conv3x3(s, wt[:, off:off + c])
+            off += c
+        wm, kbl = plan.finish()
+        wm, w3 = wm.cuda(), plan.finish_w3().cuda()
+        res = []
+        for flags in (L.B2R_CONV_GENERIC_ONLY, 0):
+            # guard rows around the outputs catch out-of-bounds stores
+            out_g = torch.full((n + 2, h, w, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+            pl_g = torch.full((n + 2, h // 2, w // 2, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+            out, pl = out_g[1:n + 1], pl_g[1:n + 1]
+            ops.conv_gemm(srcs, wm, b, kbl, act=L.B2R_ACT_PRELU, slope=0.25, out=out if (store_full or flags) else None,
+                          out_pool=pl if pool else None, weights_w3=w3, flags=flags)
+            torch.cuda.synchronize()
+            assert bool(torch.isnan(out_g[0]).all()) and bool(torch.isnan(out_g[n + 1]).all()), f"case {case}: OOB store"
+            assert bool(torch.isnan(pl_g[0]).all()) and bool(torch.isnan(pl_g[n + 1]).all()), f"case {case}: OOB pool store"
+            res.append((out.clone(), pl.clone()))
+        ref_out, ref_pl = res[0]
+        out, pl = res[1]
+        if store_full:
+            d = (out.float() - ref_out.float()).abs()
+            assert bool((d <= 2.0 ** -7 * ref_out.float().abs() + 1e-3).all()), (case, n, h, w, splits, float(d.max()))
+        if pool:
+            exact = F.max_pool2d(to_nchw_f32(out), 2, 2) if store_full else None
+            if exact is not None:
+                assert torch.equal(to_nchw_f32(pl), exact), (case, n, h, w, splits)
+            d = (pl.float() - ref_pl.float()).abs()
+            assert bool((d <= 2.0 ** -7 * ref_pl.float().abs() + 1e-3).all()), (case, "pool", float(d.max()))
