@@ -78,8 +78,14 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
     const int tiles_per_img = p.tiles_w * p.tiles_h;
     const int total_tiles = tiles_per_img * p.N;
     const int H = p.H, W = p.W;
+    // role timeline: debug builds only (-DB2R_TIMELINE, tools/c3_timeline.py); this kernel is issue-bound, so even
+    // predicated-off stamps would cost throughput
+#ifdef B2R_TIMELINE
 #define C3_STAMP(iter, slot) \
     do { if (p.dbg != nullptr && blockIdx.x == 0 && (iter) < B2R_DBG_TILES) p.dbg[(iter) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define C3_STAMP(iter, slot) do { } while (0)
+#endif
 
     if (warp_idx == kC3ProducerWarps) {
         if (lane == 0) {

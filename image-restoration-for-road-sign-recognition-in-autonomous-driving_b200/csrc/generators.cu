@@ -1,0 +1,270 @@
+// Single-degradation dataset generators with the reference's exact (quirky) arithmetic, and the image-quality
+// reduction: the callers either side of the hot path.  All are streaming kernels bound by HBM:
+// algorithmic bytes = elems x (bytes read + bytes written) per image.
+//
+//   b2r_lut_u8              out = lut[n][in]            the reference's float64 point operations on u8 images, e.g. fog on
+//                                                       image/255.0 (04_gen_fog.py:17-30, 13_pipeline_stress_test.py:50-56):
+//                                                       256 possible results per image, evaluated by the host with the
+//                                                       reference's own arithmetic
+//   b2r_minmax_u8           per-image extrema over all channels (cv2.minMaxIdx inside cv2.normalize, 03_gen_blur.py:29)
+//   b2r_normalize_minmax_u8 cv2.normalize(x, x, 0, 255, NORM_MINMAX): scale / shift in double, cast to float,
+//                           saturate(rint(fma(src, scale, shift)))  (OpenCV 4.13 cvtScale8u; pinned against cv2 in
+//                           tests/test_generators_host.py)
+//   b2r_noise02             02_gen_noise.py:12-27: float64 image/255 + noise, lower clip -1 when ANY value of the image is
+//                           negative, then np.uint8(out * 255), which wraps negative values modulo 256
+//   b2r_sse_u8              per-image sum of squared differences (PSNR = 10 log10(255^2 N / SSE), 08_run_inference.py:118-129)
+#include "b2r_internal.h"
+#include "philox.cuh"
+
+namespace b2r {
+
+constexpr int kGenThreads = 256;
+constexpr int kGenBytesPerThread = 16;
+
+__global__ void __launch_bounds__(kGenThreads) lut_u8_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ lut,
+                                                              uint8_t* __restrict__ out, long elems) {
+    __shared__ uint8_t s_lut[256];
+    const int n = blockIdx.y;
+    if (threadIdx.x < 64) reinterpret_cast<uint32_t*>(s_lut)[threadIdx.x] = reinterpret_cast<const uint32_t*>(lut + n * 256)[threadIdx.x];
+    __syncthreads();
+    const uint8_t* src = in + (long)n * elems;
+    uint8_t* dst = out + (long)n * elems;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    for (long i = ((long)blockIdx.x * kGenThreads + threadIdx.x) * kGenBytesPerThread; i < elems;
+         i += (long)gridDim.x * kGenThreads * kGenBytesPerThread) {
+        if (vec && i + kGenBytesPerThread <= elems) {
+            uint4 v = *reinterpret_cast<const uint4*>(src + i);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                w[k] = uint32_t(s_lut[w[k] & 0xFF]) | uint32_t(s_lut[(w[k] >> 8) & 0xFF]) << 8 |
+                       uint32_t(s_lut[(w[k] >> 16) & 0xFF]) << 16 | uint32_t(s_lut[w[k] >> 24]) << 24;
+            *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (long j = i; j < elems && j < i + kGenBytesPerThread; ++j) dst[j] = s_lut[src[j]];
+        }
+    }
+}
+
+__global__ void minmax_init_kernel(int32_t* minmax, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) {
+        minmax[2 * i] = 255;
+        minmax[2 * i + 1] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kGenThreads) minmax_u8_kernel(const uint8_t* __restrict__ in, int32_t* __restrict__ minmax,
+                                                                 long elems) {
+    const int n = blockIdx.y;
+    const uint8_t* src = in + (long)n * elems;
+    const bool vec = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;   // four byte lanes each
+    for (long i = ((long)blockIdx.x * kGenThreads + threadIdx.x) * kGenBytesPerThread; i < elems;
+         i += (long)gridDim.x * kGenThreads * kGenBytesPerThread) {
+        if (vec && i + kGenBytesPerThread <= elems) {
+            const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+            lo = __vminu4(__vminu4(lo, v.x), __vminu4(v.y, __vminu4(v.z, v.w)));
+            hi = __vmaxu4(__vmaxu4(hi, v.x), __vmaxu4(v.y, __vmaxu4(v.z, v.w)));
+        } else {
+            for (long j = i; j < elems && j < i + kGenBytesPerThread; ++j) {
+                const uint32_t b = src[j] * 0x01010101u;
+                lo = __vminu4(lo, b);
+                hi = __vmaxu4(hi, b);
+            }
+        }
+    }
+    int mn = min(min(lo & 0xFF, (lo >> 8) & 0xFF), min((lo >> 16) & 0xFF, lo >> 24));
+    int mx = max(max(hi & 0xFF, (hi >> 8) & 0xFF), max((hi >> 16) & 0xFF, hi >> 24));
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&minmax[2 * n], mn);
+        atomicMax(&minmax[2 * n + 1], mx);
+    }
+}
+
+__global__ void __launch_bounds__(kGenThreads) normalize_minmax_u8_kernel(const uint8_t* __restrict__ in,
+                                                                           const int32_t* __restrict__ minmax,
+                                                                           uint8_t* __restrict__ out, long elems) {
+    __shared__ uint8_t s_lut[256];
+    const int n = blockIdx.y;
+    {
+        // cv::normalize(NORM_MINMAX, alpha 0, beta 255): scale, shift in double; convertTo 8U -> 8U evaluates
+        // saturate_cast<uchar>(cvRound(fmaf(src, (float)scale, (float)shift)))
+        const double smin = minmax[2 * n], smax = minmax[2 * n + 1];
+        const double scale = 255.0 * ((smax - smin) > 2.220446049250313e-16 ? 1.0 / (smax - smin) : 0.0);
+        const double shift = 0.0 - smin * scale;
+        const float a = float(scale), b = float(shift);
+        const float r = rintf(fmaf(float(threadIdx.x), a, b));   // rintf: ties to even, as cvRound
+        s_lut[threadIdx.x] = uint8_t(fminf(fmaxf(r, 0.f), 255.f));
+    }
+    __syncthreads();
+    const uint8_t* src = in + (long)n * elems;
+    uint8_t* dst = out + (long)n * elems;
+    for (long i = (long)blockIdx.x * kGenThreads + threadIdx.x; i < elems; i += (long)gridDim.x * kGenThreads)
+        dst[i] = s_lut[src[i]];
+}
+
+// 02_gen_noise.py: out = image / 255 (float64) + noise;  pass 0 records whether any value of the image is negative,
+// pass 1 clips to [low, 1] and converts with np.uint8(out * 255): truncation toward zero, then wrap modulo 256.
+template <int PASS>
+__global__ void __launch_bounds__(kGenThreads) noise02_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                               long elems, const float* __restrict__ sigma,
+                                                               const double* __restrict__ noise, uint64_t seed,
+                                                               uint64_t image_index0, int32_t* __restrict__ neg_flags) {
+    const int n = blockIdx.y;
+    const uint8_t* src = in + (long)n * elems;
+    const double* nz = noise ? noise + (long)n * elems : nullptr;
+    const double sg = double(sigma[n]);
+    const double low = (PASS == 1 && neg_flags[n]) ? -1.0 : 0.0;
+    bool any_neg = false;
+    const long pixels = elems / 3;
+    for (long pix = (long)blockIdx.x * kGenThreads + threadIdx.x; pix < pixels; pix += (long)gridDim.x * kGenThreads) {
+        float z[3] = {0.f, 0.f, 0.f};
+        if (!nz) pixel_normals(seed, image_index0 + uint64_t(n), uint32_t(pix), z);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const long i = pix * 3 + c;
+            const double v = double(src[i]) / 255.0 + (nz ? nz[i] : sg * double(z[c]));
+            if (PASS == 0) {
+                any_neg |= v < 0.0;
+            } else {
+                const double y = fmin(fmax(v, low), 1.0) * 255.0;
+                out[(long)n * elems + i] = uint8_t(int(y) & 0xFF);   // C cast toward zero, then two's-complement wrap
+            }
+        }
+    }
+    if (PASS == 0 && __any_sync(0xffffffffu, any_neg) && (threadIdx.x & 31) == 0) atomicOr(&neg_flags[n], 1);
+}
+
+__global__ void __launch_bounds__(kGenThreads) sse_u8_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                              unsigned long long* __restrict__ sse, long elems) {
+    const int n = blockIdx.y;
+    const uint8_t* pa = a + (long)n * elems;
+    const uint8_t* pb = b + (long)n * elems;
+    const bool vec = ((reinterpret_cast<uintptr_t>(pa) | reinterpret_cast<uintptr_t>(pb)) & 15) == 0;
+    unsigned long long acc = 0;
+    for (long i = ((long)blockIdx.x * kGenThreads + threadIdx.x) * kGenBytesPerThread; i < elems;
+         i += (long)gridDim.x * kGenThreads * kGenBytesPerThread) {
+        if (vec && i + kGenBytesPerThread <= elems) {
+            const uint4 va = *reinterpret_cast<const uint4*>(pa + i), vb = *reinterpret_cast<const uint4*>(pb + i);
+            const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+            uint32_t s = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t d = __vabsdiffu4(wa[k], wb[k]);
+                s = __dp4a(d, d, s);   // sum of the four squared byte differences
+            }
+            acc += s;
+        } else {
+            for (long j = i; j < elems && j < i + kGenBytesPerThread; ++j) {
+                const int d = int(pa[j]) - int(pb[j]);
+                acc += (unsigned long long)(d * d);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&sse[n], acc);
+}
+
+static int gen_grid(long elems, int N, dim3* grid, int bytes_per_thread) {
+    long blocks = (elems + (long)kGenThreads * bytes_per_thread - 1) / ((long)kGenThreads * bytes_per_thread);
+    if (blocks < 1) blocks = 1;
+    // enough blocks per image to fill the GPU even for N = 1, without a tail of tiny blocks
+    int sms = 0;
+    int rc = device_sm_count(&sms);
+    if (rc) return rc;
+    const long cap = (8L * sms + N - 1) / N > 1 ? (8L * sms + N - 1) / N : 1;
+    if (blocks > cap) blocks = cap;
+    *grid = dim3((unsigned)blocks, (unsigned)N, 1);
+    return B2R_OK;
+}
+
+}  // namespace b2r
+
+extern "C" {
+
+int b2r_lut_u8(const uint8_t* in, const uint8_t* lut, uint8_t* out, int N, int64_t elems_per_image, void* stream_v) {
+    using namespace b2r;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    B2R_REQUIRE(in && lut && out, "null pointer");
+    B2R_REQUIRE(N > 0 && N <= 65535 && elems_per_image > 0, "bad shape N=%d elems=%lld", N, (long long)elems_per_image);
+    B2R_REQUIRE((reinterpret_cast<uintptr_t>(lut) & 3) == 0, "lut must be 4-byte aligned");
+    dim3 grid;
+    int rc = gen_grid(elems_per_image, N, &grid, kGenBytesPerThread);
+    if (rc) return rc;
+    lut_u8_kernel<<<grid, kGenThreads, 0, stream>>>(in, lut, out, elems_per_image);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
+int b2r_minmax_u8(const uint8_t* in, int32_t* minmax, int N, int64_t elems_per_image, void* stream_v) {
+    using namespace b2r;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    B2R_REQUIRE(in && minmax, "null pointer");
+    B2R_REQUIRE(N > 0 && N <= 65535 && elems_per_image > 0, "bad shape N=%d elems=%lld", N, (long long)elems_per_image);
+    minmax_init_kernel<<<(N + 255) / 256, 256, 0, stream>>>(minmax, N);
+    B2R_CHECK_LAUNCH();
+    dim3 grid;
+    int rc = gen_grid(elems_per_image, N, &grid, kGenBytesPerThread);
+    if (rc) return rc;
+    minmax_u8_kernel<<<grid, kGenThreads, 0, stream>>>(in, minmax, elems_per_image);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
+int b2r_normalize_minmax_u8(const uint8_t* in, const int32_t* minmax, uint8_t* out, int N, int64_t elems_per_image,
+                            void* stream_v) {
+    using namespace b2r;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    B2R_REQUIRE(in && minmax && out, "null pointer");
+    B2R_REQUIRE(N > 0 && N <= 65535 && elems_per_image > 0, "bad shape N=%d elems=%lld", N, (long long)elems_per_image);
+    dim3 grid;
+    int rc = gen_grid(elems_per_image, N, &grid, 4);
+    if (rc) return rc;
+    normalize_minmax_u8_kernel<<<grid, kGenThreads, 0, stream>>>(in, minmax, out, elems_per_image);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
+int b2r_noise02(const uint8_t* in, uint8_t* out, int N, int64_t elems_per_image, const float* sigma, const double* noise,
+                uint64_t seed, uint64_t image_index0, int32_t* neg_flags, int clip_rule, void* stream_v) {
+    using namespace b2r;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    B2R_REQUIRE(in && out && sigma && neg_flags, "null pointer");
+    B2R_REQUIRE(N > 0 && N <= 65535 && elems_per_image > 0 && elems_per_image % 3 == 0 && elems_per_image / 3 < (1LL << 32),
+                "bad shape N=%d elems=%lld (3 interleaved channels expected)", N, (long long)elems_per_image);
+    B2R_REQUIRE(clip_rule == B2R_NOISE_CLIP_SCRIPT02 || clip_rule == B2R_NOISE_CLIP_UNIT, "clip_rule=%d", clip_rule);
+    B2R_CUDA(cudaMemsetAsync(neg_flags, 0, sizeof(int32_t) * N, stream));
+    dim3 grid;
+    int rc = gen_grid(elems_per_image, N, &grid, 3);
+    if (rc) return rc;
+    if (clip_rule == B2R_NOISE_CLIP_SCRIPT02) {   // the lower clip depends on the whole image: decide it first
+        noise02_kernel<0><<<grid, kGenThreads, 0, stream>>>(in, out, elems_per_image, sigma, noise, seed, image_index0, neg_flags);
+        B2R_CHECK_LAUNCH();
+    }
+    noise02_kernel<1><<<grid, kGenThreads, 0, stream>>>(in, out, elems_per_image, sigma, noise, seed, image_index0, neg_flags);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
+int b2r_sse_u8(const uint8_t* a, const uint8_t* b, uint64_t* sse, int N, int64_t elems_per_image, void* stream_v) {
+    using namespace b2r;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    B2R_REQUIRE(a && b && sse, "null pointer");
+    B2R_REQUIRE(N > 0 && N <= 65535 && elems_per_image > 0, "bad shape N=%d elems=%lld", N, (long long)elems_per_image);
+    B2R_CUDA(cudaMemsetAsync(sse, 0, sizeof(uint64_t) * N, stream));
+    dim3 grid;
+    int rc = gen_grid(elems_per_image, N, &grid, kGenBytesPerThread);
+    if (rc) return rc;
+    sse_u8_kernel<<<grid, kGenThreads, 0, stream>>>(a, b, reinterpret_cast<unsigned long long*>(sse), elems_per_image);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
+}  // extern "C"

@@ -326,3 +326,87 @@ def degrade(images: torch.Tensor, ksize: Optional[torch.Tensor], taps: Optional[
                                  int(seed) & (2 ** 64 - 1), int(image_index0), int(order), int(flags), _stream()))
     STATS["launches"] += 1
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# callers either side of the hot path: exact single-degradation generators and the PSNR reduction (csrc/generators.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+def _images_u8(x: torch.Tensor, name: str):
+    _chk(x, torch.uint8, name)
+    if x.dim() < 2:
+        raise L.B2RError(f"{name} must be [N, ...] uint8")
+    return int(x.shape[0]), int(x[0].numel())
+
+
+def lut_u8(images: torch.Tensor, lut: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[n] = lut[n][images[n]]; lut uint8 [N, 256] on the same device."""
+    n, elems = _images_u8(images, "images")
+    _chk(lut, torch.uint8, "lut", 2)
+    if tuple(lut.shape) != (n, 256):
+        raise L.B2RError(f"lut shape {tuple(lut.shape)}; expected ({n}, 256)")
+    out = torch.empty_like(images) if out is None else out
+    _chk(out, torch.uint8, "out")
+    if out.shape != images.shape:
+        raise L.B2RError("out shape differs from images")
+    L.check(L.load().b2r_lut_u8(images.data_ptr(), lut.data_ptr(), out.data_ptr(), n, elems, _stream()))
+    STATS["launches"] += 1
+    return out
+
+
+def minmax_u8(images: torch.Tensor) -> torch.Tensor:
+    """Per-image (min, max) over all channels as int32 [N, 2]."""
+    n, elems = _images_u8(images, "images")
+    mm = torch.empty((n, 2), dtype=torch.int32, device=images.device)
+    L.check(L.load().b2r_minmax_u8(images.data_ptr(), mm.data_ptr(), n, elems, _stream()))
+    STATS["launches"] += 2
+    return mm
+
+
+def normalize_minmax_u8(images: torch.Tensor, minmax: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cv2.normalize(x, x, 0, 255, cv2.NORM_MINMAX) given the per-image extrema (03_gen_blur.py:29)."""
+    n, elems = _images_u8(images, "images")
+    _chk(minmax, torch.int32, "minmax", 2)
+    if tuple(minmax.shape) != (n, 2):
+        raise L.B2RError(f"minmax shape {tuple(minmax.shape)}; expected ({n}, 2)")
+    out = torch.empty_like(images) if out is None else out
+    _chk(out, torch.uint8, "out")
+    L.check(L.load().b2r_normalize_minmax_u8(images.data_ptr(), minmax.data_ptr(), out.data_ptr(), n, elems, _stream()))
+    STATS["launches"] += 1
+    return out
+
+
+def noise02(images: torch.Tensor, sigma: torch.Tensor, noise: Optional[torch.Tensor] = None, seed: int = 0,
+            image_index0: int = 0, out: Optional[torch.Tensor] = None, clip_rule: int = 0):
+    """Float64 noise generators on u8 [N,H,W,3]: clip_rule 0 = 02_gen_noise.py add_gaussian_noise (conditional -1 clip,
+    wrap-around), 1 = 13_pipeline_stress_test.py add_noise (clip to [0, 1]).  Returns (out u8, neg_flags int32 [N])."""
+    _chk(images, torch.uint8, "images", 4)
+    n, elems = _images_u8(images, "images")
+    if images.shape[3] != 3:
+        raise L.B2RError("images must be NHWC with 3 channels")
+    _chk(sigma, torch.float32, "sigma", 1)
+    if sigma.numel() != n:
+        raise L.B2RError("sigma must have one entry per image")
+    if noise is not None:
+        _chk(noise, torch.float64, "noise")
+        if noise.numel() != images.numel():
+            raise L.B2RError("noise must have one float64 per image element")
+    out = torch.empty_like(images) if out is None else out
+    _chk(out, torch.uint8, "out", 4)
+    flags = torch.empty((n,), dtype=torch.int32, device=images.device)
+    L.check(L.load().b2r_noise02(images.data_ptr(), out.data_ptr(), n, elems, sigma.data_ptr(), _ptr(noise),
+                                 int(seed) & (2 ** 64 - 1), int(image_index0), flags.data_ptr(), int(clip_rule),
+                                 _stream()))
+    STATS["launches"] += 2 if clip_rule == 0 else 1
+    return out, flags
+
+
+def sse_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Per-image sum of squared differences of two u8 batches, int64 [N] (exact)."""
+    n, elems = _images_u8(a, "a")
+    _chk(b, torch.uint8, "b")
+    if b.shape != a.shape:
+        raise L.B2RError("a and b differ in shape")
+    sse = torch.empty((n,), dtype=torch.int64, device=a.device)
+    L.check(L.load().b2r_sse_u8(a.data_ptr(), b.data_ptr(), sse.data_ptr(), n, elems, _stream()))
+    STATS["launches"] += 1
+    return sse

@@ -207,6 +207,44 @@ int b2r_linear_f32out(const void* in_bf16, const void* w_bf16, const float* bias
 int b2r_argmax_count(const float* logits, const int64_t* labels, int64_t* pred, float* conf, int64_t* counts, int N,
                      int C, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * (6) Callers either side of the hot path: the single-degradation dataset generators with the
+ * reference's exact arithmetic, and the image-quality reduction.  Images are u8, `elems_per_image` contiguous bytes
+ * each (H*W*3 for the reference's HWC arrays).  All streaming, HBM-bound.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* out[n][i] = lut[n][in[n][i]]; lut u8 [N][256] (4-byte aligned).  Carries the reference's float64 point operations on
+ * u8 images exactly, the host evaluating the 256 possible results with the reference's own arithmetic: fog on
+ * `image / 255.0` (04_gen_fog.py:12-31 with its clipped random t; 13_pipeline_stress_test.py:50-56). */
+int b2r_lut_u8(const uint8_t* in, const uint8_t* lut, uint8_t* out, int N, int64_t elems_per_image, void* stream);
+
+/* Per-image extrema over all channels, minmax int32 [N][2] = {min, max} (the cv2.minMaxIdx step of
+ * cv2.normalize(blurred, blurred, 0, 255, cv2.NORM_MINMAX), 03_gen_blur.py:29). */
+int b2r_minmax_u8(const uint8_t* in, int32_t* minmax, int N, int64_t elems_per_image, void* stream);
+
+/* The convertTo step of the same cv2.normalize call given the extrema: scale = 255 / (max - min) (0 for a constant
+ * image), shift = -min * scale in double, both cast to float, out = saturate_u8(rint(fma(in, scale, shift))).
+ * in == out is allowed (the reference normalises in place). */
+int b2r_normalize_minmax_u8(const uint8_t* in, const int32_t* minmax, uint8_t* out, int N, int64_t elems_per_image,
+                            void* stream);
+
+/* The float64 noise generators: x = image / 255 (float64) + noise, then
+ *   B2R_NOISE_CLIP_SCRIPT02  02_gen_noise.py:12-27 add_gaussian_noise: low = -1 if any x of the image < 0 else 0;
+ *                            out = np.uint8(clip(x, low, 1) * 255), i.e. truncation toward zero followed by wrap-around
+ *                            modulo 256 for negative values (-127.5 -> 129).  Two passes (the decision needs the image).
+ *   B2R_NOISE_CLIP_UNIT      13_pipeline_stress_test.py:33-38 add_noise: out = (clip(x, 0, 1) * 255).astype(uint8).
+ * noise: optional float64 [N][elems] (the reference's own draw, for parity tests); NULL draws N(0, sigma[n]^2) from
+ * Philox4x32-10 keyed by (seed, image_index0 + n, pixel) as b2r_degrade does.
+ * neg_flags: int32 [N] workspace (the per-image "any negative" decision of script 02; left filled for inspection). */
+#define B2R_NOISE_CLIP_SCRIPT02 0
+#define B2R_NOISE_CLIP_UNIT 1
+int b2r_noise02(const uint8_t* in, uint8_t* out, int N, int64_t elems_per_image, const float* sigma, const double* noise,
+                uint64_t seed, uint64_t image_index0, int32_t* neg_flags, int clip_rule, void* stream);
+
+/* sse[n] = sum_i (a[n][i] - b[n][i])^2 as uint64: PSNR = 10 log10(255^2 * elems / sse) (08_run_inference.py:118-129
+ * reports skimage's peak_signal_noise_ratio on the u8 images). */
+int b2r_sse_u8(const uint8_t* a, const uint8_t* b, uint64_t* sse, int N, int64_t elems_per_image, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

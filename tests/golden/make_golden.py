@@ -182,9 +182,70 @@ def gen_models():
     np.savez_compressed(OUT / "models_ref.npz", **res)
 
 
+def load_ref_functions(filename, names):
+    """Run ONLY the named top-level function definitions of a reference script that cannot be imported as a whole
+    (13_pipeline_stress_test.py imports matplotlib at module level): the function bodies are the reference's own code,
+    compiled from its own source file."""
+    import ast
+    import cv2
+    import torch
+    src = (REF / filename).read_text()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(keep) == len(names), [n.name for n in keep]
+    ns = {"np": np, "cv2": cv2, "torch": torch}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), str(REF / filename), "exec"), ns)
+    return ns
+
+
+def gen_generators():
+    """Single-degradation generators (02 / 03 / 04) and the stress-test distortions (13), random draws replayed."""
+    r02 = load_ref("02_gen_noise.py")
+    r03 = load_ref("03_gen_blur.py")
+    r04 = load_ref("04_gen_fog.py")
+    f13 = load_ref_functions("13_pipeline_stress_test.py", ["add_noise", "add_blur", "add_fog"])
+    imgs = test_images()
+    imgs[2] = np.clip(imgs[2].astype(np.int32) // 3 + 170, 0, 255).astype(np.uint8)   # bright image: script 02's "no negative value" branch
+    imgs[3, 5:9, 5:9] = 0
+    n, h, w, _ = imgs.shape
+    rng = np.random.default_rng(7)
+    z = rng.standard_normal((n, h, w, 3))
+    # --- 02: var 0.02 as the script calls it, and a tiny variance on the bright image so that nothing goes negative
+    var02 = np.array([0.02, 0.02, 0.0004, 0.02, 0.01, 0.05])
+    out02 = []
+    for i in range(n):
+        r02.np = NpShim(ReplayNormal(z[i]))
+        out02.append(r02.add_gaussian_noise(imgs[i], var=float(var02[i])))
+    # --- 03: blur + joint min-max stretch
+    cases03 = [(10, 45), (12, 45), (5, 0), (11, 200), (7, 90), (3, 135)]
+    out03 = [r03.apply_motion_blur(imgs[i], degree=d, angle=a) for i, (d, a) in enumerate(cases03)]
+    # --- 04: fog with the uniform draw replayed
+    u04 = np.array([0.8, 1.2, 1.0, 0.93, 1.17, 0.85])
+    inten04 = np.array([0.8, 0.8, 0.8, 0.5, 1.0, 0.1])
+    out04 = []
+    for i in range(n):
+        r04.random = ReplayRandom([float(u04[i])])
+        out04.append(r04.add_fog(imgs[i], fog_intensity=float(inten04[i])))
+    # --- 13: Blur -> Fog -> Noise with u8 re-quantisation after every stage
+    b13, f13o, n13 = [], [], []
+    for i in range(n):
+        f13["np"] = NpShim(ReplayNormal(z[i]))
+        b = f13["add_blur"](imgs[i].copy())
+        f = f13["add_fog"](b)
+        b13.append(b)
+        f13o.append(f)
+        n13.append(f13["add_noise"](f))
+    np.savez_compressed(OUT / "generators_ref.npz", images=imgs, z=z, var02=var02, out02=np.stack(out02),
+                        cases03=np.array(cases03), out03=np.stack(out03), u04=u04, inten04=inten04,
+                        out04=np.stack(out04), blur13=np.stack(b13), fog13=np.stack(f13o), noise13=np.stack(n13))
+
+
 if __name__ == "__main__":
     assert REF.exists(), "the reference is not mounted; fixtures can only be generated where /root/reference exists"
-    gen_degrade()
-    gen_models()
+    import sys as _sys
+    if "--only-generators" not in _sys.argv:
+        gen_degrade()
+        gen_models()
+    gen_generators()
     for p in sorted(OUT.glob("*.npz")):
         print(p.name, p.stat().st_size)

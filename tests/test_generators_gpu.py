@@ -1,0 +1,171 @@
+"""GPU parity of the callers either side of the hot path (csrc/generators.cu, generators.py): the exact
+single-degradation generators of scripts 02 / 03 / 04, the stress-test distortions and cascade of script 13, and PSNR.
+
+Byte work is compared bit for bit with the committed outputs of the reference's own functions
+(tests/golden/generators_ref.npz) and with the oracle on fresh seeded inputs; the cascade (floating point, bf16
+activations with fp32 accumulation vs the fp32 oracle) within the tolerance written in the test."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from _util import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_lut_minmax_normalize_sse_bit_exact_on_ragged_sizes():
+    from b200restore import ops
+    from oracle import generators_oracle as GO
+    rng = np.random.default_rng(3)
+    for n, h, w in ((1, 1, 1), (3, 7, 5), (2, 40, 56), (5, 224, 224), (2, 33, 129)):
+        img = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+        lo = rng.integers(0, 120, n)
+        hi = lo + rng.integers(1, 130, n)
+        img = (lo[:, None, None, None] + img.astype(np.int64) % (hi - lo + 1)[:, None, None, None]).astype(np.uint8)
+        lut = rng.integers(0, 256, (n, 256), dtype=np.uint8)
+        d = _cu(img)
+        assert np.array_equal(ops.lut_u8(d, _cu(lut)).cpu().numpy(), np.stack([lut[i][img[i]] for i in range(n)]))
+        mm = ops.minmax_u8(d).cpu().numpy()
+        assert np.array_equal(mm[:, 0], img.reshape(n, -1).min(1)) and np.array_equal(mm[:, 1], img.reshape(n, -1).max(1))
+        norm = ops.normalize_minmax_u8(d, _cu(mm)).cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(norm[i], GO.normalize_minmax_table(int(mm[i, 0]), int(mm[i, 1]))[img[i]]), (n, h, w, i)
+        other = rng.integers(0, 256, img.shape, dtype=np.uint8)
+        sse = ops.sse_u8(d, _cu(other)).cpu().numpy()
+        ref = ((img.astype(np.int64) - other.astype(np.int64)) ** 2).reshape(n, -1).sum(1)
+        assert np.array_equal(sse, ref)
+    # unaligned views (odd byte offset) take the scalar path
+    flat = torch.from_numpy(rng.integers(0, 256, 2 * 3001 + 1, dtype=np.uint8)).cuda()
+    view = flat[1:].view(2, 3001)
+    lut = _cu(rng.integers(0, 256, (2, 256), dtype=np.uint8))
+    assert torch.equal(ops.lut_u8(view.contiguous(), lut), torch.gather(lut.long(), 1, view.long()).to(torch.uint8))
+
+
+def test_script02_noise_with_injected_draw_matches_reference_bytes():
+    from b200restore import generators as G
+    g = golden("generators_ref.npz")
+    imgs = _cu(g["images"])
+    for i in range(len(g["images"])):
+        var = float(g["var02"][i])
+        noise = _cu(0 + (var ** 0.5) * g["z"][i:i + 1])
+        out = G.add_gaussian_noise(imgs[i:i + 1], var=var, noise=noise)
+        assert np.array_equal(out[0].cpu().numpy(), g["out02"][i]), i
+    # whole batch in one call, per-image variances through the low-level entry
+    from b200restore import ops
+    sigma = torch.tensor(np.sqrt(g["var02"]), dtype=torch.float32).cuda()
+    noise = _cu(np.sqrt(g["var02"])[:, None, None, None] * g["z"])
+    out, flags = ops.noise02(imgs, sigma, noise=noise)
+    assert np.array_equal(out.cpu().numpy(), g["out02"])
+    assert flags.cpu().tolist() == [1, 1, 0, 1, 1, 1]   # image 2 is the bright one: no negative value
+
+
+def test_script02_philox_noise_statistics_and_world_size_invariance():
+    from b200restore import generators as G
+    img = torch.full((4, 64, 64, 3), 128, dtype=torch.uint8, device="cuda")
+    a = G.add_gaussian_noise(img, var=0.02, seed=9, image_index0=100)
+    b = torch.cat([G.add_gaussian_noise(img[:1], var=0.02, seed=9, image_index0=100),
+                   G.add_gaussian_noise(img[1:], var=0.02, seed=9, image_index0=101)])
+    assert torch.equal(a, b)
+    x = a.float() / 255 - 128 / 255
+    assert abs(float(x.mean())) < 3e-3 and abs(float(x.std()) - 0.02 ** 0.5) < 4e-3
+
+
+def test_script03_blur_and_stretch():
+    from b200restore import generators as G
+    g = golden("generators_ref.npz")
+    imgs = _cu(g["images"])
+    for i, (d, a) in enumerate(g["cases03"]):
+        out = G.apply_motion_blur(imgs[i:i + 1], int(d), float(a))[0].cpu().numpy()
+        if d <= 11:      # OpenCV's direct filter2D path: the blur is bit-exact, hence the stretch too
+            assert np.array_equal(out, g["out03"][i]), (i, d, a)
+        else:            # DFT path in OpenCV (ksize > 11): blur within 1 LSB, the stretch can amplify it to 2
+            assert int(np.abs(out.astype(int) - g["out03"][i].astype(int)).max()) <= 2, (i, d, a)
+
+
+def test_script04_fog_float64_semantics():
+    import random
+    from b200restore import generators as G
+    g = golden("generators_ref.npz")
+    imgs = _cu(g["images"])
+    t = [float(np.clip(1.0 - float(g["inten04"][i]) * float(g["u04"][i]), 0.1, 0.9)) for i in range(len(g["images"]))]
+    out, used = G.add_fog(imgs, t=t)
+    assert np.array_equal(out.cpu().numpy(), g["out04"]) and used == t
+    # drawing t like the reference: same random.Random stream -> same images
+    out_a, ta = G.add_fog(imgs, 0.8, rng=random.Random(4))
+    rr = random.Random(4)
+    tb = [float(np.clip(1.0 - 0.8 * rr.uniform(0.8, 1.2), 0.1, 0.9)) for _ in range(len(g["images"]))]
+    assert ta == tb
+
+
+def test_script13_distortion_chain_bit_exact():
+    from b200restore import generators as G
+    g = golden("generators_ref.npz")
+    imgs = _cu(g["images"])
+    noise = _cu((0.01 ** 0.5) * g["z"])
+    b, f, z = G.stress_distort(imgs, noise=noise)
+    assert np.array_equal(b.cpu().numpy(), g["blur13"])
+    assert np.array_equal(f.cpu().numpy(), g["fog13"])
+    assert np.array_equal(z.cpu().numpy(), g["noise13"])
+
+
+def test_psnr_matches_definition():
+    from b200restore import generators as G
+    from oracle import generators_oracle as GO
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, (3, 50, 70, 3), dtype=np.uint8)
+    b = np.clip(a.astype(int) + rng.integers(-9, 10, a.shape), 0, 255).astype(np.uint8)
+    b[2] = a[2]
+    p = G.psnr(_cu(a), _cu(b)).cpu().numpy()
+    for i in range(2):
+        assert p[i] == pytest.approx(GO.psnr_08(a[i], b[i]), rel=1e-12)
+    assert math.isinf(p[2])
+
+
+def test_cascade_vs_oracle_and_judge_confidence():
+    """13:175-189 with three seeded SimpleUNets: unclamped f32 hand-off, per-stage snapshots, VGG confidence.
+    Tolerance: each stage is within PSNR >= 50 dB / max-abs 2e-2 of the fp32 oracle fed with the SAME input (the bar of
+    tests/test_models_gpu.py); end to end through three networks the errors compound (observed on B200: 62 dB, max-abs 3.5e-3): >= 45 dB and
+    snapshots within 6/255.  Confidence: |diff| <= 0.02 and identical arg-max wherever the oracle's margin is clear."""
+    from b200restore import generators as G, models, synth
+    from oracle import generators_oracle as GO, models_oracle as MO
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    nets, sds = {}, {}
+    for k, seed in (("Noise", 31), ("Fog", 32), ("Blur", 33)):
+        sd = synth.synthetic_state_dict("simple_unet", seed)
+        m = models.SimpleUNet()
+        m.load_state_dict(sd)
+        nets[k], sds[k] = m.cuda().eval(), {a: b.cuda() for a, b in sd.items()}
+    img, _ = synth.sign_like_images(3, 96, 128, seed=2)
+    distorted = G.stress_distort(img.cuda(), seed=1)[-1]
+    out, hist = G.CascadeRestorer(nets)(distorted)
+    with torch.no_grad():
+        ref, snaps = GO.cascade_13(sds, distorted)
+    assert [n for n, _ in hist] == ["Noise", "Fog", "Blur"] and out.dtype == torch.float32 and out.shape == ref.shape
+    mse = float(((out.double() - ref.double()) ** 2).mean())
+    p = 10 * math.log10(1.0 / mse)
+    print(f"\n[cascade] end-to-end PSNR {p:.1f} dB, max-abs {float((out - ref).abs().max()):.4g}")
+    assert p >= 45.0
+    for (name, snap), rsnap in zip(hist, snaps):
+        assert snap.dtype == torch.uint8 and snap.shape == rsnap.shape
+        assert int((snap.int() - rsnap.int()).abs().max()) <= 6, name
+    # skipping a missing model, like the reference does for absent checkpoints
+    out2, hist2 = G.CascadeRestorer({"Noise": nets["Noise"], "Blur": nets["Blur"]})(distorted)
+    assert [n for n, _ in hist2] == ["Noise", "Blur"]
+    # judge confidence on the final snapshot
+    jsd = synth.synthetic_state_dict("vgg16", 5)
+    judge = models.VGG16Judge()
+    judge.load_state_dict(jsd)
+    judge = judge.cuda().eval()
+    x224 = torch.nn.functional.interpolate(hist[-1][1].permute(0, 3, 1, 2).float(), size=(224, 224)).permute(0, 2, 3, 1).to(torch.uint8).contiguous()
+    pred, conf = G.judge_confidence(judge, x224)
+    with torch.no_grad():
+        rpred, rconf = GO.vgg_prediction({a: b.cuda() for a, b in jsd.items()}, x224)
+    assert float((conf - rconf).abs().max()) <= 0.02
+    assert bool(((pred == rpred) | (rconf < 0.2)).all())

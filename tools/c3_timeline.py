@@ -1,5 +1,9 @@
 #!/usr/bin/env python
-"""Role timeline of the first-layer kernel (conv_c3.cu), CTA 0, via b2r_debug_timeline."""
+"""Role timeline of the first-layer kernel (conv_c3.cu), CTA 0, via b2r_debug_timeline.
+
+Needs the stamp-enabled variant build:
+    python -m b200restore.build --define B2R_TIMELINE --out tools/exp/libb2r_timeline.so
+    B2R_LIB=tools/exp/libb2r_timeline.so python tools/c3_timeline.py"""
 import sys
 from pathlib import Path
 import torch
