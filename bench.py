@@ -39,8 +39,15 @@ WORKLOADS = {
     "degrade16_unet_vgg16_top1": ("simple_unet", "compound16", True),
     "degrade_fog_blur_unet": ("simple_unet", "compound16", False),        # BASELINE configs[1]
     "degrade_random_resunet": ("resunet", "random14", False),             # BASELINE configs[2]
+    # 13_pipeline_stress_test.py on the device: Blur -> Fog -> Noise (u8 after every stage),
+    # three SimpleUNets Noise -> Fog -> Blur with the unclamped f32 hand-off, VGG16 confidence of the result
+    "stress13_cascade_vgg16_conf": ("cascade3", "stress13", True),
 }
-GFLOP_PER_IMAGE_224 = {"simple_unet": 38.831, "resunet": 55.992, "vgg16": 30.933}
+GFLOP_PER_IMAGE_224 = {"simple_unet": 38.831, "resunet": 55.992, "vgg16": 30.933,
+                       "cascade3": 3 * 38.831}
+
+
+CASCADE_SEEDS = {"Noise": 31, "Fog": 33, "Blur": 34}
 
 
 def parse_args():
@@ -121,11 +128,12 @@ def cpu_reference_images_per_s(workload: str, hw: int, sample: int, repeats: int
     import numpy as np
     import torch
     from b200restore import synth
-    from oracle import degrade_oracle as DO, models_oracle as MO
+    from oracle import degrade_oracle as DO, generators_oracle as GO, models_oracle as MO
     arch, recipe, classify = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sdr = synth.synthetic_state_dict(arch, 31)
+    sdc = {k: synth.synthetic_state_dict("simple_unet", sd) for k, sd in CASCADE_SEEDS.items()} if arch == "cascade3" else None
+    sdr = synth.synthetic_state_dict("simple_unet" if arch == "cascade3" else arch, 31)
     sdj = synth.synthetic_state_dict("vgg16", 32) if classify else None
     fn = MO.simple_unet_forward if arch == "simple_unet" else MO.resunet_forward
     imgs, labels = synth.sign_like_images(sample, hw, hw, seed=7)
@@ -134,6 +142,15 @@ def cpu_reference_images_per_s(workload: str, hw: int, sample: int, repeats: int
 
     def one_pass():
         deg = []
+        if recipe == "stress13":
+            for i in range(sample):   # 13:152-171, one image per call as the reference runs it
+                z = GO.stress_add_noise(GO.stress_add_fog(GO.stress_add_blur(imgs_np[i])),
+                                        rng.normal(0, 0.01 ** 0.5, imgs_np[i].shape))
+                deg.append(z)
+            with torch.no_grad():
+                _, snaps = GO.cascade_13(sdc, torch.from_numpy(np.stack(deg)))
+                pred, conf = GO.vgg_prediction(sdj, snaps[-1])
+            return int((pred == labels).sum())
         for i in range(sample):
             noise = rng.normal(0, 0.02 ** 0.5, imgs_np[i].shape)
             if recipe == "compound16":
@@ -208,9 +225,20 @@ def run_ours(args):
     B_, hw, mb = args.batch, args.hw, args.micro_batch
     lo = rank * B_                                   # weak scaling: rank r owns global images [r*B, (r+1)*B)
 
-    restorer = (models.SimpleUNet if arch == "simple_unet" else models.ResUNet)()
-    restorer.load_state_dict(synth.synthetic_state_dict(arch, 31))
-    restorer = restorer.to(dev).eval()
+    cascade = None
+    if arch == "cascade3":
+        from b200restore import generators as G
+        nets = {}
+        for k, sd_seed in CASCADE_SEEDS.items():
+            net = models.SimpleUNet()
+            net.load_state_dict(synth.synthetic_state_dict("simple_unet", sd_seed))
+            nets[k] = net.to(dev).eval()
+        cascade = G.CascadeRestorer(nets)
+        restorer = nets["Noise"]
+    else:
+        restorer = (models.SimpleUNet if arch == "simple_unet" else models.ResUNet)()
+        restorer.load_state_dict(synth.synthetic_state_dict(arch, 31))
+        restorer = restorer.to(dev).eval()
     judge = models.VGG16Judge()
     judge.load_state_dict(synth.synthetic_state_dict("vgg16", 32))
     judge = judge.to(dev).eval()
@@ -226,11 +254,22 @@ def run_ours(args):
         host_labels[s:s + c] = lb
     dev_imgs = host_imgs.to(dev)
     dev_labels = host_labels.to(dev)
-    params = (D.compound_params(B_) if recipe == "compound16"
+    params = (D.compound_params(B_) if recipe in ("compound16", "stress13")
               else D.random_params(B_, np.random.default_rng(2 + rank), order=0)).to(dev)
 
+    def cascade_micro_batch(imgs_u8, labels, counts, index0):
+        z = G.stress_distort(imgs_u8, seed=2, image_index0=index0)[-1]
+        _, hist = cascade(z)
+        logits = judge.forward_u8(hist[-1][1])
+        ops.argmax_count(logits, labels, counts, want_conf=True)
+
     def step_device():
-        if classify:
+        if cascade is not None:
+            counts = torch.zeros(2, dtype=torch.int64, device=dev)
+            for s in range(0, B_, mb):
+                c = min(mb, B_ - s)
+                cascade_micro_batch(dev_imgs[s:s + c], dev_labels[s:s + c], counts, lo + s)
+        elif classify:
             _, counts = pipe.run(dev_imgs, dev_labels, params, seed=2, image_index0=lo)
         else:
             counts = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -244,6 +283,19 @@ def run_ours(args):
         return counts
 
     def step_host():
+        if cascade is not None:
+            counts = torch.zeros(2, dtype=torch.int64, device=dev)
+            h2d = 0
+            for s in range(0, B_, mb):
+                c = min(mb, B_ - s)
+                im = host_imgs[s:s + c].to(dev, non_blocking=True)
+                lb = host_labels[s:s + c].to(dev, non_blocking=True)
+                h2d += im.numel() + lb.numel() * 8
+                cascade_micro_batch(im, lb, counts, lo + s)
+            hc = counts.cpu()
+            cc = torch.tensor([int(hc[0]), int(hc[1])], dtype=torch.int64, device=dev)
+            B.all_reduce_counts(cc)
+            return cc, h2d, 16
         (correct, total), h2d, d2h = pipe.run_from_host(host_imgs, host_labels, params, seed=2, image_index0=lo)
         c = torch.tensor([correct, total], dtype=torch.int64, device=dev)
         B.all_reduce_counts(c)
@@ -339,7 +391,9 @@ def run_ours(args):
         v, cores, dt = cpu_reference_images_per_s(args.workload, hw, sample, repeats=1, warmup=1)
         line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                                 "sample": f"{sample} images of {hw}x{hw}, one timed pass after one warm-up pass "
-                                          f"({dt:.1f} s); oracle port of scripts 16 -> 17 -> 18 in fp32 PyTorch"}
+                                          f"({dt:.1f} s); oracle port of " +
+                                          ("script 13 (distortions, cascade, VGG confidence)" if recipe == "stress13"
+                                           else "scripts 16 -> 17 -> 18") + " in fp32 PyTorch"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

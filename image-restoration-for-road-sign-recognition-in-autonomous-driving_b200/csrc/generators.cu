@@ -21,14 +21,9 @@ namespace b2r {
 constexpr int kGenThreads = 256;
 constexpr int kGenBytesPerThread = 16;
 
-__global__ void __launch_bounds__(kGenThreads) lut_u8_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ lut,
-                                                              uint8_t* __restrict__ out, long elems) {
-    __shared__ uint8_t s_lut[256];
-    const int n = blockIdx.y;
-    if (threadIdx.x < 64) reinterpret_cast<uint32_t*>(s_lut)[threadIdx.x] = reinterpret_cast<const uint32_t*>(lut + n * 256)[threadIdx.x];
-    __syncthreads();
-    const uint8_t* src = in + (long)n * elems;
-    uint8_t* dst = out + (long)n * elems;
+// dst[i] = s_lut[src[i]] for one image: 16 bytes per thread and step when both pointers are 16-byte aligned
+__device__ __forceinline__ void apply_table(const uint8_t* s_lut, const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                            long elems) {
     const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
     for (long i = ((long)blockIdx.x * kGenThreads + threadIdx.x) * kGenBytesPerThread; i < elems;
          i += (long)gridDim.x * kGenThreads * kGenBytesPerThread) {
@@ -44,6 +39,15 @@ __global__ void __launch_bounds__(kGenThreads) lut_u8_kernel(const uint8_t* __re
             for (long j = i; j < elems && j < i + kGenBytesPerThread; ++j) dst[j] = s_lut[src[j]];
         }
     }
+}
+
+__global__ void __launch_bounds__(kGenThreads) lut_u8_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ lut,
+                                                              uint8_t* __restrict__ out, long elems) {
+    __shared__ uint8_t s_lut[256];
+    const int n = blockIdx.y;
+    if (threadIdx.x < 64) reinterpret_cast<uint32_t*>(s_lut)[threadIdx.x] = reinterpret_cast<const uint32_t*>(lut + n * 256)[threadIdx.x];
+    __syncthreads();
+    apply_table(s_lut, in + (long)n * elems, out + (long)n * elems, elems);
 }
 
 __global__ void minmax_init_kernel(int32_t* minmax, int N) {
@@ -103,10 +107,7 @@ __global__ void __launch_bounds__(kGenThreads) normalize_minmax_u8_kernel(const 
         s_lut[threadIdx.x] = uint8_t(fminf(fmaxf(r, 0.f), 255.f));
     }
     __syncthreads();
-    const uint8_t* src = in + (long)n * elems;
-    uint8_t* dst = out + (long)n * elems;
-    for (long i = (long)blockIdx.x * kGenThreads + threadIdx.x; i < elems; i += (long)gridDim.x * kGenThreads)
-        dst[i] = s_lut[src[i]];
+    apply_table(s_lut, in + (long)n * elems, out + (long)n * elems, elems);
 }
 
 // 02_gen_noise.py: out = image / 255 (float64) + noise;  pass 0 records whether any value of the image is negative,
@@ -116,6 +117,9 @@ __global__ void __launch_bounds__(kGenThreads) noise02_kernel(const uint8_t* __r
                                                                long elems, const float* __restrict__ sigma,
                                                                const double* __restrict__ noise, uint64_t seed,
                                                                uint64_t image_index0, int32_t* __restrict__ neg_flags) {
+    __shared__ double s_unit[256];   // u / 255.0 with a true float64 division, once per block
+    s_unit[threadIdx.x] = double(threadIdx.x) / 255.0;
+    __syncthreads();
     const int n = blockIdx.y;
     const uint8_t* src = in + (long)n * elems;
     const double* nz = noise ? noise + (long)n * elems : nullptr;
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(kGenThreads) noise02_kernel(const uint8_t* __r
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const long i = pix * 3 + c;
-            const double v = double(src[i]) / 255.0 + (nz ? nz[i] : sg * double(z[c]));
+            const double v = s_unit[src[i]] + (nz ? nz[i] : sg * double(z[c]));
             if (PASS == 0) {
                 any_neg |= v < 0.0;
             } else {
@@ -225,7 +229,7 @@ int b2r_normalize_minmax_u8(const uint8_t* in, const int32_t* minmax, uint8_t* o
     B2R_REQUIRE(in && minmax && out, "null pointer");
     B2R_REQUIRE(N > 0 && N <= 65535 && elems_per_image > 0, "bad shape N=%d elems=%lld", N, (long long)elems_per_image);
     dim3 grid;
-    int rc = gen_grid(elems_per_image, N, &grid, 4);
+    int rc = gen_grid(elems_per_image, N, &grid, kGenBytesPerThread);
     if (rc) return rc;
     normalize_minmax_u8_kernel<<<grid, kGenThreads, 0, stream>>>(in, minmax, out, elems_per_image);
     B2R_CHECK_LAUNCH();
