@@ -176,6 +176,48 @@ __global__ void __launch_bounds__(kGenThreads) sse_u8_kernel(const uint8_t* __re
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&sse[n], acc);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// VGG feature taps: mean over one axis of a bf16 tensor viewed as [outer][reduce][inner].
+//   inner == 1: channel mean of an NHWC feature map (11_visualize_hidden_states.py:50 torch.mean(features, dim=1));
+//               the reduce axis is contiguous: 8 lanes x 16 bytes per row step, shuffle reduction, fp32 accumulation
+//   inner  > 1: global average pooling of [N][H*W][C] (12_generate_umap_pt.py:52 torch.mean(feature, dim=[2, 3]));
+//               one thread per 8 inner columns, coalesced across the inner axis
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void acc8_bf16(const uint4 v, float (&a)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a[2 * k] += __uint_as_float(w[k] << 16);
+        a[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+    }
+}
+
+__global__ void __launch_bounds__(256) mean_last_axis_kernel(const uint4* __restrict__ in, float* __restrict__ out,
+                                                             long outer, int reduce8) {
+    // 8 consecutive lanes own one row
+    const long row = (blockIdx.x * 256L + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (row < outer)
+        for (int i = sub; i < reduce8; i += 8) acc8_bf16(__ldg(&in[row * reduce8 + i]), a);
+    float s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+#pragma unroll
+    for (int d = 4; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (row < outer && sub == 0) out[row] = s / float(reduce8 * 8);
+}
+
+__global__ void __launch_bounds__(256) mean_middle_axis_kernel(const uint4* __restrict__ in, float* __restrict__ out,
+                                                               long outer, int reduce, int inner8) {
+    const long gid = blockIdx.x * 256L + threadIdx.x;
+    if (gid >= outer * inner8) return;
+    const long o = gid / inner8;
+    const int c = int(gid - o * inner8);
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < reduce; ++r) acc8_bf16(__ldg(&in[(o * reduce + r) * inner8 + c]), a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[(o * inner8 + c) * 8 + k] = a[k] / float(reduce);
+}
+
 static int gen_grid(long elems, int N, dim3* grid, int bytes_per_thread) {
     long blocks = (elems + (long)kGenThreads * bytes_per_thread - 1) / ((long)kGenThreads * bytes_per_thread);
     if (blocks < 1) blocks = 1;
@@ -253,6 +295,27 @@ int b2r_noise02(const uint8_t* in, uint8_t* out, int N, int64_t elems_per_image,
         B2R_CHECK_LAUNCH();
     }
     noise02_kernel<1><<<grid, kGenThreads, 0, stream>>>(in, out, elems_per_image, sigma, noise, seed, image_index0, neg_flags);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
+int b2r_mean_bf16(const void* in, float* out, int64_t outer, int reduce, int inner, void* stream_v) {
+    using namespace b2r;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    B2R_REQUIRE(in && out, "null pointer");
+    B2R_REQUIRE(outer > 0 && reduce > 0 && inner > 0, "bad shape outer=%lld reduce=%d inner=%d", (long long)outer, reduce, inner);
+    B2R_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0, "input must be 16-byte aligned");
+    if (inner == 1) {
+        B2R_REQUIRE(reduce % 8 == 0, "reduce=%d must be a multiple of 8 when it is the contiguous axis", reduce);
+        const long blocks = (outer * 8 + 255) / 256;
+        B2R_REQUIRE(blocks < (1L << 31), "too many rows");
+        mean_last_axis_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const uint4*>(in), out, outer, reduce / 8);
+    } else {
+        B2R_REQUIRE(inner % 8 == 0, "inner=%d must be a multiple of 8", inner);
+        const long blocks = (outer * (inner / 8) + 255) / 256;
+        B2R_REQUIRE(blocks < (1L << 31), "too many columns");
+        mean_middle_axis_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const uint4*>(in), out, outer, reduce, inner / 8);
+    }
     B2R_CHECK_LAUNCH();
     return B2R_OK;
 }

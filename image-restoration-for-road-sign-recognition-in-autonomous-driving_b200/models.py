@@ -399,17 +399,31 @@ class VGG16Judge(_B200Module):
         P["fc3"] = (sd["classifier.6.weight"].to(torch.bfloat16).contiguous(), sd["classifier.6.bias"].float().contiguous())
         return P
 
-    def _run(self, x, normalize_u8: bool) -> torch.Tensor:
+    def _run_features(self, x, normalize_u8: bool, stop_at: Optional[int] = None):
+        """The `features` stack up to (and including) torchvision index `stop_at` (None: all 31 layers).
+        Returns (bf16 NHWC tensor, h, w, channels).  A tap on a conv index gives the PRE-ReLU output, on the following
+        ReLU index the activated one, on a pool index the pooled one, exactly like `model.features[:stop_at + 1]`."""
         P, ws = self._packed(), self._ws
         u8_in = x.dtype == torch.uint8
         n = x.shape[0]
         H, W = (x.shape[1], x.shape[2]) if u8_in else (x.shape[2], x.shape[3])
         dev = x.device
-        R = L.B2R_ACT_RELU
-        cur = ops.conv3x3_c3(x, *P["first"], act=R, normalize=u8_in and normalize_u8,
-                             out=ws.get("c0", (n, H, W, 64), dev))
-        h, w = H, W
+        R, NONE = L.B2R_ACT_RELU, L.B2R_ACT_NONE
+        idx = self._conv_indices()
+        tap = stop_at is not None
+        first_i = idx[0][0]
+        cur = ops.conv3x3_c3(x, *P["first"], act=NONE if (tap and stop_at == first_i) else R,
+                             normalize=u8_in and normalize_u8,
+                             out=ws.get("tap0" if tap else "c0", (n, H, W, 64), dev))
+        h, w, c = H, W, 64
+        if tap and stop_at <= first_i + 1:
+            return cur, h, w, c
         for li, (cv, pooled, co) in enumerate(P["convs"]):
+            ci = idx[li + 1][0]
+            if tap and stop_at in (ci, ci + 1):      # stop on this conv (pre-ReLU) or on its ReLU, un-pooled
+                out = ws.get("tap", (n, h, w, co), dev)
+                ops.conv_gemm([cur], **cv, act=NONE if stop_at == ci else R, out=out)
+                return out, h, w, co
             if pooled:
                 nxt = ws.get(f"c{li + 1}", (n, h // 2, w // 2, co), dev)
                 ops.conv_gemm([cur], **cv, act=R, out_pool=nxt)
@@ -417,7 +431,16 @@ class VGG16Judge(_B200Module):
             else:
                 nxt = ws.get(f"c{li + 1}", (n, h, w, co), dev)
                 ops.conv_gemm([cur], **cv, act=R, out=nxt)
-            cur = nxt
+            cur, c = nxt, co
+            if tap and pooled and stop_at == ci + 2:
+                return cur, h, w, c
+        return cur, h, w, c
+
+    def _run(self, x, normalize_u8: bool) -> torch.Tensor:
+        P, ws = self._packed(), self._ws
+        n, dev = x.shape[0], x.device
+        R = L.B2R_ACT_RELU
+        cur, h, w, _ = self._run_features(x, normalize_u8)
         if (h, w) != (7, 7):
             cur = ops.adaptive_avgpool7(cur)  # identity at 224x224
         flat = cur.view(1, 1, n, 7 * 7 * 512)
@@ -426,6 +449,46 @@ class VGG16Judge(_B200Module):
         f2 = ws.get("f2", (1, 1, n, 4096), dev)
         ops.conv_gemm([f1], *P["fc2"], None, act=R, out=f2)   # Dropout is the identity in eval mode
         return ops.linear_f32out(f2.view(n, 4096), *P["fc3"])
+
+    # ---- feature taps: by-products of the judge kernels for scripts 11 / 12 -----------------
+    def _tap_input(self, x):
+        if x.dtype == torch.uint8:
+            self._check_input(x, 32)
+            return x.contiguous(), True
+        if x.dtype != torch.float32:
+            raise L.B2RError("feature taps take the normalised float32 NCHW tensor or uint8 NHWC")
+        self._check_input(x, 32)
+        return x.contiguous(), False
+
+    @torch.no_grad()
+    def feature_heatmap(self, x: torch.Tensor, layer_index: int = 2, normalize: bool = True) -> torch.Tensor:
+        """get_vgg_feature_maps(model, x, layer_index) followed by plot_heatmap (11_visualize_hidden_states.py:31-56):
+        `model.features[:layer_index + 1](x)`, mean over the channels, then (h - min) / (max - min) per image.
+        Script 11 uses layer_index = 2 (the pre-ReLU output of conv1_2).  Returns f32 [N, H', W']."""
+        if not 0 <= layer_index < len(self.features):
+            raise L.B2RError(f"layer_index {layer_index} outside features[0:{len(self.features)}]")
+        x, u8 = self._tap_input(x)
+        outs = []
+        for s, cnt in self._chunks(x.shape[0], self.micro_batch):
+            f, h, w, c = self._run_features(x[s:s + cnt], u8, stop_at=layer_index)
+            outs.append(ops.mean_bf16(f, cnt * h * w, c, 1).view(cnt, h, w))
+        hm = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        if normalize:
+            lo = hm.amin(dim=(1, 2), keepdim=True)
+            hi = hm.amax(dim=(1, 2), keepdim=True)
+            hm = (hm - lo) / (hi - lo)
+        return hm
+
+    @torch.no_grad()
+    def feature_embedding(self, x: torch.Tensor) -> torch.Tensor:
+        """process_features_for_umap(get_vgg_features(model, x)) (12_generate_umap_pt.py:37-58): `model.features(x)`
+        [N,512,h,w] averaged over the spatial axes -> f32 [N, 512]."""
+        x, u8 = self._tap_input(x)
+        outs = []
+        for s, cnt in self._chunks(x.shape[0], self.micro_batch):
+            f, h, w, c = self._run_features(x[s:s + cnt], u8)
+            outs.append(ops.mean_bf16(f, cnt, h * w, c))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     def _forward(self, x: torch.Tensor, normalize_u8: bool) -> torch.Tensor:
         self._check_input(x, 32)

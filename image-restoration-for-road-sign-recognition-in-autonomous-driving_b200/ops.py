@@ -410,3 +410,14 @@ def sse_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     L.check(L.load().b2r_sse_u8(a.data_ptr(), b.data_ptr(), sse.data_ptr(), n, elems, _stream()))
     STATS["launches"] += 1
     return sse
+
+
+def mean_bf16(x: torch.Tensor, outer: int, reduce: int, inner: int) -> torch.Tensor:
+    """Mean over the middle axis of a bf16 tensor viewed as [outer][reduce][inner] -> f32 [outer, inner]."""
+    _chk(x, torch.bfloat16, "x")
+    if x.numel() != outer * reduce * inner:
+        raise L.B2RError(f"{x.numel()} elements cannot be viewed as [{outer}][{reduce}][{inner}]")
+    out = torch.empty((outer, inner), dtype=torch.float32, device=x.device)
+    L.check(L.load().b2r_mean_bf16(x.data_ptr(), out.data_ptr(), int(outer), int(reduce), int(inner), _stream()))
+    STATS["launches"] += 1
+    return out

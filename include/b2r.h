@@ -241,6 +241,12 @@ int b2r_normalize_minmax_u8(const uint8_t* in, const int32_t* minmax, uint8_t* o
 int b2r_noise02(const uint8_t* in, uint8_t* out, int N, int64_t elems_per_image, const float* sigma, const double* noise,
                 uint64_t seed, uint64_t image_index0, int32_t* neg_flags, int clip_rule, void* stream);
 
+/* VGG feature taps: mean over the middle axis of a bf16 tensor viewed as [outer][reduce][inner], f32 [outer][inner] out.
+ * inner = 1: channel mean of an NHWC feature map (11_visualize_hidden_states.py:50, torch.mean(features, dim=1));
+ * inner > 1: global average pooling of [N][H*W][C] (12_generate_umap_pt.py:52, torch.mean(feature, dim=[2, 3])).
+ * The contiguous extent (reduce if inner = 1, else inner) must be a multiple of 8; fp32 accumulation. */
+int b2r_mean_bf16(const void* in_bf16, float* out, int64_t outer, int reduce, int inner, void* stream);
+
 /* sse[n] = sum_i (a[n][i] - b[n][i])^2 as uint64: PSNR = 10 log10(255^2 * elems / sse) (08_run_inference.py:118-129
  * reports skimage's peak_signal_noise_ratio on the u8 images). */
 int b2r_sse_u8(const uint8_t* a, const uint8_t* b, uint64_t* sse, int N, int64_t elems_per_image, void* stream);

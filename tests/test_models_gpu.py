@@ -149,3 +149,32 @@ def test_vgg16_matches_committed_torchvision_output():
     err, scale = float((got - ref).abs().max()), float(ref.std())
     print(f"\n[vgg16 golden] max err {err:.4g} vs logit std {scale:.4g}")
     assert err <= JUDGE_TOL["rel_to_logit_std"] * scale
+
+
+def test_vgg_feature_taps_vs_oracle():
+    """Scripts 11 / 12 by-products: channel-mean heat-map of features[:k+1] and the 512-d GAP embedding.
+    bf16 activations vs the fp32 oracle.  Tolerances (observed on B200 in parentheses): min-max normalised heat-map
+    max-abs <= 0.02 (4e-3); embedding error <= 5 % of its standard deviation over the batch (1-2 %)."""
+    from oracle import models_oracle as O
+    from b200restore import synth
+    m, sd = _load("vgg16", 5)
+    img, _ = synth.sign_like_images(3, 96, 128, seed=4)
+    img = img.cuda()
+    x = O.normalize_imagenet(O.to_tensor_u8(img))
+    with torch.no_grad():
+        for k in (0, 1, 2, 3, 4, 5, 9):
+            ref = O.vgg16_heatmap(sd, x, k)
+            got = m.feature_heatmap(img, layer_index=k)
+            got_f32 = m.feature_heatmap(x, layer_index=k)
+            assert got.shape == ref.shape and got.dtype == torch.float32
+            e = float((got - ref).abs().max())
+            print(f"\n[heatmap layer {k}] max-abs {e:.4g}", end="")
+            assert e <= 0.02 and float((got_f32 - ref).abs().max()) <= 0.02, k
+        ref = O.vgg16_gap_embedding(sd, x)
+        got = m.feature_embedding(img)
+        assert got.shape == (3, 512)
+        rel = float((got - ref).abs().max() / ref.std())
+        print(f"\n[embedding] max error / std {rel:.4g}")
+        assert rel <= 0.05
+    with pytest.raises(Exception):
+        m.feature_heatmap(img, layer_index=31)

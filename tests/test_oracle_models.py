@@ -131,3 +131,23 @@ def test_pipeline_composition_shapes():
     assert logits.shape == (2, 43) and pred.dtype == torch.int64
     # truncation, not rounding (17_run_unified_inference.py:92)
     assert torch.equal(O.quantize_restored(torch.full((1, 3, 1, 1), 0.999)), torch.full((1, 1, 1, 3), 254, dtype=torch.uint8))
+
+
+def test_vgg_feature_taps_match_torchvision_slicing():
+    """oracle taps == torchvision's own `model.features[:k + 1]` on the same seeded weights (what scripts 11 / 12 run)."""
+    import torchvision
+    from b200restore import synth
+    from oracle import models_oracle as O
+    sd = synth.synthetic_state_dict("vgg16", 3)
+    tv = torchvision.models.vgg16(weights=None)
+    tv.classifier[6] = torch.nn.Linear(4096, 43)
+    tv.load_state_dict(sd)
+    tv.eval()
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        for k in (0, 1, 2, 3, 4, 5, 16, 30):
+            assert torch.equal(O.vgg16_features_upto(sd, x, k), tv.features[:k + 1](x)), k
+        assert torch.equal(O.vgg16_gap_embedding(sd, x), torch.mean(tv.features(x), dim=[2, 3]))
+        h = torch.mean(tv.features[:3](x), dim=1)
+        ref = torch.stack([(h[i] - h[i].min()) / (h[i].max() - h[i].min()) for i in range(2)])
+        assert torch.allclose(O.vgg16_heatmap(sd, x, 2), ref, atol=0, rtol=0)
