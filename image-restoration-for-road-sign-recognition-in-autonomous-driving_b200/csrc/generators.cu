@@ -218,6 +218,70 @@ __global__ void __launch_bounds__(256) mean_middle_axis_kernel(const uint4* __re
     for (int k = 0; k < 8; ++k) out[(o * inner8 + c) * 8 + k] = a[k] / float(reduce);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Resize of a ragged batch with Pillow's BILINEAR resampling (what transforms.Resize((224, 224)) does to the PIL images
+// of 17_run_unified_inference.py:66,79-82 and 18:28-30): separable triangle filter whose support grows with the
+// down-scaling factor, coefficients normalised in double and rounded to 22-bit fixed point, horizontal pass rounded to
+// u8, then vertical pass.  The host builds the per-size coefficient tables exactly as Pillow's precompute_coeffs /
+// normalize_coeffs_8bpc do (imageio.resample_table); this kernel does the integer accumulation:
+//     out = clip8((2^21 + sum_k pixel[min + k] * kk[k]) >> 22)
+// One CTA per (image, tile of output rows): the input rows the tile needs go through the horizontal pass into shared
+// memory, the vertical pass reads them from there.  Table layout per output index: {min, count, kk[0..K)}.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kResizeThreads = 256;
+
+__device__ __forceinline__ int clip8_fixed(int ss) { return min(max(ss >> 22, 0), 255); }
+
+__global__ void __launch_bounds__(kResizeThreads) resize_bilinear_u8_kernel(
+    const uint8_t* __restrict__ src, const long long* __restrict__ offsets, const int32_t* __restrict__ hw,
+    const int32_t* __restrict__ xtab_index, const int32_t* __restrict__ ytab_index, const int32_t* __restrict__ tabs,
+    int K, int S, uint8_t* __restrict__ out, int out_h, int out_w, int tile_rows, int max_rows) {
+    extern __shared__ uint8_t s_tmp[];   // [rows][out_w][3]
+    const int n = blockIdx.y;
+    const int yy0 = blockIdx.x * tile_rows;
+    const int yy1 = min(yy0 + tile_rows, out_h);
+    const int in_h = hw[2 * n], in_w = hw[2 * n + 1];
+    const uint8_t* img = src + offsets[n];
+    const int E = 2 + K;
+    const int32_t* xt = tabs + (long)xtab_index[n] * S * E;
+    const int32_t* yt = tabs + (long)ytab_index[n] * S * E;
+    // input rows needed by this tile of output rows
+    const int r_lo = yt[yy0 * E];
+    int r_hi = r_lo;
+    for (int yy = yy0; yy < yy1; ++yy) r_hi = max(r_hi, yt[yy * E] + yt[yy * E + 1]);
+    const int rows = min(r_hi, in_h) - r_lo;
+    if (rows > max_rows) return;   // cannot happen: the host sized max_rows from the same tables
+    // horizontal pass
+    for (int i = threadIdx.x; i < rows * out_w; i += kResizeThreads) {
+        const int r = i / out_w, xx = i - r * out_w;
+        const int32_t* t = xt + xx * E;
+        const int xmin = t[0], cnt = t[1];
+        const uint8_t* p = img + ((long)(r_lo + r) * in_w + xmin) * 3;
+        int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+        for (int k = 0; k < cnt; ++k) {
+            const int c = t[2 + k];
+            s0 += int(p[3 * k]) * c;
+            s1 += int(p[3 * k + 1]) * c;
+            s2 += int(p[3 * k + 2]) * c;
+        }
+        uint8_t* d = s_tmp + (long)i * 3;
+        d[0] = uint8_t(clip8_fixed(s0));
+        d[1] = uint8_t(clip8_fixed(s1));
+        d[2] = uint8_t(clip8_fixed(s2));
+    }
+    __syncthreads();
+    // vertical pass
+    const int row_bytes = out_w * 3;
+    for (int i = threadIdx.x; i < (yy1 - yy0) * row_bytes; i += kResizeThreads) {
+        const int yl = i / row_bytes, b = i - yl * row_bytes;
+        const int32_t* t = yt + (yy0 + yl) * E;
+        const int ymin = t[0], cnt = t[1];
+        int ss = 1 << 21;
+        for (int k = 0; k < cnt; ++k) ss += int(s_tmp[(long)(ymin - r_lo + k) * row_bytes + b]) * t[2 + k];
+        out[((long)n * out_h + yy0 + yl) * row_bytes + b] = uint8_t(clip8_fixed(ss));
+    }
+}
+
 static int gen_grid(long elems, int N, dim3* grid, int bytes_per_thread) {
     long blocks = (elems + (long)kGenThreads * bytes_per_thread - 1) / ((long)kGenThreads * bytes_per_thread);
     if (blocks < 1) blocks = 1;
@@ -295,6 +359,31 @@ int b2r_noise02(const uint8_t* in, uint8_t* out, int N, int64_t elems_per_image,
         B2R_CHECK_LAUNCH();
     }
     noise02_kernel<1><<<grid, kGenThreads, 0, stream>>>(in, out, elems_per_image, sigma, noise, seed, image_index0, neg_flags);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
+int b2r_resize_bilinear_u8(const uint8_t* src, const int64_t* offsets, const int32_t* hw, const int32_t* xtab_index,
+                           const int32_t* ytab_index, const int32_t* tabs, int K, int S, uint8_t* out, int N, int out_h,
+                           int out_w, int tile_rows, int max_rows, void* stream_v) {
+    using namespace b2r;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    B2R_REQUIRE(src && offsets && hw && xtab_index && ytab_index && tabs && out, "null pointer");
+    B2R_REQUIRE(N > 0 && N <= 65535 && out_h > 0 && out_w > 0 && K > 0 && S >= out_h && S >= out_w, "bad shape");
+    B2R_REQUIRE(tile_rows > 0 && max_rows > 0, "tile_rows=%d max_rows=%d", tile_rows, max_rows);
+    const size_t smem = (size_t)max_rows * out_w * 3;
+    B2R_REQUIRE(smem <= 200 * 1024, "the tile needs %zu bytes of shared memory: use fewer tile_rows", smem);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    B2R_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        B2R_CUDA(cudaFuncSetAttribute(resize_bilinear_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (dev < 64) attr_set[dev] = true;
+    }
+    dim3 grid((unsigned)((out_h + tile_rows - 1) / tile_rows), (unsigned)N, 1);
+    resize_bilinear_u8_kernel<<<grid, kResizeThreads, smem, stream>>>(src, reinterpret_cast<const long long*>(offsets), hw,
+                                                                      xtab_index, ytab_index, tabs, K, S, out, out_h, out_w,
+                                                                      tile_rows, max_rows);
     B2R_CHECK_LAUNCH();
     return B2R_OK;
 }

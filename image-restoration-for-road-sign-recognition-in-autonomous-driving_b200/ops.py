@@ -421,3 +421,24 @@ def mean_bf16(x: torch.Tensor, outer: int, reduce: int, inner: int) -> torch.Ten
     L.check(L.load().b2r_mean_bf16(x.data_ptr(), out.data_ptr(), int(outer), int(reduce), int(inner), _stream()))
     STATS["launches"] += 1
     return out
+
+
+def resize_bilinear_u8(src: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor, xtab_index: torch.Tensor,
+                       ytab_index: torch.Tensor, tabs: torch.Tensor, K: int, S: int, out: torch.Tensor, tile_rows: int,
+                       max_rows: int) -> torch.Tensor:
+    """b2r_resize_bilinear_u8 (Pillow BILINEAR on a ragged packed batch); see imageio.resize_batch for the tables."""
+    _chk(src, torch.uint8, "src", 1)
+    _chk(offsets, torch.int64, "offsets", 1)
+    _chk(hw, torch.int32, "hw", 2)
+    _chk(xtab_index, torch.int32, "xtab_index", 1)
+    _chk(ytab_index, torch.int32, "ytab_index", 1)
+    _chk(tabs, torch.int32, "tabs", 3)
+    _chk(out, torch.uint8, "out", 4)
+    n, out_h, out_w, c = out.shape
+    if c != 3 or offsets.numel() != n or tuple(hw.shape) != (n, 2) or tabs.shape[1] != S or tabs.shape[2] != 2 + K:
+        raise L.B2RError("inconsistent resize arguments")
+    L.check(L.load().b2r_resize_bilinear_u8(src.data_ptr(), offsets.data_ptr(), hw.data_ptr(), xtab_index.data_ptr(),
+                                            ytab_index.data_ptr(), tabs.data_ptr(), int(K), int(S), out.data_ptr(), int(n),
+                                            int(out_h), int(out_w), int(tile_rows), int(max_rows), _stream()))
+    STATS["launches"] += 1
+    return out

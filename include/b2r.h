@@ -241,6 +241,18 @@ int b2r_normalize_minmax_u8(const uint8_t* in, const int32_t* minmax, uint8_t* o
 int b2r_noise02(const uint8_t* in, uint8_t* out, int N, int64_t elems_per_image, const float* sigma, const double* noise,
                 uint64_t seed, uint64_t image_index0, int32_t* neg_flags, int clip_rule, void* stream);
 
+/* transforms.Resize((out_h, out_w)) of a ragged batch of PIL images (17_run_unified_inference.py:66,79-82;
+ * 18_test_unified_benchmark.py:28-30), i.e. Pillow's BILINEAR resampling, bit for bit.
+ * src: the images packed back to back, u8 HWC RGB; offsets int64 [N] = byte offset of image n; hw int32 [N][2] = its
+ * height, width.  tabs int32 [T][S][2 + K]: Pillow's coefficient tables, one per distinct (input size -> output size)
+ * pair, entry = {first input index, tap count, taps in 22-bit fixed point}; xtab_index / ytab_index int32 [N] select the
+ * table of image n for the horizontal / vertical pass.  out u8 [N][out_h][out_w][3].
+ * tile_rows output rows share one CTA, max_rows = the largest number of input rows such a tile needs (both from the
+ * host, which owns the tables: imageio.resize_batch). */
+int b2r_resize_bilinear_u8(const uint8_t* src, const int64_t* offsets, const int32_t* hw, const int32_t* xtab_index,
+                           const int32_t* ytab_index, const int32_t* tabs, int K, int S, uint8_t* out, int N, int out_h,
+                           int out_w, int tile_rows, int max_rows, void* stream);
+
 /* VGG feature taps: mean over the middle axis of a bf16 tensor viewed as [outer][reduce][inner], f32 [outer][inner] out.
  * inner = 1: channel mean of an NHWC feature map (11_visualize_hidden_states.py:50, torch.mean(features, dim=1));
  * inner > 1: global average pooling of [N][H*W][C] (12_generate_umap_pt.py:52, torch.mean(feature, dim=[2, 3])).
