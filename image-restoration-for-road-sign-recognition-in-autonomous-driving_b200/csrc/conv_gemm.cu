@@ -50,6 +50,11 @@ struct alignas(64) ConvGemmParams {
     int cout_per_out;     // channels per output map (CONVT2X2: C_out, four maps; NHWC: cout_total, one map)
     int store_full, store_pool;
     uint32_t kblk[B2R_MAX_KBLOCKS];
+    // halo mode (conv_gemm_halo_kernel): one (TH + 2)-row input box per (source, 64-channel chunk, dw) feeds the three
+    // kernel rows; slot encoding as in conv_common.cuh (ConvN64Params)
+    CUtensorMap a3_map[B2R_MAX_SRC];
+    int num_slots, a_slot_bytes, a_slots, b_slots;
+    uint32_t slot[kN64MaxSlots];
 };
 
 template <int BLOCK_N>
@@ -65,6 +70,89 @@ struct GemmCfg {
     static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * (kStagingFull + kStagingPool) +
                                       BLOCK_N * 4 /*bias*/ + 256 /*barriers + tmem ptr*/;
 };
+
+// Epilogue role shared by the generic and the halo kernel: warps 2..5, TMEM -> registers -> bias / activation -> bf16 ->
+// swizzled staging -> TMA store (+ fused 2x2 max-pool).  BUFS = number of (staging + pool) buffers.
+template <int BLOCK_N, int BUFS>
+__device__ __forceinline__ void conv_epilogue_role(const ConvGemmParams& p, uint32_t tmem_base, uint8_t* staging, float* bias_s,
+                                                   uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, int total_tiles,
+                                                   int warp_idx, int lane) {
+        const int quarter = warp_idx & 3;          // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;       // tile row (pixel) == TMEM lane
+        const int epi_tid = row;                   // 0..127
+        const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t chunk_counter = 0;
+        const int tw = p.tile_w, th = p.tile_h;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.n_tiles;
+            const int m = tile / p.n_tiles;
+            const int w0 = (m % p.tiles_w) * p.tile_w;
+            const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.tile_h;
+            const int n0 = (m / (p.tiles_w * p.tiles_h)) * p.tile_n;
+            // first channel of this n-tile inside its output map (CONVT2X2: an n-tile may span several of the four
+            // maps, e.g. C_out = 64 with BLOCK_N = 256 covers all four taps in one tile)
+            int out_idx = (n_tile * BLOCK_N) / p.cout_per_out;
+            int ch_in_out = n_tile * BLOCK_N - out_idx * p.cout_per_out;
+
+            // bias of this n-tile -> smem (previous tile's readers are past their last named barrier)
+            for (int i = epi_tid; i < BLOCK_N; i += kEpiThreads) bias_s[i] = p.bias[n_tile * BLOCK_N + i];
+
+            mbar_wait_warp(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 64; ++c) {
+                const int buf = BUFS == 2 ? int(chunk_counter & 1) : 0;
+                ++chunk_counter;
+                uint8_t* sfull = staging + buf * (kStagingFull + kStagingPool);
+                uint8_t* spool = sfull + kStagingFull;
+                if (epi_tid == 0) {   // the store that last read `buf` has drained
+                    if (BUFS == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                }
+                named_barrier_sync(1, kEpiThreads);
+
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * BLOCK_N + c * 64 + half * 32), v);
+                    tmem_ld_wait();
+                    float b32[32];
+                    lds_bias32(bias_s + c * 64 + half * 32, b32);
+                    epilogue_store_half(v, b32, p.act, p.slope, sfull, row, half);
+                }
+                if (c == BLOCK_N / 64 - 1) {
+                    // all of this warp's TMEM reads of the accumulator are done -> hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                fence_proxy_async_smem();
+                named_barrier_sync(1, kEpiThreads);
+
+                if (p.store_pool) {
+                    epilogue_pool_chunk(sfull, spool, epi_tid, tw, th);
+                    fence_proxy_async_smem();
+                    named_barrier_sync(1, kEpiThreads);
+                }
+
+                if (epi_tid == 0) {
+                    if (p.store_full) tma_store_4d(&p.out_map[out_idx], sfull, ch_in_out, w0, h0, n0);
+                    if (p.store_pool) tma_store_4d(&p.pool_map, spool, ch_in_out, w0 >> 1, h0 >> 1, n0);
+                    tma_store_commit();
+                }
+                ch_in_out += 64;
+                if (ch_in_out >= p.cout_per_out) {
+                    ch_in_out = 0;
+                    ++out_idx;
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (epi_tid == 0) tma_store_wait_all<0>();
+    }
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, GemmCfg<BLOCK_N>::kCtasPerSm) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -137,10 +225,18 @@ __global__ void __launch_bounds__(kNumThreads, GemmCfg<BLOCK_N>::kCtasPerSm) con
                         c0 = int(e >> 8) * kBlockK;
                     }
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     uint8_t* sa = stages + stage * Cfg::kStageBytes;
+#if defined(B2R_EXP_GEMM_NO_B)      // experiment builds only (tools/exp/README.md): is the layer bound by smem-fill traffic?
+                    mbar_arrive_expect_tx(&full_bar[stage], kAStageBytes);
+                    tma_load_4d(sa, &p.a_map[src], &full_bar[stage], c0, w0 + dw, h0 + dh, n0);
+#elif defined(B2R_EXP_GEMM_NO_A)
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes - kAStageBytes);
+                    tma_load_2d(sa + kAStageBytes, &p.b_map, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N);
+#else
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     tma_load_4d(sa, &p.a_map[src], &full_bar[stage], c0, w0 + dw, h0 + dh, n0);
                     tma_load_2d(sa + kAStageBytes, &p.b_map, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N);
+#endif
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -184,79 +280,180 @@ __global__ void __launch_bounds__(kNumThreads, GemmCfg<BLOCK_N>::kCtasPerSm) con
         }
     } else {
         // ===================================== epilogue =====================================
-        const int quarter = warp_idx & 3;          // TMEM lane quarter this warp may access
-        const int row = quarter * 32 + lane;       // tile row (pixel) == TMEM lane
-        const int epi_tid = row;                   // 0..127
-        const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        uint32_t chunk_counter = 0;
-        const int tw = p.tile_w, th = p.tile_h;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n_tile = tile % p.n_tiles;
-            const int m = tile / p.n_tiles;
-            const int w0 = (m % p.tiles_w) * p.tile_w;
-            const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.tile_h;
-            const int n0 = (m / (p.tiles_w * p.tiles_h)) * p.tile_n;
-            // first channel of this n-tile inside its output map (CONVT2X2: an n-tile may span several of the four
-            // maps, e.g. C_out = 64 with BLOCK_N = 256 covers all four taps in one tile)
-            int out_idx = (n_tile * BLOCK_N) / p.cout_per_out;
-            int ch_in_out = n_tile * BLOCK_N - out_idx * p.cout_per_out;
+        conv_epilogue_role<BLOCK_N, 2>(p, tmem_base, staging, bias_s, tmem_full_bar, tmem_empty_bar, total_tiles, warp_idx, lane);
+    }
 
-            // bias of this n-tile -> smem (previous tile's readers are past their last named barrier)
-            for (int i = epi_tid; i < BLOCK_N; i += kEpiThreads) bias_s[i] = p.bias[n_tile * BLOCK_N + i];
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        __syncwarp();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
 
-            mbar_wait_warp(&tmem_full_bar[acc], acc_phase);
-            tc_fence_after();
+// ------------------------------------------------------------------------------------------------------------
+// Halo mode: the same GEMM with 2.4x less A traffic into shared memory.
+//
+// Measured (B2R_EXP_GEMM_NO_A / NO_B experiment builds, profiles/r01_smem_fill.md): the generic kernel is bound by the
+// rate at which TMA can fill shared memory, ~55 B/clk per SM, not by the tensor pipe: at full MMA rate one k-block needs
+// 16 KB of A + BLOCK_N x 128 B of B every 4 MMAs = 94 B/clk (N = 256) or 106 B/clk (N = 128).  Every one of the nine
+// taps re-loads an A tile that is the previous one shifted by a pixel.  Here the producer loads, per (source, 64-channel
+// chunk, dw), ONE box of TH + 2 rows (the conv_n64 trick): the operand of kernel row dh is the 128 rows starting at row
+// (dh + 1) * TW of that box, a 1024-byte aligned descriptor start as long as TW is a multiple of 8.  A and B travel through
+// separate rings (an A slot lives for three k-blocks, a B slot for one).  Everything downstream of the MMA is the
+// generic epilogue.  Requirements (checked by the dispatcher): NHWC output, one image per tile, TW % 8 == 0, k-blocks in
+// the (chunk, dw, dh) order packing.py emits; 1x1 centre k-blocks (ResidualBlock shortcut) ride on the same box.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kHaloMaxRing = 8;
 
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 64; ++c) {
-                const int buf = chunk_counter & 1;
-                ++chunk_counter;
-                uint8_t* sfull = staging + buf * (kStagingFull + kStagingPool);
-                uint8_t* spool = sfull + kStagingFull;
-                if (epi_tid == 0) tma_store_wait_read<1>();  // the store that last read `buf` has drained
-                named_barrier_sync(1, kEpiThreads);
+template <int BLOCK_N>
+struct HaloCfg {
+    static constexpr int kBBytes = BLOCK_N * 128;
+    static constexpr int kCtasPerSm = BLOCK_N == 128 ? 2 : 1;
+    // one staging buffer: the shared memory is worth more as ring depth (bytes in flight = fill bandwidth x latency)
+    static constexpr int kStagingBufs = 1;
+    static constexpr int kTmemCols = 2 * BLOCK_N;
+    static constexpr int kFixedBytes = 1024 + kStagingBufs * (kStagingFull + kStagingPool) + BLOCK_N * 4 + 512;
+    static constexpr int kMaxSmem = (227 * 1024) / kCtasPerSm - (kCtasPerSm > 1 ? 1024 : 0);
+};
 
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * BLOCK_N + c * 64 + half * 32), v);
-                    tmem_ld_wait();
-                    float b32[32];
-                    lds_bias32(bias_s + c * 64 + half * 32, b32);
-                    epilogue_store_half(v, b32, p.act, p.slope, sfull, row, half);
-                }
-                if (c == BLOCK_N / 64 - 1) {
-                    // all of this warp's TMEM reads of the accumulator are done -> hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-                }
-                fence_proxy_async_smem();
-                named_barrier_sync(1, kEpiThreads);
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, HaloCfg<BLOCK_N>::kCtasPerSm) conv_gemm_halo_kernel(const __grid_constant__ ConvGemmParams p) {
+    using Cfg = HaloCfg<BLOCK_N>;
+    constexpr uint32_t kIdesc = make_idesc_bf16_f32(kBlockM, BLOCK_N);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_ring = smem;                                        // a_slots x a_slot_bytes (multiples of 1 KB)
+    uint8_t* b_ring = a_ring + p.a_slots * p.a_slot_bytes;         // b_slots x BLOCK_N x 128 B
+    uint8_t* staging = b_ring + p.b_slots * Cfg::kBBytes;
+    float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBufs * (kStagingFull + kStagingPool));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + BLOCK_N);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + kHaloMaxRing;
+    uint64_t* b_full = bars + 2 * kHaloMaxRing;
+    uint64_t* b_empty = bars + 3 * kHaloMaxRing;
+    uint64_t* tmem_full_bar = bars + 4 * kHaloMaxRing;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-                if (p.store_pool) {
-                    epilogue_pool_chunk(sfull, spool, epi_tid, tw, th);
-                    fence_proxy_async_smem();
-                    named_barrier_sync(1, kEpiThreads);
-                }
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+    const int AR = p.a_slots, BR = p.b_slots;
 
-                if (epi_tid == 0) {
-                    if (p.store_full) tma_store_4d(&p.out_map[out_idx], sfull, ch_in_out, w0, h0, n0);
-                    if (p.store_pool) tma_store_4d(&p.pool_map, spool, ch_in_out, w0 >> 1, h0 >> 1, n0);
-                    tma_store_commit();
-                }
-                ch_in_out += 64;
-                if (ch_in_out >= p.cout_per_out) {
-                    ch_in_out = 0;
-                    ++out_idx;
+    if (warp_idx == 0 && lane == 0) {
+        for (int i = 0; i < B2R_MAX_SRC; ++i) tma_prefetch_desc(&p.a3_map[i]);
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.out_map[0]);
+        tma_prefetch_desc(&p.pool_map);
+    }
+    if (warp_idx == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kHaloMaxRing; ++s) {
+                mbar_init(&a_full[s], 1);
+                mbar_init(&a_empty[s], 1);
+                mbar_init(&b_full[s], 1);
+                mbar_init(&b_empty[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], 4);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp_idx == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                const int m = tile / p.n_tiles;
+                const int w0 = (m % p.tiles_w) * p.tile_w;
+                const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.tile_h;
+                const int n0 = m / (p.tiles_w * p.tiles_h);
+                for (int s = 0; s < p.num_slots; ++s) {
+                    const uint32_t e = p.slot[s];
+                    const int src = e & 3, ntaps = ((e >> 2) & 1) ? 1 : 3, dw = int((e >> 4) & 3) - 1;
+                    const int c0 = int((e >> 8) & 0xFFF) * 64, kb0 = int(e >> 20);
+                    mbar_wait(&a_empty[as], aph ^ 1);
+                    mbar_arrive_expect_tx(&a_full[as], uint32_t(p.a_slot_bytes));
+                    tma_load_4d(a_ring + as * p.a_slot_bytes, &p.a3_map[src], &a_full[as], c0, w0 + dw, h0 - 1, n0);
+                    if (++as == AR) {
+                        as = 0;
+                        aph ^= 1;
+                    }
+                    for (int t = 0; t < ntaps; ++t) {
+                        mbar_wait(&b_empty[bs], bph ^ 1);
+                        mbar_arrive_expect_tx(&b_full[bs], Cfg::kBBytes);
+                        tma_load_2d(b_ring + bs * Cfg::kBBytes, &p.b_map, &b_full[bs], (kb0 + t) * kBlockK, n_tile * BLOCK_N);
+                        if (++bs == BR) {
+                            bs = 0;
+                            bph ^= 1;
+                        }
+                    }
                 }
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
         }
-        if (epi_tid == 0) tma_store_wait_all<0>();
+    } else if (warp_idx == 1) {
+        // ===================================== MMA issuer =====================================
+        if (lane == 0) {
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            const uint32_t row_stride = uint32_t(p.tile_w) * 128u;   // one kernel row further down the box
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + uint32_t(acc * BLOCK_N);
+                uint32_t accum = 0;
+                for (int s = 0; s < p.num_slots; ++s) {
+                    const uint32_t e = p.slot[s];
+                    const bool centre = ((e >> 2) & 1) != 0;
+                    const int ntaps = centre ? 1 : 3;
+                    mbar_wait(&a_full[as], aph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(a_ring + as * p.a_slot_bytes);
+                    for (int t = 0; t < ntaps; ++t) {
+                        mbar_wait(&b_full[bs], bph);
+                        tc_fence_after();
+                        const uint64_t adesc = make_sdesc_sw128(sa + uint32_t(centre ? 1 : t) * row_stride, 1024);
+                        const uint64_t bdesc = make_sdesc_sw128(smem_u32(b_ring + bs * Cfg::kBBytes), 1024);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            umma_bf16_ss(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, accum);
+                            accum = 1;
+                        }
+                        umma_commit(&b_empty[bs]);
+                        if (++bs == BR) {
+                            bs = 0;
+                            bph ^= 1;
+                        }
+                    }
+                    umma_commit(&a_empty[as]);
+                    if (++as == AR) {
+                        as = 0;
+                        aph ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        conv_epilogue_role<BLOCK_N, Cfg::kStagingBufs>(p, tmem_base, staging, bias_s, tmem_full_bar, tmem_empty_bar, total_tiles,
+                                                        warp_idx, lane);
     }
 
     tc_fence_before();
@@ -567,6 +764,81 @@ static int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
     return B2R_OK;
 }
 
+template <int BLOCK_N>
+static int launch_halo(const ConvGemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    B2R_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        B2R_CUDA(cudaFuncSetAttribute(conv_gemm_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      HaloCfg<BLOCK_N>::kMaxSmem));
+        if (dev < 64) attr_set[dev] = true;
+    }
+    conv_gemm_halo_kernel<BLOCK_N><<<grid, kNumThreads, smem, stream>>>(p);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
+// Fills the halo-mode fields of P when the layer qualifies; returns the dynamic shared memory size or 0.
+template <int BLOCK_N>
+static size_t plan_halo(const b2r_conv_gemm_desc* d, ConvGemmParams& P, int tw, int th, int tn, int* rc_out) {
+    *rc_out = B2R_OK;
+    if ((d->flags & B2R_CONV_NO_HALO) || d->kblocks_host == nullptr || d->out_mode != B2R_OUT_NHWC || tn != 1 || tw % 8 != 0)
+        return 0;
+    const int nk = d->num_kblocks;
+    int ns = 0;
+    for (int i = 0; i < nk;) {
+        const uint32_t e = d->kblocks_host[i];
+        const int src = e & 3, dh = int((e >> 2) & 3) - 1, dw = int((e >> 4) & 3) - 1, c64 = int(e >> 8);
+        bool group = (i + 9 <= nk);
+        for (int t = 0; group && t < 9; ++t)  // dw-major, dh-minor
+            group = d->kblocks_host[i + t] == B2R_KBLOCK(src, t % 3 - 1, t / 3 - 1, c64);
+        if (group) {
+            if (ns + 3 > kN64MaxSlots || c64 > 0xFFF || i + 8 > 0xFFF) return 0;
+            for (int j = 0; j < 3; ++j)
+                P.slot[ns++] = uint32_t(src) | (uint32_t(j) << 4) | (uint32_t(c64) << 8) | (uint32_t(i + 3 * j) << 20);
+            i += 9;
+        } else if (dh == 0 && dw == 0) {
+            if (ns + 1 > kN64MaxSlots || c64 > 0xFFF || i > 0xFFF) return 0;
+            P.slot[ns++] = uint32_t(src) | (1u << 2) | (1u << 4) | (uint32_t(c64) << 8) | (uint32_t(i) << 20);
+            i += 1;
+        } else {
+            return 0;
+        }
+    }
+    using Cfg = HaloCfg<BLOCK_N>;
+    const int a_bytes = (th + 2) * tw * 128;
+    int a_slots = 2;
+    long room = (long)Cfg::kMaxSmem - Cfg::kFixedBytes - (long)a_slots * a_bytes;
+    int b_slots = (int)(room / Cfg::kBBytes);
+    if (b_slots > kHaloMaxRing) b_slots = kHaloMaxRing;
+    if (b_slots < 2) return 0;
+    // spend what is left on a third / fourth A slot
+    room -= (long)b_slots * Cfg::kBBytes;
+    while (a_slots < 4 && room >= a_bytes) {
+        ++a_slots;
+        room -= a_bytes;
+    }
+    const uint64_t N = d->N, H = d->H, W = d->W;
+    for (int i = 0; i < B2R_MAX_SRC; ++i) {
+        const int s = i < d->num_src ? i : 0;
+        const uint64_t C = d->src_C[s];
+        const uint64_t dims[4] = {C, W, H, N};
+        const uint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+        const uint32_t box3[4] = {64, (uint32_t)tw, (uint32_t)(th + 2), 1};
+        int rc = encode_tmap_bf16(&P.a3_map[i], d->src[s], 4, dims, strides, box3);
+        if (rc) {
+            *rc_out = rc;
+            return 0;
+        }
+    }
+    P.num_slots = ns;
+    P.a_slot_bytes = a_bytes;
+    P.a_slots = a_slots;
+    P.b_slots = b_slots;
+    return (size_t)Cfg::kFixedBytes + (size_t)a_slots * a_bytes + (size_t)b_slots * Cfg::kBBytes;
+}
+
 }  // namespace b2r
 
 extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
@@ -726,6 +998,18 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
     int grid = d->max_ctas > 0 ? d->max_ctas : sms;
     if (grid > total_tiles) grid = (int)total_tiles;
 
+    if (block_n >= 128 && spatial) {
+        int hrc = B2R_OK;
+        const size_t hs = block_n == 128 ? plan_halo<128>(d, P, tw, th, tn, &hrc) : plan_halo<256>(d, P, tw, th, tn, &hrc);
+        if (hrc) return hrc;
+        if (hs) {
+            // co-resident CTAs (N = 128): twice the grid
+            const int ctas = block_n == 128 ? HaloCfg<128>::kCtasPerSm : 1;
+            int hgrid = d->max_ctas > 0 ? d->max_ctas : sms * ctas;
+            if (hgrid > total_tiles) hgrid = (int)total_tiles;
+            return block_n == 128 ? launch_halo<128>(P, hgrid, hs, stream) : launch_halo<256>(P, hgrid, hs, stream);
+        }
+    }
     switch (block_n) {
         case 64: return launch<64>(P, grid, stream);
         case 128: return launch<128>(P, grid, stream);

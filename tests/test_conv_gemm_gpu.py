@@ -352,3 +352,52 @@ def test_conv_w3_random_shapes_against_generic_kernel():
                 assert torch.equal(to_nchw_f32(pl), exact), (case, n, h, w, splits)
             d = (pl.float() - ref_pl.float()).abs()
             assert bool((d <= 2.0 ** -7 * ref_pl.float().abs() + 1e-3).all()), (case, "pool", float(d.max()))
+
+
+@pytest.mark.parametrize("n,h,w,splits,co,shortcut,pool", [
+    (2, 32, 48, (64,), 128, None, False),          # VGG conv2_1 shape class (N = 128, two co-resident CTAs)
+    (1, 112, 112, (128,), 128, None, True),        # conv2_2 with the fused pool
+    (2, 56, 56, (128, 256), 128, None, False),     # dec3.c1: concat of two sources
+    (2, 40, 24, (128,), 256, None, False),         # N = 256, ragged tiles
+    (3, 28, 28, (256,), 256, None, True),          # 32 x 4 tiles
+    (2, 14, 14, (512,), 512, None, False),         # two n-tiles per pixel tile
+    (2, 32, 32, (128,), 128, (64,), True),         # res2.c2: conv + 1x1 shortcut (centre k-blocks) + pool
+])
+def test_halo_mode_equals_per_tap_mode(n, h, w, splits, co, shortcut, pool):
+    """Halo mode (one (TH + 2)-row box per (chunk, dw), A and B in separate rings) issues the same MMAs in the same order
+    as the per-tap mode: outputs must be bit-identical, and both within bf16 tolerance of the fp32 torch reference."""
+    ops, packing, L = _ops()
+    srcs = [nhwc_bf16(rnd(n, c, h, w, seed=600 + i)) for i, c in enumerate(splits)]
+    ci = sum(splits)
+    wt = rnd(co, ci, 3, 3, scale=(2.0 / (9 * ci)) ** 0.5, seed=610)
+    b = rnd(co, scale=0.1, seed=611)
+    plan = packing.KPlan(co)
+    off = 0
+    for s, c in enumerate(splits):
+        plan.add_conv3x3(s, wt[:, off:off + c])
+        off += c
+    ref = F.conv2d(torch.cat([to_nchw_f32(s) for s in srcs], 1), wt.to(torch.bfloat16).float(), b, padding=1)
+    all_srcs = list(srcs)
+    if shortcut is not None:
+        ws = rnd(co, sum(shortcut), 1, 1, scale=(1.0 / sum(shortcut)) ** 0.5, seed=612)
+        xs = nhwc_bf16(rnd(n, shortcut[0], h, w, seed=613))
+        plan.add_1x1(len(all_srcs), ws)
+        all_srcs.append(xs)
+        ref = ref + F.conv2d(to_nchw_f32(xs), ws.to(torch.bfloat16).float())
+    ref = F.relu(ref)
+    wm, kbl = plan.finish()
+    wm = wm.cuda()
+    outs = []
+    for flags in (0, L.B2R_CONV_NO_HALO):
+        out = torch.full((n + 2, h, w, co), float("nan"), dtype=torch.bfloat16, device="cuda")
+        pl = torch.full((n + 2, h // 2, w // 2, co), float("nan"), dtype=torch.bfloat16, device="cuda") if pool else None
+        ops.conv_gemm(all_srcs, wm, b, kbl, act=L.B2R_ACT_RELU, out=out[1:n + 1], out_pool=None if pl is None else pl[1:n + 1],
+                      flags=flags)
+        torch.cuda.synchronize()
+        assert bool(torch.isnan(out[0]).all()) and bool(torch.isnan(out[n + 1]).all()), "store outside the tensor"
+        outs.append((out[1:n + 1].clone(), None if pl is None else pl[1:n + 1].clone()))
+    assert_close_bf16(to_nchw_f32(outs[0][0]), ref, "halo mode vs torch")
+    assert torch.equal(outs[0][0], outs[1][0]), "halo and per-tap modes disagree"
+    if pool:
+        assert torch.equal(outs[0][1], outs[1][1])
+        assert torch.equal(to_nchw_f32(outs[0][1]), F.max_pool2d(to_nchw_f32(outs[0][0]), 2, 2))
