@@ -809,6 +809,7 @@ static size_t plan_halo(const b2r_conv_gemm_desc* d, ConvGemmParams& P, int tw, 
     using Cfg = HaloCfg<BLOCK_N>;
     const int a_bytes = (th + 2) * tw * 128;
     int a_slots = 2;
+    if (const char* e = getenv("B2R_HALO_A_SLOTS")) a_slots = atoi(e);   // tuning knob for tools/layer_bench.py
     long room = (long)Cfg::kMaxSmem - Cfg::kFixedBytes - (long)a_slots * a_bytes;
     int b_slots = (int)(room / Cfg::kBBytes);
     if (b_slots > kHaloMaxRing) b_slots = kHaloMaxRing;
@@ -908,7 +909,31 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
     B2R_REQUIRE(n_span % block_n == 0 && (cout % block_n == 0 || block_n % cout == 0),
                 "C_out=%d (cout_total=%d) incompatible with block_n=%d", cout, d->cout_total, block_n);
     int tw = d->tile_w, th = d->tile_h, tn = d->tile_n;
-    if (tw == 0 && th == 0 && tn == 0) choose_tile(d->N, d->H, d->W, d->out_pool != nullptr, spatial, &tw, &th, &tn);
+    if (tw == 0 && th == 0 && tn == 0) {
+        choose_tile(d->N, d->H, d->W, d->out_pool != nullptr, spatial, &tw, &th, &tn);
+        if (block_n == 128 && spatial && !(d->flags & B2R_CONV_NO_HALO) && d->out_mode == B2R_OUT_NHWC && (tn != 1 || tw % 8 != 0)) {
+            // N = 128 layers are bound by shared-memory fill: a halo-capable tile (one image, TW % 8 == 0) is worth up to
+            // 15 % more (partly clipped) tiles (dec3.c1 @56: 8x8x2 -> 8x16x1, 337 -> 315 us; profiles/r01_smem_fill.md)
+            const long base = (long)ceil_div(d->W, tw) * ceil_div(d->H, th) * ceil_div(d->N, tn);
+            long best = -1;
+            int bw = 0, bh = 0;
+            for (int cw = 8; cw <= 128; cw <<= 1) {
+                const int ch = 128 / cw;
+                if (d->out_pool && ch < 2) continue;
+                const long t = (long)ceil_div(d->W, cw) * ceil_div(d->H, ch) * d->N;
+                if (best < 0 || t < best) {
+                    best = t;
+                    bw = cw;
+                    bh = ch;
+                }
+            }
+            if (best > 0 && best * 100 <= base * 115) {
+                tw = bw;
+                th = bh;
+                tn = 1;
+            }
+        }
+    }
     B2R_REQUIRE(tw > 0 && th > 0 && tn > 0 && tw * th * tn == kBlockM, "tile %dx%dx%d must cover 128 pixels", tw, th, tn);
     B2R_REQUIRE(tw <= 256 && th <= 256 && tn <= 256, "tile dims must be <= 256");
     if (d->out_pool) B2R_REQUIRE(tw % 2 == 0 && th % 2 == 0, "fused pool needs even tile_w, tile_h");

@@ -75,6 +75,8 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--no-w3", action="store_true")
+    ap.add_argument("--tile", default=None, help="force the pixel tile, e.g. 8,16,1 (W,H,N)")
+    ap.add_argument("--flags", type=int, default=0, help="b2r_conv_gemm flags (4 = B2R_CONV_NO_HALO)")
     ap.add_argument("--clocks", action="store_true", help="sample SM clock / board power (NVML) during the timed loop")
     args = ap.parse_args()
     from b200restore import ops, packing, _lib as L
@@ -120,7 +122,8 @@ def main():
 
         def run():
             ops.conv_gemm(srcs, wm, bias, kbl, act=L.B2R_ACT_RELU, out=out, out_pool=pool, out_mode=mode, weights_w3=w3,
-                          block_n=args.block_n if args.block_n and co % args.block_n == 0 else 0)
+                          block_n=args.block_n if args.block_n and co % args.block_n == 0 else 0,
+                          tile=tuple(int(v) for v in args.tile.split(",")) if args.tile else (0, 0, 0), flags=args.flags)
 
         for _ in range(3):
             run()
