@@ -466,6 +466,210 @@ __global__ void __launch_bounds__(kNumThreads, HaloCfg<BLOCK_N>::kCtasPerSm) con
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Pair mode (cta_group::2) for C_out % 256 == 0: two CTAs of a cluster, on the two SMs of a TPC, execute MMAs of
+// M = 256 x N = 256.  Each CTA owns one 128-pixel tile (its rows of A, its rows of D in its own TMEM, its own
+// epilogue and stores) and loads only HALF of each weight k-block: B is two thirds of what the generic kernel pours
+// into shared memory, and shared-memory fill is what bounds it (profiles/r01_smem_fill.md).  32 KB per k-block
+// and CTA instead of 48 KB, so the ring is also deeper (5 stages).
+// Protocol: the leader (cluster rank 0) issues all MMAs.  Its "full" barriers count the TMA bytes of both CTAs (the
+// peer's loads name the leader's barrier); tcgen05.commit multicasts to the "empty" / "accumulator ready" barriers of
+// both CTAs; the peer's epilogue releases the accumulator stage on the leader's barrier.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kPairN = 256;
+constexpr int kPairStages = 5;
+constexpr int kPairStageBytes = kAStageBytes + (kPairN / 2) * 128;   // 16 KB of A + 16 KB of B per CTA
+constexpr int kPairSmemBytes = 1024 + kPairStages * kPairStageBytes + 2 * (kStagingFull + kStagingPool) + kPairN * 4 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
+    constexpr uint32_t kIdesc = make_idesc_bf16_f32(256, kPairN);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stages = smem;
+    uint8_t* staging = smem + kPairStages * kPairStageBytes;
+    float* bias_s = reinterpret_cast<float*>(staging + 2 * (kStagingFull + kStagingPool));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + kPairN);
+    uint64_t* full_bar = bars;                            // [stages]  used in the leader only
+    uint64_t* empty_bar = bars + kPairStages;             // [stages]  one multicast commit per phase, in each CTA
+    uint64_t* tmem_full_bar = bars + 2 * kPairStages;     // [2]       one multicast commit per phase, in each CTA
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]       leader only: 4 epilogue warps x 2 CTAs
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int m_pairs = (num_m_tiles + 1) / 2;
+    const int total_pairs = m_pairs * p.n_tiles;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp_idx == 0 && lane == 0) {
+        for (int i = 0; i < B2R_MAX_SRC; ++i) tma_prefetch_desc(&p.a_map[i]);
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.out_map[0]);
+        tma_prefetch_desc(&p.pool_map);
+    }
+    if (warp_idx == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kPairStages; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], 8);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc_pair<2 * kPairN>(tmem_ptr_s);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();      // both CTAs' barriers are initialised before any remote arrive / complete_tx
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp_idx == 0) {
+        // ===================================== TMA producer (both CTAs) =====================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+                const int n_tile = pair % p.n_tiles;
+                int m = 2 * (pair / p.n_tiles) + int(rank);
+                if (m >= num_m_tiles) m = num_m_tiles - 1;   // odd tile count: the last pair computes one tile twice
+                const int w0 = (m % p.tiles_w) * p.tile_w;
+                const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.tile_h;
+                const int n0 = (m / (p.tiles_w * p.tiles_h)) * p.tile_n;
+                for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                    int src = 0, dh = 0, dw = 0, c0 = kb * kBlockK;
+                    if (!p.linear_k) {
+                        const uint32_t e = p.kblk[kb];
+                        src = e & 3;
+                        dh = int((e >> 2) & 3) - 1;
+                        dw = int((e >> 4) & 3) - 1;
+                        c0 = int(e >> 8) * kBlockK;
+                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * kPairStageBytes);   // bytes of both CTAs
+                    uint8_t* sa = stages + stage * kPairStageBytes;
+                    tma_load_4d_pair(sa, &p.a_map[src], &full_bar[stage], c0, w0 + dw, h0 + dh, n0);
+                    tma_load_2d_pair(sa + kAStageBytes, &p.b_map, &full_bar[stage], kb * kBlockK,
+                                     n_tile * kPairN + int(rank) * (kPairN / 2));
+                    if (++stage == kPairStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================================== MMA issuer (leader CTA only) =====================================
+        if (leader && lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + uint32_t(acc * kPairN);
+                for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stages + stage * kPairStageBytes);
+                    const uint64_t adesc = make_sdesc_sw128(sa, 1024);
+                    const uint64_t bdesc = make_sdesc_sw128(sa + kAStageBytes, 1024);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_bf16_ss_pair(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc,
+                                          (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_pair(&empty_bar[stage]);
+                    if (++stage == kPairStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit_pair(&tmem_full_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ===================================== epilogue (both CTAs, own tile) =====================================
+        const int quarter = warp_idx & 3;
+        const int row = quarter * 32 + lane;
+        const int epi_tid = row;
+        const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t chunk_counter = 0;
+        const int tw = p.tile_w, th = p.tile_h;
+        for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+            const int n_tile = pair % p.n_tiles;
+            const int m = 2 * (pair / p.n_tiles) + int(rank);
+            const bool valid_tile = m < num_m_tiles;
+            const int w0 = (m % p.tiles_w) * p.tile_w;
+            const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.tile_h;
+            const int n0 = (m / (p.tiles_w * p.tiles_h)) * p.tile_n;
+            for (int i = epi_tid; i < kPairN; i += kEpiThreads) bias_s[i] = p.bias[n_tile * kPairN + i];
+            mbar_wait_warp(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < kPairN / 64; ++c) {
+                const int buf = chunk_counter & 1;
+                ++chunk_counter;
+                uint8_t* sfull = staging + buf * (kStagingFull + kStagingPool);
+                uint8_t* spool = sfull + kStagingFull;
+                if (epi_tid == 0) tma_store_wait_read<1>();
+                named_barrier_sync(1, kEpiThreads);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * kPairN + c * 64 + half * 32), v);
+                    tmem_ld_wait();
+                    float b32[32];
+                    lds_bias32(bias_s + c * 64 + half * 32, b32);
+                    epilogue_store_half(v, b32, p.act, p.slope, sfull, row, half);
+                }
+                if (c == kPairN / 64 - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);   // the leader's barrier, from either CTA
+                }
+                fence_proxy_async_smem();
+                named_barrier_sync(1, kEpiThreads);
+                if (p.store_pool) {
+                    epilogue_pool_chunk(sfull, spool, epi_tid, tw, th);
+                    fence_proxy_async_smem();
+                    named_barrier_sync(1, kEpiThreads);
+                }
+                if (epi_tid == 0 && valid_tile) {
+                    const int ch0 = n_tile * kPairN + c * 64;
+                    if (p.store_full) tma_store_4d(&p.out_map[0], sfull, ch0, w0, h0, n0);
+                    if (p.store_pool) tma_store_4d(&p.pool_map, spool, ch0, w0 >> 1, h0 >> 1, n0);
+                    tma_store_commit();
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (epi_tid == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();      // nobody leaves (or frees TMEM) while the peer may still read its shared memory / barriers
+    if (warp_idx == 1) {
+        tc_fence_after();
+        __syncwarp();
+        tmem_dealloc_pair<2 * kPairN>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -1023,6 +1227,30 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
     int grid = d->max_ctas > 0 ? d->max_ctas : sms;
     if (grid > total_tiles) grid = (int)total_tiles;
 
+    if (block_n == 256 && d->out_mode == B2R_OUT_NHWC && !(d->flags & B2R_CONV_NO_PAIR) && sms >= 2 && total_tiles >= 2) {
+        static bool pair_attr[64] = {false};
+        int dev = 0;
+        B2R_CUDA(cudaGetDevice(&dev));
+        if (dev >= 64 || !pair_attr[dev]) {
+            B2R_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+            if (dev < 64) pair_attr[dev] = true;
+        }
+        {   // each CTA of the pair loads half of a weight k-block: box 64 x 128
+            const uint64_t K = (uint64_t)d->num_kblocks * 64;
+            const uint64_t dims[2] = {K, (uint64_t)d->cout_total};
+            const uint64_t strides[1] = {K * 2};
+            const uint32_t box[2] = {64, (uint32_t)(kPairN / 2)};
+            int brc = encode_tmap_bf16(&P.b_map, d->weights, 2, dims, strides, box);
+            if (brc) return brc;
+        }
+        const long pairs = ((long)P.tiles_w * P.tiles_h * P.tiles_n + 1) / 2 * P.n_tiles;
+        long clusters = d->max_ctas > 0 ? d->max_ctas / 2 : sms / 2;
+        if (clusters < 1) clusters = 1;
+        if (clusters > pairs) clusters = pairs;
+        conv_gemm_pair_kernel<<<(unsigned)(2 * clusters), kNumThreads, kPairSmemBytes, stream>>>(P);
+        B2R_CHECK_LAUNCH();
+        return B2R_OK;
+    }
     if (block_n >= 128 && spatial) {
         int hrc = B2R_OK;
         const size_t hs = block_n == 128 ? plan_halo<128>(d, P, tw, th, tn, &hrc) : plan_halo<256>(d, P, tw, th, tn, &hrc);

@@ -401,3 +401,35 @@ def test_halo_mode_equals_per_tap_mode(n, h, w, splits, co, shortcut, pool):
     if pool:
         assert torch.equal(outs[0][1], outs[1][1])
         assert torch.equal(to_nchw_f32(outs[0][1]), F.max_pool2d(to_nchw_f32(outs[0][0]), 2, 2))
+
+
+@pytest.mark.parametrize("n,h,w,ci,co,pool", [
+    (2, 16, 16, 64, 256, False),        # one pair per n-tile, tiny
+    (3, 56, 56, 128, 256, False),       # conv3_1 shape class, 8x8x2 tiles, odd number of pixel tiles
+    (2, 28, 28, 256, 512, True),        # two n-tiles, fused pool
+    (5, 14, 14, 512, 512, False),       # tiles spanning several images, odd tile count
+    (1, 40, 24, 64, 256, False),        # ragged tiles
+])
+def test_pair_mode_equals_single_cta_mode(n, h, w, ci, co, pool):
+    """cta_group::2 pair mode (M = 256 across two CTAs, each loading half of the weights) must reproduce the single-CTA
+    kernel bit for bit (same k-block order, fp32 accumulation per output element in the same order)."""
+    ops, packing, L = _ops()
+    x = nhwc_bf16(rnd(n, ci, h, w, seed=700))
+    wt = rnd(co, ci, 3, 3, scale=(2.0 / (9 * ci)) ** 0.5, seed=701)
+    b = rnd(co, scale=0.1, seed=702)
+    wm, kbl = packing.plan_conv3x3(wt).finish()
+    wm = wm.cuda()
+    ref = F.relu(F.conv2d(to_nchw_f32(x), wt.to(torch.bfloat16).float(), b, padding=1))
+    outs = []
+    for flags in (0, L.B2R_CONV_NO_PAIR):
+        out = torch.full((n + 2, h, w, co), float("nan"), dtype=torch.bfloat16, device="cuda")
+        pl = torch.full((n + 2, h // 2, w // 2, co), float("nan"), dtype=torch.bfloat16, device="cuda") if pool else None
+        ops.conv_gemm([x], wm, b, kbl, act=L.B2R_ACT_RELU, out=out[1:n + 1], out_pool=None if pl is None else pl[1:n + 1],
+                      flags=flags)
+        torch.cuda.synchronize()
+        assert bool(torch.isnan(out[0]).all()) and bool(torch.isnan(out[n + 1]).all()), "store outside the tensor"
+        outs.append((out[1:n + 1].clone(), None if pl is None else pl[1:n + 1].clone()))
+    assert_close_bf16(to_nchw_f32(outs[0][0]), ref, "pair mode vs torch")
+    assert torch.equal(outs[0][0], outs[1][0]), "pair and single-CTA modes disagree"
+    if pool:
+        assert torch.equal(outs[0][1], outs[1][1])
