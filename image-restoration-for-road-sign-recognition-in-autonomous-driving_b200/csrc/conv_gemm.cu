@@ -475,19 +475,32 @@ __global__ void __launch_bounds__(kNumThreads, HaloCfg<BLOCK_N>::kCtasPerSm) con
 // peer's loads name the leader's barrier); tcgen05.commit multicasts to the "empty" / "accumulator ready" barriers of
 // both CTAs; the peer's epilogue releases the accumulator stage on the leader's barrier.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kPairN = 256;
-constexpr int kPairStages = 5;
-constexpr int kPairStageBytes = kAStageBytes + (kPairN / 2) * 128;   // 16 KB of A + 16 KB of B per CTA
-constexpr int kPairSmemBytes = 1024 + kPairStages * kPairStageBytes + 2 * (kStagingFull + kStagingPool) + kPairN * 4 + 256;
+template <int kPairN>
+struct PairCfg {
+#ifndef B2R_PAIR_STAGES
+#define B2R_PAIR_STAGES 5
+#endif
+#ifndef B2R_PAIR_BUFS
+#define B2R_PAIR_BUFS 2
+#endif
+    static constexpr int kStages = kPairN == 256 ? B2R_PAIR_STAGES : 6;
+    static constexpr int kBufs = B2R_PAIR_BUFS;
+    static constexpr int kStageBytes = kAStageBytes + (kPairN / 2) * 128;   // 16 KB of A + half a weight k-block per CTA
+    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBufs * (kStagingFull + kStagingPool) + kPairN * 4 + 256;
+};
 
+template <int kPairN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
+    constexpr int kPairStages = PairCfg<kPairN>::kStages;
+    constexpr int kPairStageBytes = PairCfg<kPairN>::kStageBytes;
     constexpr uint32_t kIdesc = make_idesc_bf16_f32(256, kPairN);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stages = smem;
+    constexpr int kBufs = PairCfg<kPairN>::kBufs;
     uint8_t* staging = smem + kPairStages * kPairStageBytes;
-    float* bias_s = reinterpret_cast<float*>(staging + 2 * (kStagingFull + kStagingPool));
+    float* bias_s = reinterpret_cast<float*>(staging + kBufs * (kStagingFull + kStagingPool));
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + kPairN);
     uint64_t* full_bar = bars;                            // [stages]  used in the leader only
     uint64_t* empty_bar = bars + kPairStages;             // [stages]  one multicast commit per phase, in each CTA
@@ -619,11 +632,13 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < kPairN / 64; ++c) {
-                const int buf = chunk_counter & 1;
+                const int buf = kBufs == 2 ? int(chunk_counter & 1) : 0;
                 ++chunk_counter;
                 uint8_t* sfull = staging + buf * (kStagingFull + kStagingPool);
                 uint8_t* spool = sfull + kStagingFull;
-                if (epi_tid == 0) tma_store_wait_read<1>();
+                if (epi_tid == 0) {
+                    if (kBufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                }
                 named_barrier_sync(1, kEpiThreads);
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -968,6 +983,21 @@ static int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
     return B2R_OK;
 }
 
+template <int N>
+static int launch_pair(const ConvGemmParams& p, int clusters, cudaStream_t stream) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    B2R_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        B2R_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PairCfg<N>::kSmemBytes));
+        if (dev < 64) attr_set[dev] = true;
+    }
+    conv_gemm_pair_kernel<N><<<(unsigned)(2 * clusters), kNumThreads, PairCfg<N>::kSmemBytes, stream>>>(p);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
 template <int BLOCK_N>
 static int launch_halo(const ConvGemmParams& p, int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set[64] = {false};
@@ -1227,19 +1257,13 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
     int grid = d->max_ctas > 0 ? d->max_ctas : sms;
     if (grid > total_tiles) grid = (int)total_tiles;
 
-    if (block_n == 256 && d->out_mode == B2R_OUT_NHWC && !(d->flags & B2R_CONV_NO_PAIR) && sms >= 2 && total_tiles >= 2) {
-        static bool pair_attr[64] = {false};
-        int dev = 0;
-        B2R_CUDA(cudaGetDevice(&dev));
-        if (dev >= 64 || !pair_attr[dev]) {
-            B2R_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
-            if (dev < 64) pair_attr[dev] = true;
-        }
-        {   // each CTA of the pair loads half of a weight k-block: box 64 x 128
+    const bool pair128 = block_n == 128 && getenv("B2R_PAIR128") != nullptr;   // experiment switch (tools/layer_bench.py)
+    if ((block_n == 256 || pair128) && d->out_mode == B2R_OUT_NHWC && !(d->flags & B2R_CONV_NO_PAIR) && sms >= 2 && total_tiles >= 2) {
+        {   // each CTA of the pair loads half of a weight k-block: box 64 x block_n / 2
             const uint64_t K = (uint64_t)d->num_kblocks * 64;
             const uint64_t dims[2] = {K, (uint64_t)d->cout_total};
             const uint64_t strides[1] = {K * 2};
-            const uint32_t box[2] = {64, (uint32_t)(kPairN / 2)};
+            const uint32_t box[2] = {64, (uint32_t)(block_n / 2)};
             int brc = encode_tmap_bf16(&P.b_map, d->weights, 2, dims, strides, box);
             if (brc) return brc;
         }
@@ -1247,9 +1271,7 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
         long clusters = d->max_ctas > 0 ? d->max_ctas / 2 : sms / 2;
         if (clusters < 1) clusters = 1;
         if (clusters > pairs) clusters = pairs;
-        conv_gemm_pair_kernel<<<(unsigned)(2 * clusters), kNumThreads, kPairSmemBytes, stream>>>(P);
-        B2R_CHECK_LAUNCH();
-        return B2R_OK;
+        return block_n == 256 ? launch_pair<256>(P, (int)clusters, stream) : launch_pair<128>(P, (int)clusters, stream);
     }
     if (block_n >= 128 && spatial) {
         int hrc = B2R_OK;
