@@ -379,7 +379,7 @@ def run_ours(args):
                      "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
                      "peak_source": peak_src, "traffic": traffic,
                      "traffic_note": "dram__bytes_read+write per launch averaged over all tcgen05 conv launches of one "
-                                     "ncu capture (profiles/r01_launches_v8_summary.md), micro-batch 256",
+                                     "ncu capture (profiles/r01_launches_v9_summary.md), micro-batch 256",
                      "launches": ksum["launches"], "kernel_ms_per_step": ksum["ms"] / args.steps,
                      "share_of_step": ksum["ms"] / total_ms,
                      "pipeline_tflops": ips / world * gflop_img / 1e3 if hw == 224 else None},

@@ -483,14 +483,16 @@ struct PairCfg {
 #ifndef B2R_PAIR_BUFS
 #define B2R_PAIR_BUFS 2
 #endif
-    static constexpr int kStages = kPairN == 256 ? B2R_PAIR_STAGES : 6;
-    static constexpr int kBufs = B2R_PAIR_BUFS;
+    // N = 128 (experiment, B2R_PAIR128=1): two co-resident clusters per SM pair, 113 KB and 256 TMEM columns per CTA
+    static constexpr int kStages = kPairN == 256 ? B2R_PAIR_STAGES : 3;
+    static constexpr int kBufs = kPairN == 256 ? B2R_PAIR_BUFS : 1;
+    static constexpr int kCtasPerSm = kPairN == 256 ? 1 : 2;
     static constexpr int kStageBytes = kAStageBytes + (kPairN / 2) * 128;   // 16 KB of A + half a weight k-block per CTA
     static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBufs * (kStagingFull + kStagingPool) + kPairN * 4 + 256;
 };
 
 template <int kPairN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, PairCfg<kPairN>::kCtasPerSm)
 conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
     constexpr int kPairStages = PairCfg<kPairN>::kStages;
     constexpr int kPairStageBytes = PairCfg<kPairN>::kStageBytes;
@@ -1268,7 +1270,7 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
             if (brc) return brc;
         }
         const long pairs = ((long)P.tiles_w * P.tiles_h * P.tiles_n + 1) / 2 * P.n_tiles;
-        long clusters = d->max_ctas > 0 ? d->max_ctas / 2 : sms / 2;
+        long clusters = d->max_ctas > 0 ? d->max_ctas / 2 : (long)(sms / 2) * (block_n == 256 ? 1 : PairCfg<128>::kCtasPerSm);
         if (clusters < 1) clusters = 1;
         if (clusters > pairs) clusters = pairs;
         return block_n == 256 ? launch_pair<256>(P, (int)clusters, stream) : launch_pair<128>(P, (int)clusters, stream);
