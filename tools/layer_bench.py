@@ -26,6 +26,7 @@ LAYERS = [
     ("resunet.res1.c1  64->64   @224", 224, (64,), 64, "3x3", False),
     ("resunet.res1.c2  64->64+I @224 +pool", 224, (64,), 64, "3x3+sc", True),
     ("resunet.dec1.c1  128->64  @224 (cat)", 224, (64, 64), 64, "3x3", False),
+    ("resunet.dec1.c2  64->64+sc128+head @224", 224, (64,), 64, "3x3+sc128+head", False),
     ("resunet.up1      64->64   convT@112", 112, (64,), 64, "convT", False),
     ("resunet.dec2.c1  192->64  @112 (cat)", 112, (64, 128), 64, "3x3", False),
     ("vgg.conv2_1      64->128  @112", 112, (64,), 128, "3x3", False),
@@ -97,7 +98,7 @@ def main():
         if kind == "convT":
             w = torch.randn((ci, co, 2, 2), generator=g) * (1.0 / ci) ** 0.5
             wm, bias = packing.pack_convT2x2(w, torch.zeros(co))
-            kbl, mode, w3 = None, L.B2R_OUT_CONVT2X2, None
+            kbl, mode, w3, head = None, L.B2R_OUT_CONVT2X2, None, {}
             out = torch.empty((n, 2 * hw, 2 * hw, co), dtype=torch.bfloat16, device=dev)
             alg_k = ci
         else:
@@ -111,6 +112,15 @@ def main():
             if kind == "3x3+sc":
                 srcs = srcs + [srcs[0].clone()]
                 plan.add_1x1(len(srcs) - 1, torch.eye(co))
+            head = {}
+            if kind == "3x3+sc128+head":   # ResUNet dec1 second conv: 1x1 shortcut over cat(up1, skip) + fused 64 -> 3 head
+                wsc = torch.randn((co, 128), generator=g) * (1.0 / 128) ** 0.5
+                for j in range(2):
+                    srcs = srcs + [srcs[0].clone()]
+                    plan.add_1x1(len(srcs) - 1, wsc[:, 64 * j:64 * j + 64])
+                alg_k += 128
+                head = dict(head_w=(torch.randn((3, 64), generator=g) * 0.1).to(dev), head_b=torch.zeros(3, device=dev),
+                            head_out_u8=torch.empty((n, hw, hw, 3), dtype=torch.uint8, device=dev))
             wm, kbl = plan.finish()
             w3 = plan.finish_w3()
             bias, mode = torch.zeros(co), L.B2R_OUT_NHWC
@@ -121,7 +131,8 @@ def main():
         flops = 2.0 * n * hw * hw * wm.shape[0] * alg_k
 
         def run():
-            ops.conv_gemm(srcs, wm, bias, kbl, act=L.B2R_ACT_RELU, out=out, out_pool=pool, out_mode=mode, weights_w3=w3,
+            ops.conv_gemm(srcs, wm, bias, kbl, act=L.B2R_ACT_RELU, out=None if head else out, out_pool=pool, out_mode=mode,
+                          weights_w3=w3, **head,
                           block_n=args.block_n if args.block_n and co % args.block_n == 0 else 0,
                           tile=tuple(int(v) for v in args.tile.split(",")) if args.tile else (0, 0, 0), flags=args.flags)
 
