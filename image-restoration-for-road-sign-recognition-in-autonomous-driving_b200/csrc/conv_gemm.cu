@@ -1044,8 +1044,11 @@ static size_t plan_halo(const b2r_conv_gemm_desc* d, ConvGemmParams& P, int tw, 
     }
     using Cfg = HaloCfg<BLOCK_N>;
     const int a_bytes = (th + 2) * tw * 128;
-    int a_slots = 2;
-    if (const char* e = getenv("B2R_HALO_A_SLOTS")) a_slots = atoi(e);   // tuning knob for tools/layer_bench.py
+    static const int a_slots_env = [] {   // tuning knob for tools/layer_bench.py, read once
+        const char* e = getenv("B2R_HALO_A_SLOTS");
+        return e ? atoi(e) : 2;
+    }();
+    int a_slots = a_slots_env;
     long room = (long)Cfg::kMaxSmem - Cfg::kFixedBytes - (long)a_slots * a_bytes;
     int b_slots = (int)(room / Cfg::kBBytes);
     if (b_slots > kHaloMaxRing) b_slots = kHaloMaxRing;
@@ -1259,7 +1262,8 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
     int grid = d->max_ctas > 0 ? d->max_ctas : sms;
     if (grid > total_tiles) grid = (int)total_tiles;
 
-    const bool pair128 = block_n == 128 && getenv("B2R_PAIR128") != nullptr;   // experiment switch (tools/layer_bench.py)
+    static const bool pair128_env = getenv("B2R_PAIR128") != nullptr;   // experiment switch (tools/layer_bench.py), read once
+    const bool pair128 = block_n == 128 && pair128_env;
     if ((block_n == 256 || pair128) && d->out_mode == B2R_OUT_NHWC && !(d->flags & B2R_CONV_NO_PAIR) && sms >= 2 && total_tiles >= 2) {
         {   // each CTA of the pair loads half of a weight k-block: box 64 x block_n / 2
             const uint64_t K = (uint64_t)d->num_kblocks * 64;
