@@ -44,6 +44,10 @@ struct alignas(64) ConvW3Params {
     float slope;
     int act;
     int num_groups, num_ksteps, ring_slots;
+    int b_bytes;                     // shared memory of the weights region (resident blocks, or b_slots x 24 KB)
+    int stage_stride;                // bytes per staging buffer (two of them)
+    CUtensorMap b_map_c;             // box 64 x 64: the kw = 1 rows of a 1x1 k-step (compact resident layout)
+    uint32_t group_boff[kW3MaxGroups];   // resident mode: shared-memory offset of each group's weights, in 16-byte units
     int b_slots;                     // 0: weights resident (num_ksteps x 24 KB); > 0: weights streamed through this many slots
     int tiles_w, tiles_h, n_img;
     int store_full, store_pool;
@@ -56,7 +60,7 @@ struct alignas(64) ConvW3Params {
     uint32_t group[kW3MaxGroups];
 };
 
-size_t conv_w3_smem_bytes(int b_blocks, int ring_slots);
+size_t conv_w3_smem_bytes(size_t b_bytes, int ring_slots, size_t stage_stride);
 int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream);
 
 #ifdef __CUDACC__

@@ -882,15 +882,28 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
             return B2R_OK;
         }
     }
-    int ring = 4, b_slots = 0;
-    while (ring >= 2 && conv_w3_smem_bytes(nsteps, ring) > (size_t)kN64MaxSmem) --ring;
+    // shared-memory plan.  Resident weights: 24 KB per k-step of a 3x3 group, 8 KB (the kw = 1 rows) for a 1x1 group that is
+    // not the first group.  The head variant stages only its partial sums (6 KB per buffer), other layers a full + a pooled
+    // tile.  What is left goes to the input ring: two tiles' worth of slots lets the two MMA issuers really alternate
+    // (with one tile's worth the next tile's boxes cannot even be requested before this tile's MMAs retire).
+    const size_t stage_stride = d->head_w ? 6144 : (14336 + 4096);
+    uint32_t boff[kW3MaxGroups];
+    size_t b_bytes = 0;
+    for (int g = 0; g < ng; ++g) {
+        boff[g] = uint32_t(b_bytes >> 4);
+        const bool centre = (groups[g] >> 2) & 1;
+        b_bytes += centre ? (g > 0 ? 8192 : 24576) : 3 * 24576;
+    }
+    int ring = 2 * ng > kN64MaxRing ? kN64MaxRing : (2 * ng < 4 ? 4 : 2 * ng), b_slots = 0;
+    while (ring >= 2 && conv_w3_smem_bytes(b_bytes, ring, stage_stride) > (size_t)kN64MaxSmem) --ring;
     if (ring < 2) {
         // weights too large to stay resident (192 -> 64: 216 KB): stream the k-steps through a ring instead
         if (d->head_w) return B2R_OK;
         ring = 3;
         b_slots = kN64MaxRing;
-        while (b_slots >= 3 && conv_w3_smem_bytes(b_slots, ring) > (size_t)kN64MaxSmem) --b_slots;
+        while (b_slots >= 3 && conv_w3_smem_bytes((size_t)b_slots * 24576, ring, stage_stride) > (size_t)kN64MaxSmem) --b_slots;
         if (b_slots < 3) return B2R_OK;
+        b_bytes = (size_t)b_slots * 24576;
     }
 
     static thread_local ConvW3Params tp;
@@ -912,6 +925,9 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
         const uint64_t strides[1] = {K * 2};
         const uint32_t box[2] = {64, 192};
         int rc = encode_tmap_bf16(&P.b_map, d->weights_w3, 2, dims, strides, box);
+        if (rc) return rc;
+        const uint32_t box_c[2] = {64, 64};
+        rc = encode_tmap_bf16(&P.b_map_c, d->weights_w3, 2, dims, strides, box_c);
         if (rc) return rc;
     }
     const uint64_t OC = d->out_C;
@@ -950,6 +966,9 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
     P.num_ksteps = nsteps;
     P.ring_slots = ring;
     P.b_slots = b_slots;
+    P.b_bytes = (int)b_bytes;
+    P.stage_stride = (int)stage_stride;
+    memcpy(P.group_boff, boff, sizeof(uint32_t) * ng);
     P.tiles_w = ceil_div(d->W, 14);
     P.tiles_h = ceil_div(d->H, 8);
     P.n_img = d->N;

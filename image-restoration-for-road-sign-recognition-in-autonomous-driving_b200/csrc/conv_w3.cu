@@ -52,13 +52,13 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* b_res = smem;
-    const int b_blocks = p.b_slots > 0 ? p.b_slots : p.num_ksteps;   // resident weights, or a ring of weight k-steps
-    uint8_t* ring = b_res + b_blocks * kW3BStep;
+    uint8_t* ring = b_res + p.b_bytes;                             // resident weights, or a ring of weight k-steps
     uint8_t* sfull = ring + p.ring_slots * kW3Slot;                 // two (staging + pool) tile pairs, used by alternate tiles
-    float* bias_s = reinterpret_cast<float*>(sfull + 2 * (kW3Staging + kW3StagingPool));
+    float* bias_s = reinterpret_cast<float*>(sfull + 2 * p.stage_stride);
     float* head_s = bias_s + 64;                                   // [3][64] head weights + [3] head bias (+ pad)
     uint32_t* group_s = reinterpret_cast<uint32_t*>(head_s + 200);  // [kW3MaxGroups] group words (shared-memory copy)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(group_s + kW3MaxGroups);
+    uint32_t* gboff_s = group_s + kW3MaxGroups;                     // [kW3MaxGroups] weights offset of each group (16-byte units)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gboff_s + kW3MaxGroups);
     // "Data landed" barriers exist once per issuing warp: warp m only ever waits on full_bar[m][.], which the producer
     // arms for tiles of parity m, so it observes EVERY phase of the barriers it waits on.  (With one shared set, a
     // warp that skips the other warp's tile may skip a phase, and a parity wait cannot tell phase n from phase n - 2:
@@ -115,7 +115,10 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     if (threadIdx.x >= 64 && threadIdx.x < 128) bias_s[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
     if (kHead && threadIdx.x >= 128 && threadIdx.x < 128 + 195)
         head_s[threadIdx.x - 128] = threadIdx.x - 128 < 192 ? p.head_w[threadIdx.x - 128] : p.head_b[threadIdx.x - 128 - 192];
-    if (threadIdx.x >= 352 && threadIdx.x < 352 + kW3MaxGroups) group_s[threadIdx.x - 352] = p.group[threadIdx.x - 352];
+    if (threadIdx.x >= 352 && threadIdx.x < 352 + kW3MaxGroups) {
+        group_s[threadIdx.x - 352] = p.group[threadIdx.x - 352];
+        gboff_s[threadIdx.x - 352] = p.group_boff[threadIdx.x - 352];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -126,9 +129,20 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         if (lane == 0) {
             const bool stream_b = p.b_slots > 0;
             if (!stream_b) {
-                mbar_arrive_expect_tx(b_full_bar, uint32_t(p.num_ksteps) * kW3BStep);
-                for (int ks = 0; ks < p.num_ksteps; ++ks)
-                    tma_load_2d(b_res + ks * kW3BStep, &p.b_map, b_full_bar, ks * 64, 0);
+                // resident weights: 3x3 groups hold three 24 KB k-steps; a 1x1 group holds only the 64 kw = 1 rows of its
+                // k-step (8 KB) unless it is the first group (whose MMAs must initialise all 192 accumulator columns)
+                mbar_arrive_expect_tx(b_full_bar, uint32_t(p.b_bytes));
+                for (int g = 0; g < G; ++g) {
+                    const uint32_t e = p.group[g];
+                    const int ks0 = int(e >> 20);
+                    uint8_t* dst = b_res + size_t(p.group_boff[g]) * 16;
+                    if (((e >> 2) & 1) && g > 0) {
+                        tma_load_2d(dst, &p.b_map_c, b_full_bar, ks0 * 64, 64);
+                    } else {
+                        const int nk = ((e >> 2) & 1) ? 1 : 3;
+                        for (int k = 0; k < nk; ++k) tma_load_2d(dst + k * kW3BStep, &p.b_map, b_full_bar, (ks0 + k) * 64, 0);
+                    }
+                }
             }
             int stage = 0;
             uint32_t phase = 0;
@@ -240,7 +254,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 if (g == 0 && lane == 0) B2R_STAMP(iter, 7);
                 const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(kW3Slot >> 4);
                 if (!stream_b) {
-                    const uint32_t b_lo = b_lo0 + (e >> 20) * uint32_t(kW3BStep >> 4);
+                    const uint32_t b_lo = b_lo0 + gboff_s[g];
                     if (elect_one()) {
                         if (center && accum) {
                             // 1x1 k-step (ResidualBlock shortcut) on kernel row 1: A = buffer rows 16 .. 143.  Its kw = 0
@@ -249,8 +263,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                             // work and 75.6 instead of 96 cycles.  (Needs an initialised accumulator: accum != 0.)
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                umma_bf16_ss(tmem_d + 64u, desc_hi | uint64_t(a_lo + 128u + 2u * k),
-                                             desc_hi | uint64_t(b_lo + uint32_t((64 * 128) >> 4) + 2u * k), kIdesc64, 1u);
+                                umma_bf16_ss(tmem_d + 64u, desc_hi | uint64_t(a_lo + 128u + 2u * k), desc_hi | uint64_t(b_lo + 2u * k),
+                                             kIdesc64, 1u);   // compact block = the kw = 1 rows
                         } else if (center) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -322,7 +336,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             int iter = 0;
             for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter, tw.next(p.tiles_w, p.tiles_h)) {
                 const int buf = iter & 1;
-                uint8_t* sfull_b = sfull + buf * (kW3Staging + kW3StagingPool);
+                uint8_t* sfull_b = sfull + buf * p.stage_stride;
                 mbar_wait(&staged_bar[buf], (uint32_t(iter) >> 1) & 1u);
 #ifndef B2R_EXP_NO_STAGE
                 const int w0 = tw.tw * 14, h0 = tw.th * 8;
@@ -386,7 +400,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
             if (etid == 0) B2R_STAMP(iter, 4);
-            uint8_t* sfull_b = sfull + acc * (kW3Staging + kW3StagingPool);
+            uint8_t* sfull_b = sfull + acc * p.stage_stride;
             uint8_t* spool_b = sfull_b + kW3Staging;
 #ifndef B2R_EXP_NO_STAGE
             float x[16];
@@ -506,8 +520,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     }
 }
 
-size_t conv_w3_smem_bytes(int b_blocks, int ring_slots) {
-    return 1024 + size_t(b_blocks) * kW3BStep + size_t(ring_slots) * kW3Slot + 2 * (kW3Staging + kW3StagingPool) + 256 + 800 + 640;
+size_t conv_w3_smem_bytes(size_t b_bytes, int ring_slots, size_t stage_stride) {
+    return 1024 + b_bytes + size_t(ring_slots) * kW3Slot + 2 * stage_stride + 256 + 800 + 768;
 }
 
 int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream) {
@@ -519,7 +533,7 @@ int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream) {
         B2R_CUDA(cudaFuncSetAttribute(conv_w3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
         if (dev < 64) attr_set[dev] = true;
     }
-    const size_t smem = conv_w3_smem_bytes(p.b_slots > 0 ? p.b_slots : p.num_ksteps, p.ring_slots);
+    const size_t smem = conv_w3_smem_bytes(size_t(p.b_bytes), p.ring_slots, size_t(p.stage_stride));
     if (p.head_w != nullptr)
         conv_w3_kernel<true><<<grid, kW3Threads, smem, stream>>>(p);
     else
