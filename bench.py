@@ -375,7 +375,7 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convs (conv_gemm_kernel<N>, conv_w3_kernel, conv_n64_kernel)",
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convs (conv_gemm_pair_kernel<256> cta_group::2, conv_w3_kernel, conv_gemm_halo_kernel<128>, conv_gemm_kernel<N>)",
                      "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
                      "peak_source": peak_src, "traffic": traffic,
                      "traffic_note": "dram__bytes_read+write per launch averaged over all tcgen05 conv launches of one "
