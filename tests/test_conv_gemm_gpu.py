@@ -433,3 +433,47 @@ def test_pair_mode_equals_single_cta_mode(n, h, w, ci, co, pool):
     assert torch.equal(outs[0][0], outs[1][0]), "pair and single-CTA modes disagree"
     if pool:
         assert torch.equal(outs[0][1], outs[1][1])
+
+
+def test_pair_and_halo_modes_random_shapes():
+    """Seeded sweep over batch / size / channel splits / pooling / shortcuts for the C_out = 128 (halo mode) and
+    C_out = 256, 512 (cta_group::2 pair mode) kernels: bit-identical to the per-tap single-CTA kernel, NaN guards intact."""
+    ops, packing, L = _ops()
+    g = torch.Generator().manual_seed(4321)
+    ri = lambda lo, hi: int(torch.randint(lo, hi, (1,), generator=g))   # noqa: E731
+    for case in range(12):
+        co = (128, 256, 512)[ri(0, 3)]
+        n, h, w = ri(1, 6), 2 * ri(2, 30), 2 * ri(2, 30)
+        splits = [(64,), (128,), (64, 64), (128, 64), (256,)][ri(0, 5)]
+        pool = bool(ri(0, 2))
+        shortcut = bool(ri(0, 2))
+        srcs = [nhwc_bf16(rnd(n, c, h, w, seed=800 + 11 * case + i)) for i, c in enumerate(splits)]
+        ci = sum(splits)
+        wt = rnd(co, ci, 3, 3, scale=(2.0 / (9 * ci)) ** 0.5, seed=900 + case)
+        b = rnd(co, scale=0.1, seed=950 + case)
+        plan = packing.KPlan(co)
+        off = 0
+        for s, c in enumerate(splits):
+            plan.add_conv3x3(s, wt[:, off:off + c])
+            off += c
+        all_srcs = list(srcs)
+        if shortcut:
+            xs = nhwc_bf16(rnd(n, 64, h, w, seed=990 + case))
+            plan.add_1x1(len(all_srcs), rnd(co, 64, 1, 1, scale=0.1, seed=995 + case))
+            all_srcs.append(xs)
+        wm, kbl = plan.finish()
+        wm = wm.cuda()
+        res = []
+        for flags in (0, L.B2R_CONV_NO_HALO | L.B2R_CONV_NO_PAIR):
+            out = torch.full((n + 2, h, w, co), float("nan"), dtype=torch.bfloat16, device="cuda")
+            pl = torch.full((n + 2, h // 2, w // 2, co), float("nan"), dtype=torch.bfloat16, device="cuda")
+            ops.conv_gemm(all_srcs, wm, b, kbl, act=L.B2R_ACT_PRELU, slope=0.2, out=out[1:n + 1],
+                          out_pool=pl[1:n + 1] if pool else None, flags=flags)
+            torch.cuda.synchronize()
+            assert bool(torch.isnan(out[0]).all()) and bool(torch.isnan(out[n + 1]).all()), (case, "OOB store")
+            assert bool(torch.isnan(pl[0]).all()) and bool(torch.isnan(pl[n + 1]).all()), (case, "OOB pool store")
+            assert not bool(torch.isnan(out[1:n + 1]).any()), (case, "unwritten output")
+            res.append((out[1:n + 1].clone(), pl[1:n + 1].clone()))
+        assert torch.equal(res[0][0], res[1][0]), (case, co, n, h, w, splits, pool, shortcut)
+        if pool:
+            assert torch.equal(res[0][1], res[1][1]), (case, "pool")
