@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
     extern __shared__ __align__(16) float s_planes[];  // [3][srows][pitch], columns de-interleaved by 4
     __shared__ float s_taps[B2R_MAX_BLUR][B2R_MAX_BLUR + 5];  // zero padded: rows are walked in steps of 4 taps
     __shared__ float s_unit[256];
-    __shared__ int s_seg[B2R_MAX_BLUR][2];  // per kernel row: first non-zero tap / number of 4-tap steps (0: empty row)
+    __shared__ int s_seg[B2R_MAX_BLUR][2];  // per kernel row: first non-zero tap / number of taps up to the last non-zero one (0: empty row)
 
     const int n = blockIdx.y;
     const int r0 = blockIdx.x * kDegRows;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
                 last = k;
             }
         s_seg[tid][0] = first;
-        s_seg[tid][1] = last < first ? 0 : (last - first + 4) >> 2;
+        s_seg[tid][1] = last < first ? 0 : last - first + 1;   // taps from the first to the last non-zero one
     }
 
     // halo of THIS kernel: cv2 anchor = d/2, so taps reach a pixels up/left and d-1-a pixels down/right
@@ -318,11 +318,17 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
             acc[c][3] = fmaf(k, D_[c], acc[c][3]);                       \
         }                                                                \
     }
-            for (int s4 = 0; s4 < steps; ++s4) {
+            // exactly the taps first..last of this kernel row (a motion-blur kernel has one or two per row); the window
+            // registers rotate, so the loop is unrolled by four with uniform early exits
+            for (int rem = steps;;) {
                 B2R_DEG_STEP(w0, w1, w2, w3)
+                if (--rem == 0) break;
                 B2R_DEG_STEP(w1, w2, w3, w0)
+                if (--rem == 0) break;
                 B2R_DEG_STEP(w2, w3, w0, w1)
+                if (--rem == 0) break;
                 B2R_DEG_STEP(w3, w0, w1, w2)
+                if (--rem == 0) break;
             }
 #undef B2R_DEG_STEP
         }
