@@ -71,11 +71,35 @@ struct GemmCfg {
                                       BLOCK_N * 4 /*bias*/ + 256 /*barriers + tmem ptr*/;
 };
 
-// Epilogue role shared by the generic and the halo kernel: warps 2..5, TMEM -> registers -> bias / activation -> bf16 ->
-// swizzled staging -> TMA store (+ fused 2x2 max-pool).  BUFS = number of (staging + pool) buffers.
-template <int BLOCK_N, int BUFS>
+// Which tiles a CTA's epilogue walks, and where it hands the accumulator stage back.
+struct SchedSingle {   // one CTA per tile, round-robin over the grid
+    __device__ static int first() { return blockIdx.x; }
+    __device__ static int stride() { return gridDim.x; }
+    __device__ static void decode(const ConvGemmParams& p, int unit, int* n_tile, int* m, bool* valid) {
+        *n_tile = unit % p.n_tiles;
+        *m = unit / p.n_tiles;
+        *valid = true;
+    }
+    __device__ static void release(uint64_t* bar) { mbar_arrive(bar); }
+};
+struct SchedPair {     // cta_group::2: a cluster walks PAIRS of pixel tiles, rank r takes tile 2 * pair + r of the same n-tile
+    __device__ static int first() { return blockIdx.x >> 1; }
+    __device__ static int stride() { return gridDim.x >> 1; }
+    __device__ static void decode(const ConvGemmParams& p, int unit, int* n_tile, int* m, bool* valid) {
+        const int num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+        *n_tile = unit % p.n_tiles;
+        *m = 2 * (unit / p.n_tiles) + int(cluster_ctarank());
+        *valid = *m < num_m_tiles;   // odd tile count: the last pair's second CTA computes a duplicate and stores nothing
+    }
+    __device__ static void release(uint64_t* bar) { mbar_arrive_leader(bar); }   // the leader's barrier, from either CTA
+};
+
+// Epilogue role shared by the generic, halo and pair kernels: warps 2..5, TMEM -> registers -> bias / activation -> bf16
+// -> swizzled staging -> TMA store (+ fused 2x2 max-pool).  BUFS = number of (staging + pool) buffers; `total_units` =
+// tiles (SchedSingle) or tile pairs (SchedPair).
+template <int BLOCK_N, int BUFS, class Sched = SchedSingle>
 __device__ __forceinline__ void conv_epilogue_role(const ConvGemmParams& p, uint32_t tmem_base, uint8_t* staging, float* bias_s,
-                                                   uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, int total_tiles,
+                                                   uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, int total_units,
                                                    int warp_idx, int lane) {
         const int quarter = warp_idx & 3;          // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;       // tile row (pixel) == TMEM lane
@@ -85,9 +109,10 @@ __device__ __forceinline__ void conv_epilogue_role(const ConvGemmParams& p, uint
         uint32_t acc_phase = 0;
         uint32_t chunk_counter = 0;
         const int tw = p.tile_w, th = p.tile_h;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n_tile = tile % p.n_tiles;
-            const int m = tile / p.n_tiles;
+        for (int unit = Sched::first(); unit < total_units; unit += Sched::stride()) {
+            int n_tile, m;
+            bool valid_tile;
+            Sched::decode(p, unit, &n_tile, &m, &valid_tile);
             const int w0 = (m % p.tiles_w) * p.tile_w;
             const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.tile_h;
             const int n0 = (m / (p.tiles_w * p.tiles_h)) * p.tile_n;
@@ -126,7 +151,7 @@ __device__ __forceinline__ void conv_epilogue_role(const ConvGemmParams& p, uint
                     // all of this warp's TMEM reads of the accumulator are done -> hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                    if (lane == 0) Sched::release(&tmem_empty_bar[acc]);
                 }
                 fence_proxy_async_smem();
                 named_barrier_sync(1, kEpiThreads);
@@ -137,7 +162,7 @@ __device__ __forceinline__ void conv_epilogue_role(const ConvGemmParams& p, uint
                     named_barrier_sync(1, kEpiThreads);
                 }
 
-                if (epi_tid == 0) {
+                if (epi_tid == 0 && valid_tile) {
                     if (p.store_full) tma_store_4d(&p.out_map[out_idx], sfull, ch_in_out, w0, h0, n0);
                     if (p.store_pool) tma_store_4d(&p.pool_map, spool, ch_in_out, w0 >> 1, h0 >> 1, n0);
                     tma_store_commit();
@@ -614,66 +639,8 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
         }
     } else {
         // ===================================== epilogue (both CTAs, own tile) =====================================
-        const int quarter = warp_idx & 3;
-        const int row = quarter * 32 + lane;
-        const int epi_tid = row;
-        const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        uint32_t chunk_counter = 0;
-        const int tw = p.tile_w, th = p.tile_h;
-        for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
-            const int n_tile = pair % p.n_tiles;
-            const int m = 2 * (pair / p.n_tiles) + int(rank);
-            const bool valid_tile = m < num_m_tiles;
-            const int w0 = (m % p.tiles_w) * p.tile_w;
-            const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.tile_h;
-            const int n0 = (m / (p.tiles_w * p.tiles_h)) * p.tile_n;
-            for (int i = epi_tid; i < kPairN; i += kEpiThreads) bias_s[i] = p.bias[n_tile * kPairN + i];
-            mbar_wait_warp(&tmem_full_bar[acc], acc_phase);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < kPairN / 64; ++c) {
-                const int buf = kBufs == 2 ? int(chunk_counter & 1) : 0;
-                ++chunk_counter;
-                uint8_t* sfull = staging + buf * (kStagingFull + kStagingPool);
-                uint8_t* spool = sfull + kStagingFull;
-                if (epi_tid == 0) {
-                    if (kBufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
-                }
-                named_barrier_sync(1, kEpiThreads);
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + lane_base + uint32_t(acc * kPairN + c * 64 + half * 32), v);
-                    tmem_ld_wait();
-                    float b32[32];
-                    lds_bias32(bias_s + c * 64 + half * 32, b32);
-                    epilogue_store_half(v, b32, p.act, p.slope, sfull, row, half);
-                }
-                if (c == kPairN / 64 - 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);   // the leader's barrier, from either CTA
-                }
-                fence_proxy_async_smem();
-                named_barrier_sync(1, kEpiThreads);
-                if (p.store_pool) {
-                    epilogue_pool_chunk(sfull, spool, epi_tid, tw, th);
-                    fence_proxy_async_smem();
-                    named_barrier_sync(1, kEpiThreads);
-                }
-                if (epi_tid == 0 && valid_tile) {
-                    const int ch0 = n_tile * kPairN + c * 64;
-                    if (p.store_full) tma_store_4d(&p.out_map[0], sfull, ch0, w0, h0, n0);
-                    if (p.store_pool) tma_store_4d(&p.pool_map, spool, ch0, w0 >> 1, h0 >> 1, n0);
-                    tma_store_commit();
-                }
-            }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
-        }
-        if (epi_tid == 0) tma_store_wait_all<0>();
+        conv_epilogue_role<kPairN, kBufs, SchedPair>(p, tmem_base, staging, bias_s, tmem_full_bar, tmem_empty_bar, total_pairs,
+                                                     warp_idx, lane);
     }
 
     tc_fence_before();
