@@ -23,8 +23,12 @@
 // Noise: one Philox4x32-10 call per pixel keyed by (seed; pixel index, global image index) -> Box-Muller with the
 // hardware log2/sin/cos units -> three normals; fp32 chain.  When the caller injects the reference's own noise tensor
 // (parity path) the add is done in float64 exactly as NumPy promotes it.
+// Point-wise recipes (no image of the batch blurs or gets noise: fog alone, the fog half of BASELINE config 2) take
+// degrade_pointwise_kernel instead: chain() then depends on the byte value only, so every CTA evaluates it for the 256
+// possible inputs of its image and the image streams through that table at the HBM rate (16-byte loads / stores).
 #include "b2r_internal.h"
 #include "philox.cuh"
+#include "stream_u8.cuh"
 
 namespace b2r {
 
@@ -363,6 +367,33 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
     }
 }
 
+// ksize == NULL and sigma == NULL: out = table_n[in], table_n[v] = chain(v) with image n's fog parameters.
+__global__ void __launch_bounds__(kGenThreads) degrade_pointwise_kernel(const DegradeParams P) {
+    __shared__ float s_unit[256];
+    __shared__ uint8_t s_lut[256];
+    const int n = blockIdx.y;
+    const int tid = threadIdx.x;   // kGenThreads == 256: one table entry per thread
+    ImgParams ip;
+    ip.fog_on = P.fog_on ? P.fog_on[n] : 0;
+    ip.t = ip.fog_on ? P.fog_t[n] : 1.f;
+    ip.add = ip.fog_on ? P.fog_add[n] : 0.f;
+    ip.sigma = 0.f;
+    ip.noise_on = 0;
+    ip.clip_after = (P.flags & B2R_DEG_CLIP_AFTER_NOISE) != 0;
+    ip.seed = 0;
+    ip.image = 0;
+    ip.noise = nullptr;
+    s_unit[tid] = __fdiv_rn(float(tid), 255.0f);
+    __syncthreads();
+    const int v[3] = {tid, tid, tid};
+    int q[3];
+    chain3(ip, s_unit, 0u, v, q);
+    s_lut[tid] = uint8_t(q[0]);
+    __syncthreads();
+    const long elems = long(P.H) * P.W * 3;
+    apply_table(s_lut, P.in + long(n) * elems, P.out + long(n) * elems, elems);
+}
+
 static size_t degrade_smem_bytes(int W) {
     return size_t(3) * (kDegRows + B2R_MAX_BLUR - 1) * degrade_quarter(W) * 4 * sizeof(float);
 }
@@ -409,6 +440,15 @@ extern "C" int b2r_degrade(const uint8_t* in, uint8_t* out, int N, int H, int W,
     P.W = W;
     P.order = order;
     P.flags = flags;
+    if (!ksize && !sigma) {
+        static_assert(kGenThreads == 256, "one table entry per thread");
+        dim3 pgrid;
+        const int rc = gen_grid(long(H) * W * 3, N, &pgrid, kGenBytesPerThread);
+        if (rc) return rc;
+        degrade_pointwise_kernel<<<pgrid, kGenThreads, 0, stream>>>(P);
+        B2R_CHECK_LAUNCH();
+        return B2R_OK;
+    }
     dim3 grid((H + kDegRows - 1) / kDegRows, N);
     degrade_kernel<<<grid, kDegThreads, smem, stream>>>(P);
     B2R_CHECK_LAUNCH();

@@ -1,0 +1,44 @@
+// Streaming u8 -> u8 kernels (csrc/generators.cu, the point-wise path of csrc/degrade.cu): launch shape and the
+// table walk they share.  Bound by HBM: algorithmic bytes = elems x (1 read + 1 written) per image.
+#pragma once
+#include "b2r_internal.h"
+
+namespace b2r {
+
+constexpr int kGenThreads = 256;
+constexpr int kGenBytesPerThread = 16;
+
+// dst[i] = s_lut[src[i]] for one image: 16 bytes per thread and step when both pointers are 16-byte aligned
+__device__ __forceinline__ void apply_table(const uint8_t* s_lut, const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                            long elems) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    for (long i = ((long)blockIdx.x * kGenThreads + threadIdx.x) * kGenBytesPerThread; i < elems;
+         i += (long)gridDim.x * kGenThreads * kGenBytesPerThread) {
+        if (vec && i + kGenBytesPerThread <= elems) {
+            uint4 v = *reinterpret_cast<const uint4*>(src + i);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                w[k] = uint32_t(s_lut[w[k] & 0xFF]) | uint32_t(s_lut[(w[k] >> 8) & 0xFF]) << 8 |
+                       uint32_t(s_lut[(w[k] >> 16) & 0xFF]) << 16 | uint32_t(s_lut[w[k] >> 24]) << 24;
+            *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (long j = i; j < elems && j < i + kGenBytesPerThread; ++j) dst[j] = s_lut[src[j]];
+        }
+    }
+}
+
+static inline int gen_grid(long elems, int N, dim3* grid, int bytes_per_thread) {
+    long blocks = (elems + (long)kGenThreads * bytes_per_thread - 1) / ((long)kGenThreads * bytes_per_thread);
+    if (blocks < 1) blocks = 1;
+    // enough blocks per image to fill the GPU even for N = 1, without a tail of tiny blocks
+    int sms = 0;
+    int rc = device_sm_count(&sms);
+    if (rc) return rc;
+    const long cap = (8L * sms + N - 1) / N > 1 ? (8L * sms + N - 1) / N : 1;
+    if (blocks > cap) blocks = cap;
+    *grid = dim3((unsigned)blocks, (unsigned)N, 1);
+    return B2R_OK;
+}
+
+}  // namespace b2r

@@ -135,7 +135,8 @@ class DegradeParams:
     def to(self, device) -> "DeviceDegradeParams":
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
         return DeviceDegradeParams(self.n, self.order, self.flags, t(self.ksize), t(self.taps), t(self.fog_on),
-                                   t(self.fog_t), t(self.fog_add), t(self.sigma), bool((self.ksize > 1).any()))
+                                   t(self.fog_t), t(self.fog_add), t(self.sigma), bool((self.ksize > 1).any()),
+                                   bool((self.sigma > 0).any()))
 
 
 @dataclass
@@ -150,6 +151,7 @@ class DeviceDegradeParams:
     fog_add: torch.Tensor
     sigma: torch.Tensor
     any_blur: bool
+    any_noise: bool = True    # False: no image gets noise -> sigma is not passed (point-wise kernel when nothing blurs either)
 
 
 def compound_params(n: int) -> DegradeParams:
@@ -227,5 +229,5 @@ def degrade(images_u8_nhwc: torch.Tensor, params, seed: int = 0, image_index0: i
         raise L.B2RError(f"params describe {params.n} images, batch has {images_u8_nhwc.shape[0]}")
     return ops.degrade(images_u8_nhwc, params.ksize if params.any_blur else None,
                        params.taps if params.any_blur else None, params.fog_on, params.fog_t, params.fog_add,
-                       params.sigma, noise=noise, seed=seed, image_index0=image_index0, order=params.order,
+                       params.sigma if (params.any_noise or noise is not None) else None, noise=noise, seed=seed, image_index0=image_index0, order=params.order,
                        flags=params.flags, out=out)

@@ -8,6 +8,7 @@ reference's exact arithmetic.
   add_blur / add_fog / add_noise         13_pipeline_stress_test.py:33-56   stress_add_blur / stress_add_fog / stress_add_noise
   cascade Noise -> Fog -> Blur           13_pipeline_stress_test.py:27,175-189   CascadeRestorer
   psnr_metric(clean, out, data_range=255)  08_run_inference.py:118-129   psnr(clean, out)
+  ssim_metric(clean, out, data_range=255, channel_axis=2)  08:123        ssim(clean, out)
 
 Images are uint8 [N, H, W, 3] CUDA tensors (the reference's HWC arrays, batched).  Host code here only prepares
 per-image scalars and 256-entry tables; every pixel is touched by libb2r.so kernels (csrc/generators.cu, degrade.cu).
@@ -132,7 +133,7 @@ def stress_distort(images: torch.Tensor, noise: Optional[torch.Tensor] = None, s
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# PSNR
+# PSNR / SSIM
 # ---------------------------------------------------------------------------------------------------------------------
 def psnr(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """skimage.metrics.peak_signal_noise_ratio(a, b, data_range=255) per image of two u8 batches (08:118-129):
@@ -140,6 +141,13 @@ def psnr(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     sse = ops.sse_u8(a, b).to(torch.float64)
     mse = sse / float(a[0].numel())
     return 10.0 * torch.log10((255.0 ** 2) / mse)
+
+
+def ssim(a: torch.Tensor, b: torch.Tensor, data_range: float = 255.0) -> torch.Tensor:
+    """skimage.metrics.structural_similarity(a, b, data_range=255, channel_axis=2) per image of two u8 [N, H, W, 3]
+    batches (08:123): skimage's defaults (7x7 uniform window, sample covariance, K1 = .01, K2 = .03, float64, border
+    of 3 cropped, mean over channels).  f64 [N]; images smaller than the window raise, as skimage does."""
+    return ops.ssim_u8(a, b, data_range)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -412,6 +412,19 @@ def sse_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return sse
 
 
+def ssim_u8(a: torch.Tensor, b: torch.Tensor, data_range: float = 255.0) -> torch.Tensor:
+    """Per-image mean SSIM of two u8 [N, H, W, C] batches (skimage defaults, see b2r_ssim_u8), f64 [N]."""
+    _chk(a, torch.uint8, "a", 4)
+    _chk(b, torch.uint8, "b", 4)
+    if b.shape != a.shape:
+        raise L.B2RError("a and b differ in shape")
+    n, h, w, c = (int(v) for v in a.shape)
+    out = torch.empty((n,), dtype=torch.float64, device=a.device)
+    L.check(L.load().b2r_ssim_u8(a.data_ptr(), b.data_ptr(), out.data_ptr(), n, h, w, c, float(data_range), _stream()))
+    STATS["launches"] += 1
+    return out
+
+
 def mean_bf16(x: torch.Tensor, outer: int, reduce: int, inner: int) -> torch.Tensor:
     """Mean over the middle axis of a bf16 tensor viewed as [outer][reduce][inner] -> f32 [outer, inner]."""
     _chk(x, torch.bfloat16, "x")

@@ -138,4 +138,4 @@ def _slice_params(p: "D.DeviceDegradeParams", s: int, c: int) -> "D.DeviceDegrad
     if s == 0 and c == p.n:
         return p
     return D.DeviceDegradeParams(c, p.order, p.flags, p.ksize[s:s + c], p.taps[s:s + c], p.fog_on[s:s + c],
-                                 p.fog_t[s:s + c], p.fog_add[s:s + c], p.sigma[s:s + c], p.any_blur)
+                                 p.fog_t[s:s + c], p.fog_add[s:s + c], p.sigma[s:s + c], p.any_blur, p.any_noise)

@@ -265,6 +265,13 @@ int b2r_mean_bf16(const void* in_bf16, float* out, int64_t outer, int reduce, in
  * reports skimage's peak_signal_noise_ratio on the u8 images). */
 int b2r_sse_u8(const uint8_t* a, const uint8_t* b, uint64_t* sse, int N, int64_t elems_per_image, void* stream);
 
+/* ssim[n] = skimage.metrics.structural_similarity(a[n], b[n], data_range=data_range, channel_axis=2) for u8 HWC images
+ * [N][H][W][C] (08_run_inference.py:123): 7x7 uniform window, sample covariance, K1 = 0.01, K2 = 0.03, float64, the
+ * 3-pixel border cropped, mean over pixels and channels.  Window sums are exact integers; deterministic.
+ * H, W >= 7 (skimage raises ValueError below that). */
+int b2r_ssim_u8(const uint8_t* a, const uint8_t* b, double* ssim, int N, int H, int W, int C, double data_range,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

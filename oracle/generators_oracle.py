@@ -104,3 +104,38 @@ def psnr_08(a_u8: np.ndarray, b_u8: np.ndarray) -> float:
     not installed here; its published definition: 10 log10(data_range^2 / mean((a - b)^2)) in float64)."""
     err = np.mean((a_u8.astype(np.float64) - b_u8.astype(np.float64)) ** 2)
     return float(10 * np.log10((255.0 ** 2) / err)) if err > 0 else float("inf")
+
+
+def ssim_08(a_u8: np.ndarray, b_u8: np.ndarray, data_range: float = 255.0, win_size: int = 7, K1: float = 0.01,
+            K2: float = 0.03) -> float:
+    """skimage.metrics.structural_similarity(a, b, data_range=255, channel_axis=2) as 08_run_inference.py:123 calls it.
+
+    PARITY UNPINNED BY EXECUTION: scikit-image is not installed in this image and the reference pins no version, so
+    this restates its published algorithm (skimage/metrics/_structural_similarity.py, unchanged since 0.19) with the
+    same scipy.ndimage.uniform_filter calls it makes: per channel, float64 (uint8 input), uniform 7x7 window (mode
+    'reflect'), sample covariance NP / (NP - 1), C1 = (K1 R)^2, C2 = (K2 R)^2, S = (2 ux uy + C1)(2 vxy + C2) /
+    ((ux^2 + uy^2 + C1)(vx + vy + C2)), mean of S with a border of (win_size - 1) // 2 cropped, then the mean over
+    channels.  tests/test_oracle_generators.py cross-checks it against an exact integer-window evaluation."""
+    from scipy.ndimage import uniform_filter
+    if min(a_u8.shape[0], a_u8.shape[1]) < win_size:
+        raise ValueError("win_size exceeds image extent")
+    NP = win_size ** 2
+    cov_norm = NP / (NP - 1)
+    C1, C2 = (K1 * data_range) ** 2, (K2 * data_range) ** 2
+    pad = (win_size - 1) // 2
+    per_channel = []
+    for ch in range(a_u8.shape[2]):
+        im1 = a_u8[..., ch].astype(np.float64)
+        im2 = b_u8[..., ch].astype(np.float64)
+        ux = uniform_filter(im1, size=win_size)
+        uy = uniform_filter(im2, size=win_size)
+        uxx = uniform_filter(im1 * im1, size=win_size)
+        uyy = uniform_filter(im2 * im2, size=win_size)
+        uxy = uniform_filter(im1 * im2, size=win_size)
+        vx = cov_norm * (uxx - ux * ux)
+        vy = cov_norm * (uyy - uy * uy)
+        vxy = cov_norm * (uxy - ux * uy)
+        A1, A2, B1, B2 = 2 * ux * uy + C1, 2 * vxy + C2, ux ** 2 + uy ** 2 + C1, vx + vy + C2
+        S = (A1 * A2) / (B1 * B2)
+        per_channel.append(S[pad:S.shape[0] - pad, pad:S.shape[1] - pad].mean(dtype=np.float64))
+    return float(np.mean(np.asarray(per_channel, dtype=np.float64)))

@@ -97,6 +97,42 @@ def test_against_oracle_full_size_mixed_batch():
             assert np.array_equal(out[i], ref), (order, i, d)
 
 
+def test_pointwise_path_equals_generic_kernel_and_numpy():
+    """No blur, no noise anywhere in the batch -> degrade_pointwise_kernel (per-image table at the HBM rate).  It must
+    return the bytes of the generic kernel (forced here by passing an all-zero sigma tensor) and of the reference's
+    float32 fog arithmetic (16_gen_compound_data.py:30-31,37), on aligned, ragged and 1-pixel shapes."""
+    from b200restore import degrade, ops
+    from oracle import degrade_oracle as O
+    rng = np.random.default_rng(11)
+    for (n, h, w) in ((5, 224, 224), (3, 37, 53), (2, 1, 1), (1, 7, 5), (4, 64, 80)):
+        imgs = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+        p = degrade.fog_params(n, np.random.default_rng(12))
+        p.fog_on[n - 1] = 0                                    # one image passes through untouched
+        for flags in (0, 1):
+            p.flags = flags
+            dp = p.to("cuda")
+            assert not dp.any_blur and not dp.any_noise
+            x = _dev(imgs)
+            fast = degrade.degrade(x, dp)
+            slow = ops.degrade(x, None, None, dp.fog_on, dp.fog_t, dp.fog_add, torch.zeros_like(dp.sigma), flags=flags)
+            assert torch.equal(fast, slow), (n, h, w, flags)
+            # an unaligned view (offset by one image row of 3*w bytes) must take the byte path and still agree
+            if h > 1:
+                sub = x[:, 1:].contiguous()
+                big = torch.empty(sub.numel() + 1, dtype=torch.uint8, device="cuda")
+                odd_in = big[1:].view(sub.shape)
+                odd_in.copy_(sub)
+                assert torch.equal(degrade.degrade(odd_in, dp), fast[:, 1:]), (n, h, w, "unaligned")
+            out = fast.cpu().numpy()
+            for i in range(n):
+                f = imgs[i].astype(np.float32) / 255.0
+                if p.fog_on[i]:
+                    f = f * np.float32(p.fog_t[i]) + np.float32(p.fog_add[i])
+                if flags:
+                    f = np.clip(f, 0, 1)
+                assert np.array_equal(out[i], O.quant_u8(f)), (n, h, w, i)
+
+
 def test_identity_when_nothing_is_applied():
     from b200restore import degrade
     imgs = torch.randint(0, 256, (3, 64, 80, 3), dtype=torch.uint8).cuda()

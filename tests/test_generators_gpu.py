@@ -127,6 +127,34 @@ def test_psnr_matches_definition():
     assert math.isinf(p[2])
 
 
+def test_ssim_matches_oracle():
+    """08:123 structural_similarity(clean, out, data_range=255, channel_axis=2): float64 against the oracle's restatement
+    of skimage's algorithm (tolerance 1e-10: scipy's two-pass float64 window means vs exact integer window sums),
+    exactly 1 for identical images, deterministic, ragged shapes incl. the 7x7 minimum and > 256 columns per row."""
+    from b200restore import generators as G, B2RError
+    from oracle import generators_oracle as GO
+    rng = np.random.default_rng(6)
+    for (n, h, w) in ((3, 224, 224), (2, 7, 7), (2, 9, 31), (1, 50, 130), (2, 33, 100)):
+        a = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+        b = np.clip(a.astype(int) + rng.integers(-25, 26, a.shape), 0, 255).astype(np.uint8)
+        b[n - 1] = a[n - 1]
+        s = G.ssim(_cu(a), _cu(b)).cpu().numpy()
+        assert s.dtype == np.float64
+        for i in range(n - 1):
+            assert s[i] == pytest.approx(GO.ssim_08(a[i], b[i]), abs=1e-10), (n, h, w, i)
+        assert s[n - 1] == 1.0
+        assert np.array_equal(s, G.ssim(_cu(a), _cu(b)).cpu().numpy())
+    # smooth "sign-like" content with mild distortion (the regime of restored images)
+    from b200restore import synth
+    img, _ = synth.sign_like_images(4, 224, 224, seed=3)
+    noisy = np.clip(img.numpy().astype(int) + rng.integers(-6, 7, img.shape), 0, 255).astype(np.uint8)
+    s = G.ssim(img.cuda(), _cu(noisy)).cpu().numpy()
+    for i in range(4):
+        assert s[i] == pytest.approx(GO.ssim_08(img[i].numpy(), noisy[i]), abs=1e-10)
+    with pytest.raises(B2RError):
+        G.ssim(_cu(a[:, :6]), _cu(b[:, :6]))
+
+
 def test_cascade_vs_oracle_and_judge_confidence():
     """13:175-189 with three seeded SimpleUNets: unclamped f32 hand-off, per-stage snapshots, VGG confidence.
     Tolerance: each stage is within PSNR >= 50 dB / max-abs 2e-2 of the fp32 oracle fed with the SAME input (the bar of

@@ -84,6 +84,51 @@ def test_psnr_definition():
 
 
 @pytest.mark.skipif(not have_reference(), reason="/root/reference not mounted")
+def _ssim_exact_windows(a, b, data_range=255.0):
+    """SSIM from EXACT integer window sums (the form csrc/ssim.cu evaluates): independent of scipy's float64 passes."""
+    h, w, c = a.shape
+    C1, C2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    total = 0.0
+    for ch in range(c):
+        x = a[..., ch].astype(np.int64)
+        y = b[..., ch].astype(np.int64)
+
+        def win(v):
+            cs = np.pad(v.cumsum(0).cumsum(1), ((1, 0), (1, 0)))
+            return cs[7:, 7:] - cs[:-7, 7:] - cs[7:, :-7] + cs[:-7, :-7]
+
+        sx, sy, sxx, syy, sxy = win(x), win(y), win(x * x), win(y * y), win(x * y)
+        a1 = (2 * sx * sy) / 2401.0 + C1
+        b1 = (sx * sx + sy * sy) / 2401.0 + C1
+        a2 = (2 * (49 * sxy - sx * sy)) / 2352.0 + C2
+        b2 = ((49 * sxx - sx * sx) + (49 * syy - sy * sy)) / 2352.0 + C2
+        total += float(((a1 * a2) / (b1 * b2)).mean())
+    return total / c
+
+
+def test_ssim_restatement_against_exact_integer_windows():
+    """08:123 (skimage is absent: parity unpinned by execution).  The scipy-based restatement of skimage's algorithm
+    must agree with an exact integer-window evaluation, give 1 for identical images, fall with distortion, be
+    symmetric, and reject images smaller than the window as skimage does."""
+    rng = np.random.default_rng(8)
+    for (h, w) in ((7, 7), (9, 31), (64, 48), (224, 224)):
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        b = np.clip(a.astype(int) + rng.integers(-20, 21, a.shape), 0, 255).astype(np.uint8)
+        s = GO.ssim_08(a, b)
+        assert s == pytest.approx(_ssim_exact_windows(a, b), abs=1e-11), (h, w)
+        assert GO.ssim_08(b, a) == pytest.approx(s, abs=1e-12)
+        assert GO.ssim_08(a, a) == 1.0
+        assert 0.0 < s < 1.0
+    smooth = np.repeat(np.repeat(rng.integers(0, 256, (8, 8, 3), dtype=np.uint8), 8, 0), 8, 1)
+    s_lo = GO.ssim_08(smooth, np.clip(smooth.astype(int) + rng.integers(-40, 41, smooth.shape), 0, 255).astype(np.uint8))
+    s_hi = GO.ssim_08(smooth, np.clip(smooth.astype(int) + rng.integers(-4, 5, smooth.shape), 0, 255).astype(np.uint8))
+    assert s_lo < s_hi < 1.0
+    assert GO.ssim_08(np.zeros((16, 16, 3), np.uint8), np.full((16, 16, 3), 255, np.uint8)) == pytest.approx(
+        6.5025 / (255.0 ** 2 + 6.5025), rel=1e-12)          # constant images: S = C1 / (255^2 + C1)
+    with pytest.raises(ValueError):
+        GO.ssim_08(np.zeros((6, 20, 3), np.uint8), np.zeros((6, 20, 3), np.uint8))
+
+
 def test_against_live_reference():
     r02, r03, r04 = load_ref("02_gen_noise.py"), load_ref("03_gen_blur.py"), load_ref("04_gen_fog.py")
     rng = np.random.default_rng(11)

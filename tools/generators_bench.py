@@ -35,6 +35,7 @@ def main():
         ("noise02 script-02 rule, Philox (two passes)", lambda: ops.noise02(img, sigma, seed=1, out=out), 2 * px),
         ("noise02 unit clip (13), Philox", lambda: ops.noise02(img, sigma, seed=1, out=out, clip_rule=1), 2 * px),
         ("sse_u8 (PSNR)", lambda: ops.sse_u8(img, other), 2 * px),
+        ("ssim_u8 (08:123, 7x7 windows, float64)", lambda: ops.ssim_u8(img, other), 2 * px),
         ("apply_motion_blur d=12 + stretch (03)", lambda: G.apply_motion_blur(img, 12, 45), 2 * px),
     ]
     res = []
