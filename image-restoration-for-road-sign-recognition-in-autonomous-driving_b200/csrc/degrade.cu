@@ -93,8 +93,10 @@ __device__ __forceinline__ void chain3(const ImgParams& ip, const float* unit, u
     for (int c = 0; c < 3; ++c) {
         float y = x[c];
         if (ip.clip_after) y = fminf(fmaxf(y, 0.f), 1.f);
-        y = fminf(fmaxf(__fmul_rn(y, 255.0f), 0.f), 255.f);
-        q[c] = int(y);
+        // np.clip(y * 255, 0, 255).astype(np.uint8): the saturating, truncating conversion does both (F2IP.U8.TRUNC)
+        uint32_t b;
+        asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(b) : "f"(__fmul_rn(y, 255.0f)));
+        q[c] = int(b);
     }
 }
 

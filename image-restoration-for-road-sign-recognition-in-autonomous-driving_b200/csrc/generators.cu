@@ -42,8 +42,24 @@ __global__ void __launch_bounds__(kGenThreads) minmax_u8_kernel(const uint8_t* _
     const uint8_t* src = in + (long)n * elems;
     const bool vec = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     uint32_t lo = 0xFFFFFFFFu, hi = 0u;   // four byte lanes each
-    for (long i = ((long)blockIdx.x * kGenThreads + threadIdx.x) * kGenBytesPerThread; i < elems;
-         i += (long)gridDim.x * kGenThreads * kGenBytesPerThread) {
+    const long step = (long)gridDim.x * kGenThreads * kGenBytesPerThread;
+    long i = ((long)blockIdx.x * kGenThreads + threadIdx.x) * kGenBytesPerThread;
+#if B2R_STREAM_UNROLL > 1
+    constexpr int kU = 2 * B2R_STREAM_UNROLL;   // a single read stream: twice the loads in flight of the copy kernels
+    if (vec) {
+        for (; i + (kU - 1) * step + kGenBytesPerThread <= elems; i += kU * step) {
+            uint4 v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) v[u] = __ldcs(reinterpret_cast<const uint4*>(src + i + u * step));
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                lo = __vminu4(__vminu4(lo, v[u].x), __vminu4(v[u].y, __vminu4(v[u].z, v[u].w)));
+                hi = __vmaxu4(__vmaxu4(hi, v[u].x), __vmaxu4(v[u].y, __vmaxu4(v[u].z, v[u].w)));
+            }
+        }
+    }
+#endif
+    for (; i < elems; i += step) {
         if (vec && i + kGenBytesPerThread <= elems) {
             const uint4 v = *reinterpret_cast<const uint4*>(src + i);
             lo = __vminu4(__vminu4(lo, v.x), __vminu4(v.y, __vminu4(v.z, v.w)));
@@ -123,6 +139,18 @@ __global__ void __launch_bounds__(kGenThreads) noise02_kernel(const uint8_t* __r
     if (PASS == 0 && __any_sync(0xffffffffu, any_neg) && (threadIdx.x & 31) == 0) atomicOr(&neg_flags[n], 1);
 }
 
+// sum of the sixteen squared byte differences of two 16-byte words
+__device__ __forceinline__ uint32_t sq_diff16(const uint4 va, const uint4 vb) {
+    const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t d = __vabsdiffu4(wa[k], wb[k]);
+        s = __dp4a(d, d, s);
+    }
+    return s;
+}
+
 __global__ void __launch_bounds__(kGenThreads) sse_u8_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
                                                               unsigned long long* __restrict__ sse, long elems) {
     const int n = blockIdx.y;
@@ -130,18 +158,27 @@ __global__ void __launch_bounds__(kGenThreads) sse_u8_kernel(const uint8_t* __re
     const uint8_t* pb = b + (long)n * elems;
     const bool vec = ((reinterpret_cast<uintptr_t>(pa) | reinterpret_cast<uintptr_t>(pb)) & 15) == 0;
     unsigned long long acc = 0;
-    for (long i = ((long)blockIdx.x * kGenThreads + threadIdx.x) * kGenBytesPerThread; i < elems;
-         i += (long)gridDim.x * kGenThreads * kGenBytesPerThread) {
-        if (vec && i + kGenBytesPerThread <= elems) {
-            const uint4 va = *reinterpret_cast<const uint4*>(pa + i), vb = *reinterpret_cast<const uint4*>(pb + i);
-            const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
-            uint32_t s = 0;
+    const long step = (long)gridDim.x * kGenThreads * kGenBytesPerThread;
+    long i = ((long)blockIdx.x * kGenThreads + threadIdx.x) * kGenBytesPerThread;
+#if B2R_STREAM_UNROLL > 1
+    if (vec) {
+        for (; i + (B2R_STREAM_UNROLL - 1) * step + kGenBytesPerThread <= elems; i += B2R_STREAM_UNROLL * step) {
+            uint4 va[B2R_STREAM_UNROLL], vb[B2R_STREAM_UNROLL];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t d = __vabsdiffu4(wa[k], wb[k]);
-                s = __dp4a(d, d, s);   // sum of the four squared byte differences
+            for (int u = 0; u < B2R_STREAM_UNROLL; ++u) {
+                va[u] = __ldcs(reinterpret_cast<const uint4*>(pa + i + u * step));
+                vb[u] = __ldcs(reinterpret_cast<const uint4*>(pb + i + u * step));
             }
+            uint32_t s = 0;   // <= 16 * 4 * 255^2 per trip: no overflow
+#pragma unroll
+            for (int u = 0; u < B2R_STREAM_UNROLL; ++u) s += sq_diff16(va[u], vb[u]);
             acc += s;
+        }
+    }
+#endif
+    for (; i < elems; i += step) {
+        if (vec && i + kGenBytesPerThread <= elems) {
+            acc += sq_diff16(*reinterpret_cast<const uint4*>(pa + i), *reinterpret_cast<const uint4*>(pb + i));
         } else {
             for (long j = i; j < elems && j < i + kGenBytesPerThread; ++j) {
                 const int d = int(pa[j]) - int(pb[j]);

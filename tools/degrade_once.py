@@ -1,3 +1,4 @@
+"""ncu target for the degradation kernels: python tools/degrade_once.py [compound | blur | fog]  (fog = the point-wise kernel)."""
 import sys
 from pathlib import Path
 import torch
@@ -8,7 +9,10 @@ n, hw = 256, 224
 dev = torch.device("cuda", 0)
 img = torch.randint(0, 256, (n, hw, hw, 3), dtype=torch.uint8, device=dev)
 out = torch.empty_like(img)
-p = (D.blur_params(n, 10, 45) if len(sys.argv) > 1 and sys.argv[1] == "blur" else D.compound_params(n)).to(dev)
+import numpy as np
+mode = sys.argv[1] if len(sys.argv) > 1 else "compound"
+p = {"blur": lambda: D.blur_params(n, 10, 45), "fog": lambda: D.fog_params(n, np.random.default_rng(1)),
+     "compound": lambda: D.compound_params(n)}[mode]().to(dev)
 for _ in range(3):
     D.degrade(img, p, seed=1, out=out)
 torch.cuda.synchronize()
