@@ -10,15 +10,18 @@
 // (u8 -> f32/255 -> *255 -> truncate is the identity on 0..255, so the reference's intermediate re-quantisations
 //  that are not listed here are no-ops; tests/test_oracle_degrade.py checks that claim.)
 //
-// Structure (v2).  One CTA = 16 image rows x full width of one image.
+// Structure (v3).  One CTA = 16 image rows x full width of one image.
 //   stage 1  the pre-blur image (raw input, or chain(input) for the scripts-14/15 order) is staged in shared memory
-//            as three PLANAR fp32 planes with exactly the halo this image's kernel needs (REFLECT_101), so the u8->f32
-//            conversion is paid once per staged pixel instead of once per tap;
-//   stage 2  a work item is 4 consecutive pixels x 3 channels (12 accumulators).  For every kernel row that has
-//            non-zero taps the item slides a 4-wide register window along the row: ONE shared-memory load per plane
-//            per tap feeds 12 FMAs.  Taps inside a row's [first, last] non-zero span are applied in order, zeros
-//            included: fma(0, x, acc) == acc, so the result is bit-identical to OpenCV's "non-zero taps, row-major"
-//            engine (degree <= 11; larger kernels go through OpenCV's DFT path, see tests/test_degrade_gpu.py);
+//            as three PLANAR, row-major fp32 planes with the halo of this image's kernel (REFLECT_101), so the u8->f32
+//            conversion is paid once per staged pixel instead of once per tap.  Image column x sits at staged column
+//            x + 8 (kStageShift), which keeps every 4-pixel group 16-byte aligned: one STS.128 per plane and group;
+//   stage 2  a work item is 4 consecutive pixels x 3 channels (12 accumulators).  The kernel row is held as a
+//            zero-padded tap array T[t] = k[t - (8 - anchor)], so that tap t of pixel x reads staged column x + t:
+//            groups of four taps start on 16-byte boundaries for every item.  Per group ONE LDS.128 per plane (the
+//            next four staged columns) and one LDS.128 of taps feed 48 FMAs with static register indices.  Only the
+//            groups between a row's first and last non-zero tap are walked; the zero taps inside are applied too:
+//            fma(0, x, acc) == acc, so the result is bit-identical to OpenCV's "non-zero taps, row-major" engine
+//            (degree <= 11; larger kernels go through OpenCV's DFT path, see tests/test_degrade_gpu.py);
 //   stage 3  round-half-even to u8, then chain() for the script-16 order, and one aligned 12-byte store per item.
 // Noise: one Philox4x32-10 call per pixel keyed by (seed; pixel index, global image index) -> Box-Muller with the
 // hardware log2/sin/cos units -> three normals; fp32 chain.  When the caller injects the reference's own noise tensor
@@ -100,24 +103,26 @@ __device__ __forceinline__ void chain3(const ImgParams& ip, const float* unit, u
     }
 }
 
-// Planar staging layout.  Work items own 4 consecutive pixels, so lane i of a warp reads staged column 4*i + m for a
-// warp-uniform offset m: with a plain row-major plane that is a 16-byte lane stride = 4-way bank conflict on every
-// load.  Columns are therefore de-interleaved by 4: column col lives at  (col & 3) * quarter + (col >> 2)  within its
-// row, which makes those loads unit-stride; `quarter` (= pitch / 4) is chosen = 8 (mod 32) so that the staging
-// writes (consecutive lanes = consecutive columns) are conflict-free as well.
-__device__ __forceinline__ int deint(int col, int quarter) { return (col & 3) * quarter + (col >> 2); }
+// Planar staging layout: plane c, staged row sy, staged column sc at  c * plane + sy * pitch + sc,  image column x at
+// sc = x + kStageShift.  Tap t of the shifted tap array (kTapSlots entries, groups of 4) reads column x + t, so the widest
+// read of an item at x0 (a multiple of 4) is x0 + kTapSlots + 3: pitch = roundup4(W) + kTapSlots keeps it inside the row.
+constexpr int kStageShift = 8;                       // >= the largest anchor (B2R_MAX_BLUR / 2 = 7), multiple of 4
+constexpr int kTapSlots = 24;                        // (kStageShift - anchor) + B2R_MAX_BLUR <= 7 + 15, rounded up to groups of 4
+constexpr int kTapGroups = kTapSlots / 4;
 
-static __host__ __device__ int degrade_quarter(int W) {
-    int q = (W + (B2R_MAX_BLUR - 1) + 8 + 3) / 4;   // staged columns + 8 columns of slack for the unrolled window
-    while ((q & 31) != 8) ++q;
-    return q;
+static __host__ __device__ int degrade_pitch(int W) { return ((W + 3) & ~3) + kTapSlots; }
+
+__device__ __forceinline__ int round_u8(float v) {   // cvRound + saturate_cast<uchar>: round half to even, clamp
+    uint32_t b;
+    asm("cvt.rni.u8.f32 %0, %1;" : "=r"(b) : "f"(v));
+    return int(b);
 }
 
 __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParams P) {
-    extern __shared__ __align__(16) float s_planes[];  // [3][srows][pitch], columns de-interleaved by 4
-    __shared__ float s_taps[B2R_MAX_BLUR][B2R_MAX_BLUR + 5];  // zero padded: rows are walked in steps of 4 taps
+    extern __shared__ __align__(16) float s_planes[];  // [3][srows][pitch], row-major
+    __shared__ __align__(16) float s_taps[B2R_MAX_BLUR][kTapSlots];  // shifted, zero-padded tap rows (see above)
     __shared__ float s_unit[256];
-    __shared__ int s_seg[B2R_MAX_BLUR][2];  // per kernel row: first non-zero tap / number of taps up to the last non-zero one (0: empty row)
+    __shared__ int s_seg[B2R_MAX_BLUR][2];  // per kernel row: first tap group with a non-zero tap / number of groups up to the last one (0: empty row)
 
     const int n = blockIdx.y;
     const int r0 = blockIdx.x * kDegRows;
@@ -192,9 +197,14 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
         return;
     }
 
-    for (int i = tid; i < B2R_MAX_BLUR * (B2R_MAX_BLUR + 5); i += kDegThreads) {
-        const int ky = i / (B2R_MAX_BLUR + 5), kx = i - ky * (B2R_MAX_BLUR + 5);
-        s_taps[ky][kx] = (ky < d && kx < d) ? P.taps[size_t(n) * (B2R_MAX_BLUR * B2R_MAX_BLUR) + ky * d + kx] : 0.f;
+    // halo of THIS kernel: cv2 anchor = d/2, so taps reach a pixels up/left and d-1-a pixels down/right
+    const int a = d / 2;
+    const int hb = d - 1 - a;
+    const int sh = kStageShift - a;   // tap kx of pixel x reads staged column x + kx + sh
+    for (int i = tid; i < B2R_MAX_BLUR * kTapSlots; i += kDegThreads) {
+        const int ky = i / kTapSlots, kx = i - ky * kTapSlots - sh;
+        s_taps[ky][i - ky * kTapSlots] =
+            (ky < d && kx >= 0 && kx < d) ? P.taps[size_t(n) * (B2R_MAX_BLUR * B2R_MAX_BLUR) + ky * d + kx] : 0.f;
     }
     if (tid < d) {
         const float* tr = P.taps + size_t(n) * (B2R_MAX_BLUR * B2R_MAX_BLUR) + tid * d;
@@ -204,23 +214,18 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
                 if (first == d) first = k;
                 last = k;
             }
-        s_seg[tid][0] = first;
-        s_seg[tid][1] = last < first ? 0 : last - first + 1;   // taps from the first to the last non-zero one
+        s_seg[tid][0] = (first + sh) >> 2;
+        s_seg[tid][1] = last < first ? 0 : ((last + sh) >> 2) - ((first + sh) >> 2) + 1;
     }
 
-    // halo of THIS kernel: cv2 anchor = d/2, so taps reach a pixels up/left and d-1-a pixels down/right
-    const int a = d / 2;
-    const int hb = d - 1 - a;
     const int srows = rows + a + hb;
-    const int quarter = degrade_quarter(W);
-    const int pitch = quarter * 4;
+    const int pitch = degrade_pitch(W);
     const int plane = srows * pitch;
     const bool chain_first = P.order == B2R_ORDER_FOG_NOISE_BLUR;
     __syncthreads();  // s_unit
 
-    const int scols = W + a + hb;
-    // (a) interior columns: items of 4 pixels = three aligned, coalesced 32-bit loads (the staging loop is where the
-    //     kernel meets HBM latency, so it is unrolled to keep several loads per thread in flight)
+    // (a) image columns: items of 4 pixels = three aligned, coalesced 32-bit loads and one 16-byte store per plane
+    //     (the staging loop is where the kernel meets HBM latency, so it is unrolled to keep several loads in flight)
 #pragma unroll 2
     for (int it = tid; it < srows * groups; it += kDegThreads) {
         const int sy = it / groups;
@@ -228,8 +233,9 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
         const int x0 = g << 2;
         const int h = reflect101(r0 - a + sy, H);
         const size_t off = (size_t(h) * W + x0) * 3;
+        const bool full = x0 + 4 <= W;
         uint32_t bytes[3] = {0u, 0u, 0u};
-        if (rows_aligned && x0 + 4 <= W) {
+        if (rows_aligned && full) {
             const uint32_t* s32 = reinterpret_cast<const uint32_t*>(img_in + off);
             bytes[0] = __ldg(s32);
             bytes[1] = __ldg(s32 + 1);
@@ -238,37 +244,48 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
             const int nb = min(4, W - x0) * 3;
             for (int b2 = 0; b2 < nb; ++b2) bytes[b2 >> 2] |= uint32_t(img_in[off + b2]) << (8 * (b2 & 3));
         }
+        float f[3][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (x0 + j < W) {
-                int v[3];
+            int v[3];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const int b2 = 3 * j + c;
-                    v[c] = int((bytes[b2 >> 2] >> (8 * (b2 & 3))) & 0xFFu);
-                }
-                if (chain_first) {
-                    int q[3];
-                    chain3(ip, s_unit, uint32_t(h * W + x0 + j), v, q);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) v[c] = q[c];
-                }
-                const int o = sy * pitch + deint(a + x0 + j, quarter);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) s_planes[c * plane + o] = float(v[c]);
+            for (int c = 0; c < 3; ++c) {
+                const int b2 = 3 * j + c;
+                v[c] = int((bytes[b2 >> 2] >> (8 * (b2 & 3))) & 0xFFu);
             }
+            if (chain_first && x0 + j < W) {
+                int q[3];
+                chain3(ip, s_unit, uint32_t(h * W + x0 + j), v, q);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = q[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[c][j] = float(v[c]);
+        }
+        float* dstp = s_planes + sy * pitch + kStageShift + x0;
+        if (full) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                *reinterpret_cast<float4*>(dstp + c * plane) = make_float4(f[c][0], f[c][1], f[c][2], f[c][3]);
+        } else {   // the columns right of the image belong to loop (b)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if (x0 + j < W) dstp[c * plane + j] = f[c][j];
         }
     }
-    // (b) the few halo columns left / right of the image (REFLECT_101) and the zero slack columns
+    // (b) the columns left / right of the image: REFLECT_101 where this kernel's taps can reach, zero elsewhere (the
+    //     padded zero taps must never meet a NaN)
     const int hc = pitch - W;
     for (int it = tid; it < srows * hc; it += kDegThreads) {
         const int sy = it / hc;
         const int k = it - sy * hc;
-        const int sx = k < a ? k : W + k;
-        float f[3] = {0.f, 0.f, 0.f};  // slack columns are zero so that padded (zero) taps never meet a NaN
-        if (sx < scols) {
+        const int sc = k < kStageShift ? k : W + k;
+        float f[3] = {0.f, 0.f, 0.f};
+        if (sc >= kStageShift - a && sc < kStageShift + W + hb) {
             const int h = reflect101(r0 - a + sy, H);
-            const int w = reflect101(sx - a, W);
+            const int w = reflect101(sc - kStageShift, W);
             const uint32_t pix = uint32_t(h * W + w);
             int v[3];
 #pragma unroll
@@ -282,15 +299,16 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
 #pragma unroll
             for (int c = 0; c < 3; ++c) f[c] = float(v[c]);
         }
-        const int o = sy * pitch + deint(sx, quarter);
+        const int o = sy * pitch + sc;
 #pragma unroll
         for (int c = 0; c < 3; ++c) s_planes[c * plane + o] = f[c];
     }
     __syncthreads();
 
+    const int plane4 = plane >> 2;   // pitch is a multiple of 4
     for (int item = tid; item < rows * groups; item += kDegThreads) {
         const int y = item / groups;
-        const int g = item - y * groups;   // staged column of (pixel 4g + j, tap kx) = 4g + j + kx
+        const int g = item - y * groups;
         const int x0 = g << 2;
         float acc[3][4];
 #pragma unroll
@@ -298,52 +316,73 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
         for (int ky = 0; ky < d; ++ky) {
-            const int k0 = s_seg[ky][0], steps = s_seg[ky][1];
-            if (steps == 0) continue;                       // uniform: the whole CTA works on one image
-            const float* rowp = s_planes + (y + ky) * pitch + g;
-            const float* tp = &s_taps[ky][k0];
-            // window registers hold staged columns 4g + m .. 4g + m + 3; column 4g + m sits at (m & 3)*quarter + (m >> 2)
-            float w0[3], w1[3], w2[3], w3[3];
+            const int g0 = s_seg[ky][0], ng = s_seg[ky][1];
+            if (ng == 0) continue;                          // uniform: the whole CTA works on one image
+            // staged columns x0 + 4 * (g0 + i) .. + 3 for i = 0 .. ng: 16-byte aligned for every item
+            const float4* wp = reinterpret_cast<const float4*>(s_planes + (y + ky) * pitch + x0) + g0;
+            const float4* tp = reinterpret_cast<const float4*>(&s_taps[ky][0]) + g0;
+            float4 lo[3], hi[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                w0[c] = rowp[c * plane + deint(k0, quarter)];
-                w1[c] = rowp[c * plane + deint(k0 + 1, quarter)];
-                w2[c] = rowp[c * plane + deint(k0 + 2, quarter)];
-            }
-            int m = k0 + 3;
-#define B2R_DEG_STEP(A, B, C, D_)                                        \
-    {                                                                    \
-        const float k = *tp++;                                           \
-        const int o = deint(m, quarter);                                 \
-        ++m;                                                             \
-        _Pragma("unroll") for (int c = 0; c < 3; ++c) {                  \
-            D_[c] = rowp[c * plane + o];                                 \
-            acc[c][0] = fmaf(k, A[c], acc[c][0]);                        \
-            acc[c][1] = fmaf(k, B[c], acc[c][1]);                        \
-            acc[c][2] = fmaf(k, C[c], acc[c][2]);                        \
-            acc[c][3] = fmaf(k, D_[c], acc[c][3]);                       \
-        }                                                                \
+            for (int c = 0; c < 3; ++c) lo[c] = wp[c * plane4];
+#define B2R_DEG_GROUP(LO, HI, I)                                                  \
+    {                                                                             \
+        const float4 k = tp[I];                                                   \
+        _Pragma("unroll") for (int c = 0; c < 3; ++c) {                           \
+            HI[c] = wp[c * plane4 + (I) + 1];                                     \
+            acc[c][0] = fmaf(k.x, LO[c].x, acc[c][0]);                            \
+            acc[c][1] = fmaf(k.x, LO[c].y, acc[c][1]);                            \
+            acc[c][2] = fmaf(k.x, LO[c].z, acc[c][2]);                            \
+            acc[c][3] = fmaf(k.x, LO[c].w, acc[c][3]);                            \
+            acc[c][0] = fmaf(k.y, LO[c].y, acc[c][0]);                            \
+            acc[c][1] = fmaf(k.y, LO[c].z, acc[c][1]);                            \
+            acc[c][2] = fmaf(k.y, LO[c].w, acc[c][2]);                            \
+            acc[c][3] = fmaf(k.y, HI[c].x, acc[c][3]);                            \
+            acc[c][0] = fmaf(k.z, LO[c].z, acc[c][0]);                            \
+            acc[c][1] = fmaf(k.z, LO[c].w, acc[c][1]);                            \
+            acc[c][2] = fmaf(k.z, HI[c].x, acc[c][2]);                            \
+            acc[c][3] = fmaf(k.z, HI[c].y, acc[c][3]);                            \
+            acc[c][0] = fmaf(k.w, LO[c].w, acc[c][0]);                            \
+            acc[c][1] = fmaf(k.w, HI[c].x, acc[c][1]);                            \
+            acc[c][2] = fmaf(k.w, HI[c].y, acc[c][2]);                            \
+            acc[c][3] = fmaf(k.w, HI[c].z, acc[c][3]);                            \
+        }                                                                         \
     }
-            // exactly the taps first..last of this kernel row (a motion-blur kernel has one or two per row); the window
-            // registers rotate, so the loop is unrolled by four with uniform early exits
-            for (int rem = steps;;) {
-                B2R_DEG_STEP(w0, w1, w2, w3)
-                if (--rem == 0) break;
-                B2R_DEG_STEP(w1, w2, w3, w0)
-                if (--rem == 0) break;
-                B2R_DEG_STEP(w2, w3, w0, w1)
-                if (--rem == 0) break;
-                B2R_DEG_STEP(w3, w0, w1, w2)
-                if (--rem == 0) break;
+            // the two window registers swap roles, so the loop is unrolled by two with a uniform early exit
+            for (int i = 0;;) {
+                B2R_DEG_GROUP(lo, hi, i)
+                if (++i == ng) break;
+                B2R_DEG_GROUP(hi, lo, i)
+                if (++i == ng) break;
             }
-#undef B2R_DEG_STEP
+#undef B2R_DEG_GROUP
+        }
+        // OpenCV's row filter (4.13, AVX2 build; measured against cv2 for W = 21..33) runs its vector body, which fuses
+        // multiply and add, over 4 * floor(3W / 4) interleaved values of a row and a scalar loop with a separate
+        // multiply and add over the last 3W mod 4 values: channels c >= 3 - (3W mod 4) of pixel W - 1.  Those few
+        // values are recomputed here the scalar way (exact .5 ties round differently otherwise).  Absent for W = 224.
+        const int tail = (3 * W) & 3;
+        const bool tail_item = tail != 0 && x0 <= W - 1 && W - 1 < x0 + 4;
+        float tacc[3] = {0.f, 0.f, 0.f};
+        if (tail_item) {
+            for (int ky = 0; ky < d; ++ky)
+                for (int kx = 0; kx < d; ++kx) {
+                    const float k = s_taps[ky][kx + sh];
+                    if (k != 0.f) {
+                        const float* vp = s_planes + (y + ky) * pitch + (W - 1) + kx + sh;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) tacc[c] = __fadd_rn(tacc[c], __fmul_rn(k, vp[c * plane]));
+                    }
+                }
         }
         uint32_t bytes[3] = {0u, 0u, 0u};  // 12 output bytes: pixel j channel c -> byte 3*j + c
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int v[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[c] = min(max(__float2int_rn(acc[c][j]), 0), 255);
+            for (int c = 0; c < 3; ++c) {
+                v[c] = round_u8(acc[c][j]);
+                if (tail_item && x0 + j == W - 1 && c >= 3 - tail) v[c] = round_u8(tacc[c]);
+            }
             if (!chain_first && x0 + j < W) {
                 int q[3];
                 chain3(ip, s_unit, uint32_t((r0 + y) * W + x0 + j), v, q);
@@ -397,7 +436,7 @@ __global__ void __launch_bounds__(kGenThreads) degrade_pointwise_kernel(const De
 }
 
 static size_t degrade_smem_bytes(int W) {
-    return size_t(3) * (kDegRows + B2R_MAX_BLUR - 1) * degrade_quarter(W) * 4 * sizeof(float);
+    return size_t(3) * (kDegRows + B2R_MAX_BLUR - 1) * degrade_pitch(W) * sizeof(float);
 }
 
 }  // namespace b2r

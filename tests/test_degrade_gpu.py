@@ -133,6 +133,39 @@ def test_pointwise_path_equals_generic_kernel_and_numpy():
                 assert np.array_equal(out[i], O.quant_u8(f)), (n, h, w, i)
 
 
+def test_blur_ragged_shapes_all_small_degrees_vs_cv2():
+    """Widths that are not multiples of 4, heights that are not multiples of the 16-row tile, images barely larger than
+    the kernel, every degree 2..11 at assorted angles, mixed within one batch: bit-exact against cv2.filter2D on the
+    reference's own tap construction (16:23-26), for both stage orders (chain = fog here: deterministic)."""
+    import cv2
+    from b200restore import degrade
+    from oracle import degrade_oracle as O
+    rng = np.random.default_rng(21)
+    angles = [0, 17, 45, 90, 133, 200, 270, 359]
+    for (h, w) in ((37, 53), (16, 16), (12, 11), (33, 130), (50, 7 * 4 + 1)):
+        n = 10
+        imgs = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+        for order in (0, 1):
+            p = degrade.DegradeParams(n, order=order)
+            for i in range(n):
+                p.set_blur(i, 2 + i, float(angles[(i + h) % len(angles)]))
+                if i % 2:
+                    p.set_fog(i, 0.5)
+            out = degrade.degrade(_dev(imgs), p).cpu().numpy()
+            for i in range(n):
+                d = int(p.ksize[i])
+                k = p.taps[i, :d * d].reshape(d, d).astype(np.float64)
+
+                def chain(v):
+                    f = v.astype(np.float32) / 255.0
+                    if p.fog_on[i]:
+                        f = f * np.float32(p.fog_t[i]) + np.float32(p.fog_add[i])
+                    return O.quant_u8(f)
+
+                ref = chain(cv2.filter2D(imgs[i], -1, k)) if order == 0 else cv2.filter2D(chain(imgs[i]), -1, k)
+                assert np.array_equal(out[i], ref), (h, w, order, i, d, int(np.abs(out[i].astype(int) - ref).max()))
+
+
 def test_identity_when_nothing_is_applied():
     from b200restore import degrade
     imgs = torch.randint(0, 256, (3, 64, 80, 3), dtype=torch.uint8).cuda()
