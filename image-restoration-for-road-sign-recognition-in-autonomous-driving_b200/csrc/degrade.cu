@@ -36,7 +36,7 @@
 namespace b2r {
 
 constexpr int kDegRows = 16;
-constexpr int kDegThreads = 224;
+constexpr int kDegThreads = 448;   // 14 warps, two CTAs per SM (shared memory): 28 warps hide the staging loads
 
 struct DegradeParams {
     const uint8_t* in;
@@ -103,6 +103,55 @@ __device__ __forceinline__ void chain3(const ImgParams& ip, const float* unit, u
     }
 }
 
+// No blur for this image: the per-pixel chain on items of 4 pixels (three aligned 32-bit loads / stores) over image rows
+// r0 .. r0 + rows - 1.  Shared by the blur kernel (images of a mixed batch that do not blur) and degrade_noblur_kernel.
+__device__ __forceinline__ void chain_rows(const ImgParams& ip, const float* s_unit, const uint8_t* __restrict__ img_in,
+                                           uint8_t* __restrict__ img_out, int W, int r0, int rows, bool rows_aligned,
+                                           int tid, int nthreads) {
+    const int groups = (W + 3) >> 2;
+    for (int item = tid; item < rows * groups; item += nthreads) {
+        const int y = item / groups;
+        const int x0 = (item - y * groups) << 2;
+        const size_t off = (size_t(r0 + y) * W + x0) * 3;
+        const bool fast = rows_aligned && x0 + 4 <= W;
+        uint32_t bytes[3] = {0u, 0u, 0u};
+        if (fast) {
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(img_in + off);
+            bytes[0] = __ldg(s32);
+            bytes[1] = __ldg(s32 + 1);
+            bytes[2] = __ldg(s32 + 2);
+        } else {
+            const int nb = min(4, W - x0) * 3;
+            for (int b = 0; b < nb; ++b) bytes[b >> 2] |= uint32_t(img_in[off + b]) << (8 * (b & 3));
+        }
+        uint32_t outb[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int v[3], q[3] = {0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int b = 3 * j + c;
+                v[c] = int((bytes[b >> 2] >> (8 * (b & 3))) & 0xFFu);
+            }
+            if (x0 + j < W) chain3(ip, s_unit, uint32_t((r0 + y) * W + x0 + j), v, q);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int b = 3 * j + c;
+                outb[b >> 2] |= uint32_t(q[c]) << (8 * (b & 3));
+            }
+        }
+        if (fast) {
+            uint32_t* d32 = reinterpret_cast<uint32_t*>(img_out + off);
+            d32[0] = outb[0];
+            d32[1] = outb[1];
+            d32[2] = outb[2];
+        } else {
+            const int nb = min(4, W - x0) * 3;
+            for (int b = 0; b < nb; ++b) img_out[off + b] = uint8_t(outb[b >> 2] >> (8 * (b & 3)));
+        }
+    }
+}
+
 // Planar staging layout: plane c, staged row sy, staged column sc at  c * plane + sy * pitch + sc,  image column x at
 // sc = x + kStageShift.  Tap t of the shifted tap array (kTapSlots entries, groups of 4) reads column x + t, so the widest
 // read of an item at x0 (a multiple of 4) is x0 + kTapSlots + 3: pitch = roundup4(W) + kTapSlots keeps it inside the row.
@@ -118,10 +167,11 @@ __device__ __forceinline__ int round_u8(float v) {   // cvRound + saturate_cast<
     return int(b);
 }
 
-__global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParams P) {
+__global__ void __launch_bounds__(kDegThreads, 2) degrade_kernel(const DegradeParams P) {
     extern __shared__ __align__(16) float s_planes[];  // [3][srows][pitch], row-major
     __shared__ __align__(16) float s_taps[B2R_MAX_BLUR][kTapSlots];  // shifted, zero-padded tap rows (see above)
     __shared__ float s_unit[256];
+    __shared__ int s_rows[B2R_MAX_BLUR + 1];  // [0] = number of non-empty kernel rows, then ky | first group << 8 | groups << 16
     __shared__ int s_seg[B2R_MAX_BLUR][2];  // per kernel row: first tap group with a non-zero tap / number of groups up to the last one (0: empty row)
 
     const int n = blockIdx.y;
@@ -142,6 +192,8 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
     ip.seed = P.seed;
     ip.image = P.image_index0 + uint64_t(n);
     ip.noise = P.noise ? P.noise + size_t(n) * H * W * 3 : nullptr;
+    // without fog and noise chain() is the identity on 0..255 (u8 -> /255 -> *255 -> truncate; tests/test_oracle_degrade.py)
+    const bool chain_on = ip.fog_on || ip.noise_on;
 
     const uint8_t* img_in = P.in + size_t(n) * H * W * 3;
     uint8_t* img_out = P.out + size_t(n) * H * W * 3;
@@ -151,49 +203,8 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
     for (int i = tid; i < 256; i += kDegThreads) s_unit[i] = __fdiv_rn(float(i), 255.0f);
 
     if (d == 0) {
-        // no blur for this image: pure per-pixel chain on items of 4 pixels (three aligned 32-bit loads / stores)
-        __syncthreads();
-        for (int item = tid; item < rows * groups; item += kDegThreads) {
-            const int y = item / groups;
-            const int x0 = (item - y * groups) << 2;
-            const size_t off = (size_t(r0 + y) * W + x0) * 3;
-            const bool fast = rows_aligned && x0 + 4 <= W;
-            uint32_t bytes[3] = {0u, 0u, 0u};
-            if (fast) {
-                const uint32_t* s32 = reinterpret_cast<const uint32_t*>(img_in + off);
-                bytes[0] = __ldg(s32);
-                bytes[1] = __ldg(s32 + 1);
-                bytes[2] = __ldg(s32 + 2);
-            } else {
-                const int nb = min(4, W - x0) * 3;
-                for (int b = 0; b < nb; ++b) bytes[b >> 2] |= uint32_t(img_in[off + b]) << (8 * (b & 3));
-            }
-            uint32_t outb[3] = {0u, 0u, 0u};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int v[3], q[3] = {0, 0, 0};
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const int b = 3 * j + c;
-                    v[c] = int((bytes[b >> 2] >> (8 * (b & 3))) & 0xFFu);
-                }
-                if (x0 + j < W) chain3(ip, s_unit, uint32_t((r0 + y) * W + x0 + j), v, q);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const int b = 3 * j + c;
-                    outb[b >> 2] |= uint32_t(q[c]) << (8 * (b & 3));
-                }
-            }
-            if (fast) {
-                uint32_t* d32 = reinterpret_cast<uint32_t*>(img_out + off);
-                d32[0] = outb[0];
-                d32[1] = outb[1];
-                d32[2] = outb[2];
-            } else {
-                const int nb = min(4, W - x0) * 3;
-                for (int b = 0; b < nb; ++b) img_out[off + b] = uint8_t(outb[b >> 2] >> (8 * (b & 3)));
-            }
-        }
+        __syncthreads();  // s_unit
+        chain_rows(ip, s_unit, img_in, img_out, W, r0, rows, rows_aligned, tid, kDegThreads);
         return;
     }
 
@@ -222,7 +233,13 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
     const int pitch = degrade_pitch(W);
     const int plane = srows * pitch;
     const bool chain_first = P.order == B2R_ORDER_FOG_NOISE_BLUR;
-    __syncthreads();  // s_unit
+    __syncthreads();  // s_unit, s_seg
+    if (tid == 0) {
+        int m = 0;
+        for (int ky = 0; ky < d; ++ky)
+            if (s_seg[ky][1]) s_rows[++m] = ky | s_seg[ky][0] << 8 | s_seg[ky][1] << 16;
+        s_rows[0] = m;   // published by the barrier that ends the staging
+    }
 
     // (a) image columns: items of 4 pixels = three aligned, coalesced 32-bit loads and one 16-byte store per plane
     //     (the staging loop is where the kernel meets HBM latency, so it is unrolled to keep several loads in flight)
@@ -253,7 +270,7 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
                 const int b2 = 3 * j + c;
                 v[c] = int((bytes[b2 >> 2] >> (8 * (b2 & 3))) & 0xFFu);
             }
-            if (chain_first && x0 + j < W) {
+            if (chain_first && chain_on && x0 + j < W) {
                 int q[3];
                 chain3(ip, s_unit, uint32_t(h * W + x0 + j), v, q);
 #pragma unroll
@@ -290,7 +307,7 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
             int v[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) v[c] = img_in[size_t(pix) * 3 + c];
-            if (chain_first) {
+            if (chain_first && chain_on) {
                 int q[3];
                 chain3(ip, s_unit, pix, v, q);
 #pragma unroll
@@ -306,6 +323,7 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
     __syncthreads();
 
     const int plane4 = plane >> 2;   // pitch is a multiple of 4
+    const int nrows = s_rows[0];
     for (int item = tid; item < rows * groups; item += kDegThreads) {
         const int y = item / groups;
         const int g = item - y * groups;
@@ -315,9 +333,9 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
-        for (int ky = 0; ky < d; ++ky) {
-            const int g0 = s_seg[ky][0], ng = s_seg[ky][1];
-            if (ng == 0) continue;                          // uniform: the whole CTA works on one image
+        for (int r = 1; r <= nrows; ++r) {                   // non-empty kernel rows, top to bottom (uniform per CTA)
+            const int e = s_rows[r];
+            const int ky = e & 0xFF, g0 = (e >> 8) & 0xFF, ng = e >> 16;
             // staged columns x0 + 4 * (g0 + i) .. + 3 for i = 0 .. ng: 16-byte aligned for every item
             const float4* wp = reinterpret_cast<const float4*>(s_planes + (y + ky) * pitch + x0) + g0;
             const float4* tp = reinterpret_cast<const float4*>(&s_taps[ky][0]) + g0;
@@ -383,7 +401,7 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
                 v[c] = round_u8(acc[c][j]);
                 if (tail_item && x0 + j == W - 1 && c >= 3 - tail) v[c] = round_u8(tacc[c]);
             }
-            if (!chain_first && x0 + j < W) {
+            if (!chain_first && chain_on && x0 + j < W) {
                 int q[3];
                 chain3(ip, s_unit, uint32_t((r0 + y) * W + x0 + j), v, q);
 #pragma unroll
@@ -406,6 +424,32 @@ __global__ void __launch_bounds__(kDegThreads) degrade_kernel(const DegradeParam
             for (int b = 0; b < nb; ++b) dst[b] = uint8_t(bytes[b >> 2] >> (8 * (b & 3)));
         }
     }
+}
+
+// ksize == NULL (no image of the batch blurs) with noise somewhere: the chain alone, without the blur kernel's register
+// cap and shared-memory planes.  Same grid as degrade_kernel: one CTA = 16 rows of one image.
+constexpr int kNoBlurThreads = 224;
+__global__ void __launch_bounds__(kNoBlurThreads) degrade_noblur_kernel(const DegradeParams P) {
+    __shared__ float s_unit[256];
+    const int n = blockIdx.y;
+    const int r0 = blockIdx.x * kDegRows;
+    const int H = P.H, W = P.W;
+    ImgParams ip;
+    ip.fog_on = P.fog_on ? P.fog_on[n] : 0;
+    ip.t = ip.fog_on ? P.fog_t[n] : 1.f;
+    ip.add = ip.fog_on ? P.fog_add[n] : 0.f;
+    ip.sigma = P.sigma ? P.sigma[n] : 0.f;
+    ip.noise_on = ip.sigma > 0.f;
+    ip.clip_after = (P.flags & B2R_DEG_CLIP_AFTER_NOISE) != 0;
+    ip.seed = P.seed;
+    ip.image = P.image_index0 + uint64_t(n);
+    ip.noise = P.noise ? P.noise + size_t(n) * H * W * 3 : nullptr;
+    const uint8_t* img_in = P.in + size_t(n) * H * W * 3;
+    uint8_t* img_out = P.out + size_t(n) * H * W * 3;
+    const bool rows_aligned = ((W * 3) & 3) == 0 && ((reinterpret_cast<uintptr_t>(img_in) | reinterpret_cast<uintptr_t>(img_out)) & 3) == 0;
+    for (int i = threadIdx.x; i < 256; i += kNoBlurThreads) s_unit[i] = __fdiv_rn(float(i), 255.0f);
+    __syncthreads();
+    chain_rows(ip, s_unit, img_in, img_out, W, r0, min(kDegRows, H - r0), rows_aligned, threadIdx.x, kNoBlurThreads);
 }
 
 // ksize == NULL and sigma == NULL: out = table_n[in], table_n[v] = chain(v) with image n's fog parameters.
@@ -491,6 +535,11 @@ extern "C" int b2r_degrade(const uint8_t* in, uint8_t* out, int N, int H, int W,
         return B2R_OK;
     }
     dim3 grid((H + kDegRows - 1) / kDegRows, N);
+    if (!ksize) {
+        degrade_noblur_kernel<<<grid, kNoBlurThreads, 0, stream>>>(P);
+        B2R_CHECK_LAUNCH();
+        return B2R_OK;
+    }
     degrade_kernel<<<grid, kDegThreads, smem, stream>>>(P);
     B2R_CHECK_LAUNCH();
     return B2R_OK;
