@@ -17,6 +17,8 @@ Prints ONE JSON line on rank 0:
 
 `--impl reference` times the reference's CPU implementation of the same path (oracle port: the reference is Python and
 cannot travel to the GPU box; oracle/ is pinned to it bit-for-bit by tests/test_oracle_*.py) with all host threads.
+`--impl reference --ref-device cuda [--ref-precision f32|tf32|bf16]` is the opt-in same-box LIBRARY comparator of
+BASELINE.md: the same fp32 PyTorch port on cuda:0 through cuDNN / cuBLAS (what the reference does with DEVICE = 'cuda').
 """
 from __future__ import annotations
 
@@ -62,6 +64,11 @@ def parse_args():
     ap.add_argument("--hw", type=int, default=224)
     ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline sample (0 = choose)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference: 'cuda' times the same fp32 PyTorch port on the GPU through cuDNN / cuBLAS "
+                         "(the reference with DEVICE='cuda', 17:16) as the same-box library comparator")
+    ap.add_argument("--ref-precision", default="f32", choices=["f32", "tf32", "bf16"],
+                    help="--ref-device cuda: f32 (TF32 off), tf32, or bf16 autocast with channels_last tensors")
     return ap.parse_args()
 
 
@@ -184,9 +191,84 @@ def cpu_reference_images_per_s(workload: str, hw: int, sample: int, repeats: int
     return sample / dt, cores, dt
 
 
+def cuda_reference_images_per_s(workload: str, hw: int, batch: int, micro: int, steps: int, warmup: int, precision: str):
+    """BASELINE.md 'same-box GPU comparator': the fp32 PyTorch port of restore -> clamp/u8 -> Normalize -> VGG16 ->
+    arg-max on cuda:0, i.e. what the reference's modules do with DEVICE = 'cuda' (17:16): ATen -> cuDNN / cuBLAS.  The
+    degradation is NumPy/OpenCV code in the reference (no GPU form), so the batch is degraded once outside the timed
+    region and the timed step is restore + classify over `batch` resident images.  None of this repo's kernels run."""
+    import torch
+    from b200restore import synth
+    from oracle import models_oracle as MO
+    arch, recipe, classify = WORKLOADS[workload]
+    if arch == "cascade3":
+        raise SystemExit("--ref-device cuda covers the restore(+classify) workloads")
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = True
+    tf32 = precision == "tf32"
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    cl = precision == "bf16"
+
+    def put(sd):
+        out = {}
+        for k, v in sd.items():
+            v = v.to(dev)
+            out[k] = v.contiguous(memory_format=torch.channels_last) if (cl and v.dim() == 4) else v
+        return out
+
+    sdr = put(synth.synthetic_state_dict(arch, 31))
+    sdj = put(synth.synthetic_state_dict("vgg16", 32)) if classify else None
+    fn = MO.simple_unet_forward if arch == "simple_unet" else MO.resunet_forward
+    imgs, labels = synth.sign_like_images(min(batch, 512), hw, hw, seed=7)
+    reps = (batch + imgs.shape[0] - 1) // imgs.shape[0]
+    imgs = imgs.repeat(reps, 1, 1, 1)[:batch].to(dev)
+    labels = labels.repeat(reps)[:batch].to(dev)
+
+    def step():
+        correct = torch.zeros((), dtype=torch.int64, device=dev)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=cl):
+            for s0 in range(0, batch, micro):
+                u8 = imgs[s0:s0 + micro]
+                if classify:
+                    _, _, pred = MO.restore_then_classify(fn, sdr, sdj, u8)
+                    correct += (pred == labels[s0:s0 + micro]).sum()
+                else:
+                    x = MO.to_tensor_u8(u8)
+                    correct += MO.quantize_restored(fn(sdr, x.contiguous(memory_format=torch.channels_last) if cl else x)).sum()
+        return correct
+
+    for _ in range(max(warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return batch / ms * 1e3, ms
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.ref_device == "cuda":
+        batch = min(args.batch, 1024)
+        micro = min(args.micro_batch, 64)
+        ips, ms = cuda_reference_images_per_s(args.workload, args.hw, batch, micro, args.steps, args.warmup, args.ref_precision)
+        arch, recipe, classify = WORKLOADS[args.workload]
+        gflop = GFLOP_PER_IMAGE_224[arch] + (GFLOP_PER_IMAGE_224["vgg16"] if classify else 0.0)
+        print(json.dumps({
+            "impl": "reference-cudnn", "metric": "images/sec restore->VGG16 classify", "value": ips, "unit": "images/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "dtype": args.ref_precision, "data": "synthetic",
+            "config": {"workload": args.workload, "hw": args.hw, "images_per_step": batch, "micro_batch": micro,
+                       "note": "fp32 PyTorch port of the reference modules on cuda:0 (ATen -> cuDNN / cuBLAS, "
+                               "cudnn.benchmark on); degradation outside the timed region (NumPy/OpenCV in the "
+                               "reference); none of this repo's kernels"},
+            "model_tflops": ips * gflop / 1e3 if args.hw == 224 else None, "gpu_launches": 0}), flush=True)
         return
     cores = os.cpu_count() or 1
     sample = args.cpu_sample or CPU_SAMPLE
@@ -387,7 +469,7 @@ def run_ours(args):
                      "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
                      "peak_source": peak_src, "traffic": traffic,
                      "traffic_note": "dram__bytes_read+write per launch averaged over all tcgen05 conv launches of one "
-                                     "ncu capture (profiles/r01_launches_v9_summary.md), micro-batch 256",
+                                     "ncu capture (profiles/r01_launches_v11_summary.md), micro-batch 256",
                      "launches": ksum["launches"], "kernel_ms_per_step": ksum["ms"] / args.steps,
                      "share_of_step": ksum["ms"] / total_ms,
                      "pipeline_tflops": ips / world * gflop_img / 1e3 if hw == 224 else None},
