@@ -160,3 +160,44 @@ def test_top1_agreement_with_a_locally_fitted_judge():
           f"5th pct {float(margin.kthvalue(max(1, n_eval // 20))[0]):.3f}, median {float(margin.median()):.3f}")
     assert agree >= 0.999, f"top-1 agreement {agree:.4f} < 0.999"
     assert counts[1].item() == n_eval and counts[0].item() == int((pred.cpu() == labels).sum())
+
+
+def test_script08_flow_at_config0_size():
+    """BASELINE configs[0]: 08_run_inference.py's loop (SimpleUNet in the restoration_noise.pth schema -> clamp -> x255 ->
+    uint8 -> PSNR / SSIM against the clean image, 08:86-129) on 256 images of 224x224, batched on the device.
+    Full size: properties that do not need the oracle (micro-batching invisible, metrics of an image against itself,
+    every restored image closer to the clean one than the noisy input is not required - weights are synthetic - but the
+    metrics must be finite and inside their ranges).  First 6 images: the fp32 oracle forward (07:99-120) -> the same
+    quantiser -> oracle PSNR / SSIM; restored bytes differ by bf16 LSBs, so PSNR within 0.1 dB and SSIM within 5e-3."""
+    from b200restore import generators as G, models, synth
+    from oracle import generators_oracle as GO, models_oracle as MO
+    n, hw = 256, 224
+    sd = synth.synthetic_state_dict("simple_unet", 41)
+    m = models.SimpleUNet()
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    clean, _ = synth.sign_like_images(n, hw, hw, seed=9)
+    clean = clean.cuda()
+    noisy = G.add_gaussian_noise(clean, var=0.02, seed=3)                      # 02:12-27 on the device (Philox draw)
+    m.micro_batch = 256
+    restored = m.restore_u8(noisy)
+    m.micro_batch = 48                                                         # ragged split: 5 x 48 + 16
+    assert torch.equal(m.restore_u8(noisy), restored)
+    assert restored.shape == (n, hw, hw, 3) and restored.dtype == torch.uint8
+    psnr, ssim = G.psnr(clean, restored), G.ssim(clean, restored)
+    assert psnr.shape == (n,) and ssim.shape == (n,)
+    assert bool(torch.isfinite(psnr).all()) and bool(((ssim > -1) & (ssim < 1)).all())
+    assert bool(torch.isinf(G.psnr(restored, restored)).all()) and bool((G.ssim(restored, restored) == 1).all())
+    assert torch.equal(G.ssim(restored, clean), ssim)                          # symmetric, deterministic
+    k = 6
+    sdc = {a: b.cuda() for a, b in sd.items()}
+    with torch.no_grad():
+        ref = MO.quantize_restored(MO.simple_unet_forward(sdc, MO.to_tensor_u8(noisy[:k])))
+    d = (restored[:k].int() - ref.int()).abs()
+    assert float(d.float().mean()) < 0.5 and float((d > 2).float().mean()) < 1e-3
+    c_np, r_np = clean[:k].cpu().numpy(), ref.cpu().numpy()
+    for i in range(k):
+        assert float(psnr[i]) == pytest.approx(GO.psnr_08(c_np[i], r_np[i]), abs=0.1)
+        assert float(ssim[i]) == pytest.approx(GO.ssim_08(c_np[i], r_np[i]), abs=5e-3)
+    print(f"\n[script 08 @ 256 x 224^2] mean PSNR {float(psnr.mean()):.2f} dB, mean SSIM {float(ssim.mean()):.4f}; "
+          f"restored vs fp32 oracle: max |diff| {int(d.max())} LSB")
