@@ -298,6 +298,40 @@ __global__ void __launch_bounds__(kResizeThreads) resize_bilinear_u8_kernel(
 }
 
 
+// cv2.resize(img, (out_w, out_h)) with the default INTER_LINEAR on u8 images, bit for bit (08_run_inference.py:119 resizes
+// the clean image this way before PSNR / SSIM).  OpenCV's fixed-point scheme: 11-bit coefficients (cvRound(c * 2048),
+// from the host: imageio.cv_linear_table), horizontal pass kept as int, vertical pass
+//     dst = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.
+// tabs int32 [T][S][3] = {first source index, c0, c1}; rows are clamped to the image, columns are clamped by the host
+// (OpenCV zeroes the fraction there).  One thread per output pixel: 12 source bytes in, 3 bytes out.
+__global__ void __launch_bounds__(kResizeThreads) resize_cv_linear_u8_kernel(
+    const uint8_t* __restrict__ src, const long long* __restrict__ offsets, const int32_t* __restrict__ hw,
+    const int32_t* __restrict__ xtab_index, const int32_t* __restrict__ ytab_index, const int32_t* __restrict__ tabs, int S,
+    uint8_t* __restrict__ out, int out_h, int out_w) {
+    const int n = blockIdx.y;
+    const int in_h = hw[2 * n], in_w = hw[2 * n + 1];
+    const uint8_t* img = src + offsets[n];
+    const int32_t* xt = tabs + (long)xtab_index[n] * S * 3;
+    const int32_t* yt = tabs + (long)ytab_index[n] * S * 3;
+    for (int i = blockIdx.x * kResizeThreads + threadIdx.x; i < out_h * out_w; i += gridDim.x * kResizeThreads) {
+        const int yy = i / out_w, xx = i - yy * out_w;
+        const int sx = xt[3 * xx], a0 = xt[3 * xx + 1], a1 = xt[3 * xx + 2];
+        const int sy = yt[3 * yy], b0 = yt[3 * yy + 1], b1 = yt[3 * yy + 2];
+        const int x1 = min(sx + 1, in_w - 1);
+        const uint8_t* r0 = img + (long)min(max(sy, 0), in_h - 1) * in_w * 3;
+        const uint8_t* r1 = img + (long)min(max(sy + 1, 0), in_h - 1) * in_w * 3;
+        uint8_t* d = out + ((long)n * out_h * out_w + i) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int s0 = int(r0[3 * sx + c]) * a0 + int(r0[3 * x1 + c]) * a1;
+            const int s1 = int(r1[3 * sx + c]) * a0 + int(r1[3 * x1 + c]) * a1;
+            const int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+            d[c] = uint8_t(min(max(v, 0), 255));
+        }
+    }
+}
+
+
 }  // namespace b2r
 
 extern "C" {
@@ -387,6 +421,26 @@ int b2r_resize_bilinear_u8(const uint8_t* src, const int64_t* offsets, const int
     resize_bilinear_u8_kernel<<<grid, kResizeThreads, smem, stream>>>(src, reinterpret_cast<const long long*>(offsets), hw,
                                                                       xtab_index, ytab_index, tabs, K, S, out, out_h, out_w,
                                                                       tile_rows, max_rows);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
+int b2r_resize_cv_linear_u8(const uint8_t* src, const int64_t* offsets, const int32_t* hw, const int32_t* xtab_index,
+                            const int32_t* ytab_index, const int32_t* tabs, int S, uint8_t* out, int N, int out_h,
+                            int out_w, void* stream_v) {
+    using namespace b2r;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    B2R_REQUIRE(src && offsets && hw && xtab_index && ytab_index && tabs && out, "null pointer");
+    B2R_REQUIRE(N > 0 && N <= 65535 && out_h > 0 && out_w > 0 && S >= out_h && S >= out_w, "bad shape N=%d out=%dx%d S=%d",
+                N, out_h, out_w, S);
+    int sms = 0;
+    const int rc = device_sm_count(&sms);
+    if (rc) return rc;
+    long blocks = ((long)out_h * out_w + kResizeThreads - 1) / kResizeThreads;
+    const long cap = (8L * sms + N - 1) / N > 1 ? (8L * sms + N - 1) / N : 1;
+    if (blocks > cap) blocks = cap;
+    resize_cv_linear_u8_kernel<<<dim3((unsigned)blocks, (unsigned)N, 1), kResizeThreads, 0, stream>>>(
+        src, reinterpret_cast<const long long*>(offsets), hw, xtab_index, ytab_index, tabs, S, out, out_h, out_w);
     B2R_CHECK_LAUNCH();
     return B2R_OK;
 }

@@ -4,6 +4,7 @@
   evaluate_model(model, data_dir, name)   18_test_unified_benchmark.py:22-53 (= 06:23-59, 09:29-65)   evaluate_model(judge, data_dir, name)
   run_inference()                         17_run_unified_inference.py:57-101                          run_inference(model, distorted_dir, restored_dir)
   datasets.ImageFolder(root)              18:35                                                       image_folder(root)
+  process_task(task_name)                 08_run_inference.py:55-137                                  process_task(model, task_name, distorted_dir, restored_dir, clean_dir)
 
 Files are decoded on the host (imageio.load_rgb), every pixel after that is touched by libb2r.so kernels: the Pillow
 BILINEAR Resize((224, 224)) of the ragged batch, ToTensor (+ Normalize) fused into the first conv, the networks, the
@@ -19,7 +20,7 @@ from typing import List, Optional, Tuple
 import torch
 
 from . import _lib as L
-from . import imageio, ops
+from . import generators, imageio, ops
 
 # torchvision.datasets.folder.IMG_EXTENSIONS
 IMG_EXTENSIONS = (".jpg", ".jpeg", ".png", ".ppm", ".bmp", ".pgm", ".tif", ".tiff", ".webp")
@@ -112,6 +113,53 @@ def run_inference(model, distorted_dir, restored_dir, batch_size: int = 32, patt
     if verbose:
         print(f"Restoration complete! Please check: {restored_dir}")
     return written
+
+
+@torch.no_grad()
+def process_task(model, task_name: str, distorted_dir, restored_dir, clean_dir, batch_size: int = 32,
+                 verbose: bool = True) -> Optional[Tuple[float, float, int]]:
+    """08:55-137 for one task: restore every `distorted_dir/<class>/*.ppm|*.png`, write it as .png under the same
+    relative path in `restored_dir` (08:103-109), and score it against the clean image `clean_dir / rel_path` (falling
+    back to the .ppm name, 08:112-114) resized with cv2.resize(clean, (224, 224)) (08:119): PSNR and SSIM with
+    data_range 255 (08:121-123), averaged over the images whose clean counterpart exists.
+    The reference runs batch 1; here the same per-image arithmetic runs in batches on the device (restoration, both
+    resizes, PSNR, SSIM).  `model` is a SimpleUNet already loaded and on the device.  Returns (mean PSNR, mean SSIM,
+    count) or None when no image was scored, after the reference's prints."""
+    distorted_dir, restored_dir, clean_dir = Path(distorted_dir), Path(restored_dir), Path(clean_dir)
+    if verbose:
+        print(f"\n=== Starting task processing: {task_name} ===")
+    dev = _device_of(model)
+    model.eval()
+    files = list(distorted_dir.glob("*/*.ppm")) + list(distorted_dir.glob("*/*.png"))      # 08:84
+    total_psnr = total_ssim = 0.0
+    count = 0
+    for i in range(0, len(files), batch_size):
+        batch_files = files[i:i + batch_size]
+        restored = model.restore_u8(imageio.load_batch(batch_files, device=dev))
+        imageio.save_batch(restored, batch_files, distorted_dir, restored_dir, suffix=".png")
+        keep, clean = [], []
+        for k, f in enumerate(batch_files):
+            cp = clean_dir / f.relative_to(distorted_dir)
+            if not cp.exists():
+                cp = cp.with_suffix(".ppm")
+            if cp.exists():
+                keep.append(k)
+                clean.append(imageio.load_rgb(cp))
+        if keep:
+            ref = imageio.resize_batch_cv(clean, (224, 224), device=dev)
+            out = restored[torch.tensor(keep, device=dev)]
+            total_psnr += float(generators.psnr(ref, out).sum())
+            total_ssim += float(generators.ssim(ref, out).sum())
+            count += len(keep)
+    if count > 0:
+        if verbose:
+            print(f"Task [{task_name}] completed.")
+            print(f"Average PSNR: {total_psnr / count:.2f} dB")
+            print(f"Average SSIM: {total_ssim / count:.4f}")
+        return total_psnr / count, total_ssim / count, count
+    if verbose:
+        print("No images processed.")
+    return None
 
 
 def benchmark_table(judge, dirs, verbose: bool = True):

@@ -159,6 +159,76 @@ def resize_batch(images: Sequence[np.ndarray], size: Tuple[int, int] = (224, 224
     return ops.resize_bilinear_u8(out=out, **plan)
 
 
+@lru_cache(maxsize=None)
+def cv_linear_table(in_size: int, out_size: int) -> np.ndarray:
+    """OpenCV's INTER_LINEAR coordinate arithmetic for u8 images (imgproc/resize.cpp, cv2 4.13) along one axis:
+    int32 [out_size, 3] = {first source index s, cvRound((1 - f) * 2048), cvRound(f * 2048)} with
+    f = (float)((d + 0.5) * (in / out) - 0.5), s = floor(f), f -= s (s may be -1 or >= in - 1: resize_batch_cv applies
+    OpenCV's border rule, which differs between columns and rows)."""
+    scale = float(in_size) / float(out_size)
+    tab = np.zeros((out_size, 3), np.int32)
+    for d in range(out_size):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f))
+        f = np.float32(f - np.float32(s))
+        tab[d] = (s, int(np.rint(np.float32((np.float32(1.0) - f) * np.float32(2048)))),
+                  int(np.rint(np.float32(f * np.float32(2048)))))
+    tab.setflags(write=False)
+    return tab
+
+
+def _pack_ragged(images: Sequence[np.ndarray]):
+    """u8 [H_i, W_i, 3] host arrays -> (pinned packed bytes, offsets int64 [N], hw int32 [N, 2])."""
+    n = len(images)
+    hw = np.zeros((n, 2), np.int32)
+    offsets = np.zeros((n,), np.int64)
+    total = 0
+    for i, im in enumerate(images):
+        if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+            raise L.B2RError(f"image {i}: expected uint8 [H, W, 3], got {im.dtype} {im.shape}")
+        hw[i] = im.shape[:2]
+        offsets[i] = total
+        total += im.size
+    packed = torch.empty((total,), dtype=torch.uint8).pin_memory()
+    pk = packed.numpy()
+    for i, im in enumerate(images):
+        pk[offsets[i]:offsets[i] + im.size] = np.ascontiguousarray(im).reshape(-1)
+    return packed, offsets, hw
+
+
+def resize_batch_cv(images: Sequence[np.ndarray], size: Tuple[int, int] = (224, 224), device=None) -> torch.Tensor:
+    """`cv2.resize(img, (size[1], size[0]))` (INTER_LINEAR, 08_run_inference.py:119) over a list of u8 [H_i, W_i, 3] host
+    arrays -> u8 [N, size[0], size[1], 3] on the device, bit for bit; one H2D copy and one launch for the ragged batch.
+    (Channel order is irrelevant: the arithmetic is per channel.)"""
+    if not torch.cuda.is_available():
+        raise L.B2RError("resize_batch_cv needs a CUDA device (there is no CPU fallback)")
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out_h, out_w = int(size[0]), int(size[1])
+    n = len(images)
+    if n == 0:
+        return torch.empty((0, out_h, out_w, 3), dtype=torch.uint8, device=device)
+    packed, offsets, hw = _pack_ragged(images)
+    keys, xi, yi = {}, np.zeros((n,), np.int32), np.zeros((n,), np.int32)
+    for i in range(n):
+        xi[i] = keys.setdefault((int(hw[i, 1]), out_w, "x"), len(keys))
+        yi[i] = keys.setdefault((int(hw[i, 0]), out_h, "y"), len(keys))
+    S = max(out_h, out_w)
+    tabs = np.zeros((len(keys), S, 3), np.int32)
+    for (src, dst, axis), t in keys.items():
+        tab = cv_linear_table(src, dst).copy()
+        if axis == "x":
+            # columns: outside [0, src - 2] OpenCV takes the border pixel alone (index clamped, fraction zeroed)
+            outside = (tab[:, 0] < 0) | (tab[:, 0] >= src - 1)
+            tab[outside, 1], tab[outside, 2] = 2048, 0
+            tab[:, 0] = np.clip(tab[:, 0], 0, src - 1)
+        # rows: OpenCV keeps both coefficients and clamps the two row indices (the kernel does that)
+        tabs[t, :dst] = tab
+    dev = lambda a: torch.from_numpy(a).to(device, non_blocking=True)   # noqa: E731
+    out = torch.empty((n, out_h, out_w, 3), dtype=torch.uint8, device=device)
+    return ops.resize_cv_linear_u8(packed.to(device, non_blocking=True), dev(offsets), dev(hw), dev(xi), dev(yi), dev(tabs),
+                                   S, out)
+
+
 def load_batch(files: Sequence, size: Tuple[int, int] = (224, 224), device=None) -> torch.Tensor:
     """The batch-preparation loop of 17_run_unified_inference.py:76-82 without ToTensor (fused downstream)."""
     return resize_batch([load_rgb(p) for p in files], size=size, device=device)

@@ -455,3 +455,23 @@ def resize_bilinear_u8(src: torch.Tensor, offsets: torch.Tensor, hw: torch.Tenso
                                             int(out_h), int(out_w), int(tile_rows), int(max_rows), _stream()))
     STATS["launches"] += 1
     return out
+
+
+def resize_cv_linear_u8(src: torch.Tensor, offsets: torch.Tensor, hw: torch.Tensor, xtab_index: torch.Tensor,
+                        ytab_index: torch.Tensor, tabs: torch.Tensor, S: int, out: torch.Tensor) -> torch.Tensor:
+    """b2r_resize_cv_linear_u8 (cv2.resize INTER_LINEAR on a ragged packed batch); see imageio.resize_batch_cv."""
+    _chk(src, torch.uint8, "src", 1)
+    _chk(offsets, torch.int64, "offsets", 1)
+    _chk(hw, torch.int32, "hw", 2)
+    _chk(xtab_index, torch.int32, "xtab_index", 1)
+    _chk(ytab_index, torch.int32, "ytab_index", 1)
+    _chk(tabs, torch.int32, "tabs", 3)
+    _chk(out, torch.uint8, "out", 4)
+    n, out_h, out_w, c = out.shape
+    if c != 3 or offsets.numel() != n or tuple(hw.shape) != (n, 2) or tabs.shape[1] != S or tabs.shape[2] != 3:
+        raise L.B2RError("inconsistent resize arguments")
+    L.check(L.load().b2r_resize_cv_linear_u8(src.data_ptr(), offsets.data_ptr(), hw.data_ptr(), xtab_index.data_ptr(),
+                                             ytab_index.data_ptr(), tabs.data_ptr(), int(S), out.data_ptr(), int(n),
+                                             int(out_h), int(out_w), _stream()))
+    STATS["launches"] += 1
+    return out

@@ -255,6 +255,14 @@ int b2r_resize_bilinear_u8(const uint8_t* src, const int64_t* offsets, const int
                            const int32_t* ytab_index, const int32_t* tabs, int K, int S, uint8_t* out, int N, int out_h,
                            int out_w, int tile_rows, int max_rows, void* stream);
 
+/* cv2.resize(img, (out_w, out_h)) (default INTER_LINEAR) of a ragged batch of u8 HWC images, bit for bit: what
+ * 08_run_inference.py:119 applies to the clean image before PSNR / SSIM.  Packing as for b2r_resize_bilinear_u8;
+ * tabs int32 [T][S][3] = {first source index, cvRound((1 - f) * 2048), cvRound(f * 2048)} per output coordinate, from the
+ * host (imageio.cv_linear_table restates OpenCV's coordinate arithmetic); out u8 [N][out_h][out_w][3]. */
+int b2r_resize_cv_linear_u8(const uint8_t* src, const int64_t* offsets, const int32_t* hw, const int32_t* xtab_index,
+                            const int32_t* ytab_index, const int32_t* tabs, int S, uint8_t* out, int N, int out_h,
+                            int out_w, void* stream);
+
 /* VGG feature taps: mean over the middle axis of a bf16 tensor viewed as [outer][reduce][inner], f32 [outer][inner] out.
  * inner = 1: channel mean of an NHWC feature map (11_visualize_hidden_states.py:50, torch.mean(features, dim=1));
  * inner > 1: global average pooling of [N][H*W][C] (12_generate_umap_pt.py:52, torch.mean(feature, dim=[2, 3])).

@@ -26,3 +26,10 @@ def load_and_resize(files: Sequence, size=(224, 224)) -> np.ndarray:
     """The batch-preparation loop of 17:76-82 up to (not including) ToTensor: -> u8 [N, size[0], size[1], 3]."""
     t = transforms.Resize(size)
     return np.stack([np.asarray(t(Image.open(p).convert("RGB"))) for p in files])
+
+
+def resize_cv(img_u8_hwc: np.ndarray, size=(224, 224)) -> np.ndarray:
+    """`cv2.resize(clean_img, (224, 224))` as 08_run_inference.py:119 calls it (default INTER_LINEAR; dsize is (width,
+    height)).  This IS the reference's call (cv2 4.13.0 here, un-pinned in the reference)."""
+    import cv2
+    return cv2.resize(img_u8_hwc, (int(size[1]), int(size[0])))

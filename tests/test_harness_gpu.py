@@ -86,3 +86,40 @@ def test_run_inference_writes_the_restored_tree(tmp_path):
     assert d.mean() < 0.5 and (d > 2).mean() < 1e-3, (float(d.mean()), int(d.max()))
     with pytest.raises(Exception):
         harness.run_inference(models.ResUNet(), src, dst, verbose=False)           # module on the CPU: no fallback
+
+
+def test_process_task_scores_like_script_08(tmp_path, capsys):
+    """08:55-137: distorted tree -> restored .png tree + mean PSNR / SSIM against cv2.resize(clean, (224, 224)).
+    Oracle: the reference's own composition on the files this run wrote (cv2.resize + the oracle's PSNR / SSIM)."""
+    from b200restore import harness, models, synth
+    from oracle import generators_oracle as GO, imageio_oracle as IOO
+    dist, rest, clean = tmp_path / "processed" / "Noise", tmp_path / "restored" / "Noise", tmp_path / "gtsrb"
+    files = _tree(dist, ["00003", "00021"], 4, exts=("png", "ppm"), seed=2)
+    rng = np.random.default_rng(5)
+    for k, f in enumerate(files):                       # clean counterparts: other sizes, .ppm names; one missing
+        if k == 3:
+            continue
+        cp = (clean / f.relative_to(dist)).with_suffix(".ppm")
+        cp.parent.mkdir(parents=True, exist_ok=True)
+        h, w = int(rng.integers(20, 200)), int(rng.integers(20, 200))
+        Image.fromarray(synth.sign_like_images(1, h, w, seed=300 + k)[0][0].numpy()).save(cp)
+    m = models.SimpleUNet()
+    m.load_state_dict(synth.synthetic_state_dict("simple_unet", 41))
+    m = m.cuda().eval()
+    res = harness.process_task(m, "Noise", dist, rest, clean, batch_size=3)
+    out = capsys.readouterr().out
+    assert res is not None and res[2] == len(files) - 1
+    assert "=== Starting task processing: Noise ===" in out and f"Average PSNR: {res[0]:.2f} dB" in out
+    ps, ss = [], []
+    for k, f in enumerate(files):
+        written = (rest / f.relative_to(dist)).with_suffix(".png")
+        assert written.exists()
+        if k == 3:
+            continue
+        ref = IOO.resize_cv(np.asarray(Image.open((clean / f.relative_to(dist)).with_suffix(".ppm")).convert("RGB")))
+        got = np.asarray(Image.open(written))
+        ps.append(GO.psnr_08(ref, got))
+        ss.append(GO.ssim_08(ref, got))
+    assert res[0] == pytest.approx(float(np.mean(ps)), rel=1e-12)
+    assert res[1] == pytest.approx(float(np.mean(ss)), abs=1e-10)
+    assert harness.process_task(m, "Fog", tmp_path / "processed" / "Fog", rest, clean, verbose=False) is None

@@ -47,3 +47,21 @@ def test_load_restore_save_tree_roundtrip(tmp_path):
     assert [p.relative_to(dst).with_suffix("") for p in out] == [f.relative_to(src).with_suffix("") for f in files]
     for p, ref in zip(out, batch.cpu().numpy()):
         assert np.array_equal(np.asarray(Image.open(p)), ref)
+
+
+def test_resize_batch_cv_bit_exact_against_cv2():
+    """cv2.resize(img, (224, 224)) (08:119) on a ragged batch in one launch: bit-exact against OpenCV itself, including
+    up-scaling from 15 px, down-scaling from 600 px, the identity size and a non-square target."""
+    from b200restore import imageio as IO
+    from oracle import imageio_oracle as IOO
+    rng = np.random.default_rng(4)
+    sizes = [(15, 15), (15, 250), (250, 15), (224, 224), (448, 448), (600, 333), (31, 97), (100, 100), (223, 225), (1, 7)]
+    sizes += [(int(rng.integers(15, 251)), int(rng.integers(15, 251))) for _ in range(30)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    out = IO.resize_batch_cv(imgs).cpu().numpy()
+    for i, im in enumerate(imgs):
+        assert np.array_equal(out[i], IOO.resize_cv(im)), sizes[i]
+    out2 = IO.resize_batch_cv(imgs[:12], size=(96, 160)).cpu().numpy()
+    for i in range(12):
+        assert np.array_equal(out2[i], IOO.resize_cv(imgs[i], (96, 160))), sizes[i]
+    assert IO.resize_batch_cv([]).shape == (0, 224, 224, 3)

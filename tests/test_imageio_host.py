@@ -54,3 +54,32 @@ def test_ppm_reader_matches_pillow(tmp_path):
     assert np.array_equal(IO.load_rgb(g), np.repeat(img[:, :, :1], 3, 2))
     with pytest.raises(Exception):
         IO.read_ppm(g)
+
+
+def test_cv_linear_tables_reproduce_cv2_resize():
+    """08:119 cv2.resize(clean, (224, 224)): the host tables (imageio.cv_linear_table + the border rule of
+    resize_batch_cv) driven through a NumPy model of csrc/generators.cu::resize_cv_linear_u8_kernel give cv2's bytes for
+    up- and down-scaling, 1-pixel extents and the 2x case OpenCV reroutes to INTER_AREA."""
+    import cv2
+    from b200restore import imageio as IO
+
+    def model(img, oh, ow):
+        h, w, _ = img.shape
+        xt, yt = IO.cv_linear_table(w, ow).copy(), IO.cv_linear_table(h, oh)
+        outside = (xt[:, 0] < 0) | (xt[:, 0] >= w - 1)
+        xt[outside, 1], xt[outside, 2] = 2048, 0
+        xt[:, 0] = np.clip(xt[:, 0], 0, w - 1)
+        S = img.astype(np.int64)
+        sx = xt[:, 0]
+        x1 = np.minimum(sx + 1, w - 1)
+        H = S[:, sx, :] * xt[:, 1][None, :, None] + S[:, x1, :] * xt[:, 2][None, :, None]
+        r0, r1 = np.clip(yt[:, 0], 0, h - 1), np.clip(yt[:, 0] + 1, 0, h - 1)
+        b0, b1 = yt[:, 1].astype(np.int64)[:, None, None], yt[:, 2].astype(np.int64)[:, None, None]
+        return np.clip((((b0 * (H[r0] >> 4)) >> 16) + ((b1 * (H[r1] >> 4)) >> 16) + 2) >> 2, 0, 255).astype(np.uint8)
+
+    rng = np.random.default_rng(1)
+    shapes = [(int(rng.integers(1, 300)), int(rng.integers(1, 300))) for _ in range(30)] + [(448, 448), (224, 224), (1, 1), (15, 250)]
+    for t, (h, w) in enumerate(shapes):
+        oh, ow = (224, 224) if t % 3 else (int(rng.integers(1, 300)), int(rng.integers(1, 300)))
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(cv2.resize(img, (ow, oh)), model(img, oh, ow)), (h, w, oh, ow)
