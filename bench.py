@@ -64,6 +64,9 @@ def parse_args():
     ap.add_argument("--hw", type=int, default=224)
     ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline sample (0 = choose)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=0, choices=[0, 1],
+                    help="e2e leg: replay restore -> classify -> count of a micro-batch as one CUDA graph (the device-resident "
+                         "`value` leg stays eager: it times every conv launch with CUDA events)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference: 'cuda' times the same fp32 PyTorch port on the GPU through cuDNN / cuBLAS "
                          "(the reference with DEVICE='cuda', 17:16) as the same-box library comparator")
@@ -435,10 +438,13 @@ def run_ours(args):
     # ---- end-to-end (host buffers) : same K steps
     e2e = None
     if classify:
+        pipe.use_graph = bool(args.graph) and cascade is None
         step_host()
         e2e_ms, (c2, h2d, d2h) = timed(step_host, args.steps)
+        pipe.use_graph = False
         e2e = {"value": B_ * world * args.steps / (e2e_ms / 1e3), "unit": "images/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps}
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
+               "cuda_graph": bool(args.graph) and cascade is None}
 
     if rank != 0:
         if world > 1:

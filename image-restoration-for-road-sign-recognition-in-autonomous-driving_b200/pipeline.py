@@ -40,10 +40,15 @@ def all_reduce_counts(counts: torch.Tensor) -> torch.Tensor:
 class RestoreClassifyPipeline:
     """Holds a restorer (SimpleUNet / ResUNet) and the VGG16 judge on one device and streams batches through them."""
 
-    def __init__(self, restorer, judge, micro_batch: int = 256):
+    def __init__(self, restorer, judge, micro_batch: int = 256, use_graph: bool = False):
         self.restorer = restorer.eval()
         self.judge = judge.eval()
         self.micro_batch = int(micro_batch)
+        # use_graph: restore -> classify -> count of a micro-batch (everything after the degradation launch, ~200 kernel
+        # launches and as many host-side TMA descriptor encodings) is captured once per batch shape into a CUDA graph
+        # and replayed; the degradation stays a plain launch because its Philox counter base is a by-value argument.
+        self.use_graph = bool(use_graph)
+        self._graphs = {}
         self.device = next(judge.parameters()).device
         if self.device.type != "cuda":
             raise L.B2RError("RestoreClassifyPipeline needs its modules on a CUDA device (no CPU fallback)")
@@ -63,6 +68,8 @@ class RestoreClassifyPipeline:
                         keep: bool = False):
         """One resident micro-batch through all stages.  Returns (pred int64 [n], extras dict when keep=True)."""
         n, h, w, _ = clean_u8.shape
+        if self.use_graph and not keep and noise is None:
+            return self._run_micro_batch_graph(clean_u8, labels, params, seed, image_index0, counts), None
         degraded = D.degrade(clean_u8, params, seed=seed, image_index0=image_index0, noise=noise,
                              out=self._buf("deg", (n, h, w, 3), torch.uint8)) if params is not None else clean_u8
         restored = self._buf("rest", (n, h, w, 3), torch.uint8)
@@ -74,6 +81,52 @@ class RestoreClassifyPipeline:
         if keep:
             return pred, {"degraded": degraded.clone(), "restored": restored.clone(), "logits": logits.clone()}
         return pred, None
+
+    # -- CUDA-graph mode --------------------------------------------------------------------------------------------
+    def _restore_classify(self, degraded, restored, labels, counts):
+        self.restorer._check_input(degraded, self._div)
+        self.restorer._run(degraded, None, restored)
+        self.judge._check_input(restored, 32)
+        return ops.argmax_count(self.judge._run(restored, True), labels, counts)[0]
+
+    def _graph_entry(self, n: int, h: int, w: int, with_labels: bool):
+        packs = (self.restorer._packed(), self.judge._packed())
+        key = (n, h, w, with_labels)
+        ent = self._graphs.get(key)
+        if ent is not None and ent["packs"][0] is packs[0] and ent["packs"][1] is packs[1]:
+            return ent
+        dev = self.device
+        ent = {"packs": packs,                                             # re-packed weights invalidate the graph
+               "deg": torch.zeros((n, h, w, 3), dtype=torch.uint8, device=dev),
+               "rest": torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev),
+               "labels": torch.zeros((n,), dtype=torch.int64, device=dev) if with_labels else None,
+               "counts": torch.zeros((2,), dtype=torch.int64, device=dev)}
+        self._restore_classify(ent["deg"], ent["rest"], ent["labels"], ent["counts"])   # eager once: workspaces, attributes
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ent["pred"] = self._restore_classify(ent["deg"], ent["rest"], ent["labels"], ent["counts"])
+        # the graph holds raw pointers into the modules' activation workspaces: keep those tensors alive even if the
+        # workspaces later switch to another batch shape
+        ent["pinned"] = (dict(self.restorer._ws._bufs), dict(self.judge._ws._bufs))
+        ent["graph"] = graph
+        self._graphs[key] = ent
+        return ent
+
+    def _run_micro_batch_graph(self, clean_u8, labels, params, seed, image_index0, counts):
+        n, h, w, _ = clean_u8.shape
+        ent = self._graph_entry(n, h, w, labels is not None)
+        if params is not None:
+            D.degrade(clean_u8, params, seed=seed, image_index0=image_index0, out=ent["deg"])
+        else:
+            ent["deg"].copy_(clean_u8)
+        if labels is not None:
+            ent["labels"].copy_(labels)
+        ent["counts"].zero_()
+        ent["graph"].replay()
+        if counts is not None:
+            counts.add_(ent["counts"])
+        return ent["pred"]          # static output of the graph: consume it before the next micro-batch of this shape
 
     @torch.no_grad()
     def run(self, clean_u8: torch.Tensor, labels: torch.Tensor, params, seed: int = 0, image_index0: int = 0):

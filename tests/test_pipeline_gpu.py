@@ -201,3 +201,40 @@ def test_script08_flow_at_config0_size():
         assert float(ssim[i]) == pytest.approx(GO.ssim_08(c_np[i], r_np[i]), abs=5e-3)
     print(f"\n[script 08 @ 256 x 224^2] mean PSNR {float(psnr.mean()):.2f} dB, mean SSIM {float(ssim.mean()):.4f}; "
           f"restored vs fp32 oracle: max |diff| {int(d.max())} LSB")
+
+
+def test_cuda_graph_mode_is_bit_identical_to_eager():
+    """use_graph=True replays restore -> classify -> count as one CUDA graph per batch shape.  Same predictions and
+    counts as the eager path on fresh data, across a ragged tail chunk (second graph), from host buffers, after the
+    workspaces switched shape, and after load_state_dict (re-packed weights must invalidate the captured graph)."""
+    from b200restore import degrade, synth
+    pipe, _, _ = _build("resunet")
+    n, hw = 20, 64
+    params = degrade.compound_params(n)
+    for seed in (1, 2):
+        imgs, labels = synth.sign_like_images(n, hw, hw, seed=seed)
+        imgs, labels = imgs.cuda(), labels.cuda()
+        pipe.use_graph = False
+        p0, c0 = pipe.run(imgs, labels, params, seed=5, image_index0=100)
+        pipe.use_graph = True
+        p1, c1 = pipe.run(imgs, labels, params, seed=5, image_index0=100)        # chunks 8, 8, 4
+        assert torch.equal(p0, p1) and torch.equal(c0, c1)
+        c2, _, _ = pipe.run_from_host(imgs.cpu().pin_memory(), labels.cpu().pin_memory(), params, seed=5, image_index0=100)
+        assert c2 == (int(c0[0]), int(c0[1]))
+    assert len(pipe._graphs) == 2
+    # another resolution in between (the modules' workspaces are re-allocated), then the first shape again
+    big, lb = synth.sign_like_images(8, 96, 96, seed=3)
+    pipe.use_graph = False
+    pipe.run(big.cuda(), lb.cuda(), degrade.compound_params(8))
+    pipe.use_graph = True
+    p3, c3 = pipe.run(imgs, labels, params, seed=5, image_index0=100)
+    assert torch.equal(p3, p0) and torch.equal(c3, c0)
+    # new weights
+    pipe.judge.load_state_dict(synth.synthetic_state_dict("vgg16", 77))
+    pipe.use_graph = False
+    p4, c4 = pipe.run(imgs, labels, params, seed=5, image_index0=100)
+    pipe.use_graph = True
+    p5, c5 = pipe.run(imgs, labels, params, seed=5, image_index0=100)
+    assert torch.equal(p4, p5) and torch.equal(c4, c5)
+    used = [e for e in pipe._graphs.values() if e["deg"].shape[1] == hw]
+    assert used and all(e["packs"][1] is pipe.judge._packed() for e in used)      # re-captured with the new weights
