@@ -166,6 +166,25 @@ def test_blur_ragged_shapes_all_small_degrees_vs_cv2():
                 assert np.array_equal(out[i], ref), (h, w, order, i, d, int(np.abs(out[i].astype(int) - ref).max()))
 
 
+def test_no_kernel_writes_outside_its_output():
+    """Guard bands around the output of each of the three degradation kernels (point-wise, no-blur, blur) on aligned and
+    ragged shapes: the bytes before and after the [N, H, W, 3] block must stay untouched."""
+    from b200restore import degrade
+    rng = np.random.default_rng(31)
+    for (n, h, w) in ((3, 224, 224), (2, 37, 53), (4, 17, 5), (1, 16, 29)):
+        imgs = _dev(rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8))
+        kinds = {"pointwise": degrade.fog_params(n, np.random.default_rng(1)),
+                 "noblur": degrade.noise_params(n, 0.02),
+                 "blur": degrade.compound_params(n) if min(h, w) > 10 else degrade.blur_params(n, 3, 30)}
+        for name, p in kinds.items():
+            big = torch.full((n + 2, h, w, 3), 0xAB, dtype=torch.uint8, device="cuda")
+            out = big[1:n + 1]
+            res = degrade.degrade(imgs, p, seed=3, out=out)
+            assert res.data_ptr() == out.data_ptr()
+            assert bool((big[0] == 0xAB).all()) and bool((big[n + 1] == 0xAB).all()), (name, n, h, w)
+            assert torch.equal(out, degrade.degrade(imgs, p, seed=3)), (name, n, h, w)     # same bytes in a fresh buffer
+
+
 def test_identity_when_nothing_is_applied():
     from b200restore import degrade
     imgs = torch.randint(0, 256, (3, 64, 80, 3), dtype=torch.uint8).cuda()
