@@ -132,6 +132,20 @@ class DegradeParams:
     def set_noise(self, i: int, var: float) -> None:
         self.sigma[i] = np.float32(var ** 0.5)                # np.random.normal(0, var ** 0.5, ...) (16:34)
 
+    # -- the same parameters for every image of the batch (no per-image Python loop) ----------------------------------
+    def set_blur_all(self, degree: int, angle: float) -> None:
+        self.set_blur(0, degree, angle)
+        self.ksize[:] = self.ksize[0]
+        self.taps[:] = self.taps[0]
+
+    def set_fog_all(self, t: float, A: float = 0.9) -> None:
+        self.set_fog(0, t, A)
+        self.fog_on[:], self.fog_t[:], self.fog_add[:] = 1, self.fog_t[0], self.fog_add[0]
+
+    def set_noise_all(self, var: float) -> None:
+        self.set_noise(0, var)
+        self.sigma[:] = self.sigma[0]
+
     def to(self, device) -> "DeviceDegradeParams":
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
         return DeviceDegradeParams(self.n, self.order, self.flags, t(self.ksize), t(self.taps), t(self.fog_on),
@@ -157,20 +171,18 @@ class DeviceDegradeParams:
 def compound_params(n: int) -> DegradeParams:
     """apply_compound_distortion (16_gen_compound_data.py:14-37): Blur(10, 45 deg) -> Fog(0.5, A=0.9) -> Noise(var .02)."""
     p = DegradeParams(n, order=L.B2R_ORDER_BLUR_FOG_NOISE)
-    for i in range(n):
-        p.set_blur(i, 10, 45)
-        p.set_fog(i, 1.0 - 0.5)
-        p.set_noise(i, 0.02)
+    p.set_blur_all(10, 45)
+    p.set_fog_all(1.0 - 0.5)
+    p.set_noise_all(0.02)
     return p
 
 
 def demo_params(n: int) -> DegradeParams:
     """make_compound_distortion (15_test_unified.py:93-120): Fog -> Noise -> clip -> u8 -> Blur(10, 45 deg)."""
     p = DegradeParams(n, order=L.B2R_ORDER_FOG_NOISE_BLUR, flags=L.B2R_DEG_CLIP_AFTER_NOISE)
-    for i in range(n):
-        p.set_fog(i, 1.0 - 0.5)
-        p.set_noise(i, 0.02)
-        p.set_blur(i, 10, 45)
+    p.set_fog_all(1.0 - 0.5)
+    p.set_noise_all(0.02)
+    p.set_blur_all(10, 45)
     return p
 
 
@@ -206,8 +218,7 @@ def fog_params(n: int, rng: Optional[np.random.Generator] = None, fog_intensity:
 def blur_params(n: int, degree: int = 12, angle: float = 45) -> DegradeParams:
     """apply_motion_blur (03_gen_blur.py:11-30) WITHOUT its cv2.normalize min-max stretch."""
     p = DegradeParams(n)
-    for i in range(n):
-        p.set_blur(i, degree, angle)
+    p.set_blur_all(degree, angle)
     return p
 
 
@@ -215,8 +226,7 @@ def noise_params(n: int, var: float = 0.02) -> DegradeParams:
     """add_gaussian_noise (02_gen_noise.py:12-27) with the [0,1] clip; the script's wrap-around for negative values
     (np.uint8 of a negative float) is a dataset-generator quirk outside this path."""
     p = DegradeParams(n, flags=L.B2R_DEG_CLIP_AFTER_NOISE)
-    for i in range(n):
-        p.set_noise(i, var)
+    p.set_noise_all(var)
     return p
 
 

@@ -196,7 +196,8 @@ def _pack_ragged(images: Sequence[np.ndarray]):
     return packed, offsets, hw
 
 
-def resize_batch_cv(images: Sequence[np.ndarray], size: Tuple[int, int] = (224, 224), device=None) -> torch.Tensor:
+def resize_batch_cv(images: Sequence[np.ndarray], size: Tuple[int, int] = (224, 224), device=None,
+                    _return_plan: bool = False) -> torch.Tensor:
     """`cv2.resize(img, (size[1], size[0]))` (INTER_LINEAR, 08_run_inference.py:119) over a list of u8 [H_i, W_i, 3] host
     arrays -> u8 [N, size[0], size[1], 3] on the device, bit for bit; one H2D copy and one launch for the ragged batch.
     (Channel order is irrelevant: the arithmetic is per channel.)"""
@@ -225,8 +226,11 @@ def resize_batch_cv(images: Sequence[np.ndarray], size: Tuple[int, int] = (224, 
         tabs[t, :dst] = tab
     dev = lambda a: torch.from_numpy(a).to(device, non_blocking=True)   # noqa: E731
     out = torch.empty((n, out_h, out_w, 3), dtype=torch.uint8, device=device)
-    return ops.resize_cv_linear_u8(packed.to(device, non_blocking=True), dev(offsets), dev(hw), dev(xi), dev(yi), dev(tabs),
-                                   S, out)
+    plan = dict(src=packed.to(device, non_blocking=True), offsets=dev(offsets), hw=dev(hw), xtab_index=dev(xi),
+                ytab_index=dev(yi), tabs=dev(tabs), S=S)
+    if _return_plan:
+        return out, plan
+    return ops.resize_cv_linear_u8(out=out, **plan)
 
 
 def load_batch(files: Sequence, size: Tuple[int, int] = (224, 224), device=None) -> torch.Tensor:

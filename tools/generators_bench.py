@@ -73,6 +73,21 @@ def main():
     name = "resize_bilinear_u8 (Pillow BILINEAR, 15..250 px -> 224)"
     print(f"{name:46s} {ms * 1e3 / n:7.3f} us/img  {gbps:8.1f} GB/s algorithmic = {100 * gbps / hbm:5.1f}% of {hbm:.0f} GB/s")
     res.append({"kernel": name, "us_per_image": ms * 1e3 / n, "algorithmic_gbps": gbps, "frac_hbm": gbps / hbm})
+    cout, cplan = IO.resize_batch_cv(imgs, _return_plan=True)
+    for _ in range(3):
+        ops.resize_cv_linear_u8(out=cout, **cplan)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.resize_cv_linear_u8(out=cout, **cplan)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    gbps = (in_bytes + cout.numel()) / (ms * 1e-3) / 1e9
+    name = "resize_cv_linear_u8 (cv2.resize, 15..250 px -> 224)"
+    print(f"{name:46s} {ms * 1e3 / n:7.3f} us/img  {gbps:8.1f} GB/s algorithmic = {100 * gbps / hbm:5.1f}% of {hbm:.0f} GB/s")
+    res.append({"kernel": name, "us_per_image": ms * 1e3 / n, "algorithmic_gbps": gbps, "frac_hbm": gbps / hbm})
     if "--json" in sys.argv:
         Path(sys.argv[sys.argv.index("--json") + 1]).write_text(json.dumps({"batch": n, "hw": hw, "hbm_gbps": hbm, "kernels": res}, indent=1))
 
