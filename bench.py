@@ -11,8 +11,9 @@ Prints ONE JSON line on rank 0:
   value      images/s with the batch already resident in HBM when the timed region starts (CUDA events, max over ranks)
   e2e        same metric through the public API with HOST buffers (pinned H2D of every micro-batch + D2H of the counts
              inside the timed region)
-  roofline   the dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs / summed CUDA-event duration of its
-             launches inside the timed region, against MEASURED_PEAKS.json
+  roofline   the dominant kernel family (tcgen05 implicit-GEMM conv): algorithmic FLOPs / summed CUDA-event duration of its
+             launches inside the timed region, against MEASURED_PEAKS.json; `by_kernel` splits the same measurement by
+             the kernel each launch actually ran (b2r_last_conv_kernel), `dominant_kernel` names the largest share
   cpu_baseline  the oracle port of the reference path timed on this box's host cores (bounded sample, rank 0, N = 1)
 
 `--impl reference` times the reference's CPU implementation of the same path (oracle port: the reference is Python and
@@ -485,6 +486,11 @@ def run_ours(args):
                                      "ncu capture at micro-batch 256 (profiles/r01_launches_v11_summary.md), scaled to this run's "
                                      "launch size (activations dominate: traffic is linear in images per launch)",
                      "launches": ksum["launches"], "kernel_ms_per_step": ksum["ms"] / args.steps,
+                     "dominant_kernel": max(ksum.get("by_kernel", {"?": {"ms": 0}}).items(), key=lambda kv: kv[1]["ms"])[0],
+                     "by_kernel": {k: {"launches": v["launches"], "share_of_step": v["ms"] / total_ms,
+                                       "achieved": v["work"] / (v["ms"] * 1e-3) / 1e12,
+                                       "frac": v["work"] / (v["ms"] * 1e-3) / 1e12 / peak_tf}
+                                   for k, v in sorted(ksum.get("by_kernel", {}).items(), key=lambda kv: -kv[1]["ms"])},
                      "share_of_step": ksum["ms"] / total_ms,
                      "pipeline_tflops": ips / world * gflop_img / 1e3 if hw == 224 else None},
         "counts": [int(counts[0]), int(counts[1])],

@@ -20,7 +20,7 @@ B2R_CONV_GENERIC_ONLY, B2R_CONV_NO_W3, B2R_CONV_NO_HALO, B2R_CONV_NO_PAIR = 1, 2
 
 # every symbol include/b2r.h declares (tests/test_abi.py checks the list against the header and the .so)
 SYMBOLS = (
-    "b2r_version", "b2r_last_error", "b2r_debug_timeline", "b2r_degrade", "b2r_conv3x3_c3", "b2r_conv_gemm", "b2r_final_conv1x1",
+    "b2r_version", "b2r_last_error", "b2r_last_conv_kernel", "b2r_debug_timeline", "b2r_degrade", "b2r_conv3x3_c3", "b2r_conv_gemm", "b2r_final_conv1x1",
     "b2r_maxpool2x2", "b2r_adaptive_avgpool7", "b2r_linear_f32out", "b2r_argmax_count",
     "b2r_lut_u8", "b2r_minmax_u8", "b2r_normalize_minmax_u8", "b2r_noise02", "b2r_sse_u8", "b2r_ssim_u8", "b2r_mean_bf16", "b2r_resize_bilinear_u8", "b2r_resize_cv_linear_u8",
 )
@@ -88,6 +88,8 @@ def load() -> C.CDLL:
     lib.b2r_version.argtypes = []
     lib.b2r_last_error.restype = C.c_char_p
     lib.b2r_last_error.argtypes = []
+    lib.b2r_last_conv_kernel.restype = C.c_char_p
+    lib.b2r_last_conv_kernel.argtypes = []
     lib.b2r_debug_timeline.restype = None
     lib.b2r_debug_timeline.argtypes = [vp]
     lib.b2r_degrade.restype = C.c_int

@@ -8,6 +8,7 @@
 namespace b2r {
 
 static thread_local char g_err[512] = "";
+static thread_local const char* g_conv_kernel = "";
 
 char* last_error_buf() { return g_err; }
 
@@ -65,6 +66,9 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
     return B2R_OK;
 }
 
+void note_conv_kernel(const char* name) { g_conv_kernel = name; }
+const char* last_conv_kernel() { return g_conv_kernel; }
+
 int device_sm_count(int* sms) {
     static int cached[64] = {0};
     int dev = 0;
@@ -89,5 +93,6 @@ extern "C" {
 int b2r_version(void) { return B2R_VERSION; }
 
 const char* b2r_last_error(void) { return b2r::last_error_buf(); }
+const char* b2r_last_conv_kernel(void) { return b2r::last_conv_kernel(); }
 
 }  // extern "C"

@@ -43,4 +43,8 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
 
 int device_sm_count(int* sms);
 
+// name of the kernel the last b2r_conv_gemm call of this thread launched (diagnostic: b2r_last_conv_kernel())
+void note_conv_kernel(const char* name);
+const char* last_conv_kernel();
+
 }  // namespace b2r

@@ -966,6 +966,7 @@ static int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
                                       Cfg::kSmemBytes));
         if (dev < 64) attr_set[dev] = true;
     }
+    note_conv_kernel(BLOCK_N == 64 ? "conv_gemm_kernel<64>" : BLOCK_N == 128 ? "conv_gemm_kernel<128>" : "conv_gemm_kernel<256>");
     conv_gemm_kernel<BLOCK_N><<<grid * Cfg::kCtasPerSm, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
     B2R_CHECK_LAUNCH();
     return B2R_OK;
@@ -981,6 +982,7 @@ static int launch_pair(const ConvGemmParams& p, int clusters, cudaStream_t strea
                                       PairCfg<N>::kSmemBytes));
         if (dev < 64) attr_set[dev] = true;
     }
+    note_conv_kernel(N == 256 ? "conv_gemm_pair_kernel<256>" : "conv_gemm_pair_kernel<128>");
     conv_gemm_pair_kernel<N><<<(unsigned)(2 * clusters), kNumThreads, PairCfg<N>::kSmemBytes, stream>>>(p);
     B2R_CHECK_LAUNCH();
     return B2R_OK;
@@ -996,6 +998,7 @@ static int launch_halo(const ConvGemmParams& p, int grid, size_t smem, cudaStrea
                                       HaloCfg<BLOCK_N>::kMaxSmem));
         if (dev < 64) attr_set[dev] = true;
     }
+    note_conv_kernel(BLOCK_N == 128 ? "conv_gemm_halo_kernel<128>" : "conv_gemm_halo_kernel<256>");
     conv_gemm_halo_kernel<BLOCK_N><<<grid, kNumThreads, smem, stream>>>(p);
     B2R_CHECK_LAUNCH();
     return B2R_OK;

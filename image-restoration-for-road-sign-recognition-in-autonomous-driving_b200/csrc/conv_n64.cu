@@ -223,6 +223,7 @@ int launch_conv_n64(const ConvN64Params& p, int grid, size_t smem_bytes, cudaStr
         B2R_CUDA(cudaFuncSetAttribute(conv_n64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
         if (dev < 64) attr_set[dev] = true;
     }
+    note_conv_kernel("conv_n64_kernel");
     conv_n64_kernel<<<grid, kN64Threads, smem_bytes, stream>>>(p);
     B2R_CHECK_LAUNCH();
     return B2R_OK;

@@ -534,6 +534,7 @@ int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream) {
         if (dev < 64) attr_set[dev] = true;
     }
     const size_t smem = conv_w3_smem_bytes(size_t(p.b_bytes), p.ring_slots, size_t(p.stage_stride));
+    note_conv_kernel(p.head_w != nullptr ? "conv_w3_kernel<head>" : "conv_w3_kernel");
     if (p.head_w != nullptr)
         conv_w3_kernel<true><<<grid, kW3Threads, smem, stream>>>(p);
     else

@@ -26,7 +26,7 @@ class KernelTimer:
 
     def __init__(self, kinds=("conv_gemm",)):
         self.kinds = set(kinds)
-        self.records = []   # (kind, work, start_event, end_event)
+        self.records = []   # (kind, work, start_event, end_event, kernel name | None)
 
     def start(self, kind):
         if kind not in self.kinds:
@@ -35,21 +35,23 @@ class KernelTimer:
         e.record(torch.cuda.current_stream())
         return e
 
-    def stop(self, kind, work, e0):
+    def stop(self, kind, work, e0, sub=None):
         if e0 is None:
             return
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record(torch.cuda.current_stream())
-        self.records.append((kind, float(work), e0, e1))
+        self.records.append((kind, float(work), e0, e1, sub))
 
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for kind, work, e0, e1 in self.records:
-            d = out.setdefault(kind, {"launches": 0, "work": 0.0, "ms": 0.0})
-            d["launches"] += 1
-            d["work"] += work
-            d["ms"] += e0.elapsed_time(e1)
+        for kind, work, e0, e1, sub in self.records:
+            ms = e0.elapsed_time(e1)
+            d = out.setdefault(kind, {"launches": 0, "work": 0.0, "ms": 0.0, "by_kernel": {}})
+            for t in (d,) + ((d["by_kernel"].setdefault(sub, {"launches": 0, "work": 0.0, "ms": 0.0}),) if sub else ()):
+                t["launches"] += 1
+                t["work"] += work
+                t["ms"] += ms
         return out
 
 
@@ -184,7 +186,8 @@ def conv_gemm(srcs: Sequence[torch.Tensor], weights: torch.Tensor, bias: torch.T
     STATS["launches"] += 1
     if e0 is not None:
         k_alg = int(weights.shape[1]) if alg_k is None else int(alg_k)
-        _TIMER.stop("conv_gemm", 2.0 * n * h * w * d.cout_total * k_alg, e0)
+        _TIMER.stop("conv_gemm", 2.0 * n * h * w * d.cout_total * k_alg, e0,
+                    sub=(L.load().b2r_last_conv_kernel() or b"?").decode())
     del arr
 
 

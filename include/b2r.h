@@ -37,6 +37,9 @@ extern "C" {
 
 int b2r_version(void);
 const char* b2r_last_error(void);
+/* Diagnostic: name of the kernel the last b2r_conv_gemm call of this thread launched ("conv_gemm_pair_kernel<256>",
+ * "conv_w3_kernel<head>", ...); bench.py uses it to split its per-launch timings by kernel. */
+const char* b2r_last_conv_kernel(void);
 
 /* Debug facility (tools/role_timeline.py): device buffer int64[B2R_DBG_TILES][8] in which CTA 0 of the NEXT
  * b2r_conv3x3_c3 launches records clock64() stamps per warp role; NULL switches it off (the default). */
