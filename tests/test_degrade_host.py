@@ -55,3 +55,27 @@ def test_param_builders():
     assert 1 - 0.7 * 1.2 - 1e-6 <= t.min() and t.max() <= 1 - 0.3 * 0.8 + 1e-6
     with pytest.raises(ValueError):
         degrade.motion_blur_kernel(16, 0)
+
+
+def test_batch_builders_equal_the_per_image_setters():
+    """compound_params / demo_params / blur_params / noise_params fill whole batches at once; the arrays must equal
+    what the per-image setters (the form random_params uses) produce, and degree <= 1 must mean "no blur" (14:56)."""
+    from b200restore import degrade as D
+    n = 7
+    ref = D.DegradeParams(n)
+    for i in range(n):
+        ref.set_blur(i, 10, 45)
+        ref.set_fog(i, 0.5)
+        ref.set_noise(i, 0.02)
+    for got in (D.compound_params(n), D.demo_params(n)):
+        for f in ("ksize", "taps", "fog_on", "fog_t", "fog_add", "sigma"):
+            assert np.array_equal(getattr(got, f), getattr(ref, f)), f
+    assert D.demo_params(n).order == 1 and D.demo_params(n).flags == 1 and D.compound_params(n).order == 0
+    b = D.blur_params(n, 12, 30)
+    k = D.motion_blur_kernel(12, 30).astype(np.float32).reshape(-1)
+    assert (b.ksize == 12).all() and all(np.array_equal(b.taps[i, :144], k) for i in range(n)) and not b.taps[:, 144:].any()
+    assert (D.blur_params(n, 1, 45).ksize == 0).all()
+    z = D.noise_params(n, 0.03)
+    assert np.allclose(z.sigma, np.float32(0.03 ** 0.5)) and z.flags == 1 and not z.fog_on.any()
+    dev_flags = D.fog_params(n, np.random.default_rng(0))
+    assert dev_flags.fog_on.all() and not (dev_flags.sigma > 0).any() and not (dev_flags.ksize > 1).any()
