@@ -2,24 +2,32 @@
 """bench.py — images/s of the degrade -> restore -> VGG16 classify -> top-1 count path (BASELINE.json `metric`).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--batch B]
+                    [--total-images T] [--hw S]
 
-One "step" = one pass of the hot path over one batch of B synthetic GTSRB-shaped images per GPU (weak scaling: every
-rank owns a contiguous block of the global image index range; the only collective is the all-reduce of the int64
-(correct, total) pair at the end of the step).  For N > 1 launch under torchrun (one rank per GPU, NCCL).
+Default mode (what the driver runs): one "step" = one pass of the hot path over B = 4096 synthetic GTSRB-shaped images per
+GPU (weak scaling: rank r owns the contiguous block [r*B, (r+1)*B) of the global image index range).  The (correct, total)
+counts stay on each device for all K steps; ONE NCCL all-reduce at the end of the timed region combines them
+(18_test_unified_benchmark.py:44-51 accumulates per batch on the host; north star: "a single NCCL all-reduce").
+For N > 1 launch under torchrun (one rank per GPU).
+
+`--total-images T` is BASELINE.json configs[3] literally: T images (1 000 000) with global index i (Philox counter, label
+i mod 43), rank r takes [r*T/R, (r+1)*T/R) (strong scaling), one all-reduce at the end; `value` = T / seconds.
 
 Prints ONE JSON line on rank 0:
-  value      images/s with the batch already resident in HBM when the timed region starts (CUDA events, max over ranks)
-  e2e        same metric through the public API with HOST buffers (pinned H2D of every micro-batch + D2H of the counts
-             inside the timed region)
-  roofline   the dominant kernel family (tcgen05 implicit-GEMM conv): algorithmic FLOPs / summed CUDA-event duration of its
-             launches inside the timed region, against MEASURED_PEAKS.json; `by_kernel` splits the same measurement by
-             the kernel each launch actually ran (b2r_last_conv_kernel), `dominant_kernel` names the largest share
-  cpu_baseline  the oracle port of the reference path timed on this box's host cores (bounded sample, rank 0, N = 1)
+  value        images/s with the inputs already resident in HBM when the timed region starts (CUDA events, max over ranks)
+  e2e          same metric through the public API with HOST buffers (pinned H2D of every micro-batch + D2H of the counts
+               inside the timed region); restore -> classify -> count replayed as a CUDA graph per micro-batch
+  roofline     the dominant kernel family (tcgen05 implicit-GEMM conv): algorithmic FLOPs / summed CUDA-event duration of
+               its launches inside the timed region, against MEASURED_PEAKS.json; `by_kernel` splits it by the kernel each
+               launch ran
+  roofline_hbm the fused degradation kernel (HBM-bound class): algorithmic bytes / CUDA-event time, per recipe
+  per_rank     ms per step, conv kernel ms, SM clock, host launch seconds of every rank (min / median / max + the slowest)
+  library_comparator  the reference's own modules on cuda:0 through cuDNN / cuBLAS (f32 and bf16 autocast), bounded sample
+  cpu_baseline the UNMODIFIED reference scripts (baseline/_ref, tools/install_ref.py) on this box's host cores, bounded
+               sample, rank 0, N = 1
 
-`--impl reference` times the reference's CPU implementation of the same path (oracle port: the reference is Python and
-cannot travel to the GPU box; oracle/ is pinned to it bit-for-bit by tests/test_oracle_*.py) with all host threads.
-`--impl reference --ref-device cuda [--ref-precision f32|tf32|bf16]` is the opt-in same-box LIBRARY comparator of
-BASELINE.md: the same fp32 PyTorch port on cuda:0 through cuDNN / cuBLAS (what the reference does with DEVICE = 'cuda').
+`--impl reference` times that reference CPU path alone (kind "reference"; the oracle port is the fallback when
+baseline/_ref is absent, and the only other place bench.py executes oracle/).
 """
 from __future__ import annotations
 
@@ -46,34 +54,58 @@ WORKLOADS = {
     # three SimpleUNets Noise -> Fog -> Blur with the unclamped f32 hand-off, VGG16 confidence of the result
     "stress13_cascade_vgg16_conf": ("cascade3", "stress13", True),
 }
-GFLOP_PER_IMAGE_224 = {"simple_unet": 38.831, "resunet": 55.992, "vgg16": 30.933,
-                       "cascade3": 3 * 38.831}
-
-
+GFLOP_PER_IMAGE = {   # BASELINE.md section 3 (hooked reference modules): hw -> (SimpleUNet, ResUNet, VGG16-43)
+    64: (3.170, 4.571, 2.745), 128: (12.679, 18.283, 10.262), 224: (38.831, 55.992, 30.933), 256: (50.718, 73.132, 40.329)}
 CASCADE_SEEDS = {"Noise": 31, "Fog": 33, "Blur": 34}
+POOL_IMAGES = 43 * 96   # --total-images: resident pool of clean images, a multiple of 43 so that label(i) = i mod 43
+
+
+def gflop_per_image(arch: str, classify: bool, hw: int):
+    if hw not in GFLOP_PER_IMAGE:
+        return None
+    u, r, v = GFLOP_PER_IMAGE[hw]
+    return {"simple_unet": u, "resunet": r, "cascade3": 3 * u}[arch] + (v if classify else 0.0)
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="default 5 (1 with --total-images)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="degrade16_resunet_vgg16_top1", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=4096, help="images per GPU per step")
     ap.add_argument("--micro-batch", type=int, default=512)   # 256 -> 512: +1 % (fewer tail waves on the 14x14 / 28x28 layers)
     ap.add_argument("--hw", type=int, default=224)
+    ap.add_argument("--total-images", type=int, default=0,
+                    help="BASELINE configs[3]: this many images in total, sharded [r*T/R, (r+1)*T/R) over the ranks (strong "
+                         "scaling), one all-reduce at the end; --steps / --warmup then count whole passes (default 1 / 0)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline sample (0 = choose)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", type=int, default=0, choices=[0, 1],
-                    help="e2e leg: replay restore -> classify -> count of a micro-batch as one CUDA graph (the device-resident "
-                         "`value` leg stays eager: it times every conv launch with CUDA events)")
+    ap.add_argument("--no-comparator", action="store_true", help="skip the cuDNN / cuBLAS same-box comparator leg")
+    ap.add_argument("--graph", type=int, default=1, choices=[0, 1],
+                    help="e2e leg: replay restore -> classify -> count of a micro-batch as one CUDA graph (bit-identical to "
+                         "eager; the device-resident `value` leg stays eager: it times every conv launch with CUDA events)")
+    ap.add_argument("--pin-cores", type=int, default=1, choices=[0, 1],
+                    help="N > 1: give every rank its own slice of the host cores")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
-                    help="--impl reference: 'cuda' times the same fp32 PyTorch port on the GPU through cuDNN / cuBLAS "
+                    help="--impl reference: 'cuda' times the reference's modules on the GPU through cuDNN / cuBLAS "
                          "(the reference with DEVICE='cuda', 17:16) as the same-box library comparator")
     ap.add_argument("--ref-precision", default="f32", choices=["f32", "tf32", "bf16"],
                     help="--ref-device cuda: f32 (TF32 off), tf32, or bf16 autocast with channels_last tensors")
     return ap.parse_args()
+
+
+def config_dict(args, world: int):
+    """The workload description both arms print (the reference arm adds what its bounded sample was)."""
+    arch, recipe, classify = WORKLOADS[args.workload]
+    cfg = {"workload": args.workload, "images_per_gpu_per_step": args.batch, "hw": args.hw,
+           "restorer": arch, "judge": "vgg16-43" if classify else None, "degradation": recipe,
+           "weights": "seeded synthetic state_dicts in the shipped schemas"}
+    if args.total_images:
+        cfg["total_images"] = args.total_images
+        cfg["images_per_gpu_per_step"] = None
+    return cfg
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -111,7 +143,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, watts = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -120,25 +152,38 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 mx = float(f[1])
+                watts.append(float(f[2]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": statistics.median(watts) if watts else None}
 
 
 # --------------------------------------------------------------------------------------------------------------
-# reference / CPU baseline (oracle port; the ONLY place bench.py executes oracle/)
+# reference arm / CPU baseline
 # --------------------------------------------------------------------------------------------------------------
 CPU_SAMPLE = 128   # images per CPU pass: ~8 s on 16 cores (bounded sample of the 4096-image step)
 
 
 def cpu_reference_images_per_s(workload: str, hw: int, sample: int, repeats: int, warmup: int = 1):
-    """Time the oracle port of the reference path on the host cores: script-16 degradation per image (as the
-    reference runs it, one image per call), then ToTensor -> restorer -> clamp/u8 -> Normalize -> VGG16 -> arg-max in
-    fp32 PyTorch with all threads.  Returns (images/s, cores, seconds per sample)."""
+    """The reference path on the host cores.  Returns (images/s, cores, seconds per pass, kind).
+
+    kind "reference": the unmodified scripts in baseline/_ref driven by baseline/reference_arm.py.
+    kind "port": oracle/ (pinned bit-for-bit to the reference by tests/test_oracle_*.py) — only for the script-13 cascade
+    workload (13_pipeline_stress_test.py imports matplotlib, which this image lacks) or when baseline/_ref is absent."""
+    arch, recipe, classify = WORKLOADS[workload]
+    from baseline import reference_arm as RA
+    if arch != "cascade3" and RA.available():
+        ips, cores, dt, _ = RA.images_per_s(arch, recipe, classify, hw, sample, repeats, warmup)
+        return ips, cores, dt, "reference"
+    ips, cores, dt = _oracle_port_images_per_s(workload, hw, sample, repeats, warmup)
+    return ips, cores, dt, "port"
+
+
+def _oracle_port_images_per_s(workload: str, hw: int, sample: int, repeats: int, warmup: int = 1):
     import numpy as np
     import torch
     from b200restore import synth
@@ -153,30 +198,27 @@ def cpu_reference_images_per_s(workload: str, hw: int, sample: int, repeats: int
     imgs, labels = synth.sign_like_images(sample, hw, hw, seed=7)
     imgs_np = imgs.numpy()
     rng = np.random.default_rng(0)
-
     chunk = 32   # 17_run_unified_inference.py:73 restores in batches of 32
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(max_workers=cores)
 
     def one_chunk(lo, hi):
-        deg = []
         if recipe == "stress13":
+            deg = []
             for i in range(lo, hi):   # 13:152-171, one image per call as the reference runs it
-                z = GO.stress_add_noise(GO.stress_add_fog(GO.stress_add_blur(imgs_np[i])),
-                                        rng.normal(0, 0.01 ** 0.5, imgs_np[i].shape))
-                deg.append(z)
+                deg.append(GO.stress_add_noise(GO.stress_add_fog(GO.stress_add_blur(imgs_np[i])),
+                                               rng.normal(0, 0.01 ** 0.5, imgs_np[i].shape)))
             with torch.no_grad():
                 _, snaps = GO.cascade_13(sdc, torch.from_numpy(np.stack(deg)))
                 pred, conf = GO.vgg_prediction(sdj, snaps[-1])
             return int((pred == labels[lo:hi]).sum())
-        def degrade_one(i):   # one image per call as the reference runs it (16:43-47), own generator per image
+
+        def degrade_one(i):
             noise = np.random.default_rng(i).normal(0, 0.02 ** 0.5, imgs_np[i].shape)
             if recipe == "compound16":
                 return DO.compound_16(imgs_np[i], noise)
             return DO.random_14(imgs_np[i], 0.5, noise, 10, 45)
 
-        # the reference degrades serially on one core; spreading the per-image calls over the host cores (NumPy and
-        # OpenCV release the GIL) is the fair form of the baseline
         deg = torch.from_numpy(np.stack(list(pool.map(degrade_one, range(lo, hi)))))
         with torch.no_grad():
             if classify:
@@ -189,61 +231,60 @@ def cpu_reference_images_per_s(workload: str, hw: int, sample: int, repeats: int
         return sum(one_chunk(lo, min(lo + chunk, limit)) for lo in range(0, limit, chunk))
 
     for _ in range(warmup):
-        one_pass(min(sample, chunk))   # one batch warms the thread pool and the allocator
+        one_pass(min(sample, chunk))
     times = []
     for _ in range(repeats):
         t0 = time.perf_counter()
         one_pass()
         times.append(time.perf_counter() - t0)
-    dt = statistics.median(times)
     pool.shutdown()
+    dt = statistics.median(times)
     return sample / dt, cores, dt
 
 
 def cuda_reference_images_per_s(workload: str, hw: int, batch: int, micro: int, steps: int, warmup: int, precision: str):
-    """BASELINE.md 'same-box GPU comparator': the fp32 PyTorch port of restore -> clamp/u8 -> Normalize -> VGG16 ->
-    arg-max on cuda:0, i.e. what the reference's modules do with DEVICE = 'cuda' (17:16): ATen -> cuDNN / cuBLAS.  The
-    degradation is NumPy/OpenCV code in the reference (no GPU form), so the batch is degraded once outside the timed
-    region and the timed step is restore + classify over `batch` resident images.  None of this repo's kernels run."""
+    """BASELINE.md 'same-box GPU comparator': the reference's OWN modules (baseline/_ref ResUNet / SimpleUNet, torchvision
+    vgg16 + head swap) on cuda:0, i.e. what the reference does with DEVICE = 'cuda' (17:16): ATen -> cuDNN / cuBLAS,
+    restore -> clamp -> u8 -> Normalize -> VGG16 -> arg-max.  The degradation is NumPy/OpenCV code in the reference (no GPU
+    form), so the timed step is restore + classify over `batch` resident images.  None of this repo's kernels run."""
     import torch
     from b200restore import synth
-    from oracle import models_oracle as MO
+    from baseline import reference_arm as RA
     arch, recipe, classify = WORKLOADS[workload]
     if arch == "cascade3":
         raise SystemExit("--ref-device cuda covers the restore(+classify) workloads")
+    if not RA.available():
+        raise RuntimeError("baseline/_ref is missing (python tools/install_ref.py)")
     dev = torch.device("cuda", 0)
     torch.backends.cudnn.benchmark = True
     tf32 = precision == "tf32"
     torch.backends.cudnn.allow_tf32 = tf32
     torch.backends.cuda.matmul.allow_tf32 = tf32
     cl = precision == "bf16"
-
-    def put(sd):
-        out = {}
-        for k, v in sd.items():
-            v = v.to(dev)
-            out[k] = v.contiguous(memory_format=torch.channels_last) if (cl and v.dim() == 4) else v
-        return out
-
-    sdr = put(synth.synthetic_state_dict(arch, 31))
-    sdj = put(synth.synthetic_state_dict("vgg16", 32)) if classify else None
-    fn = MO.simple_unet_forward if arch == "simple_unet" else MO.resunet_forward
-    imgs, labels = synth.sign_like_images(min(batch, 512), hw, hw, seed=7)
+    restorer, judge = RA.build_models(arch, classify)
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    restorer = restorer.to(dev).to(memory_format=fmt)
+    judge = judge.to(dev).to(memory_format=fmt) if judge is not None else None
+    imgs, labels = synth.sign_like_images(min(batch, 256), hw, hw, seed=7)
     reps = (batch + imgs.shape[0] - 1) // imgs.shape[0]
     imgs = imgs.repeat(reps, 1, 1, 1)[:batch].to(dev)
     labels = labels.repeat(reps)[:batch].to(dev)
+    mean = torch.tensor([0.485, 0.456, 0.406], device=dev).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device=dev).view(1, 3, 1, 1)
 
     def step():
         correct = torch.zeros((), dtype=torch.int64, device=dev)
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=cl):
             for s0 in range(0, batch, micro):
-                u8 = imgs[s0:s0 + micro]
-                if classify:
-                    _, _, pred = MO.restore_then_classify(fn, sdr, sdj, u8)
-                    correct += (pred == labels[s0:s0 + micro]).sum()
-                else:
-                    x = MO.to_tensor_u8(u8)
-                    correct += MO.quantize_restored(fn(sdr, x.contiguous(memory_format=torch.channels_last) if cl else x)).sum()
+                x = (imgs[s0:s0 + micro].permute(0, 3, 1, 2).float() / 255.0).contiguous(memory_format=fmt)  # ToTensor (17:66)
+                out = torch.clamp(restorer(x), 0, 1)                                                        # 17:85-86
+                if judge is None:
+                    correct += (out.float() * 255).to(torch.uint8).sum()
+                    continue
+                u8 = (out.float() * 255).to(torch.uint8)                                                    # 17:92
+                xn = ((u8.float() / 255.0 - mean) / std).contiguous(memory_format=fmt)                      # 18:28-32
+                _, predicted = torch.max(judge(xn), 1)                                                      # 18:46-47
+                correct += (predicted == labels[s0:s0 + micro]).sum()
         return correct
 
     for _ in range(max(warmup, 1)):
@@ -256,6 +297,8 @@ def cuda_reference_images_per_s(workload: str, hw: int, batch: int, micro: int, 
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    del restorer, judge
+    torch.cuda.empty_cache()
     return batch / ms * 1e3, ms
 
 
@@ -263,34 +306,38 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    args.steps = args.steps or 5
+    arch, recipe, classify = WORKLOADS[args.workload]
     if args.ref_device == "cuda":
         batch = min(args.batch, 1024)
         micro = min(args.micro_batch, 64)
         ips, ms = cuda_reference_images_per_s(args.workload, args.hw, batch, micro, args.steps, args.warmup, args.ref_precision)
-        arch, recipe, classify = WORKLOADS[args.workload]
-        gflop = GFLOP_PER_IMAGE_224[arch] + (GFLOP_PER_IMAGE_224["vgg16"] if classify else 0.0)
+        gflop = gflop_per_image(arch, classify, args.hw)
         print(json.dumps({
             "impl": "reference-cudnn", "metric": "images/sec restore->VGG16 classify", "value": ips, "unit": "images/s",
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "dtype": args.ref_precision, "data": "synthetic",
             "config": {"workload": args.workload, "hw": args.hw, "images_per_step": batch, "micro_batch": micro,
-                       "note": "fp32 PyTorch port of the reference modules on cuda:0 (ATen -> cuDNN / cuBLAS, "
+                       "note": "the reference's own modules (baseline/_ref) on cuda:0 (ATen -> cuDNN / cuBLAS, "
                                "cudnn.benchmark on); degradation outside the timed region (NumPy/OpenCV in the "
                                "reference); none of this repo's kernels"},
-            "model_tflops": ips * gflop / 1e3 if args.hw == 224 else None, "gpu_launches": 0}), flush=True)
+            "model_tflops": ips * gflop / 1e3 if gflop else None, "gpu_launches": 0}), flush=True)
         return
-    cores = os.cpu_count() or 1
     sample = args.cpu_sample or CPU_SAMPLE
     t0 = time.perf_counter()
-    ips, cores, dt = cpu_reference_images_per_s(args.workload, args.hw, sample, repeats=args.steps, warmup=args.warmup)
+    ips, cores, dt, kind = cpu_reference_images_per_s(args.workload, args.hw, sample, repeats=args.steps, warmup=args.warmup)
+    cfg = config_dict(args, 1)
+    cfg["sample_images_per_step"] = sample
+    cfg["note"] = ("the unmodified reference scripts (baseline/_ref: 16 -> 17 -> 18 composed in memory) on the host cores"
+                   if kind == "reference" else "oracle port of the reference path on the host cores")
     line = {
         "impl": "reference", "metric": "images/sec restore->VGG16 classify", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "hw": args.hw, "images_per_step": sample,
-                   "note": "reference CPU path (oracle port, pinned to the reference's classes), host cores only"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} images of {args.hw}x{args.hw} per step in batches of 32 (17:73), median of {args.steps} steps"},
+        "higher_is_better": True, "scaling": "strong" if args.total_images else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} images of {args.hw}x{args.hw} per step in batches of 32 (17:73), median of "
+                                   f"{args.steps} steps; a bounded sample of the {args.batch}-image step"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
@@ -300,6 +347,27 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------------------
+def pin_cores(rank_local: int, world_local: int):
+    """Give each rank of the node its own contiguous slice of the cores this process may use."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world_local
+        if per >= 2:
+            mine = cores[rank_local * per:(rank_local + 1) * per]
+            os.sched_setaffinity(0, mine)
+            return mine
+    except (AttributeError, OSError):
+        pass
+    return None
+
+
+def minmedmax(vals):
+    vals = [v for v in vals if v is not None]
+    if not vals:
+        return None
+    return {"min": min(vals), "median": statistics.median(vals), "max": max(vals)}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -310,8 +378,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device: libb2r has no CPU fallback")
+    cores_mine = pin_cores(local, local_world) if (world > 1 and args.pin_cores) else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -322,7 +392,9 @@ def run_ours(args):
 
     arch, recipe, classify = WORKLOADS[args.workload]
     B_, hw, mb = args.batch, args.hw, args.micro_batch
-    lo = rank * B_                                   # weak scaling: rank r owns global images [r*B, (r+1)*B)
+    total_mode = args.total_images > 0
+    if total_mode and (not classify or arch == "cascade3"):
+        raise SystemExit("--total-images is the degrade -> restore -> classify -> count workload")
 
     cascade = None
     if arch == "cascade3":
@@ -343,43 +415,66 @@ def run_ours(args):
     judge = judge.to(dev).eval()
     pipe = B.RestoreClassifyPipeline(restorer, judge, micro_batch=mb)
 
-    # synthetic GTSRB-shaped batch, generated in chunks on the host into pinned memory, then copied once to HBM
-    host_imgs = torch.empty((B_, hw, hw, 3), dtype=torch.uint8).pin_memory()
-    host_labels = torch.empty((B_,), dtype=torch.int64).pin_memory()
-    for s in range(0, B_, 512):
-        c = min(512, B_ - s)
-        im, lb = synth.sign_like_images(c, hw, hw, seed=7, index0=lo + s)
+    # ---- inputs: weak mode = this rank's B images; total mode = a resident pool every rank indexes by global image index
+    if total_mode:
+        lo, hi = B.shard_range(args.total_images, rank, world)
+        n_host, index0 = POOL_IMAGES, 0
+    else:
+        lo, hi = rank * B_, (rank + 1) * B_
+        n_host, index0 = B_, lo
+    host_imgs = torch.empty((n_host, hw, hw, 3), dtype=torch.uint8).pin_memory()
+    host_labels = torch.empty((n_host,), dtype=torch.int64).pin_memory()
+    for s in range(0, n_host, 512):
+        c = min(512, n_host - s)
+        im, lb = synth.indexed_images(index0 + s, c, hw, hw, seed=7)     # image i is a pure function of its GLOBAL index
         host_imgs[s:s + c] = im
         host_labels[s:s + c] = lb
     dev_imgs = host_imgs.to(dev)
     dev_labels = host_labels.to(dev)
-    params = (D.compound_params(B_) if recipe in ("compound16", "stress13")
-              else D.random_params(B_, np.random.default_rng(2 + rank), order=0)).to(dev)
+    n_par = mb if total_mode else B_
+    params = (D.compound_params(n_par) if recipe in ("compound16", "stress13")
+              else D.random_params(n_par, np.random.default_rng(2 + rank), order=0)).to(dev)
 
-    def cascade_micro_batch(imgs_u8, labels, counts, index0):
-        z = G.stress_distort(imgs_u8, seed=2, image_index0=index0)[-1]
+    def cascade_micro_batch(imgs_u8, labels, counts, index0_):
+        z = G.stress_distort(imgs_u8, seed=2, image_index0=index0_)[-1]
         _, hist = cascade(z)
         logits = judge.forward_u8(hist[-1][1])
         ops.argmax_count(logits, labels, counts, want_conf=True)
 
+    totals = torch.zeros(2, dtype=torch.int64, device=dev)      # (correct, total) of this rank over the timed steps
+
     def step_device():
         if cascade is not None:
-            counts = torch.zeros(2, dtype=torch.int64, device=dev)
             for s in range(0, B_, mb):
                 c = min(mb, B_ - s)
-                cascade_micro_batch(dev_imgs[s:s + c], dev_labels[s:s + c], counts, lo + s)
+                cascade_micro_batch(dev_imgs[s:s + c], dev_labels[s:s + c], totals, lo + s)
         elif classify:
             _, counts = pipe.run(dev_imgs, dev_labels, params, seed=2, image_index0=lo)
+            totals.add_(counts)
         else:
-            counts = torch.zeros(2, dtype=torch.int64, device=dev)
             for s in range(0, B_, mb):
                 c = min(mb, B_ - s)
                 sub = B.pipeline._slice_params(params, s, c)
                 deg = D.degrade(dev_imgs[s:s + c], sub, seed=2, image_index0=lo + s)
                 restorer.restore_u8(deg)
-            counts[1] = B_
-        B.all_reduce_counts(counts)
-        return counts
+            totals[1] += B_
+
+    def pool_slice(imgs, labels, g0, c):
+        """c images starting at global index g0 out of the resident pool (image i = pool[i mod P], label = i mod 43)."""
+        o = g0 % POOL_IMAGES
+        if o + c <= POOL_IMAGES:
+            return imgs[o:o + c], labels[o:o + c]
+        k = POOL_IMAGES - o
+        return torch.cat((imgs[o:], imgs[:c - k])), torch.cat((labels[o:], labels[:c - k]))
+
+    def pass_total_device():
+        """BASELINE configs[3]: this rank's contiguous shard [lo, hi) of the T images, device-resident pool."""
+        for g0 in range(lo, hi, mb):
+            c = min(mb, hi - g0)
+            im, lb = pool_slice(dev_imgs, dev_labels, g0, c)
+            pipe.run_micro_batch(im, lb, B.pipeline._slice_params(params, 0, c), 2, g0, totals)
+
+    e2e_bytes = [0, 0]
 
     def step_host():
         if cascade is not None:
@@ -392,13 +487,32 @@ def run_ours(args):
                 h2d += im.numel() + lb.numel() * 8
                 cascade_micro_batch(im, lb, counts, lo + s)
             hc = counts.cpu()
-            cc = torch.tensor([int(hc[0]), int(hc[1])], dtype=torch.int64, device=dev)
-            B.all_reduce_counts(cc)
-            return cc, h2d, 16
+            totals.add_(torch.tensor([int(hc[0]), int(hc[1])], dtype=torch.int64, device=dev))
+            e2e_bytes[0], e2e_bytes[1] = h2d, 16
+            return
         (correct, total), h2d, d2h = pipe.run_from_host(host_imgs, host_labels, params, seed=2, image_index0=lo)
-        c = torch.tensor([correct, total], dtype=torch.int64, device=dev)
-        B.all_reduce_counts(c)
-        return c, h2d, d2h
+        totals.add_(torch.tensor([correct, total], dtype=torch.int64, device=dev))
+        e2e_bytes[0], e2e_bytes[1] = h2d, d2h
+
+    def pass_total_host():
+        """The same shard with HOST buffers: every micro-batch is copied from the pinned pool inside the timed region."""
+        h2d = 0
+        counts = torch.zeros(2, dtype=torch.int64, device=dev)
+        for g0 in range(lo, hi, mb):
+            c = min(mb, hi - g0)
+            o = g0 % POOL_IMAGES
+            if o + c > POOL_IMAGES:      # wrap: two pinned slices
+                k = POOL_IMAGES - o
+                im = torch.cat((host_imgs[o:].to(dev, non_blocking=True), host_imgs[:c - k].to(dev, non_blocking=True)))
+                lb = torch.cat((host_labels[o:].to(dev, non_blocking=True), host_labels[:c - k].to(dev, non_blocking=True)))
+            else:
+                im = host_imgs[o:o + c].to(dev, non_blocking=True)
+                lb = host_labels[o:o + c].to(dev, non_blocking=True)
+            h2d += im.numel() + lb.numel() * 8
+            pipe.run_micro_batch(im, lb, B.pipeline._slice_params(params, 0, c), 2, g0, counts)
+        hc = counts.cpu()
+        totals.add_(torch.tensor([int(hc[0]), int(hc[1])], dtype=torch.int64, device=dev))
+        e2e_bytes[0], e2e_bytes[1] = h2d, 16
 
     def barrier():
         if world > 1:
@@ -406,46 +520,85 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; the ONE all-reduce of the counts is inside the timed region.
+        Returns (max-over-ranks ms, this rank's ms, host seconds spent launching, global counts)."""
+        totals.zero_()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        res = None
+        t0 = time.perf_counter()
         for _ in range(steps):
-            res = fn()
+            fn()
+        host_s = time.perf_counter() - t0
+        global_counts = totals.clone()
+        B.all_reduce_counts(global_counts)
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        own = e0.elapsed_time(e1)
+        ms = torch.tensor([own], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), res
+        return float(ms.item()), own, host_s, global_counts
 
-    # ---- warm-up
-    for _ in range(max(args.warmup, 3)):
-        step_device()
+    if total_mode:
+        steps, warm = max(args.steps or 1, 1), 0
+        fn_dev, fn_host = pass_total_device, pass_total_host
+        images_per_step = args.total_images
+        # warm-up: a few micro-batches (lazy module loads, func attributes, workspaces)
+        for g0 in range(lo, min(lo + 3 * mb, hi), mb):
+            c = min(mb, hi - g0)
+            im, lb = pool_slice(dev_imgs, dev_labels, g0, c)
+            pipe.run_micro_batch(im, lb, B.pipeline._slice_params(params, 0, c), 2, g0, totals)
+    else:
+        steps, warm = args.steps or 5, max(args.warmup, 3)
+        fn_dev, fn_host = step_device, step_host
+        images_per_step = B_ * world
+        for _ in range(warm):
+            step_device()
     torch.cuda.synchronize()
 
-    # ---- timed region: K steps, per-launch events on the dominant kernel, clocks sampled
+    # ---- timed region: K steps, per-launch events on the dominant kernel family, clocks sampled on every rank
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     timer = ops.KernelTimer(kinds=("conv_gemm",))
     launches0 = ops.STATS["launches"]
     with ops.timing(timer):
-        total_ms, counts = timed(step_device, args.steps)
+        total_ms, own_ms, host_s, counts = timed(fn_dev, steps)
     launches = ops.STATS["launches"] - launches0
     ksum = timer.summary().get("conv_gemm", {"launches": 0, "work": 0.0, "ms": 1e-9})
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
 
-    # ---- end-to-end (host buffers) : same K steps
+    # ---- end-to-end (host buffers): same K steps
     e2e = None
-    if classify:
+    do_e2e = classify and (not total_mode or (hi - lo) <= 300000)
+    if do_e2e:
         pipe.use_graph = bool(args.graph) and cascade is None
-        step_host()
-        e2e_ms, (c2, h2d, d2h) = timed(step_host, args.steps)
+        if total_mode:      # capture the micro-batch graph outside the timed region
+            im, lb = pool_slice(dev_imgs, dev_labels, lo, min(mb, hi - lo))
+            pipe.run_micro_batch(im, lb, B.pipeline._slice_params(params, 0, im.shape[0]), 2, lo, totals)
+        else:
+            step_host()
+        e2e_ms, _, _, c2 = timed(fn_host, steps)
         pipe.use_graph = False
-        e2e = {"value": B_ * world * args.steps / (e2e_ms / 1e3), "unit": "images/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
-               "cuda_graph": bool(args.graph) and cascade is None}
+        e2e = {"value": images_per_step * steps / (e2e_ms / 1e3), "unit": "images/s",
+               "h2d_bytes_per_step": int(e2e_bytes[0]), "d2h_bytes_per_step": int(e2e_bytes[1]),
+               "ms_per_step": e2e_ms / steps, "cuda_graph": bool(args.graph) and cascade is None,
+               "counts": [int(c2[0]), int(c2[1])]}
+
+    # ---- HBM-bound class: the fused degradation kernel, per recipe (CUDA events on the launching stream, inputs 617 MB >> L2)
+    hbm = None
+    if rank == 0 and not total_mode:
+        hbm = degrade_roofline(torch, D, dev_imgs, hw)
+
+    # ---- per-rank record (the 1 -> N curve explains itself)
+    mine = {"rank": rank, "ms_per_step": own_ms / steps, "conv_kernel_ms_per_step": ksum["ms"] / steps,
+            "host_launch_s_per_step": host_s / steps, "sm_mhz": clocks.get("sm_mhz"), "power_w": clocks.get("power_w"),
+            "reasons": clocks.get("reasons"), "cores": len(cores_mine) if cores_mine else None, "images": int(hi - lo)}
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+    else:
+        gathered = [mine]
 
     if rank != 0:
         if world > 1:
@@ -459,54 +612,124 @@ def run_ours(args):
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF sustained"
     conv_tf = ksum["work"] / (ksum["ms"] * 1e-3) / 1e12
-    traffic = None
-    tj = ROOT / "profiles" / "r01_conv_traffic.json"      # dram bytes per launch of these kernels from one ncu capture
-    if tj.exists():
-        traffic = json.loads(tj.read_text()).get("dram_bytes_per_launch")
-        if traffic is not None:   # captured at micro-batch 256, 224x224: activation traffic scales with the launch size
-            traffic = traffic * (mb / 256.0) * (hw * hw / (224.0 * 224.0))
-    ips = B_ * world * args.steps / (total_ms / 1e3)
-    gflop_img = GFLOP_PER_IMAGE_224[arch] + (GFLOP_PER_IMAGE_224["vgg16"] if classify else 0.0)
+    traffic, traffic_note = None, None
+    for tj in (ROOT / "profiles" / "r02_conv_traffic.json", ROOT / "profiles" / "r01_conv_traffic.json"):
+        if tj.exists():      # dram bytes per launch of these kernels from one ncu capture of this workload
+            t = json.loads(tj.read_text())
+            traffic = t.get("dram_bytes_per_launch")
+            if traffic is not None:   # captured at micro-batch 256, 224x224: activation traffic is linear in images per launch
+                traffic = traffic * (mb / float(t.get("micro_batch", 256))) * (hw * hw / (224.0 * 224.0))
+            traffic_note = (f"dram__bytes_read+write per launch averaged over all tcgen05 conv launches of one ncu capture "
+                            f"({tj.name}), scaled to this run's launch size")
+            break
+    ips = images_per_step * steps / (total_ms / 1e3)
+    gflop_img = gflop_per_image(arch, classify, hw)
+    slowest = max(gathered, key=lambda g: g["ms_per_step"])
+    cfg = config_dict(args, world)
+    cfg.update({"micro_batch": mb,
+                "l2": "inputs (%.0f MB/step) larger than L2; no flush needed" % ((hi - lo if total_mode else B_) * hw * hw * 3 / 1e6),
+                "parallelism": f"dp{world} (contiguous shard of the global image index range per rank, counts stay on the "
+                               f"device, ONE int64[2] all-reduce at the end of the timed region)"})
     line = {
         "metric": "images/sec restore->VGG16 classify", "value": ips, "unit": "images/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": args.workload, "images_per_gpu_per_step": B_, "hw": hw, "micro_batch": mb,
-                   "restorer": arch, "judge": "vgg16-43" if classify else None, "degradation": recipe,
-                   "weights": "seeded synthetic state_dicts in the shipped schemas",
-                   "l2": "inputs (%.0f MB/step) larger than L2; no flush needed" % (B_ * hw * hw * 3 / 1e6),
-                   "parallelism": f"dp{world} (batch sharded, one int64[2] all-reduce per step)"},
-        "clocks": clocks,
+        "steps": steps, "warmup": warm, "ms_per_step": total_ms / steps,
+        "higher_is_better": True, "scaling": "strong" if total_mode else "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": cfg,
+        "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples", "power_w")},
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convs (conv_gemm_pair_kernel<256> cta_group::2, conv_w3_kernel, conv_gemm_halo_kernel<128>, conv_gemm_kernel<N>)",
                      "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
-                     "peak_source": peak_src, "traffic": traffic,
-                     "traffic_note": "dram__bytes_read+write per launch averaged over all tcgen05 conv launches of one "
-                                     "ncu capture at micro-batch 256 (profiles/r01_launches_v11_summary.md), scaled to this run's "
-                                     "launch size (activations dominate: traffic is linear in images per launch)",
-                     "launches": ksum["launches"], "kernel_ms_per_step": ksum["ms"] / args.steps,
+                     "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
+                     "launches": ksum["launches"], "kernel_ms_per_step": ksum["ms"] / steps,
                      "dominant_kernel": max(ksum.get("by_kernel", {"?": {"ms": 0}}).items(), key=lambda kv: kv[1]["ms"])[0],
-                     "by_kernel": {k: {"launches": v["launches"], "share_of_step": v["ms"] / total_ms,
+                     "by_kernel": {k: {"launches": v["launches"], "share_of_step": v["ms"] / own_ms,
                                        "achieved": v["work"] / (v["ms"] * 1e-3) / 1e12,
                                        "frac": v["work"] / (v["ms"] * 1e-3) / 1e12 / peak_tf}
                                    for k, v in sorted(ksum.get("by_kernel", {}).items(), key=lambda kv: -kv[1]["ms"])},
-                     "share_of_step": ksum["ms"] / total_ms,
-                     "pipeline_tflops": ips / world * gflop_img / 1e3 if hw == 224 else None},
+                     "share_of_step": ksum["ms"] / own_ms,
+                     "pipeline_tflops": ips / world * gflop_img / 1e3 if gflop_img else None},
+        "roofline_hbm": hbm,
+        "per_rank": {"ms_per_step": minmedmax([g["ms_per_step"] for g in gathered]),
+                     "conv_kernel_ms_per_step": minmedmax([g["conv_kernel_ms_per_step"] for g in gathered]),
+                     "host_launch_s_per_step": minmedmax([g["host_launch_s_per_step"] for g in gathered]),
+                     "sm_mhz": minmedmax([g["sm_mhz"] for g in gathered]),
+                     "power_w": minmedmax([g["power_w"] for g in gathered]),
+                     "slowest": slowest, "cores_per_rank": mine["cores"],
+                     "note": "the step time is the max over ranks; the counts are all-reduced once, after the last step"},
         "counts": [int(counts[0]), int(counts[1])],
     }
-    if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+    if total_mode:
+        line["seconds_for_total"] = total_ms / 1e3 / steps
+        assert int(counts[1]) == args.total_images * steps, (int(counts[1]), args.total_images)
+    if world == 1 and not total_mode and classify and cascade is None and not args.no_comparator:
+        try:
+            comp = {}
+            for prec in ("f32", "bf16"):
+                v, ms = cuda_reference_images_per_s(args.workload, hw, 256, 64, 2, 1, prec)
+                comp[prec] = {"value": v, "unit": "images/s", "ms_per_256_images": ms}
+            comp["note"] = ("the reference's own modules (baseline/_ref ResUNet, torchvision vgg16 + head swap) on cuda:0 through "
+                            "ATen -> cuDNN / cuBLAS, cudnn.benchmark on, 256 resident images in micro-batches of 64, restore + "
+                            "classify only (the reference's degradation is NumPy/OpenCV on the host); f32 = TF32 off, bf16 = "
+                            "autocast + channels_last.  Same box, same process, after the timed legs")
+            line["library_comparator"] = comp
+        except Exception as e:   # baseline/_ref absent
+            line["library_comparator"] = {"unavailable": str(e)[:200]}
+    if world == 1 and not total_mode and not args.no_cpu_baseline:
         sample = args.cpu_sample or CPU_SAMPLE
-        v, cores, dt = cpu_reference_images_per_s(args.workload, hw, sample, repeats=1, warmup=1)
-        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+        v, cores, dt, kind = cpu_reference_images_per_s(args.workload, hw, sample, repeats=1, warmup=1)
+        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": kind,
                                 "sample": f"{sample} images of {hw}x{hw} in batches of 32 (17:73), one timed pass after a warm-up batch "
-                                          f"({dt:.1f} s), degradation calls spread over the cores; oracle port of " +
-                                          ("script 13 (distortions, cascade, VGG confidence)" if recipe == "stress13"
-                                           else "scripts 16 -> 17 -> 18") + " in fp32 PyTorch"}
+                                          f"({dt:.1f} s), degradation calls spread over the cores; " +
+                                          ("the unmodified reference scripts 16 -> 17 -> 18 from baseline/_ref" if kind == "reference"
+                                           else "oracle port of " + ("script 13 (distortions, cascade, VGG confidence)"
+                                                                     if recipe == "stress13" else "scripts 16 -> 17 -> 18")) +
+                                          " in fp32 PyTorch"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def degrade_roofline(torch, D, dev_imgs, hw):
+    """Algorithmic bytes (u8 in + u8 out = 6 B/pixel) / CUDA-event time of b2r_degrade per recipe."""
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak = float(peaks.get("hbm_gbs", 6500.0))
+    n = dev_imgs.shape[0]
+    out = torch.empty_like(dev_imgs)
+    recipes = {}
+
+    def mk(blur, fog, noise):
+        p = D.DegradeParams(n)
+        if blur:
+            p.set_blur_all(10, 45)
+        if fog:
+            p.set_fog_all(0.5)
+        if noise:
+            p.set_noise_all(0.02)
+        return p.to(dev_imgs.device)
+
+    for name, p in (("compound16 (blur 10/45 + fog + noise)", mk(1, 1, 1)), ("fog + noise", mk(0, 1, 1)), ("fog", mk(0, 1, 0))):
+        for _ in range(2):
+            D.degrade(dev_imgs, p, seed=2, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            D.degrade(dev_imgs, p, seed=2, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        gbs = n * hw * hw * 6 / (ms * 1e-3) / 1e9
+        recipes[name] = {"us_per_image": ms * 1e3 / n, "achieved": gbs, "frac": gbs / peak}
+    head = recipes["compound16 (blur 10/45 + fog + noise)"]
+    return {"bound": "hbm", "kernel": "degrade_kernel (b2r_degrade)", "achieved": head["achieved"], "peak": peak, "unit": "GB/s",
+            "frac": head["frac"], "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
+            "bytes_per_image": hw * hw * 6, "by_recipe": recipes,
+            "note": "blurred and noisy recipes are instruction-issue-bound (bit-exact OpenCV tap order, Philox-10 + Box-Muller); "
+                    "the fog-only recipe runs at the HBM rate"}
 
 
 def main():

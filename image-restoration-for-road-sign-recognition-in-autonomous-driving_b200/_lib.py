@@ -10,6 +10,7 @@ from pathlib import Path
 
 from . import build as _build
 
+EXPECTED_ABI = 200   # B2R_VERSION of include/b2r.h this binding matches (bumped on every struct / signature change)
 B2R_ACT_NONE, B2R_ACT_RELU, B2R_ACT_PRELU = 0, 1, 2
 B2R_ORDER_BLUR_FOG_NOISE, B2R_ORDER_FOG_NOISE_BLUR = 0, 1
 B2R_DEG_CLIP_AFTER_NOISE = 1
@@ -20,7 +21,7 @@ B2R_CONV_GENERIC_ONLY, B2R_CONV_NO_W3, B2R_CONV_NO_HALO, B2R_CONV_NO_PAIR = 1, 2
 
 # every symbol include/b2r.h declares (tests/test_abi.py checks the list against the header and the .so)
 SYMBOLS = (
-    "b2r_version", "b2r_last_error", "b2r_last_conv_kernel", "b2r_debug_timeline", "b2r_degrade", "b2r_conv3x3_c3", "b2r_conv_gemm", "b2r_final_conv1x1",
+    "b2r_version", "b2r_abi_sizeof", "b2r_last_error", "b2r_last_conv_kernel", "b2r_degrade", "b2r_conv3x3_c3", "b2r_conv_gemm", "b2r_final_conv1x1",
     "b2r_maxpool2x2", "b2r_adaptive_avgpool7", "b2r_linear_f32out", "b2r_argmax_count",
     "b2r_lut_u8", "b2r_minmax_u8", "b2r_normalize_minmax_u8", "b2r_noise02", "b2r_sse_u8", "b2r_ssim_u8", "b2r_mean_bf16", "b2r_resize_bilinear_u8", "b2r_resize_cv_linear_u8",
 )
@@ -76,22 +77,35 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    import os
     path = lib_path()
-    if not path.exists():
+    in_tree = "B2R_LIB" not in os.environ
+    if not path.exists() or (in_tree and _build.needs_build() and _build.have_nvcc()):
         try:
             _build.build()
         except Exception as e:  # no nvcc on this box
-            raise B2RError(f"libb2r.so is missing at {path} and could not be built: {e}") from e
+            if not path.exists():
+                raise B2RError(f"libb2r.so is missing at {path} and could not be built: {e}") from e
     lib = C.CDLL(str(path))
     vp, i32, f32, u64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64
     lib.b2r_version.restype = C.c_int
     lib.b2r_version.argtypes = []
+    # a stale or foreign build would read a mis-laid descriptor: refuse it instead of corrupting memory
+    if lib.b2r_version() != EXPECTED_ABI:
+        raise B2RError(f"{path} reports ABI {lib.b2r_version()}, this binding was written for {EXPECTED_ABI}; rebuild "
+                       "(python -m b200restore.build --force)")
+    lib.b2r_abi_sizeof.restype = C.c_int
+    lib.b2r_abi_sizeof.argtypes = [C.c_int]
+    if lib.b2r_abi_sizeof(0) != C.sizeof(ConvGemmDesc):
+        raise B2RError(f"struct b2r_conv_gemm_desc is {lib.b2r_abi_sizeof(0)} bytes in {path} but {C.sizeof(ConvGemmDesc)} in "
+                       "the ctypes binding")
     lib.b2r_last_error.restype = C.c_char_p
     lib.b2r_last_error.argtypes = []
     lib.b2r_last_conv_kernel.restype = C.c_char_p
     lib.b2r_last_conv_kernel.argtypes = []
-    lib.b2r_debug_timeline.restype = None
-    lib.b2r_debug_timeline.argtypes = [vp]
+    if hasattr(lib, "b2r_debug_timeline"):      # debug builds only (csrc/b2r_debug.h), not part of the product ABI
+        lib.b2r_debug_timeline.restype = None
+        lib.b2r_debug_timeline.argtypes = [vp]
     lib.b2r_degrade.restype = C.c_int
     lib.b2r_degrade.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, u64, u64, i32, i32, vp]
     lib.b2r_conv3x3_c3.restype = C.c_int

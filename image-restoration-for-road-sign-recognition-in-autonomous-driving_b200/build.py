@@ -30,6 +30,14 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (looked at $NVCC, PATH, /usr/local/cuda/bin/nvcc)")
 
 
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
 def needs_build() -> bool:
     if not LIB_PATH.exists():
         return True

@@ -92,6 +92,13 @@ extern "C" {
 
 int b2r_version(void) { return B2R_VERSION; }
 
+int b2r_abi_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(b2r_conv_gemm_desc);
+        default: return -1;
+    }
+}
+
 const char* b2r_last_error(void) { return b2r::last_error_buf(); }
 const char* b2r_last_conv_kernel(void) { return b2r::last_conv_kernel(); }
 

@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
 
 }  // namespace b2r
 
+// debug facility of tools/c3_timeline.py (declared in csrc/b2r_debug.h, NOT part of the product header include/b2r.h)
 extern "C" void b2r_debug_timeline(int64_t* device_buf) { b2r::g_c3_dbg = reinterpret_cast<long long*>(device_buf); }
 
 extern "C" int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host, const float* std_host,

@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kDegThreads, 2) degrade_kernel(const DegradePa
 
     int d = P.ksize ? P.ksize[n] : 0;
     if (d <= 1) d = 0;  // "if degree > 1" (14_train_unified_advanced.py:56)
+    if (d > B2R_MAX_BLUR) __trap();  // ksize[] is a device array the host cannot validate: fail the launch, never overrun s_taps / s_rows
     ImgParams ip;
     ip.fog_on = P.fog_on ? P.fog_on[n] : 0;
     ip.t = ip.fog_on ? P.fog_t[n] : 1.f;
@@ -499,6 +500,11 @@ extern "C" int b2r_degrade(const uint8_t* in, uint8_t* out, int N, int H, int W,
     B2R_REQUIRE((ksize == nullptr) == (taps == nullptr), "ksize and taps must both be given or both be null");
     B2R_REQUIRE(fog_on == nullptr || (fog_t && fog_add), "fog_on given without fog_t / fog_add");
     B2R_REQUIRE(!(noise && !sigma), "injected noise needs sigma[] as the per-image on/off switch");
+    {   // the blur reads halo rows that neighbouring CTAs write when the ranges overlap
+        const size_t bytes = size_t(N) * H * W * 3;
+        const bool overlap = in < out + bytes && out < in + bytes;
+        B2R_REQUIRE(!(ksize && overlap), "in / out ranges overlap and ksize is given: the blur cannot run in place");
+    }
     const size_t smem = ksize ? degrade_smem_bytes(W) : 0;
     B2R_REQUIRE(smem <= 200 * 1024, "W=%d too wide for the staged tile", W);
     static bool attr_set[64] = {false};

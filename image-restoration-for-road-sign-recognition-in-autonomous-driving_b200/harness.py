@@ -58,6 +58,25 @@ def _device_of(module: torch.nn.Module) -> torch.device:
     return dev
 
 
+def _on_module_device(fn):
+    """Run a driver loop with the module's GPU as the current device: every op launches on the current device's current
+    stream, so a module on cuda:1 must not be driven while cuda:0 is current (ops._chk rejects that)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(module, *a, **kw):
+        try:
+            dev = next(module.parameters()).device
+        except (AttributeError, StopIteration):
+            return fn(module, *a, **kw)      # e.g. a missing path is reported before the module is ever touched (18:23-25)
+        if dev.type != "cuda":
+            return fn(module, *a, **kw)      # _device_of raises the no-CPU-fallback error where the reference would run
+        with torch.cuda.device(dev):
+            return fn(module, *a, **kw)
+    return wrapper
+
+
+@_on_module_device
 @torch.no_grad()
 def evaluate_model(judge, data_dir, name: str, batch_size: int = 64, verbose: bool = True,
                    return_predictions: bool = False):
@@ -91,6 +110,7 @@ def evaluate_model(judge, data_dir, name: str, batch_size: int = 64, verbose: bo
     return (acc, torch.cat(preds)) if return_predictions else acc
 
 
+@_on_module_device
 @torch.no_grad()
 def run_inference(model, distorted_dir, restored_dir, batch_size: int = 32, pattern: str = "*/*.png",
                   verbose: bool = True) -> Optional[List[Path]]:
@@ -115,6 +135,7 @@ def run_inference(model, distorted_dir, restored_dir, batch_size: int = 32, patt
     return written
 
 
+@_on_module_device
 @torch.no_grad()
 def process_task(model, task_name: str, distorted_dir, restored_dir, clean_dir, batch_size: int = 32,
                  verbose: bool = True) -> Optional[Tuple[float, float, int]]:

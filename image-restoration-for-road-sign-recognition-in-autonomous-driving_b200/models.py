@@ -56,6 +56,15 @@ class _B200Module(nn.Module):
     def _signature(self):
         return tuple((k, v.data_ptr(), v._version, v.device) for k, v in self.state_dict(keep_vars=True).items())
 
+    def invalidate_pack(self) -> None:
+        """Drop the packed device-layout weights so that the next forward re-packs them.  Needed only after writes that
+        PyTorch's version counter does not see (`param.data.copy_()`, `param.data.mul_()`: weight surgery / EMA code);
+        `load_state_dict`, `.to()`, in-place ops on the parameter itself and module replacement are detected."""
+        object.__setattr__(self, "_pack", None)
+        object.__setattr__(self, "_pack_sig", None)
+
+    repack = invalidate_pack
+
     def _packed(self):
         sig = self._signature()
         if self._pack is None or sig != self._pack_sig:
@@ -144,9 +153,10 @@ class SimpleUNet(_B200Module):
         P["final"] = (sd["final.weight"].float().reshape(3, 64).contiguous(), sd["final.bias"].float().contiguous())
         return P
 
-    def _run(self, x, out_f32, out_u8):
-        """x: f32 [n,3,H,W] or u8 [n,H,W,3] slice; writes the requested outputs."""
-        P, ws = self._packed(), self._ws
+    def _run(self, x, out_f32, out_u8, P=None):
+        """x: f32 [n,3,H,W] or u8 [n,H,W,3] slice; writes the requested outputs.  P: the pack (looked up once per call
+        of the public entry point, not per micro-batch)."""
+        P, ws = (P if P is not None else self._packed()), self._ws
         u8_in = x.dtype == torch.uint8
         n = x.shape[0]
         H, W = (x.shape[1], x.shape[2]) if u8_in else (x.shape[2], x.shape[3])
@@ -197,10 +207,12 @@ def _restorer_forward(m, x, div, want_f32, want_u8):
     H, W = (x.shape[1], x.shape[2]) if u8_in else (x.shape[2], x.shape[3])
     if (x.shape[3] if u8_in else x.shape[1]) != 3:
         raise L.B2RError("expected 3 image channels")
-    o32 = torch.empty((n, 3, H, W), dtype=torch.float32, device=x.device) if want_f32 else None
-    o8 = torch.empty((n, H, W, 3), dtype=torch.uint8, device=x.device) if want_u8 else None
-    for s, c in m._chunks(n, m.micro_batch):
-        m._run(x[s:s + c], None if o32 is None else o32[s:s + c], None if o8 is None else o8[s:s + c])
+    with torch.cuda.device(x.device):     # launches go to the current device's current stream (ops._chk)
+        o32 = torch.empty((n, 3, H, W), dtype=torch.float32, device=x.device) if want_f32 else None
+        o8 = torch.empty((n, H, W, 3), dtype=torch.uint8, device=x.device) if want_u8 else None
+        P = m._packed()
+        for s, c in m._chunks(n, m.micro_batch):
+            m._run(x[s:s + c], None if o32 is None else o32[s:s + c], None if o8 is None else o8[s:s + c], P)
     return o32, o8
 
 
@@ -296,8 +308,8 @@ class ResUNet(_B200Module):
         ops.conv_gemm(srcs, **c1, act=L.B2R_ACT_PRELU, slope=slope, out=y)
         ops.conv_gemm([y] + list(srcs), **c2, act=L.B2R_ACT_RELU, out=out, out_pool=out_pool, **(head or {}))
 
-    def _run(self, x, out_f32, out_u8):
-        P, ws = self._packed(), self._ws
+    def _run(self, x, out_f32, out_u8, P=None):
+        P, ws = (P if P is not None else self._packed()), self._ws
         u8_in = x.dtype == torch.uint8
         n = x.shape[0]
         H, W = (x.shape[1], x.shape[2]) if u8_in else (x.shape[2], x.shape[3])
@@ -399,11 +411,11 @@ class VGG16Judge(_B200Module):
         P["fc3"] = (sd["classifier.6.weight"].to(torch.bfloat16).contiguous(), sd["classifier.6.bias"].float().contiguous())
         return P
 
-    def _run_features(self, x, normalize_u8: bool, stop_at: Optional[int] = None):
+    def _run_features(self, x, normalize_u8: bool, stop_at: Optional[int] = None, P=None):
         """The `features` stack up to (and including) torchvision index `stop_at` (None: all 31 layers).
         Returns (bf16 NHWC tensor, h, w, channels).  A tap on a conv index gives the PRE-ReLU output, on the following
         ReLU index the activated one, on a pool index the pooled one, exactly like `model.features[:stop_at + 1]`."""
-        P, ws = self._packed(), self._ws
+        P, ws = (P if P is not None else self._packed()), self._ws
         u8_in = x.dtype == torch.uint8
         n = x.shape[0]
         H, W = (x.shape[1], x.shape[2]) if u8_in else (x.shape[2], x.shape[3])
@@ -436,11 +448,11 @@ class VGG16Judge(_B200Module):
                 return cur, h, w, c
         return cur, h, w, c
 
-    def _run(self, x, normalize_u8: bool) -> torch.Tensor:
-        P, ws = self._packed(), self._ws
+    def _run(self, x, normalize_u8: bool, P=None) -> torch.Tensor:
+        P, ws = (P if P is not None else self._packed()), self._ws
         n, dev = x.shape[0], x.device
         R = L.B2R_ACT_RELU
-        cur, h, w, _ = self._run_features(x, normalize_u8)
+        cur, h, w, _ = self._run_features(x, normalize_u8, P=P)
         if (h, w) != (7, 7):
             cur = ops.adaptive_avgpool7(cur)  # identity at 224x224
         flat = cur.view(1, 1, n, 7 * 7 * 512)
@@ -469,9 +481,10 @@ class VGG16Judge(_B200Module):
             raise L.B2RError(f"layer_index {layer_index} outside features[0:{len(self.features)}]")
         x, u8 = self._tap_input(x)
         outs = []
-        for s, cnt in self._chunks(x.shape[0], self.micro_batch):
-            f, h, w, c = self._run_features(x[s:s + cnt], u8, stop_at=layer_index)
-            outs.append(ops.mean_bf16(f, cnt * h * w, c, 1).view(cnt, h, w))
+        with torch.cuda.device(x.device):
+            for s, cnt in self._chunks(x.shape[0], self.micro_batch):
+                f, h, w, c = self._run_features(x[s:s + cnt], u8, stop_at=layer_index)
+                outs.append(ops.mean_bf16(f, cnt * h * w, c, 1).view(cnt, h, w))
         hm = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         if normalize:
             lo = hm.amin(dim=(1, 2), keepdim=True)
@@ -485,16 +498,19 @@ class VGG16Judge(_B200Module):
         [N,512,h,w] averaged over the spatial axes -> f32 [N, 512]."""
         x, u8 = self._tap_input(x)
         outs = []
-        for s, cnt in self._chunks(x.shape[0], self.micro_batch):
-            f, h, w, c = self._run_features(x[s:s + cnt], u8)
-            outs.append(ops.mean_bf16(f, cnt, h * w, c))
+        with torch.cuda.device(x.device):
+            for s, cnt in self._chunks(x.shape[0], self.micro_batch):
+                f, h, w, c = self._run_features(x[s:s + cnt], u8)
+                outs.append(ops.mean_bf16(f, cnt, h * w, c))
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     def _forward(self, x: torch.Tensor, normalize_u8: bool) -> torch.Tensor:
         self._check_input(x, 32)
         x = x.contiguous()
         n = x.shape[0]
-        outs = [self._run(x[s:s + c], normalize_u8) for s, c in self._chunks(n, self.micro_batch)]
+        with torch.cuda.device(x.device):
+            P = self._packed()
+            outs = [self._run(x[s:s + c], normalize_u8, P) for s, c in self._chunks(n, self.micro_batch)]
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     @torch.no_grad()

@@ -82,6 +82,12 @@ def _chk(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None) -> None:
         raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
     if not t.is_cuda:
         raise L.B2RError(f"{name}: tensor must live on a CUDA device (there is no CPU fallback)")
+    # every launch goes to the CURRENT device's current stream, and the C side sizes its grids / sets its function
+    # attributes for the current device: a tensor on another GPU would be reached over P2P or fault.  The modules and the
+    # pipeline enter `torch.cuda.device(x.device)` themselves; a direct op call must be made with the right device current.
+    if t.device.index != torch.cuda.current_device():
+        raise L.B2RError(f"{name}: tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                         "wrap the call in `with torch.cuda.device(tensor.device):`")
     if t.dtype != dtype:
         raise L.B2RError(f"{name}: dtype {t.dtype}, expected {dtype}")
     if not t.is_contiguous():

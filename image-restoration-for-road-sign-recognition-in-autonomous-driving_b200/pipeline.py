@@ -68,26 +68,29 @@ class RestoreClassifyPipeline:
                         keep: bool = False):
         """One resident micro-batch through all stages.  Returns (pred int64 [n], extras dict when keep=True)."""
         n, h, w, _ = clean_u8.shape
-        if self.use_graph and not keep and noise is None:
-            return self._run_micro_batch_graph(clean_u8, labels, params, seed, image_index0, counts), None
-        degraded = D.degrade(clean_u8, params, seed=seed, image_index0=image_index0, noise=noise,
-                             out=self._buf("deg", (n, h, w, 3), torch.uint8)) if params is not None else clean_u8
-        restored = self._buf("rest", (n, h, w, 3), torch.uint8)
+        with torch.cuda.device(self.device):
+            if self.use_graph and not keep and noise is None:
+                return self._run_micro_batch_graph(clean_u8, labels, params, seed, image_index0, counts), None
+            degraded = D.degrade(clean_u8, params, seed=seed, image_index0=image_index0, noise=noise,
+                                 out=self._buf("deg", (n, h, w, 3), torch.uint8)) if params is not None else clean_u8
+            restored = self._buf("rest", (n, h, w, 3), torch.uint8)
+            pred, logits = self._restore_classify(degraded, restored, labels, counts, want_logits=True)
+            if keep:
+                return pred, {"degraded": degraded.clone(), "restored": restored.clone(), "logits": logits.clone()}
+        return pred, None
+
+    # -- CUDA-graph mode --------------------------------------------------------------------------------------------
+    def _restore_classify(self, degraded, restored, labels, counts, want_logits=False):
+        """restore -> clamp/u8 -> classify -> top-1 (+ counts).  Without labels only `total` can be counted: the kernel
+        takes counts together with labels, so a predictions-only call adds n to counts[1] itself."""
         self.restorer._check_input(degraded, self._div)
         self.restorer._run(degraded, None, restored)
         self.judge._check_input(restored, 32)
         logits = self.judge._run(restored, True)
-        pred, _ = ops.argmax_count(logits, labels, counts)
-        if keep:
-            return pred, {"degraded": degraded.clone(), "restored": restored.clone(), "logits": logits.clone()}
-        return pred, None
-
-    # -- CUDA-graph mode --------------------------------------------------------------------------------------------
-    def _restore_classify(self, degraded, restored, labels, counts):
-        self.restorer._check_input(degraded, self._div)
-        self.restorer._run(degraded, None, restored)
-        self.judge._check_input(restored, 32)
-        return ops.argmax_count(self.judge._run(restored, True), labels, counts)[0]
+        pred = ops.argmax_count(logits, labels, counts if labels is not None else None)[0]
+        if labels is None and counts is not None:
+            counts[1:2].add_(degraded.shape[0])
+        return (pred, logits) if want_logits else pred
 
     def _graph_entry(self, n: int, h: int, w: int, with_labels: bool):
         packs = (self.restorer._packed(), self.judge._packed())
@@ -129,8 +132,9 @@ class RestoreClassifyPipeline:
         return ent["pred"]          # static output of the graph: consume it before the next micro-batch of this shape
 
     @torch.no_grad()
-    def run(self, clean_u8: torch.Tensor, labels: torch.Tensor, params, seed: int = 0, image_index0: int = 0):
-        """Device-resident batch [N,H,W,3] u8 -> (pred int64 [N], counts int64 [2] = (correct, total))."""
+    def run(self, clean_u8: torch.Tensor, labels: Optional[torch.Tensor], params, seed: int = 0, image_index0: int = 0):
+        """Device-resident batch [N,H,W,3] u8 -> (pred int64 [N], counts int64 [2] = (correct, total)); labels = None
+        gives predictions only (correct stays 0)."""
         n = clean_u8.shape[0]
         counts = torch.zeros(2, dtype=torch.int64, device=self.device)
         preds = torch.empty(n, dtype=torch.int64, device=self.device)
@@ -138,7 +142,8 @@ class RestoreClassifyPipeline:
         for s in range(0, n, self.micro_batch):
             c = min(self.micro_batch, n - s)
             sub = _slice_params(dparams, s, c) if dparams is not None else None
-            p, _ = self.run_micro_batch(clean_u8[s:s + c], labels[s:s + c], sub, seed, image_index0 + s, counts)
+            p, _ = self.run_micro_batch(clean_u8[s:s + c], None if labels is None else labels[s:s + c], sub, seed,
+                                        image_index0 + s, counts)
             preds[s:s + c] = p
         return preds, counts
 

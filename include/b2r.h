@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B2R_VERSION 100
+#define B2R_VERSION 200 /* bumped on every struct / signature change; the ctypes binding refuses any other value */
 
 #define B2R_OK 0
 #define B2R_EINVAL (-22)   /* bad argument (shape, alignment, null pointer) */
@@ -36,14 +36,13 @@ extern "C" {
 #define B2R_ACT_PRELU 2 /* single shared slope, nn.PReLU() default (14_train_unified_advanced.py:101) */
 
 int b2r_version(void);
+/* sizeof of an ABI struct as THIS build sees it (which = 0: b2r_conv_gemm_desc, 1: b2r_tensor), so a binding can check its
+ * own layout against the library it loaded instead of trusting the version number alone; -1 for an unknown `which`. */
+int b2r_abi_sizeof(int which);
 const char* b2r_last_error(void);
 /* Diagnostic: name of the kernel the last b2r_conv_gemm call of this thread launched ("conv_gemm_pair_kernel<256>",
  * "conv_w3_kernel<head>", ...); bench.py uses it to split its per-launch timings by kernel. */
 const char* b2r_last_conv_kernel(void);
-
-/* Debug facility (tools/role_timeline.py): device buffer int64[B2R_DBG_TILES][8] in which CTA 0 of the NEXT
- * b2r_conv3x3_c3 launches records clock64() stamps per warp role; NULL switches it off (the default). */
-void b2r_debug_timeline(int64_t* device_buf);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * (1) Fused compound degradation: motion blur (+) fog (+) AWGN, u8 NHWC in -> u8 NHWC out, one launch.
@@ -55,7 +54,8 @@ void b2r_debug_timeline(int64_t* device_buf);
  * renormalisation) and add_fog (04_gen_fog.py:12-31).
  *
  * Per-image parameters (device arrays of length N):
- *   ksize[i]   blur kernel side d (0 or 1 = no blur, else 2..15); taps[i*225 + ky*d + kx] row-major d x d f32,
+ *   ksize[i]   blur kernel side d (0 or 1 = no blur, else 2..B2R_MAX_BLUR = 15; a larger value makes the kernel trap: the
+ *              launch fails with a CUDA error instead of overrunning its tap tables); taps[i*225 + ky*d + kx] row-major d x d f32,
  *              correlation with anchor d/2 and BORDER_REFLECT_101, f32 accumulation over the non-zero taps in
  *              row-major order, round-half-even + saturate to u8 (cv2.filter2D on u8).
  *   fog_on[i]  0 skips the fog stage; fog_t[i] = transmission t; fog_add[i] = float32(A*(1-t)), the airlight term
@@ -66,6 +66,8 @@ void b2r_debug_timeline(int64_t* device_buf);
  *        (scripts 14/15), with chain(v) = quant(noise(fog(v/255))).
  * flags: B2R_DEG_CLIP_AFTER_NOISE clips to [0,1] right after the noise is added (15:108).  Every float -> u8 step
  *        is clip(x*255, 0, 255) followed by truncation, as in the reference.
+ * in == out is allowed only when nothing blurs (ksize == NULL): the blur reads a halo that neighbouring CTAs overwrite;
+ *        overlapping in / out ranges with ksize != NULL return B2R_EINVAL.
  * Noise: if `noise` is non-null it is an f64 NHWC tensor of the noise values themselves (what
  *        np.random.normal(0, sigma, shape) returned), added in float64 like NumPy does: the parity path ("AWGN is
  *        compared by injecting the same noise tensor").  Otherwise Philox4x32-10 keyed by `seed`,

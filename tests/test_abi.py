@@ -24,7 +24,8 @@ def test_header_symbols_are_exported_and_bound():
 def test_version_and_error_string():
     from b200restore import _lib
     lib = _lib.load()
-    assert lib.b2r_version() == 100
+    assert lib.b2r_version() == _lib.EXPECTED_ABI == 200
+    assert lib.b2r_abi_sizeof(0) == ctypes.sizeof(_lib.ConvGemmDesc) and lib.b2r_abi_sizeof(99) == -1
     assert isinstance(lib.b2r_last_error(), bytes)
 
 

@@ -19,7 +19,9 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0
     assert d["config"]["workload"] == "degrade16_resunet_vgg16_top1"
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    have_ref = (ROOT / "baseline" / "_ref" / "MANIFEST.json").exists()
+    assert cb["kind"] == ("reference" if have_ref else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["config"]["images_per_gpu_per_step"] == 4096 and d["config"]["sample_images_per_step"] == 2
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
