@@ -654,6 +654,184 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Pair + halo mode for C_out = 128 (round 2): cta_group::2 AND halo boxes.  The N = 128 layers are bound by the rate at
+// which TMA fills shared memory (profiles/r01_smem_fill.md): per k-block of 4 MMAs (302 cycles at the N = 128 rate) the
+// halo kernel pours 16 KB of weights + 6.7 KB of activations into each SM = 75 B/clk against ~55 B/clk available.  Here the
+// two CTAs of a cluster execute MMAs of M = 256 x N = 128: each CTA owns one 128-pixel tile (its halo boxes, its rows of D,
+// its epilogue) and loads only HALF of every weight k-block (8 KB): 49 B/clk.  Round 1 tried pair mode WITHOUT the halo
+// boxes for N = 128 (16 KB + 8 KB per k-block) and only tied halo mode; the two savings are needed together.
+// Two clusters are co-resident per SM pair (2 x 256 TMEM columns, 2 x <= 113 KB of shared memory), as in halo mode.
+// Protocol = the pair kernel's (leader issues; its "full" barriers count both CTAs' TMA bytes; commits are multicast to
+// both CTAs' "empty" / "accumulator ready" barriers) on the halo kernel's two rings.  Same MMAs in the same order as the
+// halo kernel: bit-identical results (A/B test in tests/test_conv_gemm_gpu.py).
+// ------------------------------------------------------------------------------------------------------------
+template <int kPairN>
+struct PairHaloCfg {
+    static constexpr int kBBytes = (kPairN / 2) * 128;   // this CTA's half of a weight k-block
+    static constexpr int kCtasPerSm = kPairN == 128 ? 2 : 1;
+    static constexpr int kStagingBufs = 1;
+    static constexpr int kFixedBytes = 1024 + kStagingBufs * (kStagingFull + kStagingPool) + kPairN * 4 + 512;
+    static constexpr int kMaxSmem = (227 * 1024) / kCtasPerSm - (kCtasPerSm > 1 ? 1024 : 0);
+};
+
+template <int kPairN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, PairHaloCfg<kPairN>::kCtasPerSm)
+conv_gemm_pairhalo_kernel(const __grid_constant__ ConvGemmParams p) {
+    using Cfg = PairHaloCfg<kPairN>;
+    constexpr uint32_t kIdesc = make_idesc_bf16_f32(256, kPairN);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = a_ring + p.a_slots * p.a_slot_bytes;
+    uint8_t* staging = b_ring + p.b_slots * Cfg::kBBytes;
+    float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBufs * (kStagingFull + kStagingPool));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + kPairN);
+    uint64_t* a_full = bars;                           // leader only: TMA bytes of both CTAs
+    uint64_t* a_empty = bars + kHaloMaxRing;           // each CTA: one multicast commit per phase
+    uint64_t* b_full = bars + 2 * kHaloMaxRing;
+    uint64_t* b_empty = bars + 3 * kHaloMaxRing;
+    uint64_t* tmem_full_bar = bars + 4 * kHaloMaxRing;   // each CTA: one multicast commit per phase
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // leader only: 4 epilogue warps x 2 CTAs
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int m_pairs = (num_m_tiles + 1) / 2;
+    const int total_pairs = m_pairs * p.n_tiles;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int AR = p.a_slots, BR = p.b_slots;
+
+    if (warp_idx == 0 && lane == 0) {
+        for (int i = 0; i < B2R_MAX_SRC; ++i) tma_prefetch_desc(&p.a3_map[i]);
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.out_map[0]);
+        tma_prefetch_desc(&p.pool_map);
+    }
+    if (warp_idx == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kHaloMaxRing; ++s) {
+                mbar_init(&a_full[s], 1);
+                mbar_init(&a_empty[s], 1);
+                mbar_init(&b_full[s], 1);
+                mbar_init(&b_empty[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tmem_full_bar[s], 1);
+                mbar_init(&tmem_empty_bar[s], 8);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc_pair<2 * kPairN>(tmem_ptr_s);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();      // both CTAs' barriers are initialised before any remote arrive / complete_tx
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp_idx == 0) {
+        // ===================================== TMA producer (both CTAs, own tile + own half of B) =====================================
+        if (lane == 0) {
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0;
+            for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+                const int n_tile = pair % p.n_tiles;
+                int m = 2 * (pair / p.n_tiles) + int(rank);
+                if (m >= num_m_tiles) m = num_m_tiles - 1;   // odd tile count: the last pair computes one tile twice
+                const int w0 = (m % p.tiles_w) * p.tile_w;
+                const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.tile_h;
+                const int n0 = m / (p.tiles_w * p.tiles_h);
+                for (int s = 0; s < p.num_slots; ++s) {
+                    const uint32_t e = p.slot[s];
+                    const int src = e & 3, ntaps = ((e >> 2) & 1) ? 1 : 3, dw = int((e >> 4) & 3) - 1;
+                    const int c0 = int((e >> 8) & 0xFFF) * 64, kb0 = int(e >> 20);
+                    mbar_wait(&a_empty[as], aph ^ 1);
+                    if (leader) mbar_arrive_expect_tx(&a_full[as], 2u * uint32_t(p.a_slot_bytes));
+                    tma_load_4d_pair(a_ring + as * p.a_slot_bytes, &p.a3_map[src], &a_full[as], c0, w0 + dw, h0 - 1, n0);
+                    if (++as == AR) {
+                        as = 0;
+                        aph ^= 1;
+                    }
+                    for (int t = 0; t < ntaps; ++t) {
+                        mbar_wait(&b_empty[bs], bph ^ 1);
+                        if (leader) mbar_arrive_expect_tx(&b_full[bs], 2u * Cfg::kBBytes);
+                        tma_load_2d_pair(b_ring + bs * Cfg::kBBytes, &p.b_map, &b_full[bs], (kb0 + t) * kBlockK,
+                                         n_tile * kPairN + int(rank) * (kPairN / 2));
+                        if (++bs == BR) {
+                            bs = 0;
+                            bph ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================================== MMA issuer (leader CTA only) =====================================
+        if (leader && lane == 0) {
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            const uint32_t row_stride = uint32_t(p.tile_w) * 128u;
+            for (int pair = cluster_id; pair < total_pairs; pair += num_clusters) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + uint32_t(acc * kPairN);
+                uint32_t accum = 0;
+                for (int s = 0; s < p.num_slots; ++s) {
+                    const uint32_t e = p.slot[s];
+                    const bool centre = ((e >> 2) & 1) != 0;
+                    const int ntaps = centre ? 1 : 3;
+                    mbar_wait(&a_full[as], aph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(a_ring + as * p.a_slot_bytes);
+                    for (int t = 0; t < ntaps; ++t) {
+                        mbar_wait(&b_full[bs], bph);
+                        tc_fence_after();
+                        const uint64_t adesc = make_sdesc_sw128(sa + uint32_t(centre ? 1 : t) * row_stride, 1024);
+                        const uint64_t bdesc = make_sdesc_sw128(smem_u32(b_ring + bs * Cfg::kBBytes), 1024);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            umma_bf16_ss_pair(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, accum);
+                            accum = 1;
+                        }
+                        umma_commit_pair(&b_empty[bs]);
+                        if (++bs == BR) {
+                            bs = 0;
+                            bph ^= 1;
+                        }
+                    }
+                    umma_commit_pair(&a_empty[as]);
+                    if (++as == AR) {
+                        as = 0;
+                        aph ^= 1;
+                    }
+                }
+                umma_commit_pair(&tmem_full_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        conv_epilogue_role<kPairN, Cfg::kStagingBufs, SchedPair>(p, tmem_base, staging, bias_s, tmem_full_bar, tmem_empty_bar,
+                                                                 total_pairs, warp_idx, lane);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();      // nobody leaves (or frees TMEM) while the peer may still read its shared memory / barriers
+    if (warp_idx == 1) {
+        tc_fence_after();
+        __syncwarp();
+        tmem_dealloc_pair<2 * kPairN>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -1004,8 +1182,25 @@ static int launch_halo(const ConvGemmParams& p, int grid, size_t smem, cudaStrea
     return B2R_OK;
 }
 
+template <int N>
+static int launch_pairhalo(const ConvGemmParams& p, int clusters, size_t smem, cudaStream_t stream) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    B2R_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        B2R_CUDA(cudaFuncSetAttribute(conv_gemm_pairhalo_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PairHaloCfg<N>::kMaxSmem));
+        if (dev < 64) attr_set[dev] = true;
+    }
+    note_conv_kernel(N == 128 ? "conv_gemm_pairhalo_kernel<128>" : "conv_gemm_pairhalo_kernel<256>");
+    conv_gemm_pairhalo_kernel<N><<<(unsigned)(2 * clusters), kNumThreads, smem, stream>>>(p);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
 // Fills the halo-mode fields of P when the layer qualifies; returns the dynamic shared memory size or 0.
-template <int BLOCK_N>
+// Cfg = HaloCfg<N> (one CTA per tile) or PairHaloCfg<N> (cta_group::2: half a weight k-block per CTA and slot).
+template <class Cfg>
 static size_t plan_halo(const b2r_conv_gemm_desc* d, ConvGemmParams& P, int tw, int th, int tn, int* rc_out) {
     *rc_out = B2R_OK;
     if ((d->flags & B2R_CONV_NO_HALO) || d->kblocks_host == nullptr || d->out_mode != B2R_OUT_NHWC || tn != 1 || tw % 8 != 0)
@@ -1031,7 +1226,6 @@ static size_t plan_halo(const b2r_conv_gemm_desc* d, ConvGemmParams& P, int tw, 
             return 0;
         }
     }
-    using Cfg = HaloCfg<BLOCK_N>;
     const int a_bytes = (th + 2) * tw * 128;
     static const int a_slots_env = [] {   // tuning knob for tools/layer_bench.py, read once
         const char* e = getenv("B2R_HALO_A_SLOTS");
@@ -1268,9 +1462,29 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
         if (clusters > pairs) clusters = pairs;
         return block_n == 256 ? launch_pair<256>(P, (int)clusters, stream) : launch_pair<128>(P, (int)clusters, stream);
     }
+    static const bool no_pairhalo_env = getenv("B2R_NO_PAIRHALO") != nullptr;   // A/B switch for tools/layer_bench.py, read once
+    if (block_n == 128 && spatial && !pair128 && !no_pairhalo_env && !(d->flags & B2R_CONV_NO_PAIR) && sms >= 2 &&
+        (long)P.tiles_w * P.tiles_h * P.tiles_n >= 2) {
+        int hrc = B2R_OK;
+        const size_t hs = plan_halo<PairHaloCfg<128>>(d, P, tw, th, tn, &hrc);
+        if (hrc) return hrc;
+        if (hs) {
+            const uint64_t K = (uint64_t)d->num_kblocks * 64;      // each CTA of the pair loads half of a weight k-block
+            const uint64_t dims[2] = {K, (uint64_t)d->cout_total};
+            const uint64_t strides[1] = {K * 2};
+            const uint32_t box[2] = {64, 64};
+            int brc = encode_tmap_bf16(&P.b_map, d->weights, 2, dims, strides, box);
+            if (brc) return brc;
+            const long pairs = ((long)P.tiles_w * P.tiles_h * P.tiles_n + 1) / 2 * P.n_tiles;
+            long clusters = d->max_ctas > 0 ? d->max_ctas / 2 : (long)(sms / 2) * PairHaloCfg<128>::kCtasPerSm;
+            if (clusters < 1) clusters = 1;
+            if (clusters > pairs) clusters = pairs;
+            return launch_pairhalo<128>(P, (int)clusters, hs, stream);
+        }
+    }
     if (block_n >= 128 && spatial) {
         int hrc = B2R_OK;
-        const size_t hs = block_n == 128 ? plan_halo<128>(d, P, tw, th, tn, &hrc) : plan_halo<256>(d, P, tw, th, tn, &hrc);
+        const size_t hs = block_n == 128 ? plan_halo<HaloCfg<128>>(d, P, tw, th, tn, &hrc) : plan_halo<HaloCfg<256>>(d, P, tw, th, tn, &hrc);
         if (hrc) return hrc;
         if (hs) {
             // co-resident CTAs (N = 128): twice the grid

@@ -477,3 +477,49 @@ def test_pair_and_halo_modes_random_shapes():
         assert torch.equal(res[0][0], res[1][0]), (case, co, n, h, w, splits, pool, shortcut)
         if pool:
             assert torch.equal(res[0][1], res[1][1]), (case, "pool")
+
+
+@pytest.mark.parametrize("n,h,w,splits,pool,shortcut", [
+    (1, 16, 8, (64,), False, False),           # a single tile pair
+    (3, 24, 40, (64,), False, False),          # odd number of pixel tiles: the last pair's second CTA stores nothing
+    (2, 112, 112, (128,), True, False),        # VGG conv2_2 with the fused pool
+    (5, 56, 56, (128, 256), False, True),      # dec3 second-conv shape class: two sources + centre k-blocks, odd image count
+    (1, 8, 8, (64,), True, False),             # one clipped tile only: falls back to a single-CTA kernel
+])
+def test_pair_halo_mode_equals_halo_mode(n, h, w, splits, pool, shortcut):
+    """Round 2: C_out = 128 layers run as cta_group::2 pairs ON halo boxes (conv_gemm_pairhalo_kernel<128>).  Same MMAs in the
+    same order as the single-CTA halo kernel (B2R_CONV_NO_PAIR): bit-identical outputs, nothing stored outside the tensor."""
+    ops, packing, L = _ops()
+    co = 128
+    srcs = [nhwc_bf16(rnd(n, c, h, w, seed=1200 + i)) for i, c in enumerate(splits)]
+    ci = sum(splits)
+    wt = rnd(co, ci, 3, 3, scale=(2.0 / (9 * ci)) ** 0.5, seed=1210)
+    b = rnd(co, scale=0.1, seed=1211)
+    plan = packing.KPlan(co)
+    off = 0
+    for s, c in enumerate(splits):
+        plan.add_conv3x3(s, wt[:, off:off + c])
+        off += c
+    all_srcs = list(srcs)
+    if shortcut:
+        plan.add_1x1(len(all_srcs), rnd(co, 64, 1, 1, scale=0.1, seed=1212))
+        all_srcs.append(nhwc_bf16(rnd(n, 64, h, w, seed=1213)))
+    wm, kbl = plan.finish()
+    wm = wm.cuda()
+    res, kernels = [], []
+    for flags in (0, L.B2R_CONV_NO_PAIR, L.B2R_CONV_NO_PAIR | L.B2R_CONV_NO_HALO):
+        out = torch.full((n + 2, h, w, co), float("nan"), dtype=torch.bfloat16, device="cuda")
+        pl = torch.full((n + 2, h // 2, w // 2, co), float("nan"), dtype=torch.bfloat16, device="cuda")
+        ops.conv_gemm(all_srcs, wm, b, kbl, act=L.B2R_ACT_RELU, out=out[1:n + 1], out_pool=pl[1:n + 1] if pool else None,
+                      flags=flags)
+        kernels.append(L.load().b2r_last_conv_kernel().decode())
+        torch.cuda.synchronize()
+        assert bool(torch.isnan(out[0]).all()) and bool(torch.isnan(out[n + 1]).all()), "store outside the tensor"
+        assert bool(torch.isnan(pl[0]).all()) and bool(torch.isnan(pl[n + 1]).all()), "pool store outside the tensor"
+        assert not bool(torch.isnan(out[1:n + 1]).any()), "unwritten output"
+        res.append((out[1:n + 1].clone(), pl[1:n + 1].clone()))
+    if n * h * w > 128:
+        assert kernels[0] == "conv_gemm_pairhalo_kernel<128>" and kernels[1] == "conv_gemm_halo_kernel<128>", kernels
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][0], res[2][0]), kernels
+    if pool:
+        assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][1], res[2][1])
