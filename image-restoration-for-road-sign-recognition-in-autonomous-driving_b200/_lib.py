@@ -23,6 +23,8 @@ B2R_CONV_GENERIC_ONLY, B2R_CONV_NO_W3, B2R_CONV_NO_HALO, B2R_CONV_NO_PAIR = 1, 2
 SYMBOLS = (
     "b2r_version", "b2r_abi_sizeof", "b2r_last_error", "b2r_last_conv_kernel", "b2r_degrade", "b2r_conv3x3_c3", "b2r_conv_gemm", "b2r_final_conv1x1",
     "b2r_maxpool2x2", "b2r_adaptive_avgpool7", "b2r_linear_f32out", "b2r_argmax_count",
+    "b2r_net_weight_bytes", "b2r_net_create", "b2r_net_destroy", "b2r_net_workspace_bytes", "b2r_unet_forward", "b2r_resunet_forward",
+    "b2r_vgg16_forward",
     "b2r_lut_u8", "b2r_minmax_u8", "b2r_normalize_minmax_u8", "b2r_noise02", "b2r_sse_u8", "b2r_ssim_u8", "b2r_mean_bf16", "b2r_resize_bilinear_u8", "b2r_resize_cv_linear_u8",
 )
 
@@ -56,6 +58,15 @@ class ConvGemmDesc(C.Structure):
         ("head_out_u8", C.c_void_p),
         ("debug_timeline", C.c_void_p),
     ]
+
+
+class Tensor(C.Structure):
+    """struct b2r_tensor (include/b2r.h): one state_dict entry handed to b2r_net_create."""
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("dtype", C.c_int32), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+B2R_NET_SIMPLE_UNET, B2R_NET_RESUNET, B2R_NET_VGG16 = 0, 1, 2
+B2R_DT_F32, B2R_DT_I64 = 0, 1
 
 
 class B2RError(RuntimeError):
@@ -141,6 +152,22 @@ def load() -> C.CDLL:
     lib.b2r_sse_u8.argtypes = [vp, vp, vp, i32, i64, vp]
     lib.b2r_ssim_u8.restype = C.c_int
     lib.b2r_ssim_u8.argtypes = [vp, vp, vp, i32, i32, i32, i32, C.c_double, vp]
+    if lib.b2r_abi_sizeof(1) != C.sizeof(Tensor):
+        raise B2RError("struct b2r_tensor layout differs between the library and the ctypes binding")
+    sz = C.c_size_t
+    lib.b2r_net_weight_bytes.restype = C.c_int
+    lib.b2r_net_weight_bytes.argtypes = [C.POINTER(Tensor), i32, C.POINTER(sz)]
+    lib.b2r_net_create.restype = C.c_int
+    lib.b2r_net_create.argtypes = [i32, i32, C.POINTER(Tensor), i32, vp, sz, vp, C.POINTER(vp)]
+    lib.b2r_net_destroy.restype = None
+    lib.b2r_net_destroy.argtypes = [vp]
+    lib.b2r_net_workspace_bytes.restype = C.c_int
+    lib.b2r_net_workspace_bytes.argtypes = [vp, i32, i32, i32, C.POINTER(sz)]
+    for fn in (lib.b2r_unet_forward, lib.b2r_resunet_forward):
+        fn.restype = C.c_int
+        fn.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, vp, sz, vp]
+    lib.b2r_vgg16_forward.restype = C.c_int
+    lib.b2r_vgg16_forward.argtypes = [vp, vp, i32, i32, vp, i32, i32, i32, vp, sz, vp]
     _lib = lib
     return lib
 

@@ -15,7 +15,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libb2r.so"
-SOURCES = ["api_common.cu", "conv_gemm.cu", "conv_n64.cu", "conv_w3.cu", "conv_c3.cu", "elementwise.cu", "degrade.cu", "generators.cu", "ssim.cu"]
+SOURCES = ["api_common.cu", "conv_gemm.cu", "conv_n64.cu", "conv_w3.cu", "conv_c3.cu", "elementwise.cu", "degrade.cu", "generators.cu", "ssim.cu", "net_plan.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -95,6 +95,7 @@ int b2r_version(void) { return B2R_VERSION; }
 int b2r_abi_sizeof(int which) {
     switch (which) {
         case 0: return (int)sizeof(b2r_conv_gemm_desc);
+        case 1: return (int)sizeof(b2r_tensor);
         default: return -1;
     }
 }

@@ -1,0 +1,772 @@
+// Whole-network entry points of the C-ABI: b2r_net_create packs a reference state_dict (host f32 tensors by name) into the
+// device layouts the kernels read, b2r_{unet,resunet,vgg16}_forward run the layer graphs of SimpleUNet.forward
+// (07_train_restoration.py:99-120), ResUNet.forward (14_train_unified_advanced.py:151-186) and torchvision VGG16-43
+// (18_test_unified_benchmark.py:58-59,46) as a sequence of b2r_conv3x3_c3 / b2r_conv_gemm / b2r_linear_f32out launches on
+// the caller's stream.  A host without Python (or PyTorch) can therefore run degrade -> restore -> classify -> count with
+// this library alone (examples/cabi_pipeline.c).  Host code only: no kernels here.
+//
+// The packing below restates image-restoration-..._b200/packing.py + models.py::_build_pack operation for operation
+// (fp64 BatchNorm fold, k-block order, tap-folded [192][K/3] copies for C_out = 64, ConvTranspose as four stacked 1x1
+// matrices, classifier[0] columns permuted from the NCHW flatten to NHWC, round-to-nearest-even bf16), so both hosts hand
+// the kernels the same bytes: tests/test_net_plan_gpu.py requires bit-identical outputs from the two paths.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "b2r_internal.h"
+
+namespace b2r {
+namespace netplan {
+
+constexpr double kBnEps = 1e-5;   // nn.BatchNorm2d default (14_train_unified_advanced.py:100)
+
+inline uint16_t f32_to_bf16(float f) {   // round to nearest even, like torch's .to(torch.bfloat16)
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return uint16_t((u >> 16) | 0x40);   // NaN stays NaN
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return uint16_t(u >> 16);
+}
+
+inline uint32_t kblock(int src, int dh, int dw, int c64) { return B2R_KBLOCK(src, dh, dw, c64); }
+
+struct HostTensor {
+    const float* f32 = nullptr;
+    std::vector<int64_t> shape;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (auto s : shape) n *= s;
+        return n;
+    }
+};
+
+// ---- the state_dict as handed over by the caller
+struct StateDict {
+    std::map<std::string, const b2r_tensor*> by_name;
+    std::string err;
+
+    bool get(const std::string& name, std::initializer_list<int64_t> shape, HostTensor* out) {
+        auto it = by_name.find(name);
+        if (it == by_name.end()) {
+            err = "Missing key(s) in state_dict: \"" + name + "\"";   // what strict load_state_dict reports (17:63)
+            return false;
+        }
+        const b2r_tensor* t = it->second;
+        if (t->dtype != B2R_DT_F32 || t->data == nullptr) {
+            err = "state_dict entry \"" + name + "\" must be a float32 host tensor";
+            return false;
+        }
+        bool ok = t->ndim == (int)shape.size();
+        int i = 0;
+        for (auto s : shape) {
+            if (ok && t->shape[i] != s) ok = false;
+            ++i;
+        }
+        if (!ok) {
+            err = "size mismatch for " + name;
+            return false;
+        }
+        out->f32 = static_cast<const float*>(t->data);
+        out->shape.assign(shape.begin(), shape.end());
+        return true;
+    }
+};
+
+// ---- device weight arena (caller-owned memory; 256-byte aligned sub-allocations)
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t cap = 0, used = 0;
+    bool dry = false;   // sizing pass: count only
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    void* put(const void* host, size_t bytes) {
+        used = (used + 255) & ~size_t(255);
+        void* dst = base ? base + used : nullptr;
+        used += bytes;
+        if (dry) return reinterpret_cast<void*>(uintptr_t(1));
+        if (used > cap) {
+            err = "device weight buffer too small";
+            return nullptr;
+        }
+        if (cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) {
+            err = std::string("cudaMemcpyAsync failed: ") + cudaGetErrorString(cudaGetLastError());
+            return nullptr;
+        }
+        return dst;
+    }
+};
+
+// ---- K plan of one fused layer (packing.KPlan)
+struct KPlan {
+    int cout;
+    std::vector<std::vector<float>> cols;   // per k-block: [cout][64]
+    std::vector<uint32_t> kblocks;
+    struct Group {
+        bool is3x3;
+        std::vector<float> w;   // 3x3: [cout][64][3][3]; 1x1: [cout][64]
+    };
+    std::vector<Group> groups;
+
+    explicit KPlan(int co) : cout(co) {}
+
+    // w: [cout][ci_total][3][3]; uses input channels [c_lo, c_lo + ci) of it for source `src`
+    void add_conv3x3(int src, const std::vector<float>& w, int ci_total, int c_lo, int ci) {
+        for (int c = 0; c < ci / 64; ++c) {
+            Group g;
+            g.is3x3 = true;
+            g.w.resize(size_t(cout) * 64 * 9);
+            for (int o = 0; o < cout; ++o)
+                for (int k = 0; k < 64; ++k)
+                    for (int t = 0; t < 9; ++t)
+                        g.w[(size_t(o) * 64 + k) * 9 + t] = w[(size_t(o) * ci_total + c_lo + c * 64 + k) * 9 + t];
+            for (int j = 0; j < 3; ++j)       // dw (kernel column) outer, dh (kernel row) inner: the order the kernels recognise
+                for (int i = 0; i < 3; ++i) {
+                    std::vector<float> col(size_t(cout) * 64);
+                    for (int o = 0; o < cout; ++o)
+                        for (int k = 0; k < 64; ++k) col[size_t(o) * 64 + k] = g.w[(size_t(o) * 64 + k) * 9 + i * 3 + j];
+                    cols.push_back(std::move(col));
+                    kblocks.push_back(kblock(src, i - 1, j - 1, c));
+                }
+            groups.push_back(std::move(g));
+        }
+    }
+
+    // w: [cout][ci_total]; input channels [c_lo, c_lo + ci) for source `src` (centre tap only)
+    void add_1x1(int src, const std::vector<float>& w, int ci_total, int c_lo, int ci) {
+        for (int c = 0; c < ci / 64; ++c) {
+            Group g;
+            g.is3x3 = false;
+            g.w.resize(size_t(cout) * 64);
+            for (int o = 0; o < cout; ++o)
+                for (int k = 0; k < 64; ++k) g.w[size_t(o) * 64 + k] = w[size_t(o) * ci_total + c_lo + c * 64 + k];
+            cols.push_back(g.w);
+            kblocks.push_back(kblock(src, 0, 0, c));
+            groups.push_back(std::move(g));
+        }
+    }
+
+    std::vector<uint16_t> finish() const {   // bf16 [cout][64 * k-blocks]
+        const size_t K = cols.size() * 64;
+        std::vector<uint16_t> m(size_t(cout) * K);
+        for (size_t kb = 0; kb < cols.size(); ++kb)
+            for (int o = 0; o < cout; ++o)
+                for (int k = 0; k < 64; ++k) m[size_t(o) * K + kb * 64 + k] = f32_to_bf16(cols[kb][size_t(o) * 64 + k]);
+        return m;
+    }
+
+    std::vector<uint16_t> finish_w3() const {   // bf16 [192][64 * k-steps], C_out = 64 only (packing.KPlan.finish_w3)
+        std::vector<uint16_t> m;
+        if (cout != 64) return m;
+        size_t steps = 0;
+        for (auto& g : groups) steps += g.is3x3 ? 3 : 1;
+        const size_t K = steps * 64;
+        m.assign(size_t(192) * K, 0);
+        size_t st = 0;
+        for (auto& g : groups) {
+            if (g.is3x3) {
+                for (int kh = 0; kh < 3; ++kh, ++st)
+                    for (int kw = 0; kw < 3; ++kw)
+                        for (int o = 0; o < 64; ++o)
+                            for (int k = 0; k < 64; ++k)
+                                m[size_t(kw * 64 + o) * K + st * 64 + k] = f32_to_bf16(g.w[(size_t(o) * 64 + k) * 9 + kh * 3 + kw]);
+            } else {
+                for (int o = 0; o < 64; ++o)
+                    for (int k = 0; k < 64; ++k) m[size_t(64 + o) * K + st * 64 + k] = f32_to_bf16(g.w[size_t(o) * 64 + k]);
+                ++st;
+            }
+        }
+        return m;
+    }
+};
+
+struct GemmLayer {   // one b2r_conv_gemm call's constant part
+    const void* weights = nullptr;
+    const void* weights_w3 = nullptr;
+    const float* bias = nullptr;
+    int cout_total = 0;
+    std::vector<uint32_t> kblocks;   // empty: linear K
+    int num_kblocks = 0;
+    float slope = 0.f;
+};
+
+struct C3Layer {
+    const void* weights = nullptr;
+    const float* bias = nullptr;
+    float slope = 0.f;
+};
+
+bool upload_plan(Arena& A, const KPlan& plan, const std::vector<float>& bias, GemmLayer* L) {
+    auto wm = plan.finish();
+    L->weights = A.put(wm.data(), wm.size() * 2);
+    auto w3 = plan.finish_w3();
+    L->weights_w3 = w3.empty() ? nullptr : A.put(w3.data(), w3.size() * 2);
+    L->bias = static_cast<const float*>(A.put(bias.data(), bias.size() * 4));
+    L->cout_total = plan.cout;
+    L->kblocks = plan.kblocks;
+    L->num_kblocks = (int)plan.kblocks.size();
+    return L->weights && L->bias && (w3.empty() || L->weights_w3);
+}
+
+std::vector<float> to_vec(const HostTensor& t) { return std::vector<float>(t.f32, t.f32 + t.numel()); }
+
+// BN(conv(x)) in eval mode == conv'(x): w' = w * s[co], b' = (b - mean) * s + beta, s = gamma / sqrt(var + eps), in fp64
+void fold_bn(std::vector<float>& w, std::vector<float>& b, int co, const HostTensor& gamma, const HostTensor& beta,
+             const HostTensor& mean, const HostTensor& var) {
+    const size_t per = w.size() / co;
+    for (int o = 0; o < co; ++o) {
+        const double s = double(gamma.f32[o]) / std::sqrt(double(var.f32[o]) + kBnEps);
+        for (size_t k = 0; k < per; ++k) w[size_t(o) * per + k] = float(double(w[size_t(o) * per + k]) * s);
+        b[o] = float((double(b[o]) - double(mean.f32[o])) * s + double(beta.f32[o]));
+    }
+}
+
+bool pack_c3(StateDict& sd, Arena& A, const std::string& key, C3Layer* L) {
+    HostTensor w, b;
+    if (!sd.get(key + ".weight", {64, 3, 3, 3}, &w) || !sd.get(key + ".bias", {64}, &b)) return false;
+    std::vector<uint16_t> m(64 * 64, 0);   // column 2t + j = w[co][ci][kh][kw], t = (kh*3 + kw)*3 + ci (packing.pack_conv_c3)
+    for (int o = 0; o < 64; ++o)
+        for (int ci = 0; ci < 3; ++ci)
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int t = (kh * 3 + kw) * 3 + ci;
+                    const uint16_t v = f32_to_bf16(w.f32[((o * 3 + ci) * 3 + kh) * 3 + kw]);
+                    m[o * 64 + 2 * t] = v;
+                    m[o * 64 + 2 * t + 1] = v;
+                }
+    L->weights = A.put(m.data(), m.size() * 2);
+    L->bias = static_cast<const float*>(A.put(b.f32, 64 * 4));
+    return L->weights && L->bias;
+}
+
+bool pack_conv3x3_plain(StateDict& sd, Arena& A, const std::string& key, int co, std::initializer_list<int> splits, GemmLayer* L) {
+    int ci = 0;
+    for (int s : splits) ci += s;
+    HostTensor w, b;
+    if (!sd.get(key + ".weight", {co, ci, 3, 3}, &w) || !sd.get(key + ".bias", {co}, &b)) return false;
+    const auto wv = to_vec(w);
+    KPlan plan(co);
+    int off = 0, src = 0;
+    for (int s : splits) {
+        plan.add_conv3x3(src++, wv, ci, off, s);
+        off += s;
+    }
+    return upload_plan(A, plan, to_vec(b), L);
+}
+
+bool pack_convT(StateDict& sd, Arena& A, const std::string& key, int ci, int co, GemmLayer* L) {
+    HostTensor w, b;
+    if (!sd.get(key + ".weight", {ci, co, 2, 2}, &w) || !sd.get(key + ".bias", {co}, &b)) return false;
+    std::vector<uint16_t> m(size_t(4) * co * ci);   // [(i, j, co)][ci] (packing.pack_convT2x2)
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            for (int o = 0; o < co; ++o)
+                for (int c = 0; c < ci; ++c)
+                    m[(size_t((i * 2 + j) * co + o)) * ci + c] = f32_to_bf16(w.f32[((size_t(c) * co + o) * 2 + i) * 2 + j]);
+    std::vector<float> bias(size_t(4) * co);
+    for (int q = 0; q < 4; ++q)
+        for (int o = 0; o < co; ++o) bias[q * co + o] = b.f32[o];
+    L->weights = A.put(m.data(), m.size() * 2);
+    L->bias = static_cast<const float*>(A.put(bias.data(), bias.size() * 4));
+    L->cout_total = 4 * co;
+    L->num_kblocks = ci / 64;
+    return L->weights && L->bias;
+}
+
+struct ResBlock {
+    GemmLayer c1, c2;
+    int cout = 0;
+    int nsrc = 0;
+};
+
+bool get_bn(StateDict& sd, const std::string& key, int co, HostTensor* g, HostTensor* b, HostTensor* m, HostTensor* v) {
+    return sd.get(key + ".weight", {co}, g) && sd.get(key + ".bias", {co}, b) && sd.get(key + ".running_mean", {co}, m) &&
+           sd.get(key + ".running_var", {co}, v);
+}
+
+bool pack_resblock(StateDict& sd, Arena& A, const std::string& name, std::initializer_list<int> splits, int co, ResBlock* R) {
+    int ci = 0;
+    for (int s : splits) ci += s;
+    const std::string cb = name + ".conv_block.";
+    HostTensor w1, b1, w2, b2, g, be, mu, var, slope;
+    if (!sd.get(cb + "0.weight", {co, ci, 3, 3}, &w1) || !sd.get(cb + "0.bias", {co}, &b1)) return false;
+    if (!sd.get(cb + "2.weight", {1}, &slope)) return false;
+    if (!sd.get(cb + "3.weight", {co, co, 3, 3}, &w2) || !sd.get(cb + "3.bias", {co}, &b2)) return false;
+    auto w1v = to_vec(w1), b1v = to_vec(b1), w2v = to_vec(w2), b2v = to_vec(b2);
+    if (!get_bn(sd, cb + "1", co, &g, &be, &mu, &var)) return false;
+    fold_bn(w1v, b1v, co, g, be, mu, var);
+    if (!get_bn(sd, cb + "4", co, &g, &be, &mu, &var)) return false;
+    fold_bn(w2v, b2v, co, g, be, mu, var);
+    // conv 1 over the (virtual) concat of the block's input sources
+    KPlan p1(co);
+    int off = 0, src = 0;
+    for (int s : splits) {
+        p1.add_conv3x3(src++, w1v, ci, off, s);
+        off += s;
+    }
+    if (!upload_plan(A, p1, b1v, &R->c1)) return false;
+    R->c1.slope = slope.f32[0];
+    // conv 2 over y (source 0) + the shortcut over the block input (sources 1..)
+    KPlan p2(co);
+    p2.add_conv3x3(0, w2v, co, 0, co);
+    std::vector<float> ws(size_t(co) * ci, 0.f);
+    if (ci != co) {
+        const std::string sc = name + ".shortcut.";
+        HostTensor wsc, bsc;
+        if (!sd.get(sc + "0.weight", {co, ci, 1, 1}, &wsc) || !sd.get(sc + "0.bias", {co}, &bsc)) return false;
+        ws = to_vec(wsc);
+        auto bs = to_vec(bsc);
+        if (!get_bn(sd, sc + "1", co, &g, &be, &mu, &var)) return false;
+        fold_bn(ws, bs, co, g, be, mu, var);
+        for (int o = 0; o < co; ++o) b2v[o] = b2v[o] + bs[o];
+    } else {
+        for (int o = 0; o < co; ++o) ws[size_t(o) * ci + o] = 1.f;   // nn.Sequential() shortcut == identity (14:106)
+    }
+    off = 0;
+    src = 1;
+    for (int s : splits) {
+        p2.add_1x1(src++, ws, ci, off, s);
+        off += s;
+    }
+    if (!upload_plan(A, p2, b2v, &R->c2)) return false;
+    R->cout = co;
+    R->nsrc = (int)splits.size();
+    return true;
+}
+
+}  // namespace netplan
+}  // namespace b2r
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the plan object
+// ---------------------------------------------------------------------------------------------------------------------
+struct b2r_net {
+    int arch = 0;
+    int num_classes = 43;
+    size_t weight_bytes = 0;
+    // SimpleUNet
+    b2r::netplan::C3Layer first;
+    b2r::netplan::GemmLayer u_enc1_2, u_enc2_0, u_enc2_2, u_bott_0, u_bott_2, u_up2, u_dec2_0, u_dec2_2, u_up1, u_dec1_0, u_dec1_2;
+    // ResUNet
+    b2r::netplan::ResBlock res1, res2, res3, bt0, bt1, bt2, dec3, dec2, dec1;
+    b2r::netplan::GemmLayer up3, up2, up1;
+    // both restorers: final 1x1 conv 64 -> 3 (fp32)
+    const float* final_w = nullptr;
+    const float* final_b = nullptr;
+    // VGG16
+    struct VggConv {
+        b2r::netplan::GemmLayer g;
+        bool pooled;
+        int cout;
+    };
+    std::vector<VggConv> vgg;
+    b2r::netplan::GemmLayer fc1, fc2;
+    const void* fc3_w = nullptr;
+    const float* fc3_b = nullptr;
+};
+
+namespace b2r {
+namespace netplan {
+
+bool pack_final(StateDict& sd, Arena& A, b2r_net* net) {
+    HostTensor w, b;
+    if (!sd.get("final.weight", {3, 64, 1, 1}, &w) || !sd.get("final.bias", {3}, &b)) return false;
+    net->final_w = static_cast<const float*>(A.put(w.f32, 192 * 4));
+    net->final_b = static_cast<const float*>(A.put(b.f32, 3 * 4));
+    return net->final_w && net->final_b;
+}
+
+bool build_simple_unet(StateDict& sd, Arena& A, b2r_net* n) {
+    return pack_c3(sd, A, "enc1.0", &n->first) && pack_conv3x3_plain(sd, A, "enc1.2", 64, {64}, &n->u_enc1_2) &&
+           pack_conv3x3_plain(sd, A, "enc2.0", 128, {64}, &n->u_enc2_0) && pack_conv3x3_plain(sd, A, "enc2.2", 128, {128}, &n->u_enc2_2) &&
+           pack_conv3x3_plain(sd, A, "bottleneck.0", 256, {128}, &n->u_bott_0) &&
+           pack_conv3x3_plain(sd, A, "bottleneck.2", 256, {256}, &n->u_bott_2) &&
+           pack_conv3x3_plain(sd, A, "dec2.0", 128, {128, 128}, &n->u_dec2_0) &&   // torch.cat((up2(b), e2), 1) (07:112)
+           pack_conv3x3_plain(sd, A, "dec2.2", 128, {128}, &n->u_dec2_2) &&
+           pack_conv3x3_plain(sd, A, "dec1.0", 64, {64, 64}, &n->u_dec1_0) &&      // torch.cat((up1(d2), e1), 1) (07:116)
+           pack_conv3x3_plain(sd, A, "dec1.2", 64, {64}, &n->u_dec1_2) && pack_convT(sd, A, "up2", 256, 128, &n->u_up2) &&
+           pack_convT(sd, A, "up1", 128, 64, &n->u_up1) && pack_final(sd, A, n);
+}
+
+bool build_resunet(StateDict& sd, Arena& A, b2r_net* n) {
+    HostTensor slope;
+    if (!pack_c3(sd, A, "enc1.0", &n->first) || !sd.get("enc1.1.weight", {1}, &slope)) return false;
+    n->first.slope = slope.f32[0];
+    return pack_resblock(sd, A, "res1", {64}, 64, &n->res1) && pack_resblock(sd, A, "res2", {64}, 128, &n->res2) &&
+           pack_resblock(sd, A, "res3", {128}, 256, &n->res3) && pack_resblock(sd, A, "bottleneck.0", {256}, 512, &n->bt0) &&
+           pack_resblock(sd, A, "bottleneck.1", {512}, 512, &n->bt1) && pack_resblock(sd, A, "bottleneck.2", {512}, 256, &n->bt2) &&
+           pack_resblock(sd, A, "dec3", {128, 256}, 128, &n->dec3) && pack_resblock(sd, A, "dec2", {64, 128}, 64, &n->dec2) &&
+           pack_resblock(sd, A, "dec1", {64, 64}, 64, &n->dec1) && pack_convT(sd, A, "up3", 256, 128, &n->up3) &&
+           pack_convT(sd, A, "up2", 128, 64, &n->up2) && pack_convT(sd, A, "up1", 64, 64, &n->up1) && pack_final(sd, A, n);
+}
+
+bool build_vgg16(StateDict& sd, Arena& A, b2r_net* n) {
+    // torchvision vgg16 cfg "D": features indices of the 13 convs and whether a max-pool follows (18:58)
+    static const int idx[13] = {0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28};
+    static const int cout[13] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
+    static const bool pooled[13] = {false, true, false, true, false, false, true, false, false, true, false, false, true};
+    if (!pack_c3(sd, A, "features.0", &n->first)) return false;
+    int ci = 64;
+    for (int l = 1; l < 13; ++l) {
+        b2r_net::VggConv v;
+        v.pooled = pooled[l];
+        v.cout = cout[l];
+        HostTensor w, b;
+        const std::string key = "features." + std::to_string(idx[l]);
+        if (!sd.get(key + ".weight", {cout[l], ci, 3, 3}, &w) || !sd.get(key + ".bias", {cout[l]}, &b)) return false;
+        KPlan plan(cout[l]);
+        plan.add_conv3x3(0, to_vec(w), ci, 0, ci);
+        if (!upload_plan(A, plan, to_vec(b), &v.g)) return false;
+        n->vgg.push_back(std::move(v));
+        ci = cout[l];
+    }
+    {   // classifier[0]: columns from the NCHW flatten (c*49 + h*7 + w) to the NHWC flatten ((h*7 + w)*512 + c)
+        HostTensor w, b;
+        if (!sd.get("classifier.0.weight", {4096, 25088}, &w) || !sd.get("classifier.0.bias", {4096}, &b)) return false;
+        std::vector<uint16_t> m(size_t(4096) * 25088);
+        for (int o = 0; o < 4096; ++o)
+            for (int c = 0; c < 512; ++c)
+                for (int p = 0; p < 49; ++p) m[size_t(o) * 25088 + size_t(p) * 512 + c] = f32_to_bf16(w.f32[size_t(o) * 25088 + size_t(c) * 49 + p]);
+        n->fc1.weights = A.put(m.data(), m.size() * 2);
+        n->fc1.bias = static_cast<const float*>(A.put(b.f32, 4096 * 4));
+        n->fc1.cout_total = 4096;
+        n->fc1.num_kblocks = 25088 / 64;
+        if (!n->fc1.weights || !n->fc1.bias) return false;
+    }
+    {
+        HostTensor w, b;
+        if (!sd.get("classifier.3.weight", {4096, 4096}, &w) || !sd.get("classifier.3.bias", {4096}, &b)) return false;
+        std::vector<uint16_t> m(size_t(4096) * 4096);
+        for (size_t i = 0; i < m.size(); ++i) m[i] = f32_to_bf16(w.f32[i]);
+        n->fc2.weights = A.put(m.data(), m.size() * 2);
+        n->fc2.bias = static_cast<const float*>(A.put(b.f32, 4096 * 4));
+        n->fc2.cout_total = 4096;
+        n->fc2.num_kblocks = 64;
+        if (!n->fc2.weights || !n->fc2.bias) return false;
+    }
+    {   // classifier[6] = nn.Linear(4096, num_classes) (18:59)
+        HostTensor w, b;
+        const int nc = n->num_classes;
+        if (!sd.get("classifier.6.weight", {nc, 4096}, &w) || !sd.get("classifier.6.bias", {nc}, &b)) return false;
+        std::vector<uint16_t> m(size_t(nc) * 4096);
+        for (size_t i = 0; i < m.size(); ++i) m[i] = f32_to_bf16(w.f32[i]);
+        n->fc3_w = A.put(m.data(), m.size() * 2);
+        n->fc3_b = static_cast<const float*>(A.put(b.f32, size_t(nc) * 4));
+        if (!n->fc3_w || !n->fc3_b) return false;
+    }
+    return true;
+}
+
+// ---- activation workspace: a bump allocator over caller-owned memory, sized by a dry run of the same code
+struct Workspace {
+    uint8_t* base;
+    size_t cap, used = 0;
+    bool overflow = false;
+    void* take(size_t bytes) {
+        used = (used + 1023) & ~size_t(1023);
+        void* p = base ? base + used : nullptr;
+        used += bytes;
+        if (base && used > cap) overflow = true;
+        return p;
+    }
+    void* bf16(long n, long h, long w, long c) { return take(size_t(n) * h * w * c * 2); }
+};
+
+struct Runner {   // issues the launches; in dry mode only walks the allocation
+    bool dry;
+    cudaStream_t stream;
+    int rc = B2R_OK;
+
+    void gemm(const GemmLayer& L, int N, int H, int W, std::initializer_list<const void*> srcs, std::initializer_list<int> src_c,
+              int act, float slope, void* out, void* out_pool, int out_C, int out_mode = B2R_OUT_NHWC, const float* head_w = nullptr,
+              const float* head_b = nullptr, float* head_f32 = nullptr, uint8_t* head_u8 = nullptr) {
+        if (dry || rc) return;
+        b2r_conv_gemm_desc d;
+        memset(&d, 0, sizeof(d));
+        d.N = N;
+        d.H = H;
+        d.W = W;
+        d.num_src = (int)srcs.size();
+        int i = 0;
+        for (auto s : srcs) d.src[i++] = s;
+        i = 0;
+        for (auto c : src_c) d.src_C[i++] = c;
+        d.weights = L.weights;
+        d.weights_w3 = L.weights_w3;
+        d.bias = L.bias;
+        d.cout_total = L.cout_total;
+        d.num_kblocks = L.num_kblocks;
+        d.kblocks_host = L.kblocks.empty() ? nullptr : L.kblocks.data();
+        d.act = act;
+        d.slope = slope;
+        d.out_mode = out_mode;
+        d.out = out;
+        d.out_pool = out_pool;
+        d.out_C = out_C;
+        d.head_w = head_w;
+        d.head_b = head_b;
+        d.head_out_f32 = head_f32;
+        d.head_out_u8 = head_u8;
+        rc = b2r_conv_gemm(&d, stream);
+    }
+
+    void c3(const C3Layer& L, const void* in, int in_fmt, bool normalize, int act, void* out, int N, int H, int W) {
+        if (dry || rc) return;
+        static const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};   // 18:31
+        rc = b2r_conv3x3_c3(in, in_fmt, normalize ? mean : nullptr, normalize ? stdv : nullptr, L.weights, L.bias, act, L.slope, out,
+                            N, H, W, stream);
+    }
+
+    // ResidualBlock (14:114-115): y = PReLU(BN(conv(cat(srcs)))), out = relu(BN(conv(y)) + shortcut(cat(srcs)))
+    void block(const ResBlock& B, int N, int H, int W, const void* s0, int c0, const void* s1, int c1, void* y, void* out, void* out_pool,
+               const float* head_w = nullptr, const float* head_b = nullptr, float* head_f32 = nullptr, uint8_t* head_u8 = nullptr) {
+        if (B.nsrc == 1) {
+            gemm(B.c1, N, H, W, {s0}, {c0}, B2R_ACT_PRELU, B.c1.slope, y, nullptr, B.cout);
+            gemm(B.c2, N, H, W, {y, s0}, {B.cout, c0}, B2R_ACT_RELU, 0.f, out, out_pool, B.cout, B2R_OUT_NHWC, head_w, head_b, head_f32,
+                 head_u8);
+        } else {
+            gemm(B.c1, N, H, W, {s0, s1}, {c0, c1}, B2R_ACT_PRELU, B.c1.slope, y, nullptr, B.cout);
+            gemm(B.c2, N, H, W, {y, s0, s1}, {B.cout, c0, c1}, B2R_ACT_RELU, 0.f, out, out_pool, B.cout, B2R_OUT_NHWC, head_w, head_b,
+                 head_f32, head_u8);
+        }
+    }
+};
+
+int run_simple_unet(const b2r_net* n, Runner& R, Workspace& ws, const void* in, int in_fmt, float* o32, uint8_t* o8, int N, int H, int W) {
+    const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
+    void* a = ws.bf16(N, H, W, 64);
+    void* e1 = ws.bf16(N, H, W, 64);
+    void* p1 = ws.bf16(N, H2, W2, 64);
+    void* e2a = ws.bf16(N, H2, W2, 128);
+    void* e2 = ws.bf16(N, H2, W2, 128);
+    void* p2 = ws.bf16(N, H4, W4, 128);
+    void* b1 = ws.bf16(N, H4, W4, 256);
+    void* b2 = ws.bf16(N, H4, W4, 256);
+    void* u2 = ws.bf16(N, H2, W2, 128);
+    void* d2 = ws.bf16(N, H2, W2, 128);
+    void* u1 = ws.bf16(N, H, W, 64);
+    const int RL = B2R_ACT_RELU;
+    R.c3(n->first, in, in_fmt, false, RL, a, N, H, W);
+    R.gemm(n->u_enc1_2, N, H, W, {a}, {64}, RL, 0.f, e1, p1, 64);
+    R.gemm(n->u_enc2_0, N, H2, W2, {p1}, {64}, RL, 0.f, e2a, nullptr, 128);
+    R.gemm(n->u_enc2_2, N, H2, W2, {e2a}, {128}, RL, 0.f, e2, p2, 128);
+    R.gemm(n->u_bott_0, N, H4, W4, {p2}, {128}, RL, 0.f, b1, nullptr, 256);
+    R.gemm(n->u_bott_2, N, H4, W4, {b1}, {256}, RL, 0.f, b2, nullptr, 256);
+    R.gemm(n->u_up2, N, H4, W4, {b2}, {256}, B2R_ACT_NONE, 0.f, u2, nullptr, 128, B2R_OUT_CONVT2X2);
+    R.gemm(n->u_dec2_0, N, H2, W2, {u2, e2}, {128, 128}, RL, 0.f, e2a, nullptr, 128);
+    R.gemm(n->u_dec2_2, N, H2, W2, {e2a}, {128}, RL, 0.f, d2, nullptr, 128);
+    R.gemm(n->u_up1, N, H2, W2, {d2}, {128}, B2R_ACT_NONE, 0.f, u1, nullptr, 64, B2R_OUT_CONVT2X2);
+    R.gemm(n->u_dec1_0, N, H, W, {u1, e1}, {64, 64}, RL, 0.f, a, nullptr, 64);
+    // dec1[2] + ReLU + final 1x1 (64 -> 3) + clamp / quantise in ONE launch
+    R.gemm(n->u_dec1_2, N, H, W, {a}, {64}, RL, 0.f, nullptr, nullptr, 0, B2R_OUT_NHWC, n->final_w, n->final_b, o32, o8);
+    return R.rc;
+}
+
+int run_resunet(const b2r_net* n, Runner& R, Workspace& ws, const void* in, int in_fmt, float* o32, uint8_t* o8, int N, int H, int W) {
+    const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
+    void* e1 = ws.bf16(N, H, W, 64);
+    void* y1 = ws.bf16(N, H, W, 64);
+    void* r1 = ws.bf16(N, H, W, 64);
+    void* p1 = ws.bf16(N, H2, W2, 64);
+    void* y2 = ws.bf16(N, H2, W2, 128);
+    void* r2 = ws.bf16(N, H2, W2, 128);
+    void* p2 = ws.bf16(N, H4, W4, 128);
+    void* y3 = ws.bf16(N, H4, W4, 256);
+    void* r3 = ws.bf16(N, H4, W4, 256);
+    void* p3 = ws.bf16(N, H8, W8, 256);
+    void* yb0 = ws.bf16(N, H8, W8, 512);
+    void* bt0 = ws.bf16(N, H8, W8, 512);
+    void* yb1 = ws.bf16(N, H8, W8, 512);
+    void* bt1 = ws.bf16(N, H8, W8, 512);
+    void* yb2 = ws.bf16(N, H8, W8, 256);
+    void* bt2 = ws.bf16(N, H8, W8, 256);
+    void* u3 = ws.bf16(N, H4, W4, 128);
+    void* yd3 = ws.bf16(N, H4, W4, 128);
+    void* d3 = ws.bf16(N, H4, W4, 128);
+    void* u2 = ws.bf16(N, H2, W2, 64);
+    void* yd2 = ws.bf16(N, H2, W2, 64);
+    void* d2 = ws.bf16(N, H2, W2, 64);
+    void* u1 = ws.bf16(N, H, W, 64);
+    R.c3(n->first, in, in_fmt, false, B2R_ACT_PRELU, e1, N, H, W);
+    R.block(n->res1, N, H, W, e1, 64, nullptr, 0, y1, r1, p1);
+    R.block(n->res2, N, H2, W2, p1, 64, nullptr, 0, y2, r2, p2);
+    R.block(n->res3, N, H4, W4, p2, 128, nullptr, 0, y3, r3, p3);
+    R.block(n->bt0, N, H8, W8, p3, 256, nullptr, 0, yb0, bt0, nullptr);
+    R.block(n->bt1, N, H8, W8, bt0, 512, nullptr, 0, yb1, bt1, nullptr);
+    R.block(n->bt2, N, H8, W8, bt1, 512, nullptr, 0, yb2, bt2, nullptr);
+    R.gemm(n->up3, N, H8, W8, {bt2}, {256}, B2R_ACT_NONE, 0.f, u3, nullptr, 128, B2R_OUT_CONVT2X2);
+    R.block(n->dec3, N, H4, W4, u3, 128, r3, 256, yd3, d3, nullptr);      // cat((d3, r3), 1) (14:171)
+    R.gemm(n->up2, N, H4, W4, {d3}, {128}, B2R_ACT_NONE, 0.f, u2, nullptr, 64, B2R_OUT_CONVT2X2);
+    R.block(n->dec2, N, H2, W2, u2, 64, r2, 128, yd2, d2, nullptr);       // cat((d2, r2), 1) (14:177)
+    R.gemm(n->up1, N, H2, W2, {d2}, {64}, B2R_ACT_NONE, 0.f, u1, nullptr, 64, B2R_OUT_CONVT2X2);
+    // dec1 block; its second conv also applies `final` (64 -> 3) and the clamp / quantise: d1 never goes to HBM
+    R.block(n->dec1, N, H, W, u1, 64, r1, 64, y1, nullptr, nullptr, n->final_w, n->final_b, o32, o8);   // cat((d1, r1), 1) (14:183)
+    return R.rc;
+}
+
+int run_vgg16(const b2r_net* n, Runner& R, Workspace& ws, const void* in, int in_fmt, bool normalize, float* logits, int N, int H, int W) {
+    void* cur = ws.bf16(N, H, W, 64);
+    R.c3(n->first, in, in_fmt, normalize, B2R_ACT_RELU, cur, N, H, W);
+    int h = H, w = W, c = 64;
+    for (auto& v : n->vgg) {
+        if (v.pooled) {
+            void* nxt = ws.bf16(N, h / 2, w / 2, v.cout);
+            R.gemm(v.g, N, h, w, {cur}, {c}, B2R_ACT_RELU, 0.f, nullptr, nxt, v.cout);
+            h /= 2;
+            w /= 2;
+            cur = nxt;
+        } else {
+            void* nxt = ws.bf16(N, h, w, v.cout);
+            R.gemm(v.g, N, h, w, {cur}, {c}, B2R_ACT_RELU, 0.f, nxt, nullptr, v.cout);
+            cur = nxt;
+        }
+        c = v.cout;
+    }
+    if (h != 7 || w != 7) {   // AdaptiveAvgPool2d((7, 7)): identity at 224 x 224
+        void* ap = ws.bf16(N, 7, 7, 512);
+        if (!R.dry && !R.rc) R.rc = b2r_adaptive_avgpool7(cur, ap, N, h, w, 512, R.stream);
+        cur = ap;
+    }
+    void* f1 = ws.bf16(1, 1, N, 4096);
+    void* f2 = ws.bf16(1, 1, N, 4096);
+    R.gemm(n->fc1, 1, 1, N, {cur}, {25088}, B2R_ACT_RELU, 0.f, f1, nullptr, 4096);
+    R.gemm(n->fc2, 1, 1, N, {f1}, {4096}, B2R_ACT_RELU, 0.f, f2, nullptr, 4096);   // Dropout is the identity in eval mode
+    if (!R.dry && !R.rc) R.rc = b2r_linear_f32out(f2, n->fc3_w, n->fc3_b, logits, N, 4096, n->num_classes, R.stream);
+    return R.rc;
+}
+
+int check_forward_args(const b2r_net* net, int arch, const void* in, int in_fmt, int N, int H, int W, int div) {
+    B2R_REQUIRE(net != nullptr, "net is null");
+    B2R_REQUIRE(net->arch == arch, "this plan was built for architecture %d, not %d", net->arch, arch);
+    B2R_REQUIRE(in != nullptr, "input is null");
+    B2R_REQUIRE(in_fmt == B2R_IN_F32_NCHW || in_fmt == B2R_IN_U8_NHWC, "in_fmt=%d", in_fmt);
+    B2R_REQUIRE(N > 0 && H > 0 && W > 0, "bad shape N=%d H=%d W=%d", N, H, W);
+    B2R_REQUIRE(H % div == 0 && W % div == 0,
+                "H and W must be multiples of %d (got %dx%d); the reference's F.interpolate re-alignment branch "
+                "(14_train_unified_advanced.py:169-183) is not implemented", div, H, W);
+    return B2R_OK;
+}
+
+}  // namespace netplan
+}  // namespace b2r
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C entry points
+// ---------------------------------------------------------------------------------------------------------------------
+using namespace b2r;
+using namespace b2r::netplan;
+
+static int build_net(int arch, int num_classes, const b2r_tensor* state, int num_tensors, Arena& A, b2r_net* net) {
+    StateDict sd;
+    for (int i = 0; i < num_tensors; ++i)
+        if (state[i].name) sd.by_name[state[i].name] = &state[i];
+    net->arch = arch;
+    net->num_classes = num_classes;
+    bool ok = false;
+    switch (arch) {
+        case B2R_NET_SIMPLE_UNET: ok = build_simple_unet(sd, A, net); break;
+        case B2R_NET_RESUNET: ok = build_resunet(sd, A, net); break;
+        case B2R_NET_VGG16: ok = build_vgg16(sd, A, net); break;
+        default: return set_error(B2R_EINVAL, "unknown architecture %d", arch);
+    }
+    if (!ok) return set_error(B2R_EINVAL, "%s", !sd.err.empty() ? sd.err.c_str() : (A.err.empty() ? "packing failed" : A.err.c_str()));
+    net->weight_bytes = (A.used + 255) & ~size_t(255);
+    return B2R_OK;
+}
+
+extern "C" int b2r_net_weight_bytes(const b2r_tensor* state, int num_tensors, size_t* bytes) {
+    B2R_REQUIRE(bytes != nullptr && state != nullptr && num_tensors > 0, "null argument");
+    // upper bound without packing anything: every weight becomes bf16 (2 B) plus, for C_out = 64 layers, a tap-folded bf16 copy
+    // (2 B), biases stay f32 (4 B): <= 4 B per state_dict element; + the identity shortcut matrices (<= 1 MB) + alignment
+    size_t total = size_t(2) << 20;
+    for (int i = 0; i < num_tensors; ++i) {
+        B2R_REQUIRE(state[i].ndim >= 0 && state[i].ndim <= 4, "tensor %d: ndim=%d", i, state[i].ndim);
+        size_t n = 1;
+        for (int k = 0; k < state[i].ndim; ++k) n *= size_t(state[i].shape[k]);
+        total += n * 4 + 1024;
+    }
+    *bytes = (total + 255) & ~size_t(255);
+    return B2R_OK;
+}
+
+extern "C" int b2r_net_create(int arch, int num_classes, const b2r_tensor* state, int num_tensors, void* dev_weights,
+                              size_t dev_weight_bytes, void* stream_v, b2r_net** out) {
+    B2R_REQUIRE(out != nullptr && state != nullptr && num_tensors > 0 && dev_weights != nullptr, "null argument");
+    B2R_REQUIRE((reinterpret_cast<uintptr_t>(dev_weights) & 255) == 0, "dev_weights must be 256-byte aligned");
+    *out = nullptr;
+    Arena A;
+    A.base = static_cast<uint8_t*>(dev_weights);
+    A.cap = dev_weight_bytes;
+    A.stream = static_cast<cudaStream_t>(stream_v);
+    b2r_net* net = new b2r_net();
+    int rc = build_net(arch, num_classes, state, num_tensors, A, net);
+    if (rc == B2R_OK && cudaStreamSynchronize(A.stream) != cudaSuccess)   // the host staging vectors die with this call
+        rc = set_error(B2R_ECUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc) {
+        cudaStreamSynchronize(A.stream);
+        delete net;
+        return rc;
+    }
+    *out = net;
+    return B2R_OK;
+}
+
+extern "C" void b2r_net_destroy(b2r_net* net) { delete net; }
+
+extern "C" int b2r_net_workspace_bytes(const b2r_net* net, int N, int H, int W, size_t* bytes) {
+    B2R_REQUIRE(net != nullptr && bytes != nullptr, "null argument");
+    B2R_REQUIRE(N > 0 && H > 0 && W > 0, "bad shape N=%d H=%d W=%d", N, H, W);
+    Workspace ws{nullptr, 0};
+    Runner R{true, nullptr};
+    switch (net->arch) {
+        case B2R_NET_SIMPLE_UNET: run_simple_unet(net, R, ws, nullptr, 0, nullptr, nullptr, N, H, W); break;
+        case B2R_NET_RESUNET: run_resunet(net, R, ws, nullptr, 0, nullptr, nullptr, N, H, W); break;
+        default: run_vgg16(net, R, ws, nullptr, 0, false, nullptr, N, H, W); break;
+    }
+    *bytes = (ws.used + 1023) & ~size_t(1023);
+    return B2R_OK;
+}
+
+static int restorer_forward(const b2r_net* net, int arch, int div, const void* in, int in_fmt, float* o32, uint8_t* o8, int N, int H,
+                            int W, void* workspace, size_t workspace_bytes, void* stream_v) {
+    int rc = check_forward_args(net, arch, in, in_fmt, N, H, W, div);
+    if (rc) return rc;
+    B2R_REQUIRE(o32 != nullptr || o8 != nullptr, "no output requested");
+    B2R_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "workspace must be 1024-byte aligned");
+    Workspace ws{static_cast<uint8_t*>(workspace), workspace_bytes};
+    {   // size check before the first launch
+        size_t need = 0;
+        b2r_net_workspace_bytes(net, N, H, W, &need);
+        B2R_REQUIRE(need <= workspace_bytes, "workspace has %zu bytes, %zu needed (b2r_net_workspace_bytes)", workspace_bytes, need);
+    }
+    Runner R{false, static_cast<cudaStream_t>(stream_v)};
+    return arch == B2R_NET_SIMPLE_UNET ? run_simple_unet(net, R, ws, in, in_fmt, o32, o8, N, H, W)
+                                       : run_resunet(net, R, ws, in, in_fmt, o32, o8, N, H, W);
+}
+
+extern "C" int b2r_unet_forward(const b2r_net* net, const void* in, int in_fmt, float* out_f32_nchw, uint8_t* out_u8_nhwc, int N, int H,
+                                int W, void* workspace, size_t workspace_bytes, void* stream) {
+    return restorer_forward(net, B2R_NET_SIMPLE_UNET, 4, in, in_fmt, out_f32_nchw, out_u8_nhwc, N, H, W, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b2r_resunet_forward(const b2r_net* net, const void* in, int in_fmt, float* out_f32_nchw, uint8_t* out_u8_nhwc, int N, int H,
+                                   int W, void* workspace, size_t workspace_bytes, void* stream) {
+    return restorer_forward(net, B2R_NET_RESUNET, 8, in, in_fmt, out_f32_nchw, out_u8_nhwc, N, H, W, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b2r_vgg16_forward(const b2r_net* net, const void* in, int in_fmt, int normalize, float* logits, int N, int H, int W,
+                                 void* workspace, size_t workspace_bytes, void* stream_v) {
+    int rc = check_forward_args(net, B2R_NET_VGG16, in, in_fmt, N, H, W, 32);
+    if (rc) return rc;
+    B2R_REQUIRE(logits != nullptr, "logits is null");
+    B2R_REQUIRE(!(normalize && in_fmt != B2R_IN_U8_NHWC), "normalize = 1 is the u8 hand-off; float input is taken as already normalised");
+    B2R_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "workspace must be 1024-byte aligned");
+    size_t need = 0;
+    b2r_net_workspace_bytes(net, N, H, W, &need);
+    B2R_REQUIRE(need <= workspace_bytes, "workspace has %zu bytes, %zu needed (b2r_net_workspace_bytes)", workspace_bytes, need);
+    Workspace ws{static_cast<uint8_t*>(workspace), workspace_bytes};
+    Runner R{false, static_cast<cudaStream_t>(stream_v)};
+    return run_vgg16(net, R, ws, in, in_fmt, normalize != 0, logits, N, H, W);
+}

@@ -17,6 +17,7 @@
 #ifndef B2R_H_
 #define B2R_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -284,6 +285,60 @@ int b2r_sse_u8(const uint8_t* a, const uint8_t* b, uint64_t* sse, int N, int64_t
  * H, W >= 7 (skimage raises ValueError below that). */
 int b2r_ssim_u8(const uint8_t* a, const uint8_t* b, double* ssim, int N, int H, int W, int C, double data_range,
                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * (7) Whole-network entry points: the layer graphs of the three modules behind ONE call each, for hosts that are not
+ * Python.  Replaces, for such a host, `model = ResUNet(); model.load_state_dict(torch.load(path)); model.eval()`
+ * (17_run_unified_inference.py:59-64) + `model(input_tensor)` (17:85) [+ clamp / x255 / astype(uint8), 17:86-92], the same
+ * for SimpleUNet (08_run_inference.py:68-70,93-98), and `models.vgg16` + `classifier[6] = nn.Linear(4096, 43)` +
+ * `model(inputs)` (18_test_unified_benchmark.py:58-59,46) with its Resize/ToTensor/Normalize hand-off (18:28-32).
+ *
+ * b2r_net_create packs a reference state_dict — HOST float32 tensors under the reference's own key names, e.g. what
+ * torch.load('restoration_unified_resnet.pth') holds — into the device layouts of sections (2)-(3): eval-mode BatchNorm
+ * folded in fp64, k-block ordered bf16 weight matrices, ConvTranspose as four stacked 1x1 matrices, classifier[0]
+ * columns permuted to NHWC.  Strict like load_state_dict: a missing key or a wrong shape returns B2R_EINVAL and
+ * b2r_last_error() names the key; int64 `num_batches_tracked` entries and unknown keys are ignored.
+ * Ownership: the caller owns `dev_weights` (>= b2r_net_weight_bytes, 256-byte aligned) and every workspace; the plan holds
+ * pointers into dev_weights until b2r_net_destroy.  The forwards enqueue on `stream` and never allocate.
+ * in_fmt as in section (2): B2R_IN_F32_NCHW (the nn.Module.forward argument) or B2R_IN_U8_NHWC (ToTensor fused).
+ * H, W: multiples of 4 (SimpleUNet) / 8 (ResUNet) / 32 (VGG16), else B2R_EINVAL (the reference's nearest-neighbour
+ * re-alignment, 14:169-183, is not implemented).
+ * ------------------------------------------------------------------------------------------------------------- */
+#define B2R_NET_SIMPLE_UNET 0
+#define B2R_NET_RESUNET 1
+#define B2R_NET_VGG16 2
+#define B2R_DT_F32 0
+#define B2R_DT_I64 1
+
+typedef struct b2r_tensor {      /* one state_dict entry */
+    const char* name;            /* reference key, e.g. "res1.conv_block.1.running_var" */
+    const void* data;            /* HOST pointer, contiguous */
+    int32_t dtype;               /* B2R_DT_* */
+    int32_t ndim;                /* 0..4 */
+    int64_t shape[4];
+} b2r_tensor;
+
+typedef struct b2r_net b2r_net;  /* opaque */
+
+/* upper bound of the device bytes b2r_net_create needs for this state_dict */
+int b2r_net_weight_bytes(const b2r_tensor* state, int num_tensors, size_t* bytes);
+int b2r_net_create(int arch, int num_classes /* VGG16 head; ignored otherwise */, const b2r_tensor* state, int num_tensors,
+                   void* dev_weights, size_t dev_weight_bytes, void* stream, b2r_net** net);
+void b2r_net_destroy(b2r_net* net);
+/* activation workspace (device, 1024-byte aligned) one forward of N x H x W needs */
+int b2r_net_workspace_bytes(const b2r_net* net, int N, int H, int W, size_t* bytes);
+
+/* SimpleUNet.forward (07_train_restoration.py:99-120) / ResUNet.forward (14_train_unified_advanced.py:151-186).
+ * out_f32_nchw (optional): f32 [N,3,H,W], the module output, unclamped; out_u8_nhwc (optional): clamp(0,1) * 255 truncated,
+ * u8 [N,H,W,3] (17:86-92).  At least one output. */
+int b2r_unet_forward(const b2r_net* net, const void* in, int in_fmt, float* out_f32_nchw, uint8_t* out_u8_nhwc, int N, int H,
+                     int W, void* workspace, size_t workspace_bytes, void* stream);
+int b2r_resunet_forward(const b2r_net* net, const void* in, int in_fmt, float* out_f32_nchw, uint8_t* out_u8_nhwc, int N, int H,
+                        int W, void* workspace, size_t workspace_bytes, void* stream);
+/* VGG16-43 forward: logits f32 [N, num_classes].  normalize = 1 (u8 input only): ToTensor + Normalize(ImageNet mean / std,
+ * 18:28-32) fused into the first conv; normalize = 0: the input is the already normalised tensor (f32 NCHW) or plain u8/255. */
+int b2r_vgg16_forward(const b2r_net* net, const void* in, int in_fmt, int normalize, float* logits, int N, int H, int W,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
