@@ -67,8 +67,9 @@ struct ImgParams {
 
 // chain(v): quant(noise(fog(v / 255))) for the 3 channels of the pixel at linear index `pix`.
 // `unit` = shared-memory table of float(u)/255 (IEEE division, as NumPy computes `astype(float32) / 255.0`).
-__device__ __forceinline__ void chain3(const ImgParams& ip, const float* unit, uint32_t pix, const int (&v)[3],
-                                       int (&q)[3]) {
+// (item, j) = the pixel's 4-pixel work item and its position in it: they key the Philox noise (stream 2, philox.cuh).
+__device__ __forceinline__ void chain3(const ImgParams& ip, const float* unit, uint32_t pix, uint32_t item, int j,
+                                       const int (&v)[3], int (&q)[3]) {
     float x[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -88,7 +89,7 @@ __device__ __forceinline__ void chain3(const ImgParams& ip, const float* unit, u
     }
     if (ip.noise_on) {
         float z[3];
-        pixel_normals(ip.seed, ip.image, pix, z);
+        pixel_normals_v2(ip.seed, ip.image, item, j, z);
 #pragma unroll
         for (int c = 0; c < 3; ++c) x[c] = fmaf(ip.sigma, z[c], x[c]);
     }
@@ -100,6 +101,58 @@ __device__ __forceinline__ void chain3(const ImgParams& ip, const float* unit, u
         uint32_t b;
         asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(b) : "f"(__fmul_rn(y, 255.0f)));
         q[c] = int(b);
+    }
+}
+
+// chain() for a whole work item (4 consecutive pixels of row y, group gx): the noise of the item comes from three Philox
+// calls (noise stream 2, philox.cuh).  `pix0` = linear index of the item's first pixel (injected-noise parity path only).
+__device__ __forceinline__ void chain_item(const ImgParams& ip, const float* unit, uint32_t item, uint32_t pix0, int nvalid,
+                                           const int (&v)[4][3], int (&q)[4][3]) {
+    if (ip.noise_on && ip.noise != nullptr) {   // parity path: per pixel, float64 like NumPy (chain3); never past the row end
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            q[j][0] = q[j][1] = q[j][2] = 0;
+            if (j < nvalid) chain3(ip, unit, pix0 + j, item, j, v[j], q[j]);
+        }
+        return;
+    }
+    float x[12];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float f = unit[v[j][c]];
+            if (ip.fog_on) f = __fadd_rn(__fmul_rn(f, ip.t), ip.add);  // two roundings, like NumPy (no FMA)
+            x[3 * j + c] = f;
+        }
+    if (ip.noise_on) {
+        float z[12];
+        item_normals(ip.seed, ip.image, item, z);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) x[i] = fmaf(ip.sigma, z[i], x[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        float y = x[i];
+        if (ip.clip_after) y = fminf(fmaxf(y, 0.f), 1.f);
+        uint32_t b;
+        asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(b) : "f"(__fmul_rn(y, 255.0f)));
+        q[i / 3][i % 3] = int(b);
+    }
+}
+
+// 12 bytes of an item <-> three 32-bit words (pixel j channel c = byte 3j + c), one PRMT per byte
+__device__ __forceinline__ void unpack12(const uint32_t (&w)[3], int (&v)[4][3]) {
+#pragma unroll
+    for (int b = 0; b < 12; ++b) v[b / 3][b % 3] = int(__byte_perm(w[b >> 2], 0u, 0x4440u + uint32_t(b & 3)));
+}
+__device__ __forceinline__ void pack12(const int (&q)[4][3], uint32_t (&w)[3]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int b = 4 * i;
+        const uint32_t lo = __byte_perm(uint32_t(q[b / 3][b % 3]), uint32_t(q[(b + 1) / 3][(b + 1) % 3]), 0x0040u);
+        const uint32_t hi = __byte_perm(uint32_t(q[(b + 2) / 3][(b + 2) % 3]), uint32_t(q[(b + 3) / 3][(b + 3) % 3]), 0x0040u);
+        w[i] = __byte_perm(lo, hi, 0x5410u);
     }
 }
 
@@ -124,22 +177,11 @@ __device__ __forceinline__ void chain_rows(const ImgParams& ip, const float* s_u
             const int nb = min(4, W - x0) * 3;
             for (int b = 0; b < nb; ++b) bytes[b >> 2] |= uint32_t(img_in[off + b]) << (8 * (b & 3));
         }
-        uint32_t outb[3] = {0u, 0u, 0u};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int v[3], q[3] = {0, 0, 0};
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int b = 3 * j + c;
-                v[c] = int((bytes[b >> 2] >> (8 * (b & 3))) & 0xFFu);
-            }
-            if (x0 + j < W) chain3(ip, s_unit, uint32_t((r0 + y) * W + x0 + j), v, q);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int b = 3 * j + c;
-                outb[b >> 2] |= uint32_t(q[c]) << (8 * (b & 3));
-            }
-        }
+        uint32_t outb[3];
+        int v[4][3], q[4][3];
+        unpack12(bytes, v);
+        chain_item(ip, s_unit, uint32_t((r0 + y) * groups + (x0 >> 2)), uint32_t((r0 + y) * W + x0), min(4, W - x0), v, q);
+        pack12(q, outb);
         if (fast) {
             uint32_t* d32 = reinterpret_cast<uint32_t*>(img_out + off);
             d32[0] = outb[0];
@@ -263,22 +305,21 @@ __global__ void __launch_bounds__(kDegThreads, 2) degrade_kernel(const DegradePa
             for (int b2 = 0; b2 < nb; ++b2) bytes[b2 >> 2] |= uint32_t(img_in[off + b2]) << (8 * (b2 & 3));
         }
         float f[3][4];
+        {
+            int v[4][3];
+            unpack12(bytes, v);
+            if (chain_first && chain_on) {
+                int q[4][3];
+                chain_item(ip, s_unit, uint32_t(h * groups + g), uint32_t(h * W + x0), min(4, W - x0), v, q);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int v[3];
+                for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int b2 = 3 * j + c;
-                v[c] = int((bytes[b2 >> 2] >> (8 * (b2 & 3))) & 0xFFu);
-            }
-            if (chain_first && chain_on && x0 + j < W) {
-                int q[3];
-                chain3(ip, s_unit, uint32_t(h * W + x0 + j), v, q);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) v[c] = q[c];
+                    for (int c = 0; c < 3; ++c) v[j][c] = q[j][c];
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) f[c][j] = float(v[c]);
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) f[c][j] = float(v[j][c]);
         }
         float* dstp = s_planes + sy * pitch + kStageShift + x0;
         if (full) {
@@ -310,7 +351,7 @@ __global__ void __launch_bounds__(kDegThreads, 2) degrade_kernel(const DegradePa
             for (int c = 0; c < 3; ++c) v[c] = img_in[size_t(pix) * 3 + c];
             if (chain_first && chain_on) {
                 int q[3];
-                chain3(ip, s_unit, pix, v, q);
+                chain3(ip, s_unit, pix, uint32_t(h * groups + (w >> 2)), w & 3, v, q);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) v[c] = q[c];
             }
@@ -393,25 +434,22 @@ __global__ void __launch_bounds__(kDegThreads, 2) degrade_kernel(const DegradePa
                     }
                 }
         }
-        uint32_t bytes[3] = {0u, 0u, 0u};  // 12 output bytes: pixel j channel c -> byte 3*j + c
+        uint32_t bytes[3];  // 12 output bytes: pixel j channel c -> byte 3*j + c
+        {
+            int v[4][3];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int v[3];
+            for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                v[c] = round_u8(acc[c][j]);
-                if (tail_item && x0 + j == W - 1 && c >= 3 - tail) v[c] = round_u8(tacc[c]);
-            }
-            if (!chain_first && chain_on && x0 + j < W) {
-                int q[3];
-                chain3(ip, s_unit, uint32_t((r0 + y) * W + x0 + j), v, q);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) v[c] = q[c];
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int b = 3 * j + c;
-                bytes[b >> 2] |= uint32_t(v[c]) << (8 * (b & 3));
+                for (int c = 0; c < 3; ++c) {
+                    v[j][c] = round_u8(acc[c][j]);
+                    if (tail_item && x0 + j == W - 1 && c >= 3 - tail) v[j][c] = round_u8(tacc[c]);
+                }
+            if (!chain_first && chain_on) {
+                int q[4][3];
+                chain_item(ip, s_unit, uint32_t((r0 + y) * groups + g), uint32_t((r0 + y) * W + x0), min(4, W - x0), v, q);
+                pack12(q, bytes);
+            } else {
+                pack12(v, bytes);
             }
         }
         uint8_t* dst = img_out + (size_t(r0 + y) * W + x0) * 3;
@@ -473,7 +511,7 @@ __global__ void __launch_bounds__(kGenThreads) degrade_pointwise_kernel(const De
     __syncthreads();
     const int v[3] = {tid, tid, tid};
     int q[3];
-    chain3(ip, s_unit, 0u, v, q);
+    chain3(ip, s_unit, 0u, 0u, 0, v, q);
     s_lut[tid] = uint8_t(q[0]);
     __syncthreads();
     const long elems = long(P.H) * P.W * 3;

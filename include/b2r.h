@@ -71,8 +71,11 @@ const char* b2r_last_conv_kernel(void);
  *        overlapping in / out ranges with ksize != NULL return B2R_EINVAL.
  * Noise: if `noise` is non-null it is an f64 NHWC tensor of the noise values themselves (what
  *        np.random.normal(0, sigma, shape) returned), added in float64 like NumPy does: the parity path ("AWGN is
- *        compared by injecting the same noise tensor").  Otherwise Philox4x32-10 keyed by `seed`,
- *        counter = (pixel index, image_index0 + i), Box-Muller, scaled by sigma[i].
+ *        compared by injecting the same noise tensor").  Otherwise Philox4x32-10 keyed by `seed`, noise stream 2 (ABI 200):
+ *        the 12 values of 4 consecutive pixels of a row take the four Box-Muller normals of each of three calls with
+ *        counter = (y * ceil(W / 4) + x / 4, image_index0 + i (64 bit), 4 + k), scaled by sigma[i]; a pure function of
+ *        (seed, global image index, y, x, channel, W): independent of batch split, launch geometry and world size
+ *        (oracle/degrade_oracle.py::philox_normals_v2).
  * ------------------------------------------------------------------------------------------------------------- */
 #define B2R_ORDER_BLUR_FOG_NOISE 0
 #define B2R_ORDER_FOG_NOISE_BLUR 1

@@ -195,7 +195,7 @@ def test_identity_when_nothing_is_applied():
 def test_philox_noise_matches_oracle_stream_and_is_shard_invariant():
     from b200restore import degrade
     from oracle import degrade_oracle as O
-    n, h, w = 4, 96, 128
+    n, h, w = 4, 96, 126            # w not a multiple of 4: the last work item of a row is ragged
     imgs = np.full((n, h, w, 3), 128, dtype=np.uint8)
     p = degrade.DegradeParams(n)
     for i in range(n):
@@ -212,7 +212,7 @@ def test_philox_noise_matches_oracle_stream_and_is_shard_invariant():
     #     value across a truncation boundary, so <= 1 LSB on a small fraction of bytes
     sig = np.float32(0.02 ** 0.5)
     for i in range(n):
-        zz = O.philox_normals(1234, 1000 + i, h, w)
+        zz = O.philox_normals_v2(1234, 1000 + i, h, w)
         ref = O.quant_u8((imgs[i].astype(np.float32) / 255.0) + (sig * zz).astype(np.float64))
         diff = np.abs(full[i].astype(int) - ref.astype(int))
         assert diff.max() <= 1 and (diff > 0).mean() < 2e-3, (i, int(diff.max()), float((diff > 0).mean()))
@@ -222,6 +222,18 @@ def test_philox_noise_matches_oracle_stream_and_is_shard_invariant():
     # (d) a different seed gives a different field
     other = degrade.degrade(_dev(imgs), p, seed=1235, image_index0=1000).cpu().numpy()
     assert (other != full).mean() > 0.9
+    # (e) the blur kernel's code paths draw the SAME stream: script-14 order (noise applied while staging, halo columns
+    #     through the per-pixel form) with a 1-tap identity "blur" must reproduce the no-blur bytes
+    pb = degrade.DegradeParams(n, order=1)
+    for i in range(n):
+        pb.set_noise(i, 0.02)
+        pb.ksize[i] = 3
+        pb.taps[i, :] = 0
+        pb.taps[i, 4] = 1.0                    # 3 x 3 kernel with only the centre tap: blur == identity
+    ident = degrade.degrade(_dev(imgs), pb, seed=1234, image_index0=1000).cpu().numpy()
+    assert np.array_equal(ident, full)
+    pb.order = 0                               # script-16 order: blur (identity) first, chain after
+    assert np.array_equal(degrade.degrade(_dev(imgs), pb, seed=1234, image_index0=1000).cpu().numpy(), full)
 
 
 def test_argument_errors():
