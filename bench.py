@@ -569,16 +569,43 @@ def run_ours(args):
             step_device()
     torch.cuda.synchronize()
 
-    # ---- timed region: K steps, per-launch events on the dominant kernel family, clocks sampled on every rank
+    # ---- timed region (`value`): K steps, inputs resident in HBM, clocks sampled on every rank.  restore -> classify -> count of
+    # each micro-batch is replayed as one CUDA graph (bit-identical to eager, tests/test_pipeline_gpu.py): ~330 launches per
+    # micro-batch cost the Python host ~40 ms against 45 ms of GPU work, which made a rank host-bound as soon as its core was
+    # shared (the 1 -> 8 efficiency of round 1).  --graph 0 keeps this leg eager.
     sampler = ClockSampler(local)
     sampler.start()
-    timer = ops.KernelTimer(kinds=("conv_gemm",))
-    launches0 = ops.STATS["launches"]
-    with ops.timing(timer):
-        total_ms, own_ms, host_s, counts = timed(fn_dev, steps)
-    launches = ops.STATS["launches"] - launches0
-    ksum = timer.summary().get("conv_gemm", {"launches": 0, "work": 0.0, "ms": 1e-9})
+    use_graph = bool(args.graph) and cascade is None and classify
+    pipe.use_graph = use_graph
+    if use_graph:                       # capture outside the timed region
+        if total_mode:
+            im, lb = pool_slice(dev_imgs, dev_labels, lo, min(mb, hi - lo))
+            pipe.run_micro_batch(im, lb, B.pipeline._slice_params(params, 0, im.shape[0]), 2, lo, totals)
+        else:
+            step_device()
+        torch.cuda.synchronize()
+    launches0, replayed0 = ops.STATS["launches"], pipe.graph_launches_replayed
+    total_ms, own_ms, host_s, counts = timed(fn_dev, steps)
+    graph_launches = pipe.graph_launches_replayed - replayed0
+    launches = ops.STATS["launches"] - launches0 + graph_launches
     clocks = sampler.stop()
+    pipe.use_graph = False
+
+    # ---- instrumented steps (roofline): the SAME step, eager, every tcgen05 conv launch bracketed by a CUDA-event pair on the
+    # launching stream; max(1, K / 5) steps right after the timed region (same clocks, same resident inputs)
+    inst_steps = 1 if total_mode else max(1, steps // 5)
+    timer = ops.KernelTimer(kinds=("conv_gemm",))
+    if total_mode:
+        def fn_inst():
+            for g0 in range(lo, min(lo + 8 * mb, hi), mb):
+                c = min(mb, hi - g0)
+                im, lb = pool_slice(dev_imgs, dev_labels, g0, c)
+                pipe.run_micro_batch(im, lb, B.pipeline._slice_params(params, 0, c), 2, g0, totals)
+    else:
+        fn_inst = fn_dev
+    with ops.timing(timer):
+        _, inst_ms, inst_host_s, _ = timed(fn_inst, inst_steps)
+    ksum = timer.summary().get("conv_gemm", {"launches": 0, "work": 0.0, "ms": 1e-9})
 
     # ---- end-to-end (host buffers): same K steps
     e2e = None
@@ -598,7 +625,7 @@ def run_ours(args):
                "counts": [int(c2[0]), int(c2[1])]}
 
     # ---- per-rank record (the 1 -> N curve explains itself)
-    mine = {"rank": rank, "ms_per_step": own_ms / steps, "conv_kernel_ms_per_step": ksum["ms"] / steps,
+    mine = {"rank": rank, "ms_per_step": own_ms / steps, "conv_kernel_ms_per_step": ksum["ms"] / inst_steps,
             "host_launch_s_per_step": host_s / steps, "sm_mhz": clocks.get("sm_mhz"), "power_w": clocks.get("power_w"),
             "reasons": clocks.get("reasons"), "cores": len(cores_mine) if cores_mine else None, "images": int(hi - lo)}
     if world > 1:
@@ -643,18 +670,24 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "strong" if total_mode else "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "config": cfg,
         "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples", "power_w")},
+        "cuda_graph": use_graph,
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convs (conv_gemm_pair_kernel<256> cta_group::2, conv_w3_kernel, conv_gemm_halo_kernel<128>, conv_gemm_kernel<N>)",
                      "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
                      "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
-                     "launches": ksum["launches"], "kernel_ms_per_step": ksum["ms"] / steps,
+                     "launches": ksum["launches"], "kernel_ms_per_step": ksum["ms"] / inst_steps,
+                     "instrumented": {"steps": inst_steps, "ms_per_step": inst_ms / inst_steps,
+                                      "host_launch_s_per_step": inst_host_s / inst_steps,
+                                      "note": "eager steps with one CUDA-event pair per conv launch, run right after the timed "
+                                              "region; `value` itself replays CUDA graphs" if use_graph else
+                                              "same eager path as the timed region"},
                      "dominant_kernel": max(ksum.get("by_kernel", {"?": {"ms": 0}}).items(), key=lambda kv: kv[1]["ms"])[0],
-                     "by_kernel": {k: {"launches": v["launches"], "share_of_step": v["ms"] / own_ms,
+                     "by_kernel": {k: {"launches": v["launches"], "share_of_step": v["ms"] / inst_ms,
                                        "achieved": v["work"] / (v["ms"] * 1e-3) / 1e12,
                                        "frac": v["work"] / (v["ms"] * 1e-3) / 1e12 / peak_tf}
                                    for k, v in sorted(ksum.get("by_kernel", {}).items(), key=lambda kv: -kv[1]["ms"])},
-                     "share_of_step": ksum["ms"] / own_ms,
+                     "share_of_step": ksum["ms"] / inst_ms,
                      "pipeline_tflops": ips / world * gflop_img / 1e3 if gflop_img else None},
         "roofline_hbm": hbm,
         "per_rank": {"ms_per_step": minmedmax([g["ms_per_step"] for g in gathered]),

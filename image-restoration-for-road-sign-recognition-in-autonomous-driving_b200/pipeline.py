@@ -49,6 +49,7 @@ class RestoreClassifyPipeline:
         # and replayed; the degradation stays a plain launch because its Philox counter base is a by-value argument.
         self.use_graph = bool(use_graph)
         self._graphs = {}
+        self.graph_launches_replayed = 0      # libb2r kernel launches executed through graph replays (launch accounting)
         self.device = next(judge.parameters()).device
         if self.device.type != "cuda":
             raise L.B2RError("RestoreClassifyPipeline needs its modules on a CUDA device (no CPU fallback)")
@@ -107,12 +108,14 @@ class RestoreClassifyPipeline:
         self._restore_classify(ent["deg"], ent["rest"], ent["labels"], ent["counts"])   # eager once: workspaces, attributes
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
+        launches_before = ops.STATS["launches"]
         with torch.cuda.graph(graph):
             ent["pred"] = self._restore_classify(ent["deg"], ent["rest"], ent["labels"], ent["counts"])
         # the graph holds raw pointers into the modules' activation workspaces: keep those tensors alive even if the
         # workspaces later switch to another batch shape
         ent["pinned"] = (dict(self.restorer._ws._bufs), dict(self.judge._ws._bufs))
         ent["graph"] = graph
+        ent["launches"] = ops.STATS["launches"] - launches_before
         self._graphs[key] = ent
         return ent
 
@@ -127,6 +130,7 @@ class RestoreClassifyPipeline:
             ent["labels"].copy_(labels)
         ent["counts"].zero_()
         ent["graph"].replay()
+        self.graph_launches_replayed += ent["launches"]
         if counts is not None:
             counts.add_(ent["counts"])
         return ent["pred"]          # static output of the graph: consume it before the next micro-batch of this shape
