@@ -61,7 +61,7 @@ struct alignas(64) ConvW3Params {
 };
 
 size_t conv_w3_smem_bytes(size_t b_bytes, int ring_slots, size_t stage_stride);
-int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream);
+int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream, bool pair);
 
 #ifdef __CUDACC__
 // Walks tiles first, first + stride, ... as (image, tile row, tile column) without per-tile integer divisions: the two

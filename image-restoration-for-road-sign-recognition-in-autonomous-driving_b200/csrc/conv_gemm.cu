@@ -1028,21 +1028,38 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
         }
     }
     // shared-memory plan.  Resident weights: 24 KB per k-step of a 3x3 group, 8 KB (the kw = 1 rows) for a 1x1 group that is
-    // not the first group.  The head variant stages only its partial sums (6 KB per buffer), other layers a full + a pooled
-    // tile.  What is left goes to the input ring: two tiles' worth of slots lets the two MMA issuers really alternate
-    // (with one tile's worth the next tile's boxes cannot even be requested before this tile's MMAs retire).
+    // not the first group; HALF of that per CTA in pair mode (cta_group::2, two CTAs share every weight block).  The head
+    // variant stages only its partial sums (6 KB per buffer), other layers a full + a pooled tile.  What is left goes to the
+    // input ring: two tiles' worth of slots lets the two MMA issuers really alternate (with one tile's worth the next
+    // tile's boxes cannot even be requested before this tile's MMAs retire).
     const size_t stage_stride = d->head_w ? 6144 : (14336 + 4096);
+    int sms_w3 = 0;
+    {
+        int src_ = device_sm_count(&sms_w3);
+        if (src_) return src_;
+    }
+    static const bool no_w3pair_env = getenv("B2R_NO_W3PAIR") != nullptr;   // A/B switch for tools/layer_bench.py, read once
+    const long tiles_total = (long)ceil_div(d->W, 14) * ceil_div(d->H, 8) * d->N;
+    bool pair = !no_w3pair_env && !(d->flags & B2R_CONV_NO_PAIR) && sms_w3 >= 2 && tiles_total >= 2 && d->max_ctas != 1;
     uint32_t boff[kW3MaxGroups];
     size_t b_bytes = 0;
-    for (int g = 0; g < ng; ++g) {
-        boff[g] = uint32_t(b_bytes >> 4);
-        const bool centre = (groups[g] >> 2) & 1;
-        b_bytes += centre ? (g > 0 ? 8192 : 24576) : 3 * 24576;
+    int ring = 0, b_slots = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const size_t div = pair ? 2 : 1;
+        b_bytes = 0;
+        for (int g = 0; g < ng; ++g) {
+            boff[g] = uint32_t(b_bytes >> 4);
+            const bool centre = (groups[g] >> 2) & 1;
+            b_bytes += (centre ? (g > 0 ? 8192 : 24576) : 3 * 24576) / div;
+        }
+        ring = 2 * ng > kN64MaxRing ? kN64MaxRing : (2 * ng < 4 ? 4 : 2 * ng);
+        if (pair && ring < kN64MaxRing && ring < 6) ring = 6 < kN64MaxRing ? 6 : kN64MaxRing;   // the halved weights leave room: a third tile in flight
+        while (ring >= 2 && conv_w3_smem_bytes(b_bytes, ring, stage_stride) > (size_t)kN64MaxSmem) --ring;
+        if (ring >= (pair ? ng : 2) || !pair) break;
+        pair = false;   // even the halved weights do not leave a ring of one tile: single-CTA kernel (streams the weights)
     }
-    int ring = 2 * ng > kN64MaxRing ? kN64MaxRing : (2 * ng < 4 ? 4 : 2 * ng), b_slots = 0;
-    while (ring >= 2 && conv_w3_smem_bytes(b_bytes, ring, stage_stride) > (size_t)kN64MaxSmem) --ring;
     if (ring < 2) {
-        // weights too large to stay resident (192 -> 64: 216 KB): stream the k-steps through a ring instead
+        // weights too large to stay resident (192 -> 64 without pair mode: 216 KB): stream the k-steps through a ring instead
         if (d->head_w) return B2R_OK;
         ring = 3;
         b_slots = kN64MaxRing;
@@ -1068,10 +1085,10 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
         const uint64_t K = (uint64_t)nsteps * 64;
         const uint64_t dims[2] = {K, 192};
         const uint64_t strides[1] = {K * 2};
-        const uint32_t box[2] = {64, 192};
+        const uint32_t box[2] = {64, pair ? 96u : 192u};       // pair mode: each CTA loads its half of the rows
         int rc = encode_tmap_bf16(&P.b_map, d->weights_w3, 2, dims, strides, box);
         if (rc) return rc;
-        const uint32_t box_c[2] = {64, 64};
+        const uint32_t box_c[2] = {64, pair ? 32u : 64u};
         rc = encode_tmap_bf16(&P.b_map_c, d->weights_w3, 2, dims, strides, box_c);
         if (rc) return rc;
     }
@@ -1120,14 +1137,20 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
     P.store_full = d->out != nullptr;
     P.store_pool = d->out_pool != nullptr;
     memcpy(P.group, groups, sizeof(uint32_t) * ng);
-    int sms = 0;
-    int rc = device_sm_count(&sms);
-    if (rc) return rc;
+    const int sms = sms_w3;
     const long total_tiles = (long)P.tiles_w * P.tiles_h * P.n_img;
     if (total_tiles >= (1L << 31)) return B2R_OK;
     int grid = d->max_ctas > 0 ? d->max_ctas : sms;
-    if (grid > total_tiles) grid = (int)total_tiles;
-    rc = launch_conv_w3(P, grid, stream);
+    if (pair) {
+        const long pairs = (total_tiles + 1) / 2;
+        long clusters = grid / 2;
+        if (clusters < 1) clusters = 1;
+        if (clusters > pairs) clusters = pairs;
+        grid = int(2 * clusters);
+    } else if (grid > total_tiles) {
+        grid = (int)total_tiles;
+    }
+    int rc = launch_conv_w3(P, grid, stream, pair);
     if (rc) return rc;
     *handled = true;
     return B2R_OK;

@@ -45,10 +45,23 @@ constexpr int kW3PrefetchTiles = B2R_W3_PREFETCH_TILES;   // L2 prefetch distanc
 
 // kHead = true adds the fused 64 -> 3 output head; it is a separate instantiation because even unused, the extra
 // epilogue code cost the plain layers ~5 % (A/B in one gpurun call, profiles/r01_w3_timeline.md).
-template <bool kHead>
+//
+// kPair = true (round 2) runs the same kernel as a cluster of two CTAs with tcgen05.mma.cta_group::2: one MMA of M = 256 x
+// N = 192 serves two neighbouring tiles, each CTA holding its own tile's halo box (its 128 rows of A, its 128 lanes of D,
+// its epilogue and stores) and HALF of the weight rows (96 of the 192 rows of a k-step, 32 of the 64 rows of a compact
+// 1x1 k-step).  Why: ncu on the single-CTA kernel (profiles/r02_ncu_w3.md) shows the tensor core's shared-memory operand
+// port busy 82 % of the time with the math pipe at 54 %: an N = 192 MMA reads 4 KB of A + 6 KB of B per 96 cycles =
+// 107 B/clk, and TMA fills, staging writes and TMA-store reads add ~42 B/clk on a 128 B/clk shared memory.  With B split
+// over the pair each SM reads 4 + 3 KB per MMA (73 B/clk).  The resident weights halve too (36 KB for 64 -> 64; the
+// 192 -> 64 layer fits without the streamed-weights mode) and the ring gets the space.
+// Protocol as in conv_gemm_pair_kernel: the leader (cluster rank 0) issues (both issuer warps); its "data landed" and
+// "weights landed" barriers count the TMA bytes of both CTAs; tcgen05.commit multicasts to both CTAs' "slot free" /
+// "accumulator ready" barriers; the epilogue warps of both CTAs release the accumulator on the leader's barrier.
+template <bool kHead, bool kPair = false>
 __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_constant__ ConvW3Params p) {
-    constexpr uint32_t kIdesc = make_idesc_bf16_f32(128, 192);
-    constexpr uint32_t kIdesc64 = make_idesc_bf16_f32(128, 64);
+    constexpr uint32_t kIdesc = make_idesc_bf16_f32(kPair ? 256 : 128, 192);
+    constexpr uint32_t kIdesc64 = make_idesc_bf16_f32(kPair ? 256 : 128, 64);
+    constexpr int kBStepCta = kPair ? kW3BStep / 2 : kW3BStep;   // bytes of one k-step's weights in THIS CTA
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* b_res = smem;
@@ -79,6 +92,14 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     const long total_tiles = long(p.tiles_w) * p.tiles_h * p.n_img;
     const int R = p.ring_slots;
     const int G = p.num_groups;
+    // work units: single mode = tiles, one per CTA and step; pair mode = tile pairs, rank r of the cluster takes tile 2 u + r
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const long unit0 = kPair ? long(blockIdx.x >> 1) : long(blockIdx.x);
+    const long ustride = kPair ? long(gridDim.x >> 1) : long(gridDim.x);
+    const long total_units = kPair ? (total_tiles + 1) / 2 : total_tiles;
+    const long tile0 = kPair ? 2 * unit0 + rank : unit0;          // this CTA's first tile and tile stride
+    const long tstride = kPair ? 2 * ustride : ustride;
 
     if (warp_idx == 0 && lane == 0) {
         for (int i = 0; i < B2R_MAX_SRC; ++i) tma_prefetch_desc(&p.a_map[i]);
@@ -95,7 +116,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
-                mbar_init(&tmem_empty_bar[s], kW3EpiWarps);
+                mbar_init(&tmem_empty_bar[s], kPair ? 2 * kW3EpiWarps : kW3EpiWarps);
             }
             mbar_init(b_full_bar, 1);
             for (int s = 0; s < 2; ++s) {
@@ -110,7 +131,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc<512>(tmem_ptr_s);   // 2 accumulator stages x 192 columns (power-of-two allocation)
+        if constexpr (kPair) tmem_alloc_pair<512>(tmem_ptr_s);
+        else tmem_alloc<512>(tmem_ptr_s);   // 2 accumulator stages x 192 columns (power-of-two allocation)
     }
     if (threadIdx.x >= 64 && threadIdx.x < 128) bias_s[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
     if (kHead && threadIdx.x >= 128 && threadIdx.x < 128 + 195)
@@ -121,8 +143,13 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (kPair) cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / complete_tx
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
+
+    // Pair mode with an odd tile count: the last pair's second CTA walks one tile past the end (image index n_img).  Its TMA
+    // loads are fully out of bounds (zero-filled, bytes still counted), its TMA stores are clipped away, and the head
+    // variant's plain stores check the image index.
 
     if (warp_idx == 0) {
         // ===================================== TMA producer =====================================
@@ -130,17 +157,23 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             const bool stream_b = p.b_slots > 0;
             if (!stream_b) {
                 // resident weights: 3x3 groups hold three 24 KB k-steps; a 1x1 group holds only the 64 kw = 1 rows of its
-                // k-step (8 KB) unless it is the first group (whose MMAs must initialise all 192 accumulator columns)
-                mbar_arrive_expect_tx(b_full_bar, uint32_t(p.b_bytes));
+                // k-step (8 KB) unless it is the first group (whose MMAs must initialise all 192 accumulator columns).
+                // Pair mode: this CTA's half of every block (rows 96 r .. of a k-step, rows 64 + 32 r .. of a compact block),
+                // counted on the leader's barrier.
+                if (leader) mbar_arrive_expect_tx(b_full_bar, uint32_t(p.b_bytes) * (kPair ? 2u : 1u));
                 for (int g = 0; g < G; ++g) {
                     const uint32_t e = p.group[g];
                     const int ks0 = int(e >> 20);
                     uint8_t* dst = b_res + size_t(p.group_boff[g]) * 16;
                     if (((e >> 2) & 1) && g > 0) {
-                        tma_load_2d(dst, &p.b_map_c, b_full_bar, ks0 * 64, 64);
+                        if constexpr (kPair) tma_load_2d_pair(dst, &p.b_map_c, b_full_bar, ks0 * 64, 64 + 32 * int(rank));
+                        else tma_load_2d(dst, &p.b_map_c, b_full_bar, ks0 * 64, 64);
                     } else {
                         const int nk = ((e >> 2) & 1) ? 1 : 3;
-                        for (int k = 0; k < nk; ++k) tma_load_2d(dst + k * kW3BStep, &p.b_map, b_full_bar, (ks0 + k) * 64, 0);
+                        for (int k = 0; k < nk; ++k) {
+                            if constexpr (kPair) tma_load_2d_pair(dst + k * kBStepCta, &p.b_map, b_full_bar, (ks0 + k) * 64, 96 * int(rank));
+                            else tma_load_2d(dst + k * kW3BStep, &p.b_map, b_full_bar, (ks0 + k) * 64, 0);
+                        }
                     }
                 }
             }
@@ -149,15 +182,15 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             int bs = 0;
             uint32_t bphase = 0;
             TileWalk tw;
-            tw.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h);
+            tw.init(tile0, tstride, p.tiles_w, p.tiles_h);
             // L2 prefetch cursor, kW3PrefetchTiles tiles ahead of the tile being loaded: the ring (2-4 slots, as few as
             // one tile for 128 -> 64) cannot cover HBM latency under load; without this the MMA warps waited ~270-800
             // cycles per tile for their first A box (profiles/r01_w3_timeline.md)
             TileWalk pf;
-            long pf_tile = (long)blockIdx.x + (long)kW3PrefetchTiles * gridDim.x;
-            pf.init(pf_tile, gridDim.x, p.tiles_w, p.tiles_h);
+            long pf_tile = tile0 + (long)kW3PrefetchTiles * tstride;
+            pf.init(pf_tile < total_tiles ? pf_tile : 0, tstride, p.tiles_w, p.tiles_h);
             int par = 0;   // which issuing warp consumes this tile
-            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tw.next(p.tiles_w, p.tiles_h), par ^= 1) {
+            for (long unit = unit0; unit < total_units; unit += ustride, tw.next(p.tiles_w, p.tiles_h), par ^= 1) {
 #ifndef B2R_EXP_NO_PREFETCH
                 if (pf_tile < total_tiles) {
                     for (int g = 0; g < G; ++g) {
@@ -165,7 +198,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                         tma_prefetch_l2_4d(&p.a_map[e & 3], int((e >> 8) & 0xFFF) * 64, pf.tw * 14 - 1, pf.th * 8 - 1, pf.n);
                     }
                 }
-                pf_tile += gridDim.x;
+                pf_tile += tstride;
                 pf.next(p.tiles_w, p.tiles_h);
 #endif
                 const int n0 = tw.n, w0 = tw.tw * 14, h0 = tw.th * 8;
@@ -179,8 +212,13 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 #ifdef B2R_EXP_NO_LOAD   // experiment builds only (tools/exp/README.md): which role paces the tile?
                     mbar_arrive(&full_m[stage]);
 #else
-                    mbar_arrive_expect_tx(&full_m[stage], kW3Slot);
-                    tma_load_4d(ring + stage * kW3Slot, &p.a_map[src], &full_m[stage], c0, w0 - 1, h0 - 1, n0);
+                    if constexpr (kPair) {
+                        if (leader) mbar_arrive_expect_tx(&full_m[stage], 2u * kW3Slot);   // the boxes of both CTAs
+                        tma_load_4d_pair(ring + stage * kW3Slot, &p.a_map[src], &full_m[stage], c0, w0 - 1, h0 - 1, n0);
+                    } else {
+                        mbar_arrive_expect_tx(&full_m[stage], kW3Slot);
+                        tma_load_4d(ring + stage * kW3Slot, &p.a_map[src], &full_m[stage], c0, w0 - 1, h0 - 1, n0);
+                    }
 #endif
                     if (++stage == R) {
                         stage = 0;
@@ -214,8 +252,17 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         // datapath), single-probe waits, group words from shared memory fetched one group ahead.
         const int m = warp_idx - 1;
         const bool stream_b = p.b_slots > 0;
+        if (leader) {     // pair mode: the peer CTA's issuer warps have nothing to do
         if (!stream_b) mbar_wait_uniform(b_full_bar, 0);
         tc_fence_after();
+        auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc_) {
+            if constexpr (kPair) umma_bf16_ss_pair(d, a, b, idesc, acc_);
+            else umma_bf16_ss(d, a, b, idesc, acc_);
+        };
+        auto commit = [](uint64_t* bar) {
+            if constexpr (kPair) umma_commit_pair(bar);
+            else umma_commit(bar);
+        };
         const uint64_t desc_hi = make_sdesc_sw128(0, 1024) & 0xFFFFFFFF00000000ull;   // SBO / version / swizzle bits
         const uint32_t a_lo0 = ((smem_u32(ring) >> 4) & 0x3FFF) | (1u << 16);
         const uint32_t b_lo0 = ((smem_u32(b_res) >> 4) & 0x3FFF) | (1u << 16);
@@ -239,7 +286,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         uint32_t acc_phase = 0;
         uint32_t e_next = group_s[0];
         [[maybe_unused]] int iter = m;
-        for (long tile = (long)blockIdx.x + (long)m * gridDim.x; tile < total_tiles; tile += 2L * gridDim.x, iter += 2) {
+        for (long unit = unit0 + (long)m * ustride; unit < total_units; unit += 2L * ustride, iter += 2) {
             mbar_wait_uniform(&tmem_empty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             if (lane == 0) B2R_STAMP(iter, 1);
@@ -263,13 +310,13 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                             // work and 75.6 instead of 96 cycles.  (Needs an initialised accumulator: accum != 0.)
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                umma_bf16_ss(tmem_d + 64u, desc_hi | uint64_t(a_lo + 128u + 2u * k), desc_hi | uint64_t(b_lo + 2u * k),
-                                             kIdesc64, 1u);   // compact block = the kw = 1 rows
+                                mma(tmem_d + 64u, desc_hi | uint64_t(a_lo + 128u + 2u * k), desc_hi | uint64_t(b_lo + 2u * k),
+                                    kIdesc64, 1u);   // compact block = the kw = 1 rows
                         } else if (center) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                umma_bf16_ss(tmem_d, desc_hi | uint64_t(a_lo + 128u + 2u * k), desc_hi | uint64_t(b_lo + 2u * k),
-                                             kIdesc, accum);
+                                mma(tmem_d, desc_hi | uint64_t(a_lo + 128u + 2u * k), desc_hi | uint64_t(b_lo + 2u * k),
+                                    kIdesc, accum);
                                 accum = 1;
                             }
                         } else {
@@ -277,13 +324,13 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                             for (int t = 0; t < 3; ++t) {   // kernel row t: A = buffer rows 16 t .. 16 t + 127 (2048 B apart)
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    umma_bf16_ss(tmem_d, desc_hi | uint64_t(a_lo + 128u * t + 2u * k),
-                                                 desc_hi | uint64_t(b_lo + uint32_t(kW3BStep >> 4) * t + 2u * k), kIdesc, accum);
+                                    mma(tmem_d, desc_hi | uint64_t(a_lo + 128u * t + 2u * k),
+                                        desc_hi | uint64_t(b_lo + uint32_t(kBStepCta >> 4) * t + 2u * k), kIdesc, accum);
                                     accum = 1;
                                 }
                             }
                         }
-                        umma_commit(&empty_bar[stage]);
+                        commit(&empty_bar[stage]);
                     }
                     __syncwarp();
                 } else {
@@ -319,12 +366,13 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 accum = 1;
                 if (++stage == R) stage = 0;
             }
-            if (elect_one()) umma_commit(&tmem_full_bar[acc]);
+            if (elect_one()) commit(&tmem_full_bar[acc]);
             __syncwarp();
             if (lane == 0) B2R_STAMP(iter, 2);
             acc_phase ^= 1u;
             skip_tile();   // the other issuer's tile
         }
+        }   // leader
     } else if (warp_idx == 3 + kW3EpiWarps) {
         // ===================================== TMA store issuer =====================================
         // One thread: waits until all 16 epilogue warps have staged a tile, stores it, and hands the staging buffer
@@ -332,9 +380,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         // ~340 cycles per tile from their critical path (profiles/r01_w3_timeline.md).
         if (!kHead && lane == 0) {
             TileWalk tw;
-            tw.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h);
+            tw.init(tile0, tstride, p.tiles_w, p.tiles_h);
             int iter = 0;
-            for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter, tw.next(p.tiles_w, p.tiles_h)) {
+            for (long unit = unit0; unit < total_units; unit += ustride, ++iter, tw.next(p.tiles_w, p.tiles_h)) {
                 const int buf = iter & 1;
                 uint8_t* sfull_b = sfull + buf * p.stage_stride;
                 mbar_wait(&staged_bar[buf], (uint32_t(iter) >> 1) & 1u);
@@ -383,9 +431,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                              : "r"(ba + 16 * i));
         }
         TileWalk tw;
-        tw.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h);
+        tw.init(tile0, tstride, p.tiles_w, p.tiles_h);
         int iter = 0;
-        for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter, tw.next(p.tiles_w, p.tiles_h)) {
+        for (long unit = unit0; unit < total_units; unit += ustride, ++iter, tw.next(p.tiles_w, p.tiles_h)) {
             const uint32_t acc = uint32_t(iter) & 1u;
             mbar_wait_uniform(&tmem_full_bar[acc], (uint32_t(iter) >> 1) & 1u);
             tc_fence_after();
@@ -398,7 +446,10 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) {
+                if constexpr (kPair) mbar_arrive_leader(&tmem_empty_bar[acc]);   // the leader's barrier, from either CTA
+                else mbar_arrive(&tmem_empty_bar[acc]);
+            }
             if (etid == 0) B2R_STAMP(iter, 4);
             uint8_t* sfull_b = sfull + acc * p.stage_stride;
             uint8_t* spool_b = sfull_b + kW3Staging;
@@ -444,7 +495,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                     // one thread per pixel: add the four partial sums + bias, then the reference's outputs
                     const int w = tw.tw * 14 + cc;
                     const int h = tw.th * 8 + hh;
-                    if (valid && w < p.W && h < p.H) {
+                    if (valid && w < p.W && h < p.H && tw.n < p.n_img) {
                         const float* pr = reinterpret_cast<const float*>(sfull_b) + quarter * 32 + lane;
                         float v[3];
 #pragma unroll
@@ -513,10 +564,12 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (kPair) cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still use its shared memory / barriers
     if (warp_idx == 1) {
         tc_fence_after();
         __syncwarp();
-        tmem_dealloc<512>(tmem_base);
+        if constexpr (kPair) tmem_dealloc_pair<512>(tmem_base);
+        else tmem_dealloc<512>(tmem_base);
     }
 }
 
@@ -524,21 +577,44 @@ size_t conv_w3_smem_bytes(size_t b_bytes, int ring_slots, size_t stage_stride) {
     return 1024 + b_bytes + size_t(ring_slots) * kW3Slot + 2 * stage_stride + 256 + 800 + 768;
 }
 
-int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream) {
+template <bool kHead, bool kPair>
+static int launch_w3_variant(const ConvW3Params& p, int grid, size_t smem, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kW3Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kPair ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2R_CUDA(cudaLaunchKernelEx(&cfg, conv_w3_kernel<kHead, kPair>, p));
+    return B2R_OK;
+}
+
+// grid = CTAs (pair mode: an even number, two per cluster)
+int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream, bool pair) {
     static bool attr_set[64] = {false};
     int dev = 0;
     B2R_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        B2R_CUDA(cudaFuncSetAttribute(conv_w3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
-        B2R_CUDA(cudaFuncSetAttribute(conv_w3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
+        B2R_CUDA(cudaFuncSetAttribute((conv_w3_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
+        B2R_CUDA(cudaFuncSetAttribute((conv_w3_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
+        B2R_CUDA(cudaFuncSetAttribute((conv_w3_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
+        B2R_CUDA(cudaFuncSetAttribute((conv_w3_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
         if (dev < 64) attr_set[dev] = true;
     }
     const size_t smem = conv_w3_smem_bytes(size_t(p.b_bytes), p.ring_slots, size_t(p.stage_stride));
-    note_conv_kernel(p.head_w != nullptr ? "conv_w3_kernel<head>" : "conv_w3_kernel");
-    if (p.head_w != nullptr)
-        conv_w3_kernel<true><<<grid, kW3Threads, smem, stream>>>(p);
-    else
-        conv_w3_kernel<false><<<grid, kW3Threads, smem, stream>>>(p);
+    const bool head = p.head_w != nullptr;
+    note_conv_kernel(head ? (pair ? "conv_w3_kernel<head,pair>" : "conv_w3_kernel<head>") : (pair ? "conv_w3_kernel<pair>" : "conv_w3_kernel"));
+    int rc;
+    if (head) rc = pair ? launch_w3_variant<true, true>(p, grid, smem, stream) : launch_w3_variant<true, false>(p, grid, smem, stream);
+    else rc = pair ? launch_w3_variant<false, true>(p, grid, smem, stream) : launch_w3_variant<false, false>(p, grid, smem, stream);
+    if (rc) return rc;
     B2R_CHECK_LAUNCH();
     return B2R_OK;
 }

@@ -523,3 +523,66 @@ def test_pair_halo_mode_equals_halo_mode(n, h, w, splits, pool, shortcut):
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][0], res[2][0]), kernels
     if pool:
         assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][1], res[2][1])
+
+
+def test_conv_w3_pair_mode_equals_single_cta_mode():
+    """Round 2: the tap-folded kernel as cta_group::2 pairs (two neighbouring tiles per MMA of M = 256 x N = 192, each CTA
+    holding half of the weight rows) must reproduce the single-CTA kernel (B2R_CONV_NO_PAIR) bit for bit: same k-steps in the
+    same order.  Covers odd tile counts (the last pair's second CTA walks one tile past the end), pooled and head outputs,
+    two sources, 1x1 centre groups (N = 64 MMAs on 32 + 32 weight rows), a first group that is a centre group, and the
+    192 -> 64 layer whose weights only stay resident in pair mode (the single-CTA kernel streams them)."""
+    ops, packing, L = _ops()
+    g = torch.Generator().manual_seed(77)
+    ri = lambda lo, hi: int(torch.randint(lo, hi, (1,), generator=g))   # noqa: E731
+    cases = [(1, 8, 14, (64,), (), False, False), (1, 8, 28, (64,), (), False, False), (3, 24, 42, (64,), (), True, False),
+             (2, 224, 224, (64,), (64,), True, False), (2, 112, 112, (64, 128), (), False, False),
+             (2, 56, 70, (64,), (64, 128), False, False), (3, 40, 30, (64,), (64, 64), False, True),
+             (1, 16, 16, (), (64,), False, False)]
+    for _ in range(6):
+        cases.append((ri(1, 5), 2 * ri(1, 40), 2 * ri(1, 60), [(64,), (64, 64), (128,)][ri(0, 3)], [(), (64,), (128,)][ri(0, 3)],
+                      bool(ri(0, 2)), False))
+    for ci_, (n, h, w, splits, sc, pool, head) in enumerate(cases):
+        srcs = [nhwc_bf16(rnd(n, c, h, w, seed=1400 + 13 * ci_ + i)) for i, c in enumerate(splits)]
+        plan = packing.KPlan(64)
+        if splits:
+            ci = sum(splits)
+            wt = rnd(64, ci, 3, 3, scale=(2.0 / (9 * ci)) ** 0.5, seed=1500 + ci_)
+            off = 0
+            for s, c in enumerate(splits):
+                plan.add_conv3x3(s, wt[:, off:off + c])
+                off += c
+        for c in sc:   # 1x1 centre groups over extra sources (ResidualBlock shortcut); with no 3x3 group it comes first
+            srcs.append(nhwc_bf16(rnd(n, c, h, w, seed=1600 + 17 * ci_ + len(srcs))))
+            plan.add_1x1(len(srcs) - 1, rnd(64, c, 1, 1, scale=(1.0 / c) ** 0.5, seed=1700 + ci_ + len(srcs)))
+        b = rnd(64, scale=0.1, seed=1800 + ci_)
+        wm, kbl = plan.finish()
+        wm, w3 = wm.cuda(), plan.finish_w3().cuda()
+        hw_ = rnd(3, 64, scale=0.1, seed=1900 + ci_).contiguous() if head else None
+        hb_ = rnd(3, scale=0.1, seed=1950 + ci_) if head else None
+        res, kernels = [], []
+        for flags in (0, L.B2R_CONV_NO_PAIR):
+            out_g = torch.full((n + 2, h, w, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+            pl_g = torch.full((n + 2, h // 2, w // 2, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+            h32 = torch.full((n + 2, 3, h, w), float("nan"), device="cuda") if head else None
+            h8 = torch.full((n + 2, h, w, 3), 77, dtype=torch.uint8, device="cuda") if head else None
+            ops.conv_gemm(srcs, wm, b, kbl, act=L.B2R_ACT_PRELU, slope=0.25, out=None if head else out_g[1:n + 1],
+                          out_pool=pl_g[1:n + 1] if pool else None, weights_w3=w3, flags=flags, head_w=hw_, head_b=hb_,
+                          head_out_f32=None if h32 is None else h32[1:n + 1], head_out_u8=None if h8 is None else h8[1:n + 1])
+            kernels.append(L.load().b2r_last_conv_kernel().decode())
+            torch.cuda.synchronize()
+            assert bool(torch.isnan(out_g[0]).all()) and bool(torch.isnan(out_g[n + 1]).all()), (ci_, "OOB store")
+            assert bool(torch.isnan(pl_g[0]).all()) and bool(torch.isnan(pl_g[n + 1]).all()), (ci_, "OOB pool store")
+            if head:
+                assert bool(torch.isnan(h32[0]).all()) and bool(torch.isnan(h32[n + 1]).all()), (ci_, "OOB head store")
+                assert bool((h8[0] == 77).all()) and bool((h8[n + 1] == 77).all())
+                assert not bool(torch.isnan(h32[1:n + 1]).any())
+                res.append((h32[1:n + 1].clone(), h8[1:n + 1].clone()))
+            else:
+                assert not bool(torch.isnan(out_g[1:n + 1]).any()), (ci_, "unwritten output")
+                res.append((out_g[1:n + 1].clone(), pl_g[1:n + 1].clone()))
+        tiles = n * ((h + 7) // 8) * ((w + 13) // 14)
+        if tiles >= 2:
+            assert "pair" in kernels[0] and "pair" not in kernels[1], kernels
+        assert torch.equal(res[0][0], res[1][0]), (ci_, n, h, w, splits, sc, kernels)
+        if pool or head:
+            assert torch.equal(res[0][1], res[1][1]), (ci_, "second output")
