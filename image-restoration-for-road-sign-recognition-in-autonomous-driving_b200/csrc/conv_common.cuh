@@ -36,6 +36,7 @@ int launch_conv_n64(const ConvN64Params& p, int grid, size_t smem_bytes, cudaStr
 
 // conv_w3 group encoding: [0,2) source | [2] centre (one k-step, kernel row 1) | [8,20) channel chunk | [20,32) first k-step
 constexpr int kW3MaxGroups = 24;
+constexpr int kW3MaxStageBufs = 4;
 struct alignas(64) ConvW3Params {
     CUtensorMap a_map[B2R_MAX_SRC];  // box 64 ch x 16 x 10 x 1
     CUtensorMap b_map;               // wide weights [192][64 * num_ksteps], box 64 x 192
@@ -45,7 +46,8 @@ struct alignas(64) ConvW3Params {
     int act;
     int num_groups, num_ksteps, ring_slots;
     int b_bytes;                     // shared memory of the weights region (resident blocks, or b_slots x 24 KB)
-    int stage_stride;                // bytes per staging buffer (two of them)
+    int stage_stride;                // bytes per staging buffer
+    int stage_bufs;                  // 2..kW3MaxStageBufs staging buffers, used round-robin (decouples the epilogue from slow TMA stores)
     CUtensorMap b_map_c;             // box 64 x 64: the kw = 1 rows of a 1x1 k-step (compact resident layout)
     uint32_t group_boff[kW3MaxGroups];   // resident mode: shared-memory offset of each group's weights, in 16-byte units
     int b_slots;                     // 0: weights resident (num_ksteps x 24 KB); > 0: weights streamed through this many slots
@@ -60,7 +62,7 @@ struct alignas(64) ConvW3Params {
     uint32_t group[kW3MaxGroups];
 };
 
-size_t conv_w3_smem_bytes(size_t b_bytes, int ring_slots, size_t stage_stride);
+size_t conv_w3_smem_bytes(size_t b_bytes, int ring_slots, size_t stage_stride, int stage_bufs);
 int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream, bool pair);
 
 #ifdef __CUDACC__

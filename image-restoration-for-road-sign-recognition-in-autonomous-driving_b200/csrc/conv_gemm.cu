@@ -1054,7 +1054,7 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
         }
         ring = 2 * ng > kN64MaxRing ? kN64MaxRing : (2 * ng < 4 ? 4 : 2 * ng);
         if (pair && ring < kN64MaxRing && ring < 6) ring = 6 < kN64MaxRing ? 6 : kN64MaxRing;   // the halved weights leave room: a third tile in flight
-        while (ring >= 2 && conv_w3_smem_bytes(b_bytes, ring, stage_stride) > (size_t)kN64MaxSmem) --ring;
+        while (ring >= 2 && conv_w3_smem_bytes(b_bytes, ring, stage_stride, 2) > (size_t)kN64MaxSmem) --ring;
         if (ring >= (pair ? ng : 2) || !pair) break;
         pair = false;   // even the halved weights do not leave a ring of one tile: single-CTA kernel (streams the weights)
     }
@@ -1063,9 +1063,20 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
         if (d->head_w) return B2R_OK;
         ring = 3;
         b_slots = kN64MaxRing;
-        while (b_slots >= 3 && conv_w3_smem_bytes((size_t)b_slots * 24576, ring, stage_stride) > (size_t)kN64MaxSmem) --b_slots;
+        while (b_slots >= 3 && conv_w3_smem_bytes((size_t)b_slots * 24576, ring, stage_stride, 2) > (size_t)kN64MaxSmem) --b_slots;
         if (b_slots < 3) return B2R_OK;
         b_bytes = (size_t)b_slots * 24576;
+    }
+    // staging buffers: two are the minimum (one being stored while the next is written); what the ring leaves over buys up
+    // to two more, which decouples the epilogue (and through it the TMEM stage and the MMA issuers) from TMA stores that the
+    // HBM write path delays.  B2R_W3_STAGE_BUFS / B2R_W3_RING pin either for experiments (tools/layer_bench.py).
+    static const int stage_bufs_env = [] { const char* e = getenv("B2R_W3_STAGE_BUFS"); return e ? atoi(e) : 0; }();
+    static const int ring_env = [] { const char* e = getenv("B2R_W3_RING"); return e ? atoi(e) : 0; }();
+    if (ring_env >= 2 && ring_env <= ring && b_slots == 0) ring = ring_env;
+    int stage_bufs = 2;
+    if (!d->head_w && b_slots == 0) {
+        const int want = stage_bufs_env >= 2 && stage_bufs_env <= kW3MaxStageBufs ? stage_bufs_env : 3;
+        while (stage_bufs < want && conv_w3_smem_bytes(b_bytes, ring, stage_stride, stage_bufs + 1) <= (size_t)kN64MaxSmem) ++stage_bufs;
     }
 
     static thread_local ConvW3Params tp;
@@ -1130,6 +1141,7 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
     P.b_slots = b_slots;
     P.b_bytes = (int)b_bytes;
     P.stage_stride = (int)stage_stride;
+    P.stage_bufs = stage_bufs;
     memcpy(P.group_boff, boff, sizeof(uint32_t) * ng);
     P.tiles_w = ceil_div(d->W, 14);
     P.tiles_h = ceil_div(d->H, 8);

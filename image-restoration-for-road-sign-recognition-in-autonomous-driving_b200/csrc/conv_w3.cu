@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* b_res = smem;
     uint8_t* ring = b_res + p.b_bytes;                             // resident weights, or a ring of weight k-steps
-    uint8_t* sfull = ring + p.ring_slots * kW3Slot;                 // two (staging + pool) tile pairs, used by alternate tiles
-    float* bias_s = reinterpret_cast<float*>(sfull + 2 * p.stage_stride);
+    uint8_t* sfull = ring + p.ring_slots * kW3Slot;                 // p.stage_bufs (2..4) staging (+ pool) tile buffers, used round-robin
+    float* bias_s = reinterpret_cast<float*>(sfull + p.stage_bufs * p.stage_stride);
     float* head_s = bias_s + 64;                                   // [3][64] head weights + [3] head bias (+ pad)
     uint32_t* group_s = reinterpret_cast<uint32_t*>(head_s + 200);  // [kW3MaxGroups] group words (shared-memory copy)
     uint32_t* gboff_s = group_s + kW3MaxGroups;                     // [kW3MaxGroups] weights offset of each group (16-byte units)
@@ -83,9 +83,10 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     uint64_t* b_full_bar = tmem_empty_bar + 2;
     uint64_t* bs_full_bar = b_full_bar + 1;                  // [2][kN64MaxRing] streamed-weights ring
     uint64_t* bs_empty_bar = bs_full_bar + 2 * kN64MaxRing;  // [kN64MaxRing]
-    uint64_t* staged_bar = bs_empty_bar + kN64MaxRing;   // [2] staging buffer written by all 16 epilogue warps
-    uint64_t* free_bar = staged_bar + 2;                 // [2] its TMA store has been read: reusable
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(free_bar + 2);
+    uint64_t* staged_bar = bs_empty_bar + kN64MaxRing;   // [kW3MaxStageBufs] staging buffer written by all 16 epilogue warps
+    uint64_t* free_bar = staged_bar + kW3MaxStageBufs;   // [kW3MaxStageBufs] its TMA store has been read: reusable
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(free_bar + kW3MaxStageBufs);
+    const int NB = p.stage_bufs;
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 mbar_init(&tmem_empty_bar[s], kPair ? 2 * kW3EpiWarps : kW3EpiWarps);
             }
             mbar_init(b_full_bar, 1);
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < kW3MaxStageBufs; ++s) {
                 mbar_init(&staged_bar[s], kW3EpiWarps);
                 mbar_init(&free_bar[s], 1);
             }
@@ -381,12 +382,12 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         if (!kHead && lane == 0) {
             TileWalk tw;
             tw.init(tile0, tstride, p.tiles_w, p.tiles_h);
-            int iter = 0;
+            int iter = 0, buf = 0;
+            uint32_t bph = 0;     // staging buffers are used round-robin: buffer `buf`, phase parity `bph` (flips when buf wraps)
             for (long unit = unit0; unit < total_units; unit += ustride, ++iter, tw.next(p.tiles_w, p.tiles_h)) {
-                const int buf = iter & 1;
                 uint8_t* sfull_b = sfull + buf * p.stage_stride;
-                mbar_wait(&staged_bar[buf], (uint32_t(iter) >> 1) & 1u);
-#ifndef B2R_EXP_NO_STAGE
+                mbar_wait(&staged_bar[buf], bph);
+#if !defined(B2R_EXP_NO_STAGE) && !defined(B2R_EXP_NO_TMASTORE)
                 const int w0 = tw.tw * 14, h0 = tw.th * 8;
                 if (p.store_full) tma_store_4d(&p.out_map, sfull_b, 0, w0, h0, tw.n);
                 if (p.store_pool) tma_store_4d(&p.pool_map, sfull_b + kW3Staging, 0, w0 >> 1, h0 >> 1, tw.n);
@@ -395,6 +396,10 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 #endif
                 B2R_STAMP(iter, 6);
                 mbar_arrive(&free_bar[buf]);
+                if (++buf == NB) {
+                    buf = 0;
+                    bph ^= 1u;
+                }
             }
             tma_store_wait_all<0>();
         }
@@ -432,7 +437,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         }
         TileWalk tw;
         tw.init(tile0, tstride, p.tiles_w, p.tiles_h);
-        int iter = 0;
+        int iter = 0, sb = 0;
+        uint32_t sph = 0;     // staging buffer index / phase parity (round-robin over p.stage_bufs buffers)
         for (long unit = unit0; unit < total_units; unit += ustride, ++iter, tw.next(p.tiles_w, p.tiles_h)) {
             const uint32_t acc = uint32_t(iter) & 1u;
             mbar_wait_uniform(&tmem_full_bar[acc], (uint32_t(iter) >> 1) & 1u);
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 else mbar_arrive(&tmem_empty_bar[acc]);
             }
             if (etid == 0) B2R_STAMP(iter, 4);
-            uint8_t* sfull_b = sfull + acc * p.stage_stride;
+            uint8_t* sfull_b = sfull + sb * p.stage_stride;
             uint8_t* spool_b = sfull_b + kW3Staging;
 #ifndef B2R_EXP_NO_STAGE
             float x[16];
@@ -517,8 +523,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 uint32_t pk[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
-                // the store of this buffer's previous tile (two tiles ago) has been read
-                mbar_wait_uniform(&free_bar[acc], ((uint32_t(iter) >> 1) & 1u) ^ 1u);
+                // the store of this buffer's previous tile (stage_bufs tiles ago) has been read
+                mbar_wait_uniform(&free_bar[sb], sph ^ 1u);
                 if (p.store_full && valid) {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
@@ -552,12 +558,16 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
 #else
             (void)valid; (void)srow; (void)relu_only; (void)ns; (void)b16; (void)d0; (void)d1; (void)d2; (void)spool_b; (void)sfull_b;
             (void)prow; (void)pool_lane; (void)hh;
-            if (!kHead) mbar_wait_uniform(&free_bar[acc], ((uint32_t(iter) >> 1) & 1u) ^ 1u);
+            if (!kHead) mbar_wait_uniform(&free_bar[sb], sph ^ 1u);
 #endif
             if (etid == 0) B2R_STAMP(iter, 5);
             if (!kHead) {
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&staged_bar[acc]);
+                if (lane == 0) mbar_arrive(&staged_bar[sb]);
+            }
+            if (++sb == NB) {
+                sb = 0;
+                sph ^= 1u;
             }
         }
     }
@@ -573,8 +583,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     }
 }
 
-size_t conv_w3_smem_bytes(size_t b_bytes, int ring_slots, size_t stage_stride) {
-    return 1024 + b_bytes + size_t(ring_slots) * kW3Slot + 2 * stage_stride + 256 + 800 + 768;
+size_t conv_w3_smem_bytes(size_t b_bytes, int ring_slots, size_t stage_stride, int stage_bufs) {
+    return 1024 + b_bytes + size_t(ring_slots) * kW3Slot + size_t(stage_bufs) * stage_stride + 256 + 800 + 768;
 }
 
 template <bool kHead, bool kPair>
@@ -608,7 +618,7 @@ int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream, bool pa
         B2R_CUDA(cudaFuncSetAttribute((conv_w3_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
         if (dev < 64) attr_set[dev] = true;
     }
-    const size_t smem = conv_w3_smem_bytes(size_t(p.b_bytes), p.ring_slots, size_t(p.stage_stride));
+    const size_t smem = conv_w3_smem_bytes(size_t(p.b_bytes), p.ring_slots, size_t(p.stage_stride), p.stage_bufs);
     const bool head = p.head_w != nullptr;
     note_conv_kernel(head ? (pair ? "conv_w3_kernel<head,pair>" : "conv_w3_kernel<head>") : (pair ? "conv_w3_kernel<pair>" : "conv_w3_kernel"));
     int rc;
