@@ -47,6 +47,7 @@ struct alignas(64) ConvW3Params {
     int num_groups, num_ksteps, ring_slots;
     int b_bytes;                     // shared memory of the weights region (resident blocks, or b_slots x 24 KB)
     int stage_stride;                // bytes per staging buffer
+    int prefetch;                    // 1: L2-prefetch the boxes of the tile four steps ahead (only pays when the ring holds < 2 tiles)
     int stage_bufs;                  // 2..kW3MaxStageBufs staging buffers, used round-robin (decouples the epilogue from slow TMA stores)
     CUtensorMap b_map_c;             // box 64 x 64: the kw = 1 rows of a 1x1 k-step (compact resident layout)
     uint32_t group_boff[kW3MaxGroups];   // resident mode: shared-memory offset of each group's weights, in 16-byte units

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             // one tile for 128 -> 64) cannot cover HBM latency under load; without this the MMA warps waited ~270-800
             // cycles per tile for their first A box (profiles/r01_w3_timeline.md)
             TileWalk pf;
-            long pf_tile = tile0 + (long)kW3PrefetchTiles * tstride;
+            long pf_tile = p.prefetch ? tile0 + (long)kW3PrefetchTiles * tstride : total_tiles;   // 0: no L2 prefetch
             pf.init(pf_tile < total_tiles ? pf_tile : 0, tstride, p.tiles_w, p.tiles_h);
             int par = 0;   // which issuing warp consumes this tile
             for (long unit = unit0; unit < total_units; unit += ustride, tw.next(p.tiles_w, p.tiles_h), par ^= 1) {
