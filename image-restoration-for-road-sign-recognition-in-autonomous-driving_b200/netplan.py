@@ -62,9 +62,11 @@ class NetPlan:
     def _workspace(self, n, h, w):
         need = C.c_size_t()
         L.check(L.load().b2r_net_workspace_bytes(self.handle, n, h, w, C.byref(need)))
-        if self._ws is None or self._ws.numel() < need.value:
-            self._ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
-        return self._ws
+        if self._ws is None or self._ws.numel() < need.value + 1024:
+            self._ws = torch.empty(int(need.value) + 1024, dtype=torch.uint8, device=self.device)
+        # the library wants a 1024-byte aligned workspace (TMA swizzle atoms); torch's allocator guarantees 512
+        ptr = (self._ws.data_ptr() + 1023) & ~1023
+        return ptr, self._ws.numel() - (ptr - self._ws.data_ptr())
 
     @staticmethod
     def _fmt(x):
@@ -82,10 +84,10 @@ class NetPlan:
         with torch.cuda.device(self.device):
             o32 = torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device) if want_f32 else None
             o8 = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device) if want_u8 else None
-            ws = self._workspace(n, h, w)
+            ws_ptr, ws_bytes = self._workspace(n, h, w)
             fn = L.load().b2r_unet_forward if self.arch == "simple_unet" else L.load().b2r_resunet_forward
             L.check(fn(self.handle, x.data_ptr(), fmt, None if o32 is None else o32.data_ptr(), None if o8 is None else o8.data_ptr(),
-                       n, h, w, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+                       n, h, w, ws_ptr, ws_bytes, torch.cuda.current_stream().cuda_stream))
         return o32, o8
 
     @torch.no_grad()
@@ -95,8 +97,8 @@ class NetPlan:
         x = x.contiguous()
         with torch.cuda.device(self.device):
             logits = torch.empty((n, self.num_classes), dtype=torch.float32, device=self.device)
-            ws = self._workspace(n, h, w)
+            ws_ptr, ws_bytes = self._workspace(n, h, w)
             L.check(L.load().b2r_vgg16_forward(self.handle, x.data_ptr(), fmt, int(bool(normalize) and fmt == L.B2R_IN_U8_NHWC),
-                                               logits.data_ptr(), n, h, w, ws.data_ptr(), ws.numel(),
+                                               logits.data_ptr(), n, h, w, ws_ptr, ws_bytes,
                                                torch.cuda.current_stream().cuda_stream))
         return logits
