@@ -119,12 +119,39 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, nvml: bool = False):
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = nvml          # ranks > 0 poll NVML in-process (the same counters nvidia-smi prints) instead of forking a poller each
+        self._go = False
+
+    def mark(self) -> int:
+        return len(self.lines)
+
+    def _poll_nvml(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while self._go:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.lines.append("%d, %d, %.2f, %s" % (nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                                        ", ".join("Active" if r & b else "Not Active" for b in bits.values())))
+                time.sleep(0.2)
+        except Exception:      # no NVML: this rank reports no clocks
+            pass
 
     def start(self):
+        if self.nvml:
+            self._go = True
+            self.proc = True
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -140,15 +167,24 @@ class ClockSampler:
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return
+        if self.nvml:
+            self._go = False
+            self.thread.join(timeout=2)
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+
+    def summary(self, lo: int = 0, hi=None):
+        """clocks over the samples [lo, hi) (marks taken with mark())"""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons, watts = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[lo:hi]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -573,7 +609,7 @@ def run_ours(args):
     # each micro-batch is replayed as one CUDA graph (bit-identical to eager, tests/test_pipeline_gpu.py): ~330 launches per
     # micro-batch cost the Python host ~40 ms against 45 ms of GPU work, which made a rank host-bound as soon as its core was
     # shared (the 1 -> 8 efficiency of round 1).  --graph 0 keeps this leg eager.
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, nvml=rank != 0)
     sampler.start()
     use_graph = bool(args.graph) and cascade is None and classify
     pipe.use_graph = use_graph
@@ -584,16 +620,17 @@ def run_ours(args):
         else:
             step_device()
         torch.cuda.synchronize()
+    mark_start = sampler.mark()
     launches0, replayed0 = ops.STATS["launches"], pipe.graph_launches_replayed
     total_ms, own_ms, host_s, counts = timed(fn_dev, steps)
     graph_launches = pipe.graph_launches_replayed - replayed0
     launches = ops.STATS["launches"] - launches0 + graph_launches
-    clocks = sampler.stop()
+    mark_timed = sampler.mark()
     pipe.use_graph = False
 
     # ---- instrumented steps (roofline): the SAME step, eager, every tcgen05 conv launch bracketed by a CUDA-event pair on the
     # launching stream; max(1, K / 5) steps right after the timed region (same clocks, same resident inputs)
-    inst_steps = 1 if total_mode else max(1, steps // 5)
+    inst_steps = 1 if total_mode else max(2, steps // 4)
     timer = ops.KernelTimer(kinds=("conv_gemm",))
     if total_mode:
         def fn_inst():
@@ -606,6 +643,9 @@ def run_ours(args):
     with ops.timing(timer):
         _, inst_ms, inst_host_s, _ = timed(fn_inst, inst_steps)
     ksum = timer.summary().get("conv_gemm", {"launches": 0, "work": 0.0, "ms": 1e-9})
+    sampler.stop()
+    clocks = sampler.summary(mark_start, mark_timed)      # the timed region
+    clocks_inst = sampler.summary(mark_timed, None)       # the instrumented steps
 
     # ---- end-to-end (host buffers): same K steps
     e2e = None
@@ -677,7 +717,7 @@ def run_ours(args):
                      "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
                      "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
                      "launches": ksum["launches"], "kernel_ms_per_step": ksum["ms"] / inst_steps,
-                     "instrumented": {"steps": inst_steps, "ms_per_step": inst_ms / inst_steps,
+                     "instrumented": {"steps": inst_steps, "ms_per_step": inst_ms / inst_steps, "sm_mhz": clocks_inst.get("sm_mhz"),
                                       "host_launch_s_per_step": inst_host_s / inst_steps,
                                       "note": "eager steps with one CUDA-event pair per conv launch, run right after the timed "
                                               "region; `value` itself replays CUDA graphs" if use_graph else
