@@ -571,11 +571,14 @@ def run_ours(args):
         for _ in range(steps):
             fn()
         host_s = time.perf_counter() - t0
+        em = torch.cuda.Event(enable_timing=True)
+        em.record()                       # this rank's own work ends here; the all-reduce then waits for the slowest rank
         global_counts = totals.clone()
         B.all_reduce_counts(global_counts)
         e1.record()
         barrier()
         own = e0.elapsed_time(e1)
+        timed.compute_ms = e0.elapsed_time(em)
         ms = torch.tensor([own], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -623,6 +626,7 @@ def run_ours(args):
     mark_start = sampler.mark()
     launches0, replayed0 = ops.STATS["launches"], pipe.graph_launches_replayed
     total_ms, own_ms, host_s, counts = timed(fn_dev, steps)
+    compute_ms = timed.compute_ms         # before the all-reduce: shows which rank the others waited for
     graph_launches = pipe.graph_launches_replayed - replayed0
     launches = ops.STATS["launches"] - launches0 + graph_launches
     mark_timed = sampler.mark()
@@ -665,7 +669,8 @@ def run_ours(args):
                "counts": [int(c2[0]), int(c2[1])]}
 
     # ---- per-rank record (the 1 -> N curve explains itself)
-    mine = {"rank": rank, "ms_per_step": own_ms / steps, "conv_kernel_ms_per_step": ksum["ms"] / inst_steps,
+    mine = {"rank": rank, "ms_per_step": own_ms / steps, "compute_ms_per_step": compute_ms / steps,
+            "conv_kernel_ms_per_step": ksum["ms"] / inst_steps,
             "host_launch_s_per_step": host_s / steps, "sm_mhz": clocks.get("sm_mhz"), "power_w": clocks.get("power_w"),
             "reasons": clocks.get("reasons"), "cores": len(cores_mine) if cores_mine else None, "images": int(hi - lo)}
     if world > 1:
@@ -698,7 +703,7 @@ def run_ours(args):
             break
     ips = images_per_step * steps / (total_ms / 1e3)
     gflop_img = gflop_per_image(arch, classify, hw)
-    slowest = max(gathered, key=lambda g: g["ms_per_step"])
+    slowest = max(gathered, key=lambda g: g["compute_ms_per_step"])
     cfg = config_dict(args, world)
     cfg.update({"micro_batch": mb,
                 "l2": "inputs (%.0f MB/step) larger than L2; no flush needed" % ((hi - lo if total_mode else B_) * hw * hw * 3 / 1e6),
@@ -731,12 +736,14 @@ def run_ours(args):
                      "pipeline_tflops": ips / world * gflop_img / 1e3 if gflop_img else None},
         "roofline_hbm": hbm,
         "per_rank": {"ms_per_step": minmedmax([g["ms_per_step"] for g in gathered]),
+                     "compute_ms_per_step": minmedmax([g["compute_ms_per_step"] for g in gathered]),
                      "conv_kernel_ms_per_step": minmedmax([g["conv_kernel_ms_per_step"] for g in gathered]),
                      "host_launch_s_per_step": minmedmax([g["host_launch_s_per_step"] for g in gathered]),
                      "sm_mhz": minmedmax([g["sm_mhz"] for g in gathered]),
                      "power_w": minmedmax([g["power_w"] for g in gathered]),
                      "slowest": slowest, "cores_per_rank": mine["cores"],
-                     "note": "the step time is the max over ranks; the counts are all-reduced once, after the last step"},
+                     "note": "ms_per_step includes the single all-reduce at the end (every rank then waits for the slowest); "
+                             "compute_ms_per_step is each rank's own work before it"},
         "counts": [int(counts[0]), int(counts[1])],
     }
     if total_mode:

@@ -607,10 +607,33 @@ int run_resunet(const b2r_net* n, Runner& R, Workspace& ws, const void* in, int 
 }
 
 int run_vgg16(const b2r_net* n, Runner& R, Workspace& ws, const void* in, int in_fmt, bool normalize, float* logits, int N, int H, int W) {
-    void* cur = ws.bf16(N, H, W, 64);
-    R.c3(n->first, in, in_fmt, normalize, B2R_ACT_RELU, cur, N, H, W);
+    // conv1_1 (HBM-write-bound) and conv1_2 (tensor-bound, pooled output only) alternate over sub-batches of 32 images so that
+    // conv1_1's write-back drains from L2 while conv1_2 computes (models.VGG16Judge.first_stage_sub; same bytes either way)
+    constexpr int kSub = 32;
+    const bool alternate = N >= 2 * kSub && !n->vgg.empty() && n->vgg[0].pooled;
+    void* cur = ws.bf16(alternate ? kSub : N, H, W, 64);
     int h = H, w = W, c = 64;
-    for (auto& v : n->vgg) {
+    size_t first = 0;
+    if (alternate) {
+        auto& v = n->vgg[0];
+        uint8_t* nxt = static_cast<uint8_t*>(ws.bf16(N, H / 2, W / 2, v.cout));
+        const size_t in_img = size_t(H) * W * 3 * (in_fmt == B2R_IN_U8_NHWC ? 1 : 4);
+        const size_t out_img = size_t(H / 2) * (W / 2) * v.cout * 2;
+        for (int s0 = 0; s0 < N; s0 += kSub) {
+            const int k = N - s0 < kSub ? N - s0 : kSub;
+            R.c3(n->first, static_cast<const uint8_t*>(in) + (R.dry ? 0 : s0 * in_img), in_fmt, normalize, B2R_ACT_RELU, cur, k, H, W);
+            R.gemm(v.g, k, H, W, {cur}, {64}, B2R_ACT_RELU, 0.f, nullptr, R.dry ? nullptr : nxt + s0 * out_img, v.cout);
+        }
+        cur = nxt;
+        h = H / 2;
+        w = W / 2;
+        c = v.cout;
+        first = 1;
+    } else {
+        R.c3(n->first, in, in_fmt, normalize, B2R_ACT_RELU, cur, N, H, W);
+    }
+    for (size_t li = first; li < n->vgg.size(); ++li) {
+        auto& v = n->vgg[li];
         if (v.pooled) {
             void* nxt = ws.bf16(N, h / 2, w / 2, v.cout);
             R.gemm(v.g, N, h, w, {cur}, {c}, B2R_ACT_RELU, 0.f, nullptr, nxt, v.cout);

@@ -367,6 +367,8 @@ class VGG16Judge(_B200Module):
     forward_u8(x): x = u8 NHWC, ToTensor + Normalize fused into the first conv.  H, W multiples of 32.
     """
 
+    first_stage_sub: int = 32   # images per launch pair of the first two layers (0 = whole micro-batch per launch)
+
     def __init__(self, num_classes: int = 43):
         super().__init__()
         layers: List[nn.Module] = []
@@ -424,13 +426,31 @@ class VGG16Judge(_B200Module):
         idx = self._conv_indices()
         tap = stop_at is not None
         first_i = idx[0][0]
-        cur = ops.conv3x3_c3(x, *P["first"], act=NONE if (tap and stop_at == first_i) else R,
-                             normalize=u8_in and normalize_u8,
-                             out=ws.get("tap0" if tap else "c0", (n, H, W, 64), dev))
-        h, w, c = H, W, 64
+        sub = self.first_stage_sub
+        fused_first = (not tap) and sub > 0 and n >= 2 * sub and P["convs"][0][1]
+        if fused_first:
+            # conv1_1 (HBM-write-bound: 128 B out per 3 B in) and conv1_2 (tensor-bound, writes only the pooled quarter)
+            # alternate over sub-batches of `first_stage_sub` images, so the write-back of conv1_1's output drains from L2
+            # while conv1_2 computes: 1.52 -> 1.28 ms per 256 images (tools/exp/l2_subbatch.py, profiles/r02_l2_subbatch.md).
+            # Same kernels on the same bytes: bit-identical to the two whole-batch launches.
+            cv, _, co = P["convs"][0]
+            c0 = ws.get("c0s", (sub, H, W, 64), dev)
+            nxt = ws.get("c1", (n, H // 2, W // 2, co), dev)
+            for s0 in range(0, n, sub):
+                k = min(sub, n - s0)
+                ops.conv3x3_c3(x[s0:s0 + k], *P["first"], act=R, normalize=u8_in and normalize_u8, out=c0[:k])
+                ops.conv_gemm([c0[:k]], **cv, act=R, out_pool=nxt[s0:s0 + k])
+            cur, h, w, c = nxt, H // 2, W // 2, co
+        else:
+            cur = ops.conv3x3_c3(x, *P["first"], act=NONE if (tap and stop_at == first_i) else R,
+                                 normalize=u8_in and normalize_u8,
+                                 out=ws.get("tap0" if tap else "c0", (n, H, W, 64), dev))
+            h, w, c = H, W, 64
         if tap and stop_at <= first_i + 1:
             return cur, h, w, c
         for li, (cv, pooled, co) in enumerate(P["convs"]):
+            if fused_first and li == 0:
+                continue
             ci = idx[li + 1][0]
             if tap and stop_at in (ci, ci + 1):      # stop on this conv (pre-ReLU) or on its ReLU, un-pooled
                 out = ws.get("tap", (n, h, w, co), dev)

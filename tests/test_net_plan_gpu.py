@@ -29,17 +29,23 @@ def test_restorer_plan_equals_module(arch, hw):
     plan.close()
 
 
-@pytest.mark.parametrize("hw", [(224, 224), (64, 64)])
-def test_vgg_plan_equals_module(hw):
+@pytest.mark.parametrize("hw,n", [((224, 224), 5), ((64, 64), 5), ((64, 64), 70)])
+def test_vgg_plan_equals_module(hw, n):
+    """n = 70 takes the path that alternates conv1_1 / conv1_2 over sub-batches of 32 images (both hosts), which must also equal
+    the whole-batch launches bit for bit (first_stage_sub = 0)."""
     from b200restore import NetPlan, models, synth
     sd = synth.synthetic_state_dict("vgg16", 32)
     j = models.VGG16Judge()
     j.load_state_dict(sd)
     j = j.cuda().eval()
     plan = NetPlan("vgg16", sd, "cuda")
-    imgs, _ = synth.indexed_images(10, 5, hw[0], hw[1], seed=4)
+    imgs, _ = synth.indexed_images(10, n, hw[0], hw[1], seed=4)
     u8 = imgs.cuda()
-    assert torch.equal(plan.classify(u8), j.forward_u8(u8))
+    ref = j.forward_u8(u8)
+    assert torch.equal(plan.classify(u8), ref)
+    j.first_stage_sub = 0
+    assert torch.equal(j.forward_u8(u8), ref)
+    j.first_stage_sub = 32
     x = torch.randn((2, 3, hw[0], hw[1]), device="cuda")
     assert torch.equal(plan.classify(x), j(x))
     plan.close()
