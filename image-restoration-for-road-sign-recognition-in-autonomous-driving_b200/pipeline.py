@@ -66,35 +66,38 @@ class RestoreClassifyPipeline:
     @torch.no_grad()
     def run_micro_batch(self, clean_u8: torch.Tensor, labels: Optional[torch.Tensor], params, seed: int,
                         image_index0: int, counts: Optional[torch.Tensor], noise: Optional[torch.Tensor] = None,
-                        keep: bool = False):
-        """One resident micro-batch through all stages.  Returns (pred int64 [n], extras dict when keep=True)."""
+                        keep: bool = False, packs=None):
+        """One resident micro-batch through all stages.  Returns (pred int64 [n], extras dict when keep=True).
+        `packs` = (restorer._packed(), judge._packed()) when the caller already looked them up (run / run_from_host do it
+        once per call instead of walking both state_dicts for every micro-batch)."""
         n, h, w, _ = clean_u8.shape
         with torch.cuda.device(self.device):
             if self.use_graph and not keep and noise is None:
-                return self._run_micro_batch_graph(clean_u8, labels, params, seed, image_index0, counts), None
+                return self._run_micro_batch_graph(clean_u8, labels, params, seed, image_index0, counts, packs), None
             degraded = D.degrade(clean_u8, params, seed=seed, image_index0=image_index0, noise=noise,
                                  out=self._buf("deg", (n, h, w, 3), torch.uint8)) if params is not None else clean_u8
             restored = self._buf("rest", (n, h, w, 3), torch.uint8)
-            pred, logits = self._restore_classify(degraded, restored, labels, counts, want_logits=True)
+            pred, logits = self._restore_classify(degraded, restored, labels, counts, want_logits=True, packs=packs)
             if keep:
                 return pred, {"degraded": degraded.clone(), "restored": restored.clone(), "logits": logits.clone()}
         return pred, None
 
     # -- CUDA-graph mode --------------------------------------------------------------------------------------------
-    def _restore_classify(self, degraded, restored, labels, counts, want_logits=False):
+    def _restore_classify(self, degraded, restored, labels, counts, want_logits=False, packs=None):
         """restore -> clamp/u8 -> classify -> top-1 (+ counts).  Without labels only `total` can be counted: the kernel
         takes counts together with labels, so a predictions-only call adds n to counts[1] itself."""
+        pr, pj = packs if packs is not None else (None, None)
         self.restorer._check_input(degraded, self._div)
-        self.restorer._run(degraded, None, restored)
+        self.restorer._run(degraded, None, restored, pr)
         self.judge._check_input(restored, 32)
-        logits = self.judge._run(restored, True)
+        logits = self.judge._run(restored, True, pj)
         pred = ops.argmax_count(logits, labels, counts if labels is not None else None)[0]
         if labels is None and counts is not None:
             counts[1:2].add_(degraded.shape[0])
         return (pred, logits) if want_logits else pred
 
-    def _graph_entry(self, n: int, h: int, w: int, with_labels: bool):
-        packs = (self.restorer._packed(), self.judge._packed())
+    def _graph_entry(self, n: int, h: int, w: int, with_labels: bool, packs=None):
+        packs = packs if packs is not None else (self.restorer._packed(), self.judge._packed())
         key = (n, h, w, with_labels)
         ent = self._graphs.get(key)
         if ent is not None and ent["packs"][0] is packs[0] and ent["packs"][1] is packs[1]:
@@ -105,12 +108,12 @@ class RestoreClassifyPipeline:
                "rest": torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev),
                "labels": torch.zeros((n,), dtype=torch.int64, device=dev) if with_labels else None,
                "counts": torch.zeros((2,), dtype=torch.int64, device=dev)}
-        self._restore_classify(ent["deg"], ent["rest"], ent["labels"], ent["counts"])   # eager once: workspaces, attributes
+        self._restore_classify(ent["deg"], ent["rest"], ent["labels"], ent["counts"], packs=packs)   # eager once: workspaces, attributes
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         launches_before = ops.STATS["launches"]
         with torch.cuda.graph(graph):
-            ent["pred"] = self._restore_classify(ent["deg"], ent["rest"], ent["labels"], ent["counts"])
+            ent["pred"] = self._restore_classify(ent["deg"], ent["rest"], ent["labels"], ent["counts"], packs=packs)
         # the graph holds raw pointers into the modules' activation workspaces: keep those tensors alive even if the
         # workspaces later switch to another batch shape
         ent["pinned"] = (dict(self.restorer._ws._bufs), dict(self.judge._ws._bufs))
@@ -119,9 +122,9 @@ class RestoreClassifyPipeline:
         self._graphs[key] = ent
         return ent
 
-    def _run_micro_batch_graph(self, clean_u8, labels, params, seed, image_index0, counts):
+    def _run_micro_batch_graph(self, clean_u8, labels, params, seed, image_index0, counts, packs=None):
         n, h, w, _ = clean_u8.shape
-        ent = self._graph_entry(n, h, w, labels is not None)
+        ent = self._graph_entry(n, h, w, labels is not None, packs)
         if params is not None:
             D.degrade(clean_u8, params, seed=seed, image_index0=image_index0, out=ent["deg"])
         else:
@@ -143,11 +146,12 @@ class RestoreClassifyPipeline:
         counts = torch.zeros(2, dtype=torch.int64, device=self.device)
         preds = torch.empty(n, dtype=torch.int64, device=self.device)
         dparams = params.to(self.device) if isinstance(params, D.DegradeParams) else params
+        packs = (self.restorer._packed(), self.judge._packed())
         for s in range(0, n, self.micro_batch):
             c = min(self.micro_batch, n - s)
             sub = _slice_params(dparams, s, c) if dparams is not None else None
             p, _ = self.run_micro_batch(clean_u8[s:s + c], None if labels is None else labels[s:s + c], sub, seed,
-                                        image_index0 + s, counts)
+                                        image_index0 + s, counts, packs=packs)
             preds[s:s + c] = p
         return preds, counts
 
@@ -169,6 +173,7 @@ class RestoreClassifyPipeline:
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
         h2d = 0
+        packs = (self.restorer._packed(), self.judge._packed())
         chunks = [(s, min(mb, n - s)) for s in range(0, n, mb)]
 
         def issue(i):
@@ -189,7 +194,7 @@ class RestoreClassifyPipeline:
             b = i & 1
             main.wait_event(ready[b])
             sub = _slice_params(dparams, s, c) if dparams is not None else None
-            self.run_micro_batch(stage[b][0][:c], stage[b][1][:c], sub, seed, image_index0 + s, counts)
+            self.run_micro_batch(stage[b][0][:c], stage[b][1][:c], sub, seed, image_index0 + s, counts, packs=packs)
             freed[b].record(main)
             h2d += c * h * w * 3 + c * 8
         host_counts = counts.cpu()           # the device -> host read of the step's result (synchronises)
