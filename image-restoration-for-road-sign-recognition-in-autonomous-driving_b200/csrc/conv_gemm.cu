@@ -667,9 +667,12 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
 // ------------------------------------------------------------------------------------------------------------
 template <int kPairN>
 struct PairHaloCfg {
+#ifndef B2R_PAIRHALO_BUFS
+#define B2R_PAIRHALO_BUFS 1
+#endif
     static constexpr int kBBytes = (kPairN / 2) * 128;   // this CTA's half of a weight k-block
     static constexpr int kCtasPerSm = kPairN == 128 ? 2 : 1;
-    static constexpr int kStagingBufs = 1;
+    static constexpr int kStagingBufs = B2R_PAIRHALO_BUFS;
     static constexpr int kFixedBytes = 1024 + kStagingBufs * (kStagingFull + kStagingPool) + kPairN * 4 + 512;
     static constexpr int kMaxSmem = (227 * 1024) / kCtasPerSm - (kCtasPerSm > 1 ? 1024 : 0);
 };

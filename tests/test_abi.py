@@ -53,3 +53,18 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.ConvGemmDesc) == size
     assert _lib.ConvGemmDesc.weights.offset == off_w
     assert _lib.ConvGemmDesc.out_C.offset == off_oc
+
+
+def test_net_weight_bytes_bounds_the_packed_checkpoint():
+    """b2r_net_weight_bytes is host-only arithmetic: an upper bound of what b2r_net_create writes (bf16 weights, tap-folded
+    copies for C_out = 64 layers, f32 biases, identity shortcut matrices), from the state_dict's shapes alone."""
+    import ctypes as C
+    from b200restore import _lib, netplan, synth
+    lib = _lib.load()
+    for arch, params in (("simple_unet", 1_862_979), ("resunet", 12_625_869)):
+        sd = synth.synthetic_state_dict(arch, 0)
+        arr, keep = netplan.state_to_ctypes(sd)
+        n = C.c_size_t()
+        assert lib.b2r_net_weight_bytes(arr, len(sd), C.byref(n)) == 0
+        assert 2 * params < n.value < 4 * params + (4 << 20) and n.value % 256 == 0
+    assert lib.b2r_net_weight_bytes(None, 0, C.byref(n)) == -22 and b"null" in lib.b2r_last_error()
