@@ -362,7 +362,8 @@ def run_reference(args):
                                "reference); none of this repo's kernels"},
             "model_tflops": ips * gflop / 1e3 if gflop else None, "gpu_launches": 0}), flush=True)
         return
-    sample = args.cpu_sample or CPU_SAMPLE
+    # a bounded sample per step so that the whole K-step run ends within a few minutes (~11 images/s on 16 cores at 224x224)
+    sample = args.cpu_sample or (CPU_SAMPLE if args.steps <= 8 else CPU_SAMPLE // 2)
     t0 = time.perf_counter()
     ips, cores, dt, kind = cpu_reference_images_per_s(args.workload, args.hw, sample, repeats=args.steps, warmup=args.warmup)
     cfg = config_dict(args, 1)
