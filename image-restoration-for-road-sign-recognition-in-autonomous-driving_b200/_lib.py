@@ -22,7 +22,7 @@ B2R_CONV_GENERIC_ONLY, B2R_CONV_NO_W3, B2R_CONV_NO_HALO, B2R_CONV_NO_PAIR = 1, 2
 # every symbol include/b2r.h declares (tests/test_abi.py checks the list against the header and the .so)
 SYMBOLS = (
     "b2r_version", "b2r_abi_sizeof", "b2r_last_error", "b2r_last_conv_kernel", "b2r_degrade", "b2r_conv3x3_c3", "b2r_conv_gemm", "b2r_final_conv1x1",
-    "b2r_maxpool2x2", "b2r_adaptive_avgpool7", "b2r_linear_f32out", "b2r_argmax_count",
+    "b2r_maxpool2x2", "b2r_resize_nearest_bf16", "b2r_adaptive_avgpool7", "b2r_linear_f32out", "b2r_argmax_count",
     "b2r_net_weight_bytes", "b2r_net_create", "b2r_net_destroy", "b2r_net_workspace_bytes", "b2r_unet_forward", "b2r_resunet_forward",
     "b2r_vgg16_forward",
     "b2r_lut_u8", "b2r_minmax_u8", "b2r_normalize_minmax_u8", "b2r_noise02", "b2r_sse_u8", "b2r_ssim_u8", "b2r_mean_bf16", "b2r_resize_bilinear_u8", "b2r_resize_cv_linear_u8",
@@ -127,6 +127,8 @@ def load() -> C.CDLL:
     lib.b2r_final_conv1x1.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.b2r_maxpool2x2.restype = C.c_int
     lib.b2r_maxpool2x2.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.b2r_resize_nearest_bf16.restype = C.c_int
+    lib.b2r_resize_nearest_bf16.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.b2r_adaptive_avgpool7.restype = C.c_int
     lib.b2r_adaptive_avgpool7.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.b2r_linear_f32out.restype = C.c_int

@@ -73,6 +73,27 @@ __global__ void __launch_bounds__(256) final_conv1x1_kernel(const uint4* __restr
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// F.interpolate(x, size=(out_h, out_w)) with the default mode 'nearest' on NHWC bf16, 8 channels (16 B) per thread: the
+// re-alignment of ResUNet.forward (14_train_unified_advanced.py:169-183).  PyTorch's rule: src = min(int(floorf(dst *
+// scale)), in - 1) with scale = float(in) / float(out).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_nearest_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H,
+                                                             int W, int Ho, int Wo, int C8, float sh, float sw) {
+    const long total = (long)N * Ho * Wo * C8;
+    const long gid = blockIdx.x * 256L + threadIdx.x;
+    if (gid >= total) return;
+    const int c = int(gid % C8);
+    long t = gid / C8;
+    const int wo = int(t % Wo);
+    t /= Wo;
+    const int ho = int(t % Ho);
+    const int n = int(t / Ho);
+    const int hi = min(int(floorf(float(ho) * sh)), H - 1);
+    const int wi = min(int(floorf(float(wo) * sw)), W - 1);
+    out[gid] = __ldg(&in[(((long)n * H + hi) * W + wi) * C8 + c]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // pooling on NHWC bf16, 8 channels (16 B) per thread
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) maxpool2x2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N,
@@ -244,12 +265,26 @@ int b2r_maxpool2x2(const void* in, void* out, int N, int H, int W, int C, void* 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     B2R_REQUIRE(in && out, "null pointer");
     B2R_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad shape");
-    B2R_REQUIRE(H % 2 == 0 && W % 2 == 0, "maxpool2x2 needs even H, W");
+    B2R_REQUIRE(H >= 2 && W >= 2, "maxpool2x2 needs H, W >= 2");   // odd sizes: the last row / column is dropped (floor), like nn.MaxPool2d(2, 2)
     const long total = (long)N * (H / 2) * (W / 2) * (C / 8);
     const long blocks = (total + 255) / 256;
     B2R_REQUIRE(blocks < (1L << 31), "too large");
     maxpool2x2_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), N,
                                                             H, W, C / 8);
+    B2R_CHECK_LAUNCH();
+    return B2R_OK;
+}
+
+int b2r_resize_nearest_bf16(const void* in, void* out, int N, int H, int W, int out_h, int out_w, int C, void* stream_v) {
+    using namespace b2r;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    B2R_REQUIRE(in && out, "null pointer");
+    B2R_REQUIRE(N > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0 && C > 0 && C % 8 == 0, "bad shape");
+    const long total = (long)N * out_h * out_w * (C / 8);
+    const long blocks = (total + 255) / 256;
+    B2R_REQUIRE(blocks < (1L << 31), "too large");
+    resize_nearest_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), N, H, W,
+                                                                out_h, out_w, C / 8, float(H) / float(out_h), float(W) / float(out_w));
     B2R_CHECK_LAUNCH();
     return B2R_OK;
 }

@@ -667,8 +667,9 @@ int check_forward_args(const b2r_net* net, int arch, const void* in, int in_fmt,
     B2R_REQUIRE(in_fmt == B2R_IN_F32_NCHW || in_fmt == B2R_IN_U8_NHWC, "in_fmt=%d", in_fmt);
     B2R_REQUIRE(N > 0 && H > 0 && W > 0, "bad shape N=%d H=%d W=%d", N, H, W);
     B2R_REQUIRE(H % div == 0 && W % div == 0,
-                "H and W must be multiples of %d (got %dx%d); the reference's F.interpolate re-alignment branch "
-                "(14_train_unified_advanced.py:169-183) is not implemented", div, H, W);
+                "H and W must be multiples of %d (got %dx%d); the one-call forward runs the fully fused graph only (the Python "
+                "module covers other ResUNet sizes with the reference's nearest re-alignment, 14_train_unified_advanced.py:169-183)",
+                div, H, W);
     return B2R_OK;
 }
 

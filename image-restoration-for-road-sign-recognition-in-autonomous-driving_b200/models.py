@@ -91,8 +91,10 @@ class _B200Module(nn.Module):
             raise L.B2RError(f"module parameters are on {dev}, input on {x.device}; call .to(device) first")
         h, w = (x.shape[1], x.shape[2]) if x.dtype == torch.uint8 else (x.shape[2], x.shape[3])
         if h % div or w % div:
-            raise L.B2RError(f"H and W must be multiples of {div} (got {h}x{w}); the reference's F.interpolate "
-                             "re-alignment branch (14_train_unified_advanced.py:169-183) is not implemented")
+            raise L.B2RError(f"H and W must be multiples of {div} (got {h}x{w}): the reference's torch.cat of the up-sampled "
+                             "tensor with its skip connection fails for other sizes too (07_train_restoration.py:112,116)")
+        if type(self).__name__ == "ResUNet" and (h < 8 or w < 8):
+            raise L.B2RError(f"ResUNet needs H, W >= 8 (three 2x2 max-pools); got {h}x{w}")
 
     @staticmethod
     def _chunks(n: int, mb: int):
@@ -219,8 +221,51 @@ def _restorer_forward(m, x, div, want_f32, want_u8):
 # =================================================================================================================
 # ResUNet
 # =================================================================================================================
-class ResidualBlock(nn.Module):
-    """Parameter container with the reference's key layout: conv_block.{0,1,2,3,4}, shortcut.{0,1} (14:96-112)."""
+def _pack_residual_block(sd, prefix: str, splits, co: int, dev):
+    """Device layouts of one ResidualBlock (14:96-115) whose input is the (virtual) concat of sources with `splits` channels:
+    (conv1 pack, PReLU slope, conv2 + shortcut pack).  BN folded in fp64; the shortcut (1x1 conv + BN, or the identity when
+    in_c == out_c, 14:106-112) rides in conv2's K loop as centre k-blocks over the block's input sources."""
+    cb = prefix + "conv_block."
+    bn = lambda i: (sd[cb + f"{i}.weight"], sd[cb + f"{i}.bias"], sd[cb + f"{i}.running_mean"],  # noqa: E731
+                    sd[cb + f"{i}.running_var"])
+    w1, b1 = packing.fold_bn(sd[cb + "0.weight"], sd[cb + "0.bias"], *bn(1))
+    w2, b2 = packing.fold_bn(sd[cb + "3.weight"], sd[cb + "3.bias"], *bn(4))
+    slope = float(sd[cb + "2.weight"].float().reshape(-1)[0])
+    ci = sum(splits)
+    # conv 1 over the (virtual) concat of the block's input sources
+    plan1 = packing.plan_conv3x3(w1, splits)
+    wm1, kb1 = plan1.finish()
+    # conv 2 over y (source 0) + the shortcut over the block input (sources 1..)
+    plan = packing.KPlan(co).add_conv3x3(0, w2)
+    if ci != co:
+        sc = prefix + "shortcut."
+        ws_, bs_ = packing.fold_bn(sd[sc + "0.weight"], sd[sc + "0.bias"], sd[sc + "1.weight"],
+                                   sd[sc + "1.bias"], sd[sc + "1.running_mean"], sd[sc + "1.running_var"])
+        ws_ = ws_.reshape(co, ci)
+        b2 = b2 + bs_
+    else:
+        ws_ = torch.eye(co, device=w2.device)  # nn.Sequential() shortcut == identity (14:106)
+    off = 0
+    for s, c in enumerate(splits):
+        plan.add_1x1(1 + s, ws_[:, off:off + c])
+        off += c
+    wm2, kb2 = plan.finish()
+    alg_k2 = int(wm2.shape[1]) - (0 if ci != co else co)   # the identity block is not algorithmic work
+    return (dict(weights=wm1.to(dev), bias=b1.to(dev).contiguous(), kblocks=kb1, weights_w3=plan1.finish_w3(dev)), slope,
+            dict(weights=wm2.to(dev), bias=b2.to(dev).contiguous(), kblocks=kb2, weights_w3=plan.finish_w3(dev), alg_k=alg_k2))
+
+
+def _run_residual_block(pack, srcs, y, out, out_pool=None, head=None):
+    c1, slope, c2 = pack
+    ops.conv_gemm(srcs, **c1, act=L.B2R_ACT_PRELU, slope=slope, out=y)
+    ops.conv_gemm([y] + list(srcs), **c2, act=L.B2R_ACT_RELU, out=out, out_pool=out_pool, **(head or {}))
+
+
+class ResidualBlock(_B200Module):
+    """relu(BN(conv3x3(PReLU(BN(conv3x3(x))))) + shortcut(x)) with the reference's key layout conv_block.{0,1,2,3,4},
+    shortcut.{0,1} (14_train_unified_advanced.py:96-115).  Inside ResUNet it is a parameter container (ResUNet.forward packs
+    and runs all nine blocks itself); called on its own, `forward(x f32 [N, in_c, H, W]) -> f32 [N, out_c, H, W]` runs the
+    same two fused launches (activations pass through NHWC bf16 like everywhere else); in_c and out_c multiples of 64."""
 
     def __init__(self, in_c: int, out_c: int):
         super().__init__()
@@ -231,12 +276,34 @@ class ResidualBlock(nn.Module):
             self.shortcut = nn.Sequential(nn.Conv2d(in_c, out_c, 1), nn.BatchNorm2d(out_c))
         self.in_c, self.out_c = in_c, out_c
 
-    def forward(self, x):  # never used by ResUNet.forward; kept so the container is not silently callable
-        raise L.B2RError("ResidualBlock is a parameter container here; call ResUNet.forward")
+    def _build_pack(self, sd):
+        return _pack_residual_block(sd, "", (self.in_c,), self.out_c, sd["conv_block.0.weight"].device)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self._check_input(x, 1)
+        if x.dtype != torch.float32 or x.shape[1] != self.in_c:
+            raise L.B2RError(f"ResidualBlock({self.in_c}, {self.out_c}) takes float32 [N, {self.in_c}, H, W]")
+        if self.in_c % 64 or self.out_c % 64:
+            raise L.B2RError("the tensor-core path needs in_c and out_c to be multiples of 64 (all nine blocks of ResUNet are)")
+        n, _, h, w = x.shape
+        with torch.cuda.device(x.device):
+            P = self._packed()
+            outs = []
+            for s, c in self._chunks(n, self.micro_batch):
+                src = x[s:s + c].permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)      # layout plumbing only
+                y = self._ws.get("y", (c, h, w, self.out_c), x.device)
+                o = self._ws.get("o", (c, h, w, self.out_c), x.device)
+                _run_residual_block(P, [src], y, o)
+                outs.append(o.permute(0, 3, 1, 2).float())
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
 
 class ResUNet(_B200Module):
-    """Three-level residual U-Net, f32 [N,3,H,W] -> f32 [N,3,H,W] (unclamped), H and W multiples of 8."""
+    """Three-level residual U-Net, f32 [N,3,H,W] -> f32 [N,3,H,W] (unclamped), any H, W >= 8.  When H or W is not a multiple
+    of 8 the max-pools floor and the up-sampled tensors are re-aligned to their skip connections with nearest-neighbour
+    interpolation, as the reference does (14_train_unified_advanced.py:169-183); multiples of 8 (every reference transform
+    emits 224 x 224) take the fully fused path."""
 
     # (attribute path, C_in split over the concat sources, C_out)
     _BLOCKS = (("res1", (64,), 64), ("res2", (64,), 128), ("res3", (128,), 256),
@@ -267,36 +334,7 @@ class ResUNet(_B200Module):
         P["enc1"] = (packing.pack_conv_c3(sd["enc1.0.weight"].float()), sd["enc1.0.bias"].float().contiguous(),
                      float(sd["enc1.1.weight"].float().reshape(-1)[0]))
         for name, splits, co in self._BLOCKS:
-            cb = name + ".conv_block."
-            bn = lambda i: (sd[cb + f"{i}.weight"], sd[cb + f"{i}.bias"], sd[cb + f"{i}.running_mean"],  # noqa: E731
-                            sd[cb + f"{i}.running_var"])
-            w1, b1 = packing.fold_bn(sd[cb + "0.weight"], sd[cb + "0.bias"], *bn(1))
-            w2, b2 = packing.fold_bn(sd[cb + "3.weight"], sd[cb + "3.bias"], *bn(4))
-            slope = float(sd[cb + "2.weight"].float().reshape(-1)[0])
-            ci = sum(splits)
-            # conv 1 over the (virtual) concat of the block's input sources
-            plan1 = packing.plan_conv3x3(w1, splits)
-            wm1, kb1 = plan1.finish()
-            # conv 2 over y (source 0) + the shortcut over the block input (sources 1..)
-            plan = packing.KPlan(co).add_conv3x3(0, w2)
-            if ci != co:
-                sc = name + ".shortcut."
-                ws_, bs_ = packing.fold_bn(sd[sc + "0.weight"], sd[sc + "0.bias"], sd[sc + "1.weight"],
-                                           sd[sc + "1.bias"], sd[sc + "1.running_mean"], sd[sc + "1.running_var"])
-                ws_ = ws_.reshape(co, ci)
-                b2 = b2 + bs_
-            else:
-                ws_ = torch.eye(co, device=w2.device)  # nn.Sequential() shortcut == identity (14:106)
-            off = 0
-            for s, c in enumerate(splits):
-                plan.add_1x1(1 + s, ws_[:, off:off + c])
-                off += c
-            wm2, kb2 = plan.finish()
-            alg_k2 = int(wm2.shape[1]) - (0 if ci != co else co)   # the identity block is not algorithmic work
-            P[name] = (dict(weights=wm1.to(dev), bias=b1.to(dev).contiguous(), kblocks=kb1,
-                            weights_w3=plan1.finish_w3(dev)), slope,
-                       dict(weights=wm2.to(dev), bias=b2.to(dev).contiguous(), kblocks=kb2,
-                            weights_w3=plan.finish_w3(dev), alg_k=alg_k2))
+            P[name] = _pack_residual_block(sd, name + ".", splits, co, dev)
         for up in ("up3", "up2", "up1"):
             w, b = packing.pack_convT2x2(sd[up + ".weight"].float(), sd[up + ".bias"].float())
             P[up] = (w.to(dev), b.to(dev))
@@ -304,9 +342,23 @@ class ResUNet(_B200Module):
         return P
 
     def _block(self, P, name, srcs, y, out, out_pool=None, head=None):
-        c1, slope, c2 = P[name]
-        ops.conv_gemm(srcs, **c1, act=L.B2R_ACT_PRELU, slope=slope, out=y)
-        ops.conv_gemm([y] + list(srcs), **c2, act=L.B2R_ACT_RELU, out=out, out_pool=out_pool, **(head or {}))
+        h, w = srcs[0].shape[1], srcs[0].shape[2]
+        if out_pool is not None and (h % 2 or w % 2):
+            # odd map: nn.MaxPool2d(2, 2) drops the last row / column, which the fused tile pool cannot express
+            _run_residual_block(P[name], srcs, y, out, None, head)
+            ops.maxpool2x2(out, out=out_pool)
+        else:
+            _run_residual_block(P[name], srcs, y, out, out_pool, head)
+
+    def _up(self, P, name, src, skip, g):
+        """ConvTranspose2d(k = 2, s = 2) + the reference's re-alignment to the skip connection's size (14:167-170)."""
+        n, h, w, _ = src.shape
+        co = {"up3": 128, "up2": 64, "up1": 64}[name]
+        u = g("u" + name[-1], 2 * h, 2 * w, co)
+        ops.conv_gemm([src], *P[name], None, out=u, out_mode=L.B2R_OUT_CONVT2X2)
+        if (2 * h, 2 * w) != (skip.shape[1], skip.shape[2]):
+            u = ops.resize_nearest(u, skip.shape[1], skip.shape[2], out=g("a" + name[-1], skip.shape[1], skip.shape[2], co))
+        return u
 
     def _run(self, x, out_f32, out_u8, P=None):
         P, ws = (P if P is not None else self._packed()), self._ws
@@ -315,7 +367,9 @@ class ResUNet(_B200Module):
         H, W = (x.shape[1], x.shape[2]) if u8_in else (x.shape[2], x.shape[3])
         dev = x.device
         g = lambda name, h, w, c: ws.get(name, (n, h, w, c), dev)  # noqa: E731
-        H2, W2, H4, W4, H8, W8 = H // 2, W // 2, H // 4, W // 4, H // 8, W // 8
+        H2, W2 = H // 2, W // 2
+        H4, W4 = H2 // 2, W2 // 2
+        H8, W8 = H4 // 2, W4 // 2
 
         w0, b0, s0 = P["enc1"]
         e1 = ops.conv3x3_c3(x, w0, b0, act=L.B2R_ACT_PRELU, slope=s0, out=g("e1", H, W, 64))
@@ -329,27 +383,24 @@ class ResUNet(_B200Module):
         self._block(P, "bottleneck.0", [p3], g("yb0", H8, W8, 512), bt0)
         self._block(P, "bottleneck.1", [bt0], g("yb1", H8, W8, 512), bt1)
         self._block(P, "bottleneck.2", [bt1], g("yb2", H8, W8, 256), bt2)
-        u3 = g("u3", H4, W4, 128)
-        ops.conv_gemm([bt2], *P["up3"], None, out=u3, out_mode=L.B2R_OUT_CONVT2X2)
+        u3 = self._up(P, "up3", bt2, r3, g)
         d3 = g("d3", H4, W4, 128)
         self._block(P, "dec3", [u3, r3], g("yd3", H4, W4, 128), d3)      # cat((d3, r3), 1) (14:171)
-        u2 = g("u2", H2, W2, 64)
-        ops.conv_gemm([d3], *P["up2"], None, out=u2, out_mode=L.B2R_OUT_CONVT2X2)
+        u2 = self._up(P, "up2", d3, r2, g)
         d2 = g("d2", H2, W2, 64)
         self._block(P, "dec2", [u2, r2], g("yd2", H2, W2, 64), d2)       # cat((d2, r2), 1) (14:177)
-        u1 = g("u1", H, W, 64)
-        ops.conv_gemm([d2], *P["up1"], None, out=u1, out_mode=L.B2R_OUT_CONVT2X2)
+        u1 = self._up(P, "up1", d2, r1, g)
         # dec1 block; its second conv also applies `final` (64 -> 3) and the clamp/quantise: d1 never goes to HBM
         self._block(P, "dec1", [u1, r1], g("y1", H, W, 64), None,        # cat((d1, r1), 1) (14:183)
                     head=dict(head_w=P["final"][0], head_b=P["final"][1], head_out_f32=out_f32, head_out_u8=out_u8))
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return _restorer_forward(self, x, 8, want_f32=True, want_u8=False)[0]
+        return _restorer_forward(self, x, 1, want_f32=True, want_u8=False)[0]
 
     @torch.no_grad()
     def restore_u8(self, x: torch.Tensor) -> torch.Tensor:
-        return _restorer_forward(self, x, 8, want_f32=False, want_u8=True)[1]
+        return _restorer_forward(self, x, 1, want_f32=False, want_u8=True)[1]
 
 
 # =================================================================================================================

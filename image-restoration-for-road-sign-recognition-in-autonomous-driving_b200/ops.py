@@ -260,6 +260,21 @@ def maxpool2x2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
     return out
 
 
+def resize_nearest(x: torch.Tensor, out_h: int, out_w: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F.interpolate(x, size=(out_h, out_w)) (mode 'nearest') on NHWC bf16 (14_train_unified_advanced.py:169-170)."""
+    _chk(x, torch.bfloat16, "x", 4)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, out_h, out_w, c), dtype=torch.bfloat16, device=x.device)
+    _chk(out, torch.bfloat16, "out", 4)
+    if tuple(out.shape) != (n, out_h, out_w, c):
+        raise L.B2RError(f"out shape {tuple(out.shape)} != {(n, out_h, out_w, c)}")
+    L.check(L.load().b2r_resize_nearest_bf16(x.data_ptr(), out.data_ptr(), int(n), int(h), int(w), int(out_h), int(out_w), int(c),
+                                             _stream()))
+    STATS["launches"] += 1
+    return out
+
+
 def adaptive_avgpool7(x: torch.Tensor) -> torch.Tensor:
     _chk(x, torch.bfloat16, "x", 4)
     n, h, w, c = x.shape

@@ -53,7 +53,7 @@ class RestoreClassifyPipeline:
         self.device = next(judge.parameters()).device
         if self.device.type != "cuda":
             raise L.B2RError("RestoreClassifyPipeline needs its modules on a CUDA device (no CPU fallback)")
-        self._div = 8 if type(restorer).__name__ == "ResUNet" else 4
+        self._div = 1 if type(restorer).__name__ == "ResUNet" else 4   # ResUNet re-aligns odd sizes (14:169-183)
         self._bufs = {}
 
     def _buf(self, name, shape, dtype):

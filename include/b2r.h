@@ -198,8 +198,15 @@ int b2r_conv_gemm(const b2r_conv_gemm_desc* desc /* host */, void* stream);
 int b2r_final_conv1x1(const void* in_nhwc_bf16, const float* weights, const float* bias, float* out_f32_nchw,
                       uint8_t* out_u8_nhwc, int N, int H, int W, void* stream);
 
-/* 2x2/2 max-pool on NHWC bf16 (nn.MaxPool2d(2,2): 07:81, 14:124) — standalone form of the fused epilogue. */
+/* 2x2/2 max-pool on NHWC bf16 (nn.MaxPool2d(2,2): 07:81, 14:124) — standalone form of the fused epilogue; odd H / W drop the
+ * last row / column like PyTorch (output [N, H/2, W/2, C] with floor division). */
 int b2r_maxpool2x2(const void* in_nhwc_bf16, void* out_nhwc_bf16, int N, int H, int W, int C, void* stream);
+
+/* torch.nn.functional.interpolate(x, size=(out_h, out_w)) in its default mode 'nearest' on NHWC bf16: the re-alignment of the
+ * up-sampled tensor to its skip connection in ResUNet.forward when H or W is not a multiple of 8
+ * (14_train_unified_advanced.py:169-170, 175-176, 181-182).  src = min(floor(dst * (float)in / out), in - 1).  C % 8 == 0. */
+int b2r_resize_nearest_bf16(const void* in_nhwc_bf16, void* out_nhwc_bf16, int N, int H, int W, int out_h, int out_w, int C,
+                            void* stream);
 
 /* AdaptiveAvgPool2d((7,7)) of torchvision VGG16 on NHWC bf16 [N,H,W,C] -> [N,7,7,C] (identity at H=W=7). */
 int b2r_adaptive_avgpool7(const void* in_nhwc_bf16, void* out_nhwc_bf16, int N, int H, int W, int C, void* stream);
@@ -304,8 +311,9 @@ int b2r_ssim_u8(const uint8_t* a, const uint8_t* b, double* ssim, int N, int H, 
  * Ownership: the caller owns `dev_weights` (>= b2r_net_weight_bytes, 256-byte aligned) and every workspace; the plan holds
  * pointers into dev_weights until b2r_net_destroy.  The forwards enqueue on `stream` and never allocate.
  * in_fmt as in section (2): B2R_IN_F32_NCHW (the nn.Module.forward argument) or B2R_IN_U8_NHWC (ToTensor fused).
- * H, W: multiples of 4 (SimpleUNet) / 8 (ResUNet) / 32 (VGG16), else B2R_EINVAL (the reference's nearest-neighbour
- * re-alignment, 14:169-183, is not implemented).
+ * H, W: multiples of 4 (SimpleUNet) / 8 (ResUNet) / 32 (VGG16), else B2R_EINVAL.  (The reference's nearest-neighbour
+ * re-alignment for other ResUNet sizes, 14:169-183, is available to a C host through b2r_maxpool2x2 + b2r_resize_nearest_bf16
+ * + b2r_conv_gemm and is what the Python module does; the one-call forward keeps the fully fused graph.)
  * ------------------------------------------------------------------------------------------------------------- */
 #define B2R_NET_SIMPLE_UNET 0
 #define B2R_NET_RESUNET 1

@@ -178,3 +178,54 @@ def test_vgg_feature_taps_vs_oracle():
         assert rel <= 0.05
     with pytest.raises(Exception):
         m.feature_heatmap(img, layer_index=31)
+
+
+@pytest.mark.parametrize("hw", [(100, 90), (37, 51), (9, 8), (226, 222)])
+def test_resunet_sizes_that_need_the_nearest_realignment(hw):
+    """H or W not a multiple of 8: the max-pools floor and F.interpolate (nearest) re-aligns every up-sampled tensor to its
+    skip connection (14_train_unified_advanced.py:169-183) — round 1 rejected these sizes.  Same bars as the fused path."""
+    from b200restore import models, synth
+    from oracle import models_oracle as MO
+    sd = synth.synthetic_state_dict("resunet", 12)
+    m = models.ResUNet()
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = torch.rand((2, 3, hw[0], hw[1]), device="cuda")
+    with torch.no_grad():
+        ref = MO.resunet_forward({k: v.cuda() for k, v in sd.items()}, x)
+    out = m(x)
+    assert out.shape == ref.shape
+    err = float((out - ref).abs().max())
+    mse = float(((out - ref) ** 2).mean())
+    psnr = 10 * math.log10(float((ref.max() - ref.min()) ** 2) / mse)
+    print(f"\n[resunet {hw}] PSNR {psnr:.1f} dB, max-abs {err:.4g}")
+    assert psnr >= 50.0 and err <= 2e-2
+    u8 = (x.permute(0, 2, 3, 1) * 255).to(torch.uint8).contiguous()
+    d = (m.restore_u8(u8).int() - MO.quantize_restored(MO.resunet_forward({k: v.cuda() for k, v in sd.items()}, MO.to_tensor_u8(u8))).int()).abs()
+    assert float(d.float().mean()) < 0.5 and int(d.max()) <= 4
+
+
+@pytest.mark.parametrize("in_c,out_c,hw", [(64, 64, (24, 40)), (128, 256, (28, 28)), (384, 128, (14, 30)), (512, 512, (8, 8))])
+def test_residual_block_stand_alone_forward(in_c, out_c, hw):
+    """ResidualBlock.forward on its own (14:114-115) against the fp32 oracle; identity and 1x1 + BN shortcuts."""
+    from b200restore import models, synth
+    from oracle import models_oracle as MO
+    full = synth.synthetic_state_dict("resunet", 5)
+    name = {(64, 64): "res1", (128, 256): "res3", (384, 128): "dec3", (512, 512): "bottleneck.1"}[(in_c, out_c)]
+    sd = {k[len(name) + 1:]: v for k, v in full.items() if k.startswith(name + ".")}
+    rb = models.ResidualBlock(in_c, out_c)
+    rb.load_state_dict(sd)
+    rb = rb.cuda().eval()
+    x = torch.randn((3, in_c, hw[0], hw[1]), device="cuda") * 0.5
+    xb = x.to(torch.bfloat16).float()                      # what the block sees (NHWC bf16 inside)
+    with torch.no_grad():
+        ref = MO.residual_block_forward({k: v.cuda() for k, v in full.items()}, name, xb)
+    out = rb(x)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    scale = float(ref.abs().max())
+    err = float((out - ref).abs().max())
+    print(f"\n[ResidualBlock {in_c}->{out_c}] max-abs {err:.4g} of range {scale:.3g}")
+    assert err <= 2.0 ** -6 * scale + 1e-3
+    from b200restore import B2RError
+    with pytest.raises(B2RError):
+        rb(x[:, :in_c - 1])
