@@ -719,7 +719,7 @@ def run_ours(args):
         "cuda_graph": use_graph,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convs (conv_gemm_pair_kernel<256> cta_group::2, conv_w3_kernel, conv_gemm_halo_kernel<128>, conv_gemm_kernel<N>)",
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convs (conv_gemm_pair_kernel<256>, conv_w3_kernel<pair>, conv_gemm_pairhalo_kernel<128>: all cta_group::2; conv_gemm_kernel<N>)",
                      "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
                      "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
                      "launches": ksum["launches"], "kernel_ms_per_step": ksum["ms"] / inst_steps,
