@@ -146,7 +146,9 @@ def psnr(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 def ssim(a: torch.Tensor, b: torch.Tensor, data_range: float = 255.0) -> torch.Tensor:
     """skimage.metrics.structural_similarity(a, b, data_range=255, channel_axis=2) per image of two u8 [N, H, W, 3]
     batches (08:123): skimage's defaults (7x7 uniform window, sample covariance, K1 = .01, K2 = .03, float64, border
-    of 3 cropped, mean over channels).  f64 [N]; images smaller than the window raise, as skimage does."""
+    of 3 cropped, mean over channels).  f64 [N]; images smaller than the window raise, as skimage does.
+    Parity note: skimage is not installed in this image, so this is pinned to the oracle's restatement of skimage's published
+    algorithm (same scipy.ndimage.uniform_filter calls), not to an execution of skimage itself."""
     return ops.ssim_u8(a, b, data_range)
 
 
