@@ -49,11 +49,9 @@ constexpr int kW3PrefetchTiles = B2R_W3_PREFETCH_TILES;   // L2 prefetch distanc
 // kPair = true (round 2) runs the same kernel as a cluster of two CTAs with tcgen05.mma.cta_group::2: one MMA of M = 256 x
 // N = 192 serves two neighbouring tiles, each CTA holding its own tile's halo box (its 128 rows of A, its 128 lanes of D,
 // its epilogue and stores) and HALF of the weight rows (96 of the 192 rows of a k-step, 32 of the 64 rows of a compact
-// 1x1 k-step).  Why: ncu on the single-CTA kernel (profiles/r02_ncu_w3.md) shows the tensor core's shared-memory operand
-// port busy 82 % of the time with the math pipe at 54 %: an N = 192 MMA reads 4 KB of A + 6 KB of B per 96 cycles =
-// 107 B/clk, and TMA fills, staging writes and TMA-store reads add ~42 B/clk on a 128 B/clk shared memory.  With B split
-// over the pair each SM reads 4 + 3 KB per MMA (73 B/clk).  The resident weights halve too (36 KB for 64 -> 64; the
-// 192 -> 64 layer fits without the streamed-weights mode) and the ring gets the space.
+// 1x1 k-step).  Why: the resident weights halve (36 KB for 64 -> 64; the 192 -> 64 layer fits without the streamed-weights
+// mode: 375 -> 283 us) and the ring gets the space (128 -> 64: 915 -> 805 us); each SM also reads 4 + 3 KB instead of
+// 4 + 6 KB of operands per MMA.  Single-group layers (64 -> 64) run at the same speed in both modes.
 // Protocol as in conv_gemm_pair_kernel: the leader (cluster rank 0) issues (both issuer warps); its "data landed" and
 // "weights landed" barriers count the TMA bytes of both CTAs; tcgen05.commit multicasts to both CTAs' "slot free" /
 // "accumulator ready" barriers; the epilogue warps of both CTAs release the accumulator on the leader's barrier.
