@@ -494,7 +494,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 part[0] = hs0;
                 part[128] = hs1;
                 part[256] = hs2;
-                named_barrier_sync(1, kW3EpiWarps * 32);   // the only cross-warp exchange: four partial sums per pixel
+                // the only cross-warp exchange: four partial sums per pixel, all from warps of the SAME TMEM lane quarter, so each
+                // quarter synchronises on its own named barrier (4 warps) instead of all 16 epilogue warps on one
+                named_barrier_sync(1 + quarter, 4 * 32);
                 if (cq == 0) {
                     // one thread per pixel: add the four partial sums + bias, then the reference's outputs
                     const int w = tw.tw * 14 + cc;
