@@ -497,26 +497,19 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 // the only cross-warp exchange: four partial sums per pixel, all from warps of the SAME TMEM lane quarter, so each
                 // quarter synchronises on its own named barrier (4 warps) instead of all 16 epilogue warps on one
                 named_barrier_sync(1 + quarter, 4 * 32);
-                if (cq == 0) {
-                    // one thread per pixel: add the four partial sums + bias, then the reference's outputs
+                if (cq < 3) {
+                    // warp cq of the quarter finishes output channel o = cq for the quarter's 32 pixels: add the four partial
+                    // sums (same order as before: bit-identical) + bias, then the reference's outputs
+                    const int o = cq;
                     const int w = tw.tw * 14 + cc;
                     const int h = tw.th * 8 + hh;
                     if (valid && w < p.W && h < p.H && tw.n < p.n_img) {
                         const float* pr = reinterpret_cast<const float*>(sfull_b) + quarter * 32 + lane;
-                        float v[3];
-#pragma unroll
-                        for (int o = 0; o < 3; ++o)
-                            v[o] = ((pr[o * 128] + pr[(3 + o) * 128]) + (pr[(6 + o) * 128] + pr[(9 + o) * 128])) + head_s[192 + o];
+                        const float v = ((pr[o * 128] + pr[(3 + o) * 128]) + (pr[(6 + o) * 128] + pr[(9 + o) * 128])) + head_s[192 + o];
                         const size_t hw = size_t(p.H) * p.W, pix = size_t(h) * p.W + w;
-                        if (p.head_f32) {
-#pragma unroll
-                            for (int o = 0; o < 3; ++o) p.head_f32[(size_t(tw.n) * 3 + o) * hw + pix] = v[o];
-                        }
-                        if (p.head_u8) {
-#pragma unroll
-                            for (int o = 0; o < 3; ++o)   // torch.clamp(x, 0, 1); (x * 255).astype(np.uint8): truncation (17:86-92)
-                                p.head_u8[(size_t(tw.n) * hw + pix) * 3 + o] = static_cast<uint8_t>(fminf(fmaxf(v[o], 0.f), 1.f) * 255.0f);
-                        }
+                        if (p.head_f32) p.head_f32[(size_t(tw.n) * 3 + o) * hw + pix] = v;
+                        if (p.head_u8)   // torch.clamp(x, 0, 1); (x * 255).astype(np.uint8): truncation (17:86-92)
+                            p.head_u8[(size_t(tw.n) * hw + pix) * 3 + o] = static_cast<uint8_t>(fminf(fmaxf(v, 0.f), 1.f) * 255.0f);
                     }
                 }
             } else {
