@@ -17,7 +17,7 @@ B2R_DEG_CLIP_AFTER_NOISE = 1
 B2R_IN_F32_NCHW, B2R_IN_U8_NHWC = 0, 1
 B2R_OUT_NHWC, B2R_OUT_CONVT2X2 = 0, 1
 B2R_MAX_SRC, B2R_MAX_KBLOCKS, B2R_MAX_BLUR = 3, 96, 15
-B2R_CONV_GENERIC_ONLY, B2R_CONV_NO_W3, B2R_CONV_NO_HALO, B2R_CONV_NO_PAIR, B2R_CONV_NO_CARRY = 1, 2, 4, 8, 16
+B2R_CONV_GENERIC_ONLY, B2R_CONV_NO_W3, B2R_CONV_NO_HALO, B2R_CONV_NO_PAIR = 1, 2, 4, 8
 
 # every symbol include/b2r.h declares (tests/test_abi.py checks the list against the header and the .so)
 SYMBOLS = (

@@ -40,8 +40,7 @@ constexpr int kW3MaxStageBufs = 4;
 struct alignas(64) ConvW3Params {
     CUtensorMap a_map[B2R_MAX_SRC];  // box 64 ch x 16 x 10 x 1
     CUtensorMap b_map;               // wide weights [192][64 * num_ksteps], box 64 x 192
-    CUtensorMap out_map, pool_map;   // boxes 64 x 14 x 8 x 1 and 64 x 7 x 4 x 1 (carry mode: 64 x 16 x 8 x 1 and 64 x 8 x 4 x 1)
-    CUtensorMap out_map0, pool_map0; // carry mode: the basic 14 / 7 column boxes for a band's first tile
+    CUtensorMap out_map, pool_map;   // boxes 64 x 14 x 8 x 1 and 64 x 7 x 4 x 1
     const float* bias;
     float slope;
     int act;
@@ -64,8 +63,8 @@ struct alignas(64) ConvW3Params {
     uint32_t group[kW3MaxGroups];
 };
 
-size_t conv_w3_smem_bytes(size_t b_bytes, int ring_slots, size_t stage_stride, int stage_bufs, bool carry);
-int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream, bool pair, bool carry);
+size_t conv_w3_smem_bytes(size_t b_bytes, int ring_slots, size_t stage_stride, int stage_bufs);
+int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream, bool pair);
 
 #ifdef __CUDACC__
 // Walks tiles first, first + stride, ... as (image, tile row, tile column) without per-tile integer divisions: the two

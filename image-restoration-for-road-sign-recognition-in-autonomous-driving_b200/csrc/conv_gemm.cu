@@ -1035,21 +1035,14 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
     // variant stages only its partial sums (6 KB per buffer), other layers a full + a pooled tile.  What is left goes to the
     // input ring: two tiles' worth of slots lets the two MMA issuers really alternate (with one tile's worth the next
     // tile's boxes cannot even be requested before this tile's MMAs retire).
-    // carry mode (csrc/conv_w3.cu): tiles of a band start 16 columns apart and carry their two unfinished outputs to the next
-    // tile: ceil((W - 14) / 16) + 1 tiles per band instead of ceil(W / 14).  Taken when it saves tiles and there are enough
-    // bands to give every CTA (pair) whole bands.
-    static const bool no_carry_env = getenv("B2R_NO_W3CARRY") != nullptr;   // A/B switch, read once
-    const int tiles_basic = ceil_div(d->W, 14), tiles_carry = (d->W > 14 ? ceil_div(d->W - 14, 16) : 0) + 1;
+    const size_t stage_stride = d->head_w ? 6144 : (14336 + 4096);
     int sms_w3 = 0;
     {
         int src_ = device_sm_count(&sms_w3);
         if (src_) return src_;
     }
-    const long bands = (long)ceil_div(d->H, 8) * d->N;
-    const bool carry = !no_carry_env && !(d->flags & B2R_CONV_NO_CARRY) && tiles_carry < tiles_basic && bands >= 2L * sms_w3;
-    const size_t stage_stride = d->head_w ? 6144 : ((carry ? 16384 : 14336) + 4096);
     static const bool no_w3pair_env = getenv("B2R_NO_W3PAIR") != nullptr;   // A/B switch for tools/layer_bench.py, read once
-    const long tiles_total = (long)(carry ? tiles_carry : tiles_basic) * ceil_div(d->H, 8) * d->N;
+    const long tiles_total = (long)ceil_div(d->W, 14) * ceil_div(d->H, 8) * d->N;
     bool pair = !no_w3pair_env && !(d->flags & B2R_CONV_NO_PAIR) && sms_w3 >= 2 && tiles_total >= 2 && d->max_ctas != 1;
     uint32_t boff[kW3MaxGroups];
     size_t b_bytes = 0;
@@ -1064,7 +1057,7 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
         }
         ring = 2 * ng > kN64MaxRing ? kN64MaxRing : (2 * ng < 4 ? 4 : 2 * ng);
         if (pair && ring < kN64MaxRing && ring < 6) ring = 6 < kN64MaxRing ? 6 : kN64MaxRing;   // the halved weights leave room: a third tile in flight
-        while (ring >= 2 && conv_w3_smem_bytes(b_bytes, ring, stage_stride, 2, carry) > (size_t)kN64MaxSmem) --ring;
+        while (ring >= 2 && conv_w3_smem_bytes(b_bytes, ring, stage_stride, 2) > (size_t)kN64MaxSmem) --ring;
         if (ring >= (pair ? ng : 2) || !pair) break;
         pair = false;   // even the halved weights do not leave a ring of one tile: single-CTA kernel (streams the weights)
     }
@@ -1073,7 +1066,7 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
         if (d->head_w) return B2R_OK;
         ring = 3;
         b_slots = kN64MaxRing;
-        while (b_slots >= 3 && conv_w3_smem_bytes((size_t)b_slots * 24576, ring, stage_stride, 2, carry) > (size_t)kN64MaxSmem) --b_slots;
+        while (b_slots >= 3 && conv_w3_smem_bytes((size_t)b_slots * 24576, ring, stage_stride, 2) > (size_t)kN64MaxSmem) --b_slots;
         if (b_slots < 3) return B2R_OK;
         b_bytes = (size_t)b_slots * 24576;
     }
@@ -1086,7 +1079,7 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
     int stage_bufs = 2;
     if (!d->head_w && b_slots == 0) {
         const int want = stage_bufs_env >= 2 && stage_bufs_env <= kW3MaxStageBufs ? stage_bufs_env : 3;
-        while (stage_bufs < want && conv_w3_smem_bytes(b_bytes, ring, stage_stride, stage_bufs + 1, carry) <= (size_t)kN64MaxSmem) ++stage_bufs;
+        while (stage_bufs < want && conv_w3_smem_bytes(b_bytes, ring, stage_stride, stage_bufs + 1) <= (size_t)kN64MaxSmem) ++stage_bufs;
     }
 
     static thread_local ConvW3Params tp;
@@ -1117,36 +1110,23 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
     if (d->out) {
         const uint64_t dims[4] = {OC, W, H, N};
         const uint64_t strides[3] = {OC * 2, W * OC * 2, H * W * OC * 2};
-        const uint32_t box[4] = {64, carry ? 16u : 14u, 8, 1};
+        const uint32_t box[4] = {64, 14, 8, 1};
         int rc = encode_tmap_bf16(&P.out_map, d->out, 4, dims, strides, box);
-        if (rc) return rc;
-        const uint32_t box0[4] = {64, 14, 8, 1};
-        rc = encode_tmap_bf16(&P.out_map0, d->out, 4, dims, strides, box0);
         if (rc) return rc;
     }
     if (d->out_pool) {
         const uint64_t pd[4] = {OC, W / 2, H / 2, N};
         const uint64_t ps[3] = {OC * 2, (W / 2) * OC * 2, (H / 2) * (W / 2) * OC * 2};
-        const uint32_t pb[4] = {64, carry ? 8u : 7u, 4, 1};
+        const uint32_t pb[4] = {64, 7, 4, 1};
         int rc = encode_tmap_bf16(&P.pool_map, d->out_pool, 4, pd, ps, pb);
-        if (rc) return rc;
-        const uint32_t pb0[4] = {64, 7, 4, 1};
-        rc = encode_tmap_bf16(&P.pool_map0, d->out_pool, 4, pd, ps, pb0);
         if (rc) return rc;
     }
     if (!d->out && !d->out_pool) {
         P.out_map = P.a_map[0];   // never used for a store (store_full = store_pool = 0); keeps prefetch valid
         P.pool_map = P.a_map[0];
-        P.out_map0 = P.pool_map0 = P.a_map[0];
     } else {
-        if (!d->out) {
-            P.out_map = P.pool_map;
-            P.out_map0 = P.pool_map0;
-        }
-        if (!d->out_pool) {
-            P.pool_map = P.out_map;
-            P.pool_map0 = P.out_map0;
-        }
+        if (!d->out) P.out_map = P.pool_map;
+        if (!d->out_pool) P.pool_map = P.out_map;
     }
     P.bias = d->bias;
     P.slope = d->slope;
@@ -1170,15 +1150,15 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
     // same pattern without MMAs runs 250 us without and 306 us with the prefetch)
     P.prefetch = ring < 2 * ng ? 1 : 0;
     memcpy(P.group_boff, boff, sizeof(uint32_t) * ng);
-    P.tiles_w = carry ? tiles_carry : tiles_basic;
+    P.tiles_w = ceil_div(d->W, 14);
     P.tiles_h = ceil_div(d->H, 8);
     P.n_img = d->N;
     P.store_full = d->out != nullptr;
     P.store_pool = d->out_pool != nullptr;
     memcpy(P.group, groups, sizeof(uint32_t) * ng);
     const int sms = sms_w3;
-    if ((long)P.tiles_w * P.tiles_h * P.n_img >= (1L << 31)) return B2R_OK;
-    const long total_tiles = carry ? bands : (long)P.tiles_w * P.tiles_h * P.n_img;   // work items: bands in carry mode
+    const long total_tiles = (long)P.tiles_w * P.tiles_h * P.n_img;
+    if (total_tiles >= (1L << 31)) return B2R_OK;
     int grid = d->max_ctas > 0 ? d->max_ctas : sms;
     if (pair) {
         const long pairs = (total_tiles + 1) / 2;
@@ -1189,7 +1169,7 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
     } else if (grid > total_tiles) {
         grid = (int)total_tiles;
     }
-    int rc = launch_conv_w3(P, grid, stream, pair, carry);
+    int rc = launch_conv_w3(P, grid, stream, pair);
     if (rc) return rc;
     *handled = true;
     return B2R_OK;

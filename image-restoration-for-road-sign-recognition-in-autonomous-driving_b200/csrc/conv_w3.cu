@@ -55,32 +55,17 @@ constexpr int kW3PrefetchTiles = B2R_W3_PREFETCH_TILES;   // L2 prefetch distanc
 // Protocol as in conv_gemm_pair_kernel: the leader (cluster rank 0) issues (both issuer warps); its "data landed" and
 // "weights landed" barriers count the TMA bytes of both CTAs; tcgen05.commit multicasts to both CTAs' "slot free" /
 // "accumulator ready" barriers; the epilogue warps of both CTAs release the accumulator on the leader's barrier.
-//
-// kCarry = true (round 2) removes most of the halo waste.  In the basic scheme a tile of 16 input columns yields 14 outputs and
-// the next tile starts 14 columns further: the partial sums D0[14], D1[15], D0[15] of the last two columns are thrown away
-// and recomputed (12.5 % of all MMA rows).  Here consecutive tiles of an 8-row band start 16 columns apart (no overlap) and
-// the two unfinished outputs are CARRIED: a CTA walks a whole band left to right, lanes 14 / 15 of every tile row keep
-//     P14 = D0[14] + D1[15],   P15 = D0[15]
-// (in shared memory, private to the warp) and finish them in the next tile with that tile's D2[0] resp. D1[0] + D2[1], which
-// the same two lane exchanges deliver when they ROTATE inside the 16-lane row instead of shifting.  Same additions in the same
-// order as before: bit-identical results.  A tile then stores 16 columns (2 carried + 14 own, box origin 16 k - 2; columns
-// -2, -1 of a band's first tile and columns >= W are clipped by TMA).  Tiles per band: ceil((W - 14) / 16) + 1, i.e. 15 instead
-// of 16 at W = 224 (-6.25 % MMA work), 17 instead of 19 at 256, 9 instead of 10 at 128, the same 8 at 112.
-template <bool kHead, bool kPair = false, bool kCarry = false>
+template <bool kHead, bool kPair = false>
 __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_constant__ ConvW3Params p) {
     constexpr uint32_t kIdesc = make_idesc_bf16_f32(kPair ? 256 : 128, 192);
     constexpr uint32_t kIdesc64 = make_idesc_bf16_f32(kPair ? 256 : 128, 64);
     constexpr int kBStepCta = kPair ? kW3BStep / 2 : kW3BStep;   // bytes of one k-step's weights in THIS CTA
-    constexpr int kCols = kCarry ? 16 : 14;                       // output columns a tile stores
-    constexpr int kStep = kCarry ? 16 : 14;                       // input columns between consecutive tiles
-    constexpr int kStaging = 8 * kCols * 128;                     // bytes of the full-resolution staging tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* b_res = smem;
     uint8_t* ring = b_res + p.b_bytes;                             // resident weights, or a ring of weight k-steps
     uint8_t* sfull = ring + p.ring_slots * kW3Slot;                 // p.stage_bufs (2..4) staging (+ pool) tile buffers, used round-robin
-    float* carry_s = reinterpret_cast<float*>(sfull + p.stage_bufs * p.stage_stride);   // kCarry: [16 warps][4 lanes][16] f32 = 4 KB
-    float* bias_s = carry_s + (kCarry ? 1024 : 0);
+    float* bias_s = reinterpret_cast<float*>(sfull + p.stage_bufs * p.stage_stride);
     float* head_s = bias_s + 64;                                   // [3][64] head weights + [3] head bias (+ pad)
     uint32_t* group_s = reinterpret_cast<uint32_t*>(head_s + 200);  // [kW3MaxGroups] group words (shared-memory copy)
     uint32_t* gboff_s = group_s + kW3MaxGroups;                     // [kW3MaxGroups] weights offset of each group (16-byte units)
@@ -106,43 +91,14 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     const long total_tiles = long(p.tiles_w) * p.tiles_h * p.n_img;
     const int R = p.ring_slots;
     const int G = p.num_groups;
-    // Work items: tiles (basic scheme: any order) or 8-row bands (kCarry: a band's tiles_w tiles are walked left to right by one
-    // CTA).  Pair mode: rank r of the cluster takes item 2 u + r of unit u.  `my_iters` = tiles this CTA processes in all.
+    // work units: single mode = tiles, one per CTA and step; pair mode = tile pairs, rank r of the cluster takes tile 2 u + r
     const uint32_t rank = kPair ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
     const long unit0 = kPair ? long(blockIdx.x >> 1) : long(blockIdx.x);
     const long ustride = kPair ? long(gridDim.x >> 1) : long(gridDim.x);
-    const long total_items = kCarry ? long(p.tiles_h) * p.n_img : total_tiles;
-    const long total_units = kPair ? (total_items + 1) / 2 : total_items;
-    const long item0 = kPair ? 2 * unit0 + rank : unit0;          // this CTA's first item and item stride
-    const long istride = kPair ? 2 * ustride : ustride;
-    const long my_units = unit0 < total_units ? (total_units - unit0 + ustride - 1) / ustride : 0;
-    const long my_iters = my_units * (kCarry ? p.tiles_w : 1);
-    // (image, tile row, tile column) of this CTA's tiles in processing order
-    struct Walk {
-        TileWalk b;
-        int tcol, tiles_w, tiles_h;
-        __device__ __forceinline__ void init(long first, long stride, int tw_, int th_) {
-            tiles_w = tw_;
-            tiles_h = th_;
-            tcol = 0;
-            if (kCarry) b.init(first, stride, 1, th_);   // bands: a grid of 1 x tiles_h "tiles" per image
-            else b.init(first, stride, tw_, th_);
-        }
-        __device__ __forceinline__ void next() {
-            if (kCarry) {
-                if (++tcol == tiles_w) {
-                    tcol = 0;
-                    b.next(1, tiles_h);
-                }
-            } else {
-                b.next(tiles_w, tiles_h);
-            }
-        }
-        __device__ __forceinline__ int n() const { return b.n; }
-        __device__ __forceinline__ int th() const { return b.th; }
-        __device__ __forceinline__ int tw() const { return kCarry ? tcol : b.tw; }
-    };
+    const long total_units = kPair ? (total_tiles + 1) / 2 : total_tiles;
+    const long tile0 = kPair ? 2 * unit0 + rank : unit0;          // this CTA's first tile and tile stride
+    const long tstride = kPair ? 2 * ustride : ustride;
 
     if (warp_idx == 0 && lane == 0) {
         for (int i = 0; i < B2R_MAX_SRC; ++i) tma_prefetch_desc(&p.a_map[i]);
@@ -224,28 +180,27 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             uint32_t phase = 0;
             int bs = 0;
             uint32_t bphase = 0;
-            Walk tw;
-            tw.init(item0, istride, p.tiles_w, p.tiles_h);
+            TileWalk tw;
+            tw.init(tile0, tstride, p.tiles_w, p.tiles_h);
             // L2 prefetch cursor, kW3PrefetchTiles tiles ahead of the tile being loaded: the ring (2-4 slots, as few as
             // one tile for 128 -> 64) cannot cover HBM latency under load; without this the MMA warps waited ~270-800
             // cycles per tile for their first A box (profiles/r01_w3_timeline.md)
-            Walk pf;
-            pf.init(item0, istride, p.tiles_w, p.tiles_h);
-            long pf_it = p.prefetch ? kW3PrefetchTiles : my_iters;   // my_iters: no L2 prefetch
-            for (int i = 0; i < kW3PrefetchTiles && p.prefetch; ++i) pf.next();
+            TileWalk pf;
+            long pf_tile = p.prefetch ? tile0 + (long)kW3PrefetchTiles * tstride : total_tiles;   // 0: no L2 prefetch
+            pf.init(pf_tile < total_tiles ? pf_tile : 0, tstride, p.tiles_w, p.tiles_h);
             int par = 0;   // which issuing warp consumes this tile
-            for (long it = 0; it < my_iters; ++it, tw.next(), par ^= 1) {
+            for (long unit = unit0; unit < total_units; unit += ustride, tw.next(p.tiles_w, p.tiles_h), par ^= 1) {
 #ifndef B2R_EXP_NO_PREFETCH
-                if (pf_it < my_iters) {
+                if (pf_tile < total_tiles) {
                     for (int g = 0; g < G; ++g) {
                         const uint32_t e = group_s[g];
-                        tma_prefetch_l2_4d(&p.a_map[e & 3], int((e >> 8) & 0xFFF) * 64, pf.tw() * kStep - 1, pf.th() * 8 - 1, pf.n());
+                        tma_prefetch_l2_4d(&p.a_map[e & 3], int((e >> 8) & 0xFFF) * 64, pf.tw * 14 - 1, pf.th * 8 - 1, pf.n);
                     }
-                    pf.next();
                 }
-                ++pf_it;
+                pf_tile += tstride;
+                pf.next(p.tiles_w, p.tiles_h);
 #endif
-                const int n0 = tw.n(), w0 = tw.tw() * kStep, h0 = tw.th() * 8;
+                const int n0 = tw.n, w0 = tw.tw * 14, h0 = tw.th * 8;
                 uint64_t* full_m = full_bar + par * kN64MaxRing;
                 uint64_t* bs_full_m = bs_full_bar + par * kN64MaxRing;
                 for (int g = 0; g < G; ++g) {
@@ -330,7 +285,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         uint32_t acc_phase = 0;
         uint32_t e_next = group_s[0];
         [[maybe_unused]] int iter = m;
-        for (long it = m; it < my_iters; it += 2, iter += 2) {
+        for (long unit = unit0 + (long)m * ustride; unit < total_units; unit += 2L * ustride, iter += 2) {
             mbar_wait_uniform(&tmem_empty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             if (lane == 0) B2R_STAMP(iter, 1);
@@ -423,22 +378,17 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         // back once the store has read it.  Keeping this off the epilogue warps removed the last CTA-wide barrier and
         // ~340 cycles per tile from their critical path (profiles/r01_w3_timeline.md).
         if (!kHead && lane == 0) {
-            Walk tw;
-            tw.init(item0, istride, p.tiles_w, p.tiles_h);
+            TileWalk tw;
+            tw.init(tile0, tstride, p.tiles_w, p.tiles_h);
             int iter = 0, buf = 0;
             uint32_t bph = 0;     // staging buffers are used round-robin: buffer `buf`, phase parity `bph` (flips when buf wraps)
-            for (long it = 0; it < my_iters; ++it, ++iter, tw.next()) {
+            for (long unit = unit0; unit < total_units; unit += ustride, ++iter, tw.next(p.tiles_w, p.tiles_h)) {
                 uint8_t* sfull_b = sfull + buf * p.stage_stride;
                 mbar_wait(&staged_bar[buf], bph);
 #if !defined(B2R_EXP_NO_STAGE) && !defined(B2R_EXP_NO_TMASTORE)
-                // kCarry: 16 columns from 16 k - 2 (two carried + fourteen own; negative / >= W columns are clipped)
-                // kCarry: 16 columns from 16 k - 2 (two carried + fourteen own; columns >= W are clipped).  TMA STORES reject
-                // negative coordinates ("illegal instruction", unlike loads), so a band's first tile, which has nothing carried
-                // in, is staged and stored like a basic 14-column tile at column 0 (out_map0 / pool_map0).
-                const bool first = kCarry && tw.tw() == 0;
-                const int w0 = kCarry ? (first ? 0 : tw.tw() * 16 - 2) : tw.tw() * 14, h0 = tw.th() * 8;
-                if (p.store_full) tma_store_4d(first ? &p.out_map0 : &p.out_map, sfull_b, 0, w0, h0, tw.n());
-                if (p.store_pool) tma_store_4d(first ? &p.pool_map0 : &p.pool_map, sfull_b + kStaging, 0, w0 >> 1, h0 >> 1, tw.n());
+                const int w0 = tw.tw * 14, h0 = tw.th * 8;
+                if (p.store_full) tma_store_4d(&p.out_map, sfull_b, 0, w0, h0, tw.n);
+                if (p.store_pool) tma_store_4d(&p.pool_map, sfull_b + kW3Staging, 0, w0 >> 1, h0 >> 1, tw.n);
                 tma_store_commit();
                 tma_store_wait_read<0>();
 #endif
@@ -466,17 +416,11 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         const int cq = e >> 2;                         // channels cq*16 .. cq*16+15
         const int etid = e * 32 + lane;                // 0..511
         const int hh = quarter * 2 + (lane >> 4);      // tile row of this lane's pixel
-        const int cc = lane & 15;                      // buffer column; basic scheme: output column w = cc is valid for cc < 14
-        // kCarry: lanes 0..13 finish this tile's outputs 16 k + cc (staging columns 2..15), lanes 14 / 15 finish the outputs
-        // 16 k - 2 / 16 k - 1 carried over from the previous tile of the band (staging columns 0 / 1)
-        const int scol = kCarry ? ((cc + 2) & 15) : cc;
-        const int srow = hh * kCols + scol;            // row of the 8 x kCols staging tile
-        const bool valid = kCarry || cc < 14;
-        const int prow = quarter * (kCols / 2) + (scol >> 1);   // row of the pooled staging tile (lanes with even cc, lane < 16)
-        const bool pool_lane = lane < kCols && (lane & 1) == 0;
-        const bool is14 = kCarry && cc == 14, is_carry_lane = kCarry && cc >= 14;
-        const int rot1 = (lane & 16) | ((lane + 1) & 15), rot2 = (lane & 16) | ((lane + 2) & 15);   // rotate inside the 16-lane row
-        const uint32_t carry_addr = smem_u32(carry_s + ((e * 4 + (lane >> 4) * 2 + (cc & 1)) * 16));
+        const int cc = lane & 15;                      // buffer column; output column w = cc is valid for cc < 14
+        const int srow = hh * 14 + cc;                 // row of the 8 x 14 staging tile
+        const bool valid = cc < 14;
+        const int prow = quarter * 7 + (cc >> 1);      // row of the 4 x 7 pooled staging tile (lanes with even cc, lane < 16)
+        const bool pool_lane = lane < 14 && (lane & 1) == 0;
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
         const bool relu_only = p.act == B2R_ACT_RELU;
         const float ns = act_neg_slope(p.act, p.slope);
@@ -489,11 +433,11 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                              : "=f"(b16[4 * i]), "=f"(b16[4 * i + 1]), "=f"(b16[4 * i + 2]), "=f"(b16[4 * i + 3])
                              : "r"(ba + 16 * i));
         }
-        Walk tw;
-        tw.init(item0, istride, p.tiles_w, p.tiles_h);
+        TileWalk tw;
+        tw.init(tile0, tstride, p.tiles_w, p.tiles_h);
         int iter = 0, sb = 0;
         uint32_t sph = 0;     // staging buffer index / phase parity (round-robin over p.stage_bufs buffers)
-        for (long it = 0; it < my_iters; ++it, ++iter, tw.next()) {
+        for (long unit = unit0; unit < total_units; unit += ustride, ++iter, tw.next(p.tiles_w, p.tiles_h)) {
             const uint32_t acc = uint32_t(iter) & 1u;
             mbar_wait_uniform(&tmem_full_bar[acc], (uint32_t(iter) >> 1) & 1u);
             tc_fence_after();
@@ -512,48 +456,14 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
             }
             if (etid == 0) B2R_STAMP(iter, 4);
             uint8_t* sfull_b = sfull + sb * p.stage_stride;
-            uint8_t* spool_b = sfull_b + kStaging;
-            // kCarry: a band's first tile has no carried outputs and is staged like a basic 14-column tile (see the store warp)
-            const bool first = kCarry && tw.tw() == 0;
-            const int srow_t = first ? hh * 14 + cc : srow;
-            const int prow_t = first ? quarter * 7 + (cc >> 1) : prow;
-            const bool valid_t = first ? cc < 14 : valid;
-            const bool pool_lane_t = first ? (lane < 14 && (lane & 1) == 0) : pool_lane;
+            uint8_t* spool_b = sfull_b + kW3Staging;
 #ifndef B2R_EXP_NO_STAGE
             float x[16];
-            if constexpr (kCarry) {
-                if (is_carry_lane) {   // P14 / P15 of the previous tile of this band (garbage at the band's first tile: clipped)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                     : "=f"(x[4 * i]), "=f"(x[4 * i + 1]), "=f"(x[4 * i + 2]), "=f"(x[4 * i + 3])
-                                     : "r"(carry_addr + 16 * i));
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float a1 = __shfl_sync(0xffffffffu, __uint_as_float(d1[j]), rot1);
-                    const float a2 = __shfl_sync(0xffffffffu, __uint_as_float(d2[j]), rot2);
-                    const float v0 = __uint_as_float(d0[j]);
-                    const float t = v0 + a1;                          // lanes 0..13: D0 + D1; lane 14: P14 of THIS tile
-                    const float base = is_carry_lane ? x[j] : v0;     // lane 14: P14 + D2'[0]; lane 15: (P15 + D1'[0]) + D2'[1]
-                    const float add1 = is14 ? -0.0f : a1;             // x + (-0) == x exactly
-                    d0[j] = __float_as_uint(is14 ? t : v0);           // carry out: lane 14 keeps D0 + D1, lane 15 keeps D0
-                    x[j] = ((base + add1) + a2) + b16[j];
-                }
-                if (is_carry_lane) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(carry_addr + 16 * i), "r"(d0[4 * i]),
-                                     "r"(d0[4 * i + 1]), "r"(d0[4 * i + 2]), "r"(d0[4 * i + 3])
-                                     : "memory");
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[j]), 1);
-                    const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[j]), 2);
-                    x[j] = ((__uint_as_float(d0[j]) + a1) + a2) + b16[j];
-                }
+            for (int j = 0; j < 16; ++j) {
+                const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[j]), 1);
+                const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[j]), 2);
+                x[j] = ((__uint_as_float(d0[j]) + a1) + a2) + b16[j];
             }
             if (relu_only) {
 #pragma unroll
@@ -591,15 +501,15 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                     // warp cq of the quarter finishes output channel o = cq for the quarter's 32 pixels: add the four partial
                     // sums (same order as before: bit-identical) + bias, then the reference's outputs
                     const int o = cq;
-                    const int w = kCarry ? tw.tw() * 16 - 2 + scol : tw.tw() * 14 + cc;
-                    const int h = tw.th() * 8 + hh;
-                    if (valid && w >= 0 && w < p.W && h < p.H && tw.n() < p.n_img) {   // w < 0: the carried lanes of a band's first tile
+                    const int w = tw.tw * 14 + cc;
+                    const int h = tw.th * 8 + hh;
+                    if (valid && w < p.W && h < p.H && tw.n < p.n_img) {
                         const float* pr = reinterpret_cast<const float*>(sfull_b) + quarter * 32 + lane;
                         const float v = ((pr[o * 128] + pr[(3 + o) * 128]) + (pr[(6 + o) * 128] + pr[(9 + o) * 128])) + head_s[192 + o];
                         const size_t hw = size_t(p.H) * p.W, pix = size_t(h) * p.W + w;
-                        if (p.head_f32) p.head_f32[(size_t(tw.n()) * 3 + o) * hw + pix] = v;
+                        if (p.head_f32) p.head_f32[(size_t(tw.n) * 3 + o) * hw + pix] = v;
                         if (p.head_u8)   // torch.clamp(x, 0, 1); (x * 255).astype(np.uint8): truncation (17:86-92)
-                            p.head_u8[(size_t(tw.n()) * hw + pix) * 3 + o] = static_cast<uint8_t>(fminf(fmaxf(v, 0.f), 1.f) * 255.0f);
+                            p.head_u8[(size_t(tw.n) * hw + pix) * 3 + o] = static_cast<uint8_t>(fminf(fmaxf(v, 0.f), 1.f) * 255.0f);
                     }
                 }
             } else {
@@ -608,11 +518,11 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
                 // the store of this buffer's previous tile (stage_bufs tiles ago) has been read
                 mbar_wait_uniform(&free_bar[sb], sph ^ 1u);
-                if (p.store_full && valid_t) {
+                if (p.store_full && valid) {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const int jj = cq * 2 + q;   // 16-byte chunk of the 128-byte staging row
-                        const uint32_t addr = smem_u32(sfull_b) + uint32_t(srow_t * 128 + ((jj ^ (srow_t & 7)) << 4));
+                        const uint32_t addr = smem_u32(sfull_b) + uint32_t(srow * 128 + ((jj ^ (srow & 7)) << 4));
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
                                      "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
                                      : "memory");
@@ -625,11 +535,11 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                         pk[j] = bf16x2_max(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
                         pk[j] = bf16x2_max(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 16));
                     }
-                    if (pool_lane_t) {
+                    if (pool_lane) {
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
                             const int jj = cq * 2 + q;
-                            const uint32_t addr = smem_u32(spool_b) + uint32_t(prow_t * 128 + ((jj ^ (prow_t & 7)) << 4));
+                            const uint32_t addr = smem_u32(spool_b) + uint32_t(prow * 128 + ((jj ^ (prow & 7)) << 4));
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
                                          "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
                                          : "memory");
@@ -639,8 +549,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 fence_proxy_async_smem();
             }
 #else
-            (void)valid_t; (void)srow_t; (void)relu_only; (void)ns; (void)b16; (void)d0; (void)d1; (void)d2; (void)spool_b; (void)sfull_b;
-            (void)prow_t; (void)pool_lane_t; (void)hh; (void)rot1; (void)rot2; (void)is14; (void)is_carry_lane; (void)carry_addr;
+            (void)valid; (void)srow; (void)relu_only; (void)ns; (void)b16; (void)d0; (void)d1; (void)d2; (void)spool_b; (void)sfull_b;
+            (void)prow; (void)pool_lane; (void)hh;
             if (!kHead) mbar_wait_uniform(&free_bar[sb], sph ^ 1u);
 #endif
             if (etid == 0) B2R_STAMP(iter, 5);
@@ -666,19 +576,12 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
     }
 }
 
-size_t conv_w3_smem_bytes(size_t b_bytes, int ring_slots, size_t stage_stride, int stage_bufs, bool carry) {
-    return 1024 + b_bytes + size_t(ring_slots) * kW3Slot + size_t(stage_bufs) * stage_stride + (carry ? 4096 : 0) + 256 + 800 + 768;
+size_t conv_w3_smem_bytes(size_t b_bytes, int ring_slots, size_t stage_stride, int stage_bufs) {
+    return 1024 + b_bytes + size_t(ring_slots) * kW3Slot + size_t(stage_bufs) * stage_stride + 256 + 800 + 768;
 }
 
-template <bool kHead, bool kPair, bool kCarry>
+template <bool kHead, bool kPair>
 static int launch_w3_variant(const ConvW3Params& p, int grid, size_t smem, cudaStream_t stream) {
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    B2R_CUDA(cudaGetDevice(&dev));
-    if (dev >= 64 || !attr_set[dev]) {
-        B2R_CUDA(cudaFuncSetAttribute((conv_w3_kernel<kHead, kPair, kCarry>), cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
-        if (dev < 64) attr_set[dev] = true;
-    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
@@ -692,30 +595,28 @@ static int launch_w3_variant(const ConvW3Params& p, int grid, size_t smem, cudaS
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B2R_CUDA(cudaLaunchKernelEx(&cfg, conv_w3_kernel<kHead, kPair, kCarry>, p));
+    B2R_CUDA(cudaLaunchKernelEx(&cfg, conv_w3_kernel<kHead, kPair>, p));
     return B2R_OK;
 }
 
 // grid = CTAs (pair mode: an even number, two per cluster)
-int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream, bool pair, bool carry) {
-    const size_t smem = conv_w3_smem_bytes(size_t(p.b_bytes), p.ring_slots, size_t(p.stage_stride), p.stage_bufs, carry);
-    const bool head = p.head_w != nullptr;
-    static const char* names[8] = {"conv_w3_kernel", "conv_w3_kernel<carry>", "conv_w3_kernel<pair>", "conv_w3_kernel<pair,carry>",
-                                   "conv_w3_kernel<head>", "conv_w3_kernel<head,carry>", "conv_w3_kernel<head,pair>",
-                                   "conv_w3_kernel<head,pair,carry>"};
-    const int v = (head ? 4 : 0) | (pair ? 2 : 0) | (carry ? 1 : 0);
-    note_conv_kernel(names[v]);
-    int rc;
-    switch (v) {
-        case 0: rc = launch_w3_variant<false, false, false>(p, grid, smem, stream); break;
-        case 1: rc = launch_w3_variant<false, false, true>(p, grid, smem, stream); break;
-        case 2: rc = launch_w3_variant<false, true, false>(p, grid, smem, stream); break;
-        case 3: rc = launch_w3_variant<false, true, true>(p, grid, smem, stream); break;
-        case 4: rc = launch_w3_variant<true, false, false>(p, grid, smem, stream); break;
-        case 5: rc = launch_w3_variant<true, false, true>(p, grid, smem, stream); break;
-        case 6: rc = launch_w3_variant<true, true, false>(p, grid, smem, stream); break;
-        default: rc = launch_w3_variant<true, true, true>(p, grid, smem, stream); break;
+int launch_conv_w3(const ConvW3Params& p, int grid, cudaStream_t stream, bool pair) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    B2R_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        B2R_CUDA(cudaFuncSetAttribute((conv_w3_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
+        B2R_CUDA(cudaFuncSetAttribute((conv_w3_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
+        B2R_CUDA(cudaFuncSetAttribute((conv_w3_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
+        B2R_CUDA(cudaFuncSetAttribute((conv_w3_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, kN64MaxSmem));
+        if (dev < 64) attr_set[dev] = true;
     }
+    const size_t smem = conv_w3_smem_bytes(size_t(p.b_bytes), p.ring_slots, size_t(p.stage_stride), p.stage_bufs);
+    const bool head = p.head_w != nullptr;
+    note_conv_kernel(head ? (pair ? "conv_w3_kernel<head,pair>" : "conv_w3_kernel<head>") : (pair ? "conv_w3_kernel<pair>" : "conv_w3_kernel"));
+    int rc;
+    if (head) rc = pair ? launch_w3_variant<true, true>(p, grid, smem, stream) : launch_w3_variant<true, false>(p, grid, smem, stream);
+    else rc = pair ? launch_w3_variant<false, true>(p, grid, smem, stream) : launch_w3_variant<false, false>(p, grid, smem, stream);
     if (rc) return rc;
     B2R_CHECK_LAUNCH();
     return B2R_OK;

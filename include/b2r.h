@@ -142,7 +142,6 @@ int b2r_conv3x3_c3(const void* in, int in_fmt, const float* mean_host, const flo
 #define B2R_CONV_GENERIC_ONLY 1
 #define B2R_CONV_NO_W3 2 /* skip the tap-folded kernel (csrc/conv_w3.cu) even if weights_w3 is given */
 #define B2R_CONV_NO_PAIR 8 /* C_out % 256 == 0 layers: one CTA per tile instead of cta_group::2 CTA pairs (A/B parity test) */
-#define B2R_CONV_NO_CARRY 16 /* tap-folded kernel: 14-column tiles that recompute their two border columns instead of 16-column tiles that carry them (A/B parity test) */
 #define B2R_CONV_NO_HALO 4 /* generic kernel: one box per tap instead of the (TH + 2)-row halo boxes (A/B parity test) */
 
 /* k-block encoding: bits [0,2) source index, [2,4) dh+1, [4,6) dw+1, [8,24) first channel / 64 */

@@ -586,61 +586,3 @@ def test_conv_w3_pair_mode_equals_single_cta_mode():
         assert torch.equal(res[0][0], res[1][0]), (ci_, n, h, w, splits, sc, kernels)
         if pool or head:
             assert torch.equal(res[0][1], res[1][1]), (ci_, "second output")
-
-
-@pytest.mark.parametrize("n,h,w,splits,sc,pool,head", [
-    (40, 64, 224, (64,), (), False, False),          # 15 instead of 16 tiles per band
-    (38, 64, 224, (64,), (64,), True, False),        # pooled + centre group; 304 bands
-    (75, 32, 128, (64, 64), (), False, False),       # two sources; 9 instead of 10 tiles; odd band count (300)
-    (101, 24, 60, (64,), (), True, False),           # 4 instead of 5 tiles, ragged right edge (60 = 3 * 16 + 12), odd band count
-    (40, 64, 224, (64,), (64, 64), False, True),     # fused head (plain stores: the carried columns of a band's first tile are skipped)
-    (150, 16, 30, (128,), (), False, False),         # 2 instead of 3 tiles
-])
-def test_conv_w3_carry_mode_equals_basic_tiles(n, h, w, splits, sc, pool, head):
-    """Round 2: 16-column tiles that CARRY their two unfinished border outputs to the next tile of the band (conv_w3_kernel<..., carry>)
-    instead of 14-column tiles that recompute them.  Same additions in the same order: bit-identical to the basic tiling
-    (B2R_CONV_NO_CARRY), in pair and single-CTA mode, with pooled and head outputs; nothing outside the tensors is touched
-    (a band's first tile stores to columns -2, -1, its last tile beyond W: TMA must clip both)."""
-    ops, packing, L = _ops()
-    srcs = [nhwc_bf16(rnd(n, c, h, w, seed=2100 + i)) for i, c in enumerate(splits)]
-    ci = sum(splits)
-    wt = rnd(64, ci, 3, 3, scale=(2.0 / (9 * ci)) ** 0.5, seed=2110)
-    plan = packing.KPlan(64)
-    off = 0
-    for s, c in enumerate(splits):
-        plan.add_conv3x3(s, wt[:, off:off + c])
-        off += c
-    for c in sc:
-        srcs.append(nhwc_bf16(rnd(n, c, h, w, seed=2120 + len(srcs))))
-        plan.add_1x1(len(srcs) - 1, rnd(64, c, 1, 1, scale=(1.0 / c) ** 0.5, seed=2130 + len(srcs)))
-    b = rnd(64, scale=0.1, seed=2140)
-    wm, kbl = plan.finish()
-    wm, w3 = wm.cuda(), plan.finish_w3().cuda()
-    hw_ = rnd(3, 64, scale=0.1, seed=2150).contiguous() if head else None
-    hb_ = rnd(3, scale=0.1, seed=2151) if head else None
-    res, kernels = [], []
-    for flags in (0, L.B2R_CONV_NO_CARRY, L.B2R_CONV_NO_PAIR, L.B2R_CONV_NO_PAIR | L.B2R_CONV_NO_CARRY):
-        out_g = torch.full((n + 2, h, w, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
-        pl_g = torch.full((n + 2, h // 2, w // 2, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
-        h32 = torch.full((n + 2, 3, h, w), float("nan"), device="cuda") if head else None
-        ops.conv_gemm(srcs, wm, b, kbl, act=L.B2R_ACT_PRELU, slope=0.25, out=None if head else out_g[1:n + 1],
-                      out_pool=pl_g[1:n + 1] if pool else None, weights_w3=w3, flags=flags, head_w=hw_, head_b=hb_,
-                      head_out_f32=None if h32 is None else h32[1:n + 1])
-        kernels.append(L.load().b2r_last_conv_kernel().decode())
-        torch.cuda.synchronize()
-        assert bool(torch.isnan(out_g[0]).all()) and bool(torch.isnan(out_g[n + 1]).all()), (kernels[-1], "OOB store")
-        assert bool(torch.isnan(pl_g[0]).all()) and bool(torch.isnan(pl_g[n + 1]).all()), (kernels[-1], "OOB pool store")
-        if head:
-            assert bool(torch.isnan(h32[0]).all()) and bool(torch.isnan(h32[n + 1]).all())
-            assert not bool(torch.isnan(h32[1:n + 1]).any()), (kernels[-1], "unwritten head output")
-            res.append((h32[1:n + 1].clone(), None))
-        else:
-            assert not bool(torch.isnan(out_g[1:n + 1]).any()), (kernels[-1], "unwritten output")
-            if pool:
-                assert not bool(torch.isnan(pl_g[1:n + 1]).any()), (kernels[-1], "unwritten pooled output")
-            res.append((out_g[1:n + 1].clone(), pl_g[1:n + 1].clone()))
-    assert "carry" in kernels[0] and "carry" not in kernels[1] and "carry" in kernels[2] and "pair" not in kernels[2], kernels
-    for k in (1, 2, 3):
-        assert torch.equal(res[0][0], res[k][0]), (kernels[0], kernels[k])
-        if pool:
-            assert torch.equal(res[0][1], res[k][1]), (kernels[0], kernels[k], "pool")
