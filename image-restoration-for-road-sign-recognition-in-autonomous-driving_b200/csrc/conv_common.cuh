@@ -131,9 +131,19 @@ __device__ __forceinline__ void lds_bias32(const float* bias_smem, float (&b)[32
                      : "r"(a + 16 * i));
 }
 
-__device__ __forceinline__ void epilogue_store_half(const uint32_t (&v)[32], const float (&bias32)[32], int act,
-                                                    float slope, uint8_t* sfull, int row, int half) {
-    const float ns = act_neg_slope(act, slope);
+// Activation forms, chosen once per launch (warp-uniform).  PReLU with 0 <= slope <= 1 (every trained slope we have seen; nn.PReLU
+// starts at 0.25) is max(x, slope * x): two ops instead of three and the same single rounding of slope * x as the general form;
+// no activation is a plain pack.  (Only an exact -0 accumulator can differ from the general form, as +0 vs -0.)
+enum : int { kActNone = 0, kActRelu = 1, kActPrelu01 = 2, kActGeneral = 3 };
+__device__ __forceinline__ int act_form(int act, float slope) {
+    if (act == B2R_ACT_RELU) return kActRelu;
+    if (act == B2R_ACT_PRELU) return (slope >= 0.f && slope <= 1.f) ? kActPrelu01 : kActGeneral;
+    return kActNone;
+}
+
+template <int FORM>
+__device__ __forceinline__ void epilogue_store_half_form(const uint32_t (&v)[32], const float (&bias32)[32], float ns,
+                                                         uint8_t* sfull, int row, int half) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint32_t o[4];
@@ -141,8 +151,12 @@ __device__ __forceinline__ void epilogue_store_half(const uint32_t (&v)[32], con
         for (int e = 0; e < 4; ++e) {
             const int j = q * 8 + e * 2;
             const float y0 = __uint_as_float(v[j]) + bias32[j], y1 = __uint_as_float(v[j + 1]) + bias32[j + 1];
-            if (act == B2R_ACT_RELU)   // warp-uniform; rounding is monotonic and max(+0, -0) = +0, so this is
+            if (FORM == kActRelu)           // rounding is monotonic and max(+0, -0) = +0, so this is
                 o[e] = bf16x2_max(pack_bf16x2(y0, y1), 0u);   // bit-identical to rounding max(y, 0)
+            else if (FORM == kActNone)
+                o[e] = pack_bf16x2(y0, y1);
+            else if (FORM == kActPrelu01)
+                o[e] = pack_bf16x2(fmaxf(y0, ns * y0), fmaxf(y1, ns * y1));
             else
                 o[e] = pack_bf16x2(apply_act_ns(y0, ns), apply_act_ns(y1, ns));
         }
@@ -150,6 +164,17 @@ __device__ __forceinline__ void epilogue_store_half(const uint32_t (&v)[32], con
         const uint32_t addr = smem_u32(sfull) + uint32_t(row * 128 + ((jj ^ (row & 7)) << 4));
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
                      : "memory");
+    }
+}
+
+__device__ __forceinline__ void epilogue_store_half(const uint32_t (&v)[32], const float (&bias32)[32], int act,
+                                                    float slope, uint8_t* sfull, int row, int half) {
+    const float ns = act_neg_slope(act, slope);
+    switch (act_form(act, slope)) {   // warp-uniform
+        case kActRelu: epilogue_store_half_form<kActRelu>(v, bias32, ns, sfull, row, half); break;
+        case kActNone: epilogue_store_half_form<kActNone>(v, bias32, ns, sfull, row, half); break;
+        case kActPrelu01: epilogue_store_half_form<kActPrelu01>(v, bias32, ns, sfull, row, half); break;
+        default: epilogue_store_half_form<kActGeneral>(v, bias32, ns, sfull, row, half); break;
     }
 }
 

@@ -57,7 +57,7 @@ struct alignas(64) ConvGemmParams {
     uint32_t slot[kN64MaxSlots];
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kDeep = false>
 struct GemmCfg {
     static constexpr int kBStageBytes = BLOCK_N * 128;
     static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
@@ -67,8 +67,21 @@ struct GemmCfg {
     static constexpr int kStages = BLOCK_N == 64 ? 6 : (BLOCK_N == 128 ? 2 : 3);
     static constexpr int kCtasPerSm = BLOCK_N == 128 ? 2 : 1;
     static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: powers of two
-    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * (kStagingFull + kStagingPool) +
-                                      BLOCK_N * 4 /*bias*/ + 256 /*barriers + tmem ptr*/;
+    // Two epilogue warpgroups (warps 2..5 and 6..9) take alternate 64-column chunks of a tile, each with its own staging
+    // buffer(s), bias copy, named barrier and TMA-store queue.  A lone warp per scheduler cannot hide tcgen05.ld / LDS / STS
+    // latency, and with short K (ConvTranspose as four 1x1 taps: ONE k-block per 128 x 256 tile) nothing else hides the
+    // epilogue either: measured on up1 (64 -> 4 x 64 @112, 256 images) epilogue maths alone 413 us, stores alone 374 us,
+    // together 532 us with one group (profiles/r02_convt_epilogue.md).
+    // kDeep (short-K layers without a fused pool, i.e. the ConvTranspose layers): the pooled staging is dropped and each
+    // group gets TWO 16 KB buffers, so a group converts its next chunk while the store of the previous one drains.
+    static constexpr int kEpiGroups = BLOCK_N >= 128 ? 2 : 1;
+    static constexpr int kGroupBufs = kDeep ? 2 : 1;
+    static constexpr int kBufStride = kDeep ? kStagingFull : kStagingFull + kStagingPool;
+    static constexpr int kStagingBytes = kDeep ? 4 * kStagingFull : 2 * (kStagingFull + kStagingPool);
+    static constexpr int kThreads = 64 + 128 * kEpiGroups;
+    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes +
+                                      kEpiGroups * BLOCK_N * 4 /*bias*/ + 256 /*barriers + tmem ptr*/;
+    static_assert(!kDeep || kEpiGroups == 2, "deep staging is for the two-group epilogue");
 };
 
 // Which tiles a CTA's epilogue walks, and where it hands the accumulator stage back.
@@ -97,14 +110,26 @@ struct SchedPair {     // cta_group::2: a cluster walks PAIRS of pixel tiles, ra
 // Epilogue role shared by the generic, halo and pair kernels: warps 2..5, TMEM -> registers -> bias / activation -> bf16
 // -> swizzled staging -> TMA store (+ fused 2x2 max-pool).  BUFS = number of (staging + pool) buffers; `total_units` =
 // tiles (SchedSingle) or tile pairs (SchedPair).
-template <int BLOCK_N, int BUFS, class Sched = SchedSingle>
+// Named barrier of one epilogue group's 128 threads: ids 1 / 2 as immediates (a register id makes ptxas reserve all 16).
+template <int GROUPS>
+__device__ __forceinline__ void group_barrier(int grp) {
+    if (GROUPS == 1 || grp == 0) named_barrier_sync(1, kEpiThreads);
+    else named_barrier_sync(2, kEpiThreads);
+}
+
+template <int BLOCK_N, int BUFS, class Sched = SchedSingle, int GROUPS = 1, int GBUFS = 1, int BUF_STRIDE = kStagingFull + kStagingPool>
 __device__ __forceinline__ void conv_epilogue_role(const ConvGemmParams& p, uint32_t tmem_base, uint8_t* staging, float* bias_s,
                                                    uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, int total_units,
                                                    int warp_idx, int lane) {
+        static_assert(GROUPS == 1 || (GROUPS == 2 && BUFS == 2), "two epilogue groups own one staging buffer each");
+        constexpr int kChunks = BLOCK_N / 64;
+        const int grp = GROUPS == 2 ? ((warp_idx - 2) >> 2) : 0;   // warps 2..5 / 6..9
         const int quarter = warp_idx & 3;          // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;       // tile row (pixel) == TMEM lane
-        const int epi_tid = row;                   // 0..127
+        const int epi_tid = row;                   // 0..127 inside the group
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+        if (GROUPS == 2) bias_s += grp * BLOCK_N;  // private copy: no cross-group hazard when the groups are a tile apart
+        const bool idle = grp >= kChunks;          // (never true for the instantiations in use)
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t chunk_counter = 0;
@@ -116,10 +141,10 @@ __device__ __forceinline__ void conv_epilogue_role(const ConvGemmParams& p, uint
             const int w0 = (m % p.tiles_w) * p.tile_w;
             const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.tile_h;
             const int n0 = (m / (p.tiles_w * p.tiles_h)) * p.tile_n;
-            // first channel of this n-tile inside its output map (CONVT2X2: an n-tile may span several of the four
-            // maps, e.g. C_out = 64 with BLOCK_N = 256 covers all four taps in one tile)
-            int out_idx = (n_tile * BLOCK_N) / p.cout_per_out;
-            int ch_in_out = n_tile * BLOCK_N - out_idx * p.cout_per_out;
+            // first channel of this group's first chunk inside its output map (CONVT2X2: an n-tile may span several of
+            // the four maps, e.g. C_out = 64 with BLOCK_N = 256 covers all four taps in one tile)
+            int out_idx = (n_tile * BLOCK_N + grp * 64) / p.cout_per_out;
+            int ch_in_out = n_tile * BLOCK_N + grp * 64 - out_idx * p.cout_per_out;
 
             // bias of this n-tile -> smem (previous tile's readers are past their last named barrier)
             for (int i = epi_tid; i < BLOCK_N; i += kEpiThreads) bias_s[i] = p.bias[n_tile * BLOCK_N + i];
@@ -128,16 +153,19 @@ __device__ __forceinline__ void conv_epilogue_role(const ConvGemmParams& p, uint
             tc_fence_after();
 
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 64; ++c) {
-                const int buf = BUFS == 2 ? int(chunk_counter & 1) : 0;
+            for (int c = grp; c < kChunks; c += GROUPS) {
+                const int buf = GROUPS == 2 ? grp * GBUFS + (GBUFS == 2 ? int(chunk_counter & 1) : 0)
+                                            : (BUFS == 2 ? int(chunk_counter & 1) : 0);
                 ++chunk_counter;
-                uint8_t* sfull = staging + buf * (kStagingFull + kStagingPool);
-                uint8_t* spool = sfull + kStagingFull;
-                if (epi_tid == 0) {   // the store that last read `buf` has drained
-                    if (BUFS == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                uint8_t* sfull = staging + buf * BUF_STRIDE;
+                uint8_t* spool = sfull + kStagingFull;   // (unused when the stride leaves no pooled staging: store_pool == 0)
+                if (epi_tid == 0) {   // the store that last read `buf` has drained (bulk groups are per issuing thread)
+                    if ((GROUPS == 1 && BUFS == 2) || (GROUPS == 2 && GBUFS == 2)) tma_store_wait_read<1>();
+                    else tma_store_wait_read<0>();
                 }
-                named_barrier_sync(1, kEpiThreads);
+                group_barrier<GROUPS>(grp);
 
+#if !defined(B2R_EXP_EPI_NO_MATH)   // experiment builds only (tools/exp/README.md): what bounds a short-K layer's epilogue?
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t v[32];
@@ -147,31 +175,39 @@ __device__ __forceinline__ void conv_epilogue_role(const ConvGemmParams& p, uint
                     lds_bias32(bias_s + c * 64 + half * 32, b32);
                     epilogue_store_half(v, b32, p.act, p.slope, sfull, row, half);
                 }
-                if (c == BLOCK_N / 64 - 1) {
+#endif
+                if (c + GROUPS >= kChunks) {
                     // all of this warp's TMEM reads of the accumulator are done -> hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) Sched::release(&tmem_empty_bar[acc]);
                 }
                 fence_proxy_async_smem();
-                named_barrier_sync(1, kEpiThreads);
+                group_barrier<GROUPS>(grp);
 
                 if (p.store_pool) {
                     epilogue_pool_chunk(sfull, spool, epi_tid, tw, th);
                     fence_proxy_async_smem();
-                    named_barrier_sync(1, kEpiThreads);
+                    group_barrier<GROUPS>(grp);
                 }
 
                 if (epi_tid == 0 && valid_tile) {
+#if !defined(B2R_EXP_EPI_NO_STORE)
                     if (p.store_full) tma_store_4d(&p.out_map[out_idx], sfull, ch_in_out, w0, h0, n0);
                     if (p.store_pool) tma_store_4d(&p.pool_map, spool, ch_in_out, w0 >> 1, h0 >> 1, n0);
+#endif
                     tma_store_commit();
                 }
-                ch_in_out += 64;
-                if (ch_in_out >= p.cout_per_out) {
-                    ch_in_out = 0;
+                ch_in_out += 64 * GROUPS;
+                while (ch_in_out >= p.cout_per_out) {
+                    ch_in_out -= p.cout_per_out;
                     ++out_idx;
                 }
+            }
+            if (idle) {   // a group without a chunk still owes its share of the accumulator hand-back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) Sched::release(&tmem_empty_bar[acc]);
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -179,9 +215,9 @@ __device__ __forceinline__ void conv_epilogue_role(const ConvGemmParams& p, uint
         if (epi_tid == 0) tma_store_wait_all<0>();
     }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kNumThreads, GemmCfg<BLOCK_N>::kCtasPerSm) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-    using Cfg = GemmCfg<BLOCK_N>;
+template <int BLOCK_N, bool kDeep = false>
+__global__ void __launch_bounds__(GemmCfg<BLOCK_N>::kThreads, GemmCfg<BLOCK_N>::kCtasPerSm) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N, kDeep>;
     constexpr int kStages = Cfg::kStages;
     constexpr uint32_t kIdesc = make_idesc_bf16_f32(kBlockM, BLOCK_N);
 
@@ -189,8 +225,8 @@ __global__ void __launch_bounds__(kNumThreads, GemmCfg<BLOCK_N>::kCtasPerSm) con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stages = smem;
     uint8_t* staging = smem + kStages * Cfg::kStageBytes;
-    float* bias_s = reinterpret_cast<float*>(staging + 2 * (kStagingFull + kStagingPool));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + BLOCK_N);
+    float* bias_s = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + Cfg::kEpiGroups * BLOCK_N);
     uint64_t* full_bar = bars;                       // [kStages]
     uint64_t* empty_bar = bars + kStages;            // [kStages]
     uint64_t* tmem_full_bar = bars + 2 * kStages;    // [2]
@@ -217,7 +253,7 @@ __global__ void __launch_bounds__(kNumThreads, GemmCfg<BLOCK_N>::kCtasPerSm) con
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
-                mbar_init(&tmem_empty_bar[s], 4);
+                mbar_init(&tmem_empty_bar[s], 4 * Cfg::kEpiGroups);
             }
             fence_mbar_init();
         }
@@ -305,7 +341,8 @@ __global__ void __launch_bounds__(kNumThreads, GemmCfg<BLOCK_N>::kCtasPerSm) con
         }
     } else {
         // ===================================== epilogue =====================================
-        conv_epilogue_role<BLOCK_N, 2>(p, tmem_base, staging, bias_s, tmem_full_bar, tmem_empty_bar, total_tiles, warp_idx, lane);
+        conv_epilogue_role<BLOCK_N, 2, SchedSingle, Cfg::kEpiGroups, Cfg::kGroupBufs, Cfg::kBufStride>(
+            p, tmem_base, staging, bias_s, tmem_full_bar, tmem_empty_bar, total_tiles, warp_idx, lane);
     }
 
     tc_fence_before();
@@ -513,11 +550,19 @@ struct PairCfg {
     static constexpr int kBufs = kPairN == 256 ? B2R_PAIR_BUFS : 1;
     static constexpr int kCtasPerSm = kPairN == 256 ? 1 : 2;
     static constexpr int kStageBytes = kAStageBytes + (kPairN / 2) * 128;   // 16 KB of A + half a weight k-block per CTA
-    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBufs * (kStagingFull + kStagingPool) + kPairN * 4 + 256;
+#ifndef B2R_PAIR_GROUPS
+#define B2R_PAIR_GROUPS 1
+#endif
+    // two epilogue warpgroups on alternate 64-column chunks (see GemmCfg): measured 1-1.5 % SLOWER on every pair layer
+    // (conv3_1 337 -> 342 us, conv4_2 621 -> 624 us at 256 images): with K >= 1152 the epilogue is already hidden and the
+    // extra warps only take issue slots.  Kept as a variant-build knob (--define B2R_PAIR_GROUPS=2).
+    static constexpr int kEpiGroups = (kPairN == 256 && kBufs == 2) ? B2R_PAIR_GROUPS : 1;
+    static constexpr int kThreads = 64 + 128 * kEpiGroups;
+    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBufs * (kStagingFull + kStagingPool) + kEpiGroups * kPairN * 4 + 256;
 };
 
 template <int kPairN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, PairCfg<kPairN>::kCtasPerSm)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<kPairN>::kThreads, PairCfg<kPairN>::kCtasPerSm)
 conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
     constexpr int kPairStages = PairCfg<kPairN>::kStages;
     constexpr int kPairStageBytes = PairCfg<kPairN>::kStageBytes;
@@ -528,7 +573,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
     constexpr int kBufs = PairCfg<kPairN>::kBufs;
     uint8_t* staging = smem + kPairStages * kPairStageBytes;
     float* bias_s = reinterpret_cast<float*>(staging + kBufs * (kStagingFull + kStagingPool));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + kPairN);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + PairCfg<kPairN>::kEpiGroups * kPairN);
     uint64_t* full_bar = bars;                            // [stages]  used in the leader only
     uint64_t* empty_bar = bars + kPairStages;             // [stages]  one multicast commit per phase, in each CTA
     uint64_t* tmem_full_bar = bars + 2 * kPairStages;     // [2]       one multicast commit per phase, in each CTA
@@ -558,7 +603,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
-                mbar_init(&tmem_empty_bar[s], 8);
+                mbar_init(&tmem_empty_bar[s], 8 * PairCfg<kPairN>::kEpiGroups);
             }
             fence_mbar_init();
         }
@@ -639,8 +684,8 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
         }
     } else {
         // ===================================== epilogue (both CTAs, own tile) =====================================
-        conv_epilogue_role<kPairN, kBufs, SchedPair>(p, tmem_base, staging, bias_s, tmem_full_bar, tmem_empty_bar, total_pairs,
-                                                     warp_idx, lane);
+        conv_epilogue_role<kPairN, kBufs, SchedPair, PairCfg<kPairN>::kEpiGroups>(p, tmem_base, staging, bias_s, tmem_full_bar,
+                                                                                  tmem_empty_bar, total_pairs, warp_idx, lane);
     }
 
     tc_fence_before();
@@ -1175,19 +1220,20 @@ static int try_conv_w3(const b2r_conv_gemm_desc* d, cudaStream_t stream, bool* h
     return B2R_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kDeep = false>
 static int launch(const ConvGemmParams& p, int grid, cudaStream_t stream) {
-    using Cfg = GemmCfg<BLOCK_N>;
+    using Cfg = GemmCfg<BLOCK_N, kDeep>;
     static bool attr_set[64] = {false};
     int dev = 0;
     B2R_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        B2R_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B2R_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::kSmemBytes));
         if (dev < 64) attr_set[dev] = true;
     }
-    note_conv_kernel(BLOCK_N == 64 ? "conv_gemm_kernel<64>" : BLOCK_N == 128 ? "conv_gemm_kernel<128>" : "conv_gemm_kernel<256>");
-    conv_gemm_kernel<BLOCK_N><<<grid * Cfg::kCtasPerSm, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
+    note_conv_kernel(BLOCK_N == 64 ? "conv_gemm_kernel<64>" : BLOCK_N == 128 ? "conv_gemm_kernel<128>"
+                     : kDeep ? "conv_gemm_kernel<256,deep>" : "conv_gemm_kernel<256>");
+    conv_gemm_kernel<BLOCK_N, kDeep><<<grid * Cfg::kCtasPerSm, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(p);
     B2R_CHECK_LAUNCH();
     return B2R_OK;
 }
@@ -1203,7 +1249,7 @@ static int launch_pair(const ConvGemmParams& p, int clusters, cudaStream_t strea
         if (dev < 64) attr_set[dev] = true;
     }
     note_conv_kernel(N == 256 ? "conv_gemm_pair_kernel<256>" : "conv_gemm_pair_kernel<128>");
-    conv_gemm_pair_kernel<N><<<(unsigned)(2 * clusters), kNumThreads, PairCfg<N>::kSmemBytes, stream>>>(p);
+    conv_gemm_pair_kernel<N><<<(unsigned)(2 * clusters), PairCfg<N>::kThreads, PairCfg<N>::kSmemBytes, stream>>>(p);
     B2R_CHECK_LAUNCH();
     return B2R_OK;
 }
@@ -1539,6 +1585,11 @@ extern "C" int b2r_conv_gemm(const b2r_conv_gemm_desc* d, void* stream_v) {
     switch (block_n) {
         case 64: return launch<64>(P, grid, stream);
         case 128: return launch<128>(P, grid, stream);
-        default: return launch<256>(P, grid, stream);
+        default: {
+            // short K without a fused pool (the ConvTranspose layers): the epilogue is all there is to hide
+            static const bool no_deep_env = getenv("B2R_NO_DEEP_EPI") != nullptr;   // A/B switch, read once
+            if (!d->out_pool && d->num_kblocks <= 8 && !no_deep_env) return launch<256, true>(P, grid, stream);
+            return launch<256>(P, grid, stream);
+        }
     }
 }

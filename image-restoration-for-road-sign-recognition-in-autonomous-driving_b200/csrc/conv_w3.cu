@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
         const int prow = quarter * 7 + (cc >> 1);      // row of the 4 x 7 pooled staging tile (lanes with even cc, lane < 16)
         const bool pool_lane = lane < 14 && (lane & 1) == 0;
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-        const bool relu_only = p.act == B2R_ACT_RELU;
+        const int form = act_form(p.act, p.slope);
         const float ns = act_neg_slope(p.act, p.slope);
         float b16[16];
         {
@@ -465,10 +465,13 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[j]), 2);
                 x[j] = ((__uint_as_float(d0[j]) + a1) + a2) + b16[j];
             }
-            if (relu_only) {
+            if (form == kActRelu) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
-            } else {
+            } else if (form == kActPrelu01) {   // max(x, slope x): see act_form()
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], ns * x[j]);
+            } else if (form == kActGeneral) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) x[j] = apply_act_ns(x[j], ns);
             }
@@ -549,7 +552,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv_w3_kernel(const __grid_con
                 fence_proxy_async_smem();
             }
 #else
-            (void)valid; (void)srow; (void)relu_only; (void)ns; (void)b16; (void)d0; (void)d1; (void)d2; (void)spool_b; (void)sfull_b;
+            (void)valid; (void)srow; (void)form; (void)ns; (void)b16; (void)d0; (void)d1; (void)d2; (void)spool_b; (void)sfull_b;
             (void)prow; (void)pool_lane; (void)hh;
             if (!kHead) mbar_wait_uniform(&free_bar[sb], sph ^ 1u);
 #endif

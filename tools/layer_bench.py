@@ -38,6 +38,7 @@ LAYERS = [
     ("vgg.conv4_2      512->512 @28", 28, (512,), 512, "3x3", False),
     ("vgg.conv5_1      512->512 @14", 14, (512,), 512, "3x3", False),
     ("resunet.up3      256->128 convT@28", 28, (256,), 128, "convT", False),
+    ("resunet.up2      128->64  convT@56", 56, (128,), 64, "convT", False),
 ]
 
 
@@ -131,7 +132,7 @@ def main():
         flops = 2.0 * n * hw * hw * wm.shape[0] * alg_k
 
         def run():
-            ops.conv_gemm(srcs, wm, bias, kbl, act=L.B2R_ACT_RELU, out=None if head else out, out_pool=pool, out_mode=mode,
+            ops.conv_gemm(srcs, wm, bias, kbl, act=L.B2R_ACT_NONE if kind == "convT" else L.B2R_ACT_RELU, out=None if head else out, out_pool=pool, out_mode=mode,
                           weights_w3=w3, **head,
                           block_n=args.block_n if args.block_n and co % args.block_n == 0 else 0,
                           tile=tuple(int(v) for v in args.tile.split(",")) if args.tile else (0, 0, 0), flags=args.flags)
