@@ -608,8 +608,10 @@ int run_resunet(const b2r_net* n, Runner& R, Workspace& ws, const void* in, int 
 
 int run_vgg16(const b2r_net* n, Runner& R, Workspace& ws, const void* in, int in_fmt, bool normalize, float* logits, int N, int H, int W) {
     // conv1_1 (HBM-write-bound) and conv1_2 (tensor-bound, pooled output only) alternate over sub-batches of 32 images so that
-    // conv1_1's write-back drains from L2 while conv1_2 computes (models.VGG16Judge.first_stage_sub; same bytes either way)
-    constexpr int kSub = 32;
+    // conv1_1's write-back drains from L2 while conv1_2 computes (models.VGG16Judge.first_stage_sub; same bytes either way);
+    // other sizes take the same number of pixels per launch
+    const long sub_px = 32L * 224 * 224 / (long(H) * W);
+    const int kSub = sub_px < 1 ? 1 : int(sub_px);
     const bool alternate = N >= 2 * kSub && !n->vgg.empty() && n->vgg[0].pooled;
     void* cur = ws.bf16(alternate ? kSub : N, H, W, 64);
     int h = H, w = W, c = 64;

@@ -418,7 +418,12 @@ class VGG16Judge(_B200Module):
     forward_u8(x): x = u8 NHWC, ToTensor + Normalize fused into the first conv.  H, W multiples of 32.
     """
 
-    first_stage_sub: int = 32   # images per launch pair of the first two layers (0 = whole micro-batch per launch)
+    # images per launch pair of the first two layers AT 224 x 224 (0 = whole micro-batch per launch); other sizes use the
+    # same number of PIXELS per launch (64 x 64: 392 images), so that small maps do not pay a launch per 8 tiles per SM
+    first_stage_sub: int = 32
+
+    def _first_stage_sub(self, H: int, W: int) -> int:
+        return max(1, self.first_stage_sub * 224 * 224 // (H * W)) if self.first_stage_sub > 0 else 0
 
     def __init__(self, num_classes: int = 43):
         super().__init__()
@@ -477,7 +482,7 @@ class VGG16Judge(_B200Module):
         idx = self._conv_indices()
         tap = stop_at is not None
         first_i = idx[0][0]
-        sub = self.first_stage_sub
+        sub = self._first_stage_sub(H, W)
         fused_first = (not tap) and sub > 0 and n >= 2 * sub and P["convs"][0][1]
         if fused_first:
             # conv1_1 (HBM-write-bound: 128 B out per 3 B in) and conv1_2 (tensor-bound, writes only the pooled quarter)

@@ -29,10 +29,10 @@ def test_restorer_plan_equals_module(arch, hw):
     plan.close()
 
 
-@pytest.mark.parametrize("hw,n", [((224, 224), 5), ((64, 64), 5), ((64, 64), 70)])
+@pytest.mark.parametrize("hw,n", [((224, 224), 5), ((64, 64), 5), ((224, 224), 70), ((64, 64), 800)])
 def test_vgg_plan_equals_module(hw, n):
-    """n = 70 takes the path that alternates conv1_1 / conv1_2 over sub-batches of 32 images (both hosts), which must also equal
-    the whole-batch launches bit for bit (first_stage_sub = 0)."""
+    """n = 70 at 224 x 224 and n = 800 at 64 x 64 take the path that alternates conv1_1 / conv1_2 over sub-batches of 32 x 224^2
+    pixels (32 / 392 images; both hosts), which must also equal the whole-batch launches bit for bit (first_stage_sub = 0)."""
     from b200restore import NetPlan, models, synth
     sd = synth.synthetic_state_dict("vgg16", 32)
     j = models.VGG16Judge()
