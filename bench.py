@@ -822,6 +822,12 @@ def degrade_roofline(torch, D, dev_imgs, hw):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE line, the JSON record: anything a library writes to file descriptor 1 (NCCL prints its version
+    # banner there on rank 0) is sent to stderr; Python-level print() keeps the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:

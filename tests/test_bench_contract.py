@@ -13,6 +13,7 @@ def test_reference_arm_prints_one_contract_line():
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
+    assert [l for l in r.stdout.splitlines() if l.strip()] == lines, "stdout must carry the JSON line and nothing else"
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "images/sec restore->VGG16 classify" and d["unit"] == "images/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
