@@ -204,12 +204,20 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
             ti.next(p.tiles_w, p.tiles_h);
             if (next < total_tiles) gather();   // these loads complete while the row is built
             named_barrier_sync(2 + group, 128);
+#if defined(B2R_EXP_C3_HALF_TAPS)
+            uint32_t wrd[32] = {0u};
+#else
             uint32_t wrd[32];
+#endif
             const uint32_t px_addr = hb + uint32_t((ph * kC3HaloRS + pw * 3) * 4);
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
+#if defined(B2R_EXP_C3_HALF_TAPS)   // experiment: half of the tap reads (as if two bf16 values came per word).  Timing only.
+                for (int i = 0; i < 5; ++i)
+#else
                 for (int i = 0; i < 9; ++i)   // i = kw * 3 + c: nine consecutive words of halo row ph + kh
+#endif
                     asm volatile("ld.shared.b32 %0, [%1];"
                                  : "=r"(wrd[kh * 9 + i])
                                  : "r"(px_addr + uint32_t((kh * kC3HaloRS + i) * 4)));
@@ -221,8 +229,13 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
             mbar_wait_warp(&empty_bar[stage], phase ^ 1);
             if (r == 0) C3_STAMP(it, 1);
             const uint32_t row_addr = smem_u32(a_st + stage * 16384) + uint32_t(r * 128);
+#if defined(B2R_EXP_C3_HALF_ROW)   // experiment builds only (tools/exp/README.md): what would a 64-byte A row (K = 32) buy?  Timing only.
+            constexpr int kRowChunks = 4;
+#else
+            constexpr int kRowChunks = 8;
+#endif
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < kRowChunks; ++j) {
                 const uint32_t addr = row_addr + uint32_t((j ^ (r & 7)) << 4);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(wrd[4 * j]), "r"(wrd[4 * j + 1]),
                              "r"(wrd[4 * j + 2]), "r"(wrd[4 * j + 3])
@@ -252,8 +265,13 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv_c3_kernel(const __grid_con
                 C3_STAMP(it, 3);
                 const uint64_t adesc = make_sdesc_sw128(smem_u32(a_st + stage * 16384), 1024);
                 const uint32_t tmem_d = tmem_base + uint32_t(acc * 64);
+#if defined(B2R_EXP_C3_HALF_ROW)
+                constexpr int kSteps = 2;
+#else
+                constexpr int kSteps = 4;
+#endif
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < kSteps; ++k)
                     umma_bf16_ss(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, k > 0 ? 1u : 0u);
                 umma_commit(&empty_bar[stage]);
                 umma_commit(&tmem_full_bar[acc]);
