@@ -58,6 +58,8 @@ def _src(n, h, w, c, seed):
     (3, 12, 12, (128,), 256, True, 0),
     (3, 12, 12, (128,), 256, False, 8),      # single-CTA N = 256 (two epilogue groups)
     (5, 6, 6, (64,), 128, False, 4),         # B2R_CONV_NO_HALO: generic N = 128 (two co-resident CTAs, two epilogue groups)
+    (3, 12, 12, (128,), 256, False, 12),     # NO_PAIR | NO_HALO: generic N = 256, two epilogue groups, one staging buffer each
+    (3, 12, 12, (128,), 256, True, 12),
 ])
 def test_conv_outputs_stay_inside_their_buffers(n, h, w, srcs_c, co, pooled, flags):
     from b200restore import ops, packing, _lib as L
