@@ -586,3 +586,28 @@ def test_conv_w3_pair_mode_equals_single_cta_mode():
         assert torch.equal(res[0][0], res[1][0]), (ci_, n, h, w, splits, sc, kernels)
         if pool or head:
             assert torch.equal(res[0][1], res[1][1]), (ci_, "second output")
+
+
+@pytest.mark.parametrize("co,with_w3", [(64, True), (64, False), (128, False), (256, False)])
+@pytest.mark.parametrize("act,slope", [("none", 0.0), ("relu", 0.0), ("prelu", 0.25), ("prelu", 1.0), ("prelu", -0.3), ("prelu", 1.7)])
+def test_every_activation_form(co, with_w3, act, slope):
+    """The epilogues pick one of four forms per launch (conv_common.cuh::act_form): plain pack, ReLU on the packed pair,
+    max(x, slope x) for 0 <= slope <= 1, and the general max(x,0) + slope min(x,0) for any other slope (a trained PReLU may
+    leave [0, 1]).  All of them against torch on the tap-folded kernel (co = 64 with the folded weights) and the generic family."""
+    ops, packing, L = _ops()
+    n, h, w, ci = 2, 16, 28, 64
+    x = rnd(n, ci, h, w, seed=21)
+    wt = rnd(co, ci, 3, 3, scale=(2.0 / (9 * ci)) ** 0.5, seed=22)
+    b = rnd(co, scale=0.3, seed=23)
+    plan = packing.plan_conv3x3(wt.cpu())
+    wm, kbl = plan.finish()
+    w3 = plan.finish_w3().cuda() if with_w3 else None
+    out = torch.empty((n, h, w, co), dtype=torch.bfloat16, device="cuda")
+    code = {"none": L.B2R_ACT_NONE, "relu": L.B2R_ACT_RELU, "prelu": L.B2R_ACT_PRELU}[act]
+    ops.conv_gemm([nhwc_bf16(x)], wm.cuda(), b, kbl, act=code, slope=slope, out=out, weights_w3=w3)
+    ref = F.conv2d(nhwc_bf16(x).float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), b, padding=1)
+    if act == "relu":
+        ref = F.relu(ref)
+    elif act == "prelu":
+        ref = F.prelu(ref, torch.tensor([slope], device="cuda"))
+    assert_close_bf16(to_nchw_f32(out), ref, f"{act} slope {slope} co {co} ({(L.load().b2r_last_conv_kernel() or b'?').decode()})")
